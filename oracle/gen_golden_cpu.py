@@ -1,0 +1,134 @@
+"""Generate tests/golden/ref_py_*.npz by importing the REAL reference Python modules from /root/reference.
+
+TEST INFRASTRUCTURE ONLY.  Runs only in the build container (needs /root/reference); the fixtures it writes
+are committed and are what the tests read.  Run:  python oracle/gen_golden_cpu.py
+
+What is pinned here
+  * the module wiring of the reference (concat orders, weight formula, max-pool axis, score head, output
+    transposes) -- by running multi_model.score_network.ScoreNetwork / pn2_utils.modules.PointNetSAModule /
+    PointnetFPModule unmodified, on CPU, with `pn2_ext` provided by the C oracle (oracle/pn2_oracle.c);
+  * that oracle/ref_modules.py (the travelling restatement) reproduces those outputs exactly (asserted below).
+The kernels' own arithmetic (FPS / ball query / 3-NN index semantics) is pinned separately against the real
+reference CUDA kernels by oracle/gen_golden_gpu.py.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pn2_oracle, ref_modules  # noqa: E402
+from regnet_for_3d_grasping_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    sys.modules["pn2_ext"] = pn2_oracle.as_pn2_ext()
+    sys.modules["dgcnn_ext"] = pn2_oracle.as_dgcnn_ext()
+    sys.path.insert(0, "/root/reference")
+    from multi_model.score_network import ScoreNetwork
+    from multi_model.utils.pn2_utils import modules as ref_mods
+    return ScoreNetwork, ref_mods
+
+
+def gen_scorenet(ScoreNetwork):
+    torch.manual_seed(0)
+    B, N = 1, 6144
+    pc = torch.from_numpy(synth.batch("table", [11], N))
+    sd = ref_modules.random_scorenet_state(seed=3)
+    net = ScoreNetwork(training=False).eval()
+    missing = net.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert set(net.state_dict().keys()) == set(ref_modules.scorenet_state_shapes().keys())
+    with torch.no_grad():
+        feat, score, loss = net(pc)
+        feat2, score2, dbg = ref_modules.scorenet_forward(sd, pc, pn2_oracle.as_pn2_ext(), keep=True)
+    assert loss is None
+    assert feat.shape == (B, N, 256) and score.shape == (B, N)
+    assert torch.equal(feat, feat2) and torch.equal(score, score2), "ref_modules.py deviates from the reference modules"
+    rows = np.arange(0, N, 97)
+    np.savez_compressed(
+        os.path.join(OUT, "ref_py_scorenet_n6144.npz"),
+        meta=np.array("synth.table seed 11, N=6144, B=1; weights ref_modules.random_scorenet_state(seed=3); eval mode"),
+        rows=rows.astype(np.int32),
+        all_feature_rows=feat[0, rows].numpy(),
+        score=score[0].numpy(),
+        fps0=dbg["fps0"][0].numpy().astype(np.int32), fps1=dbg["fps1"][0].numpy().astype(np.int32),
+        fps2=dbg["fps2"][0].numpy().astype(np.int32),
+        bqcnt0=dbg["bqcnt0"][0].numpy().astype(np.int16), bqcnt1=dbg["bqcnt1"][0].numpy().astype(np.int16),
+        bqcnt2=dbg["bqcnt2"][0].numpy().astype(np.int16),
+        bq0_sum=dbg["bq0"][0].sum(1).numpy(), bq1_sum=dbg["bq1"][0].sum(1).numpy(), bq2_sum=dbg["bq2"][0].sum(1).numpy(),
+        nn2=dbg["nn2"][0, ::13].numpy().astype(np.int32),
+        sa2_rows=dbg["sa2"][0, :, ::16].numpy(),
+    )
+    # train-mode loss path: MSE against pc_score (score_network.py:19-29,50-51); dropout makes the score
+    # random in train mode, so only eval-with-loss is pinned: is_training=True but module in eval()
+    net.is_training = True
+    tgt = torch.from_numpy(synth.scores_like_dataset(5, B, N))
+    with torch.no_grad():
+        _, s3, loss3 = net(pc, tgt)
+    np.savez_compressed(os.path.join(OUT, "ref_py_scorenet_loss.npz"), loss=loss3.numpy(),
+                        meta=np.array("same input; pc_score = synth.scores_like_dataset(5,1,6144); MSELoss mean"))
+    print("scorenet golden ok: loss", float(loss3))
+
+
+def gen_modules(ref_mods):
+    """Small SA / FP module fixtures with the full tensors stored (weights included)."""
+    g = torch.Generator().manual_seed(7)
+    B, N, M, K, C = 2, 512, 128, 16, 5
+    pc = torch.from_numpy(synth.batch("cube", [21, 22], N))
+    xyz = pc[:, :, :3].permute(0, 2, 1)
+    feat = torch.randn(B, C, N, generator=g)
+    sa = ref_mods.PointNetSAModule(in_channels=C, mlp_channels=(16, 24), num_centroids=M, radius=0.15,
+                                   num_neighbours=K, use_xyz=True).eval()
+    fp = ref_mods.PointnetFPModule(in_channels=24 + C, mlp_channels=(20, 12), num_neighbors=3).eval()
+    with torch.no_grad():
+        for mod in list(sa.modules()) + list(fp.modules()):
+            if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+                mod.running_mean.copy_(torch.randn(mod.running_mean.shape, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+                mod.weight.copy_(torch.rand(mod.weight.shape, generator=g) + 0.5)
+                mod.bias.copy_(torch.randn(mod.bias.shape, generator=g) * 0.1)
+        new_xyz, new_feat = sa(xyz, feat)
+        up = fp(xyz, new_xyz, feat, new_feat)
+        gi = ref_mods._F.farthest_point_sample(xyz, M)
+        bi, bc = ref_mods._F.ball_query(xyz, new_xyz, 0.15, K)
+        ni, nd = ref_mods._F.search_nn_distance(xyz, new_xyz, 3)
+    out = {"pc": pc.numpy(), "feat": feat.numpy(), "new_xyz": new_xyz.numpy(), "new_feat": new_feat.numpy(),
+           "up": up.numpy(), "fps": gi.numpy().astype(np.int32), "bq": bi.numpy().astype(np.int32),
+           "bqcnt": bc.numpy().astype(np.int32), "nn": ni.numpy().astype(np.int32), "nnd": nd.numpy(),
+           "meta": np.array("PointNetSAModule(C=5,(16,24),M=128,r=.15,K=16) + PointnetFPModule(29,(20,12),3), eval")}
+    for k, v in sa.state_dict().items():
+        out["sa." + k] = v.numpy()
+    for k, v in fp.state_dict().items():
+        out["fp." + k] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, "ref_py_modules_small.npz"), **out)
+    print("module golden ok", new_feat.shape, up.shape)
+
+    # autograd through the reference's Function wrappers (function.py:84-107, 146-172): gradient fixtures
+    x = torch.randn(B, C, N, generator=g, requires_grad=True)
+    grouped = ref_mods._F.group_points(x, bi)
+    wsum = torch.randn(grouped.shape, generator=g)
+    (grouped * wsum).sum().backward()
+    g_group = x.grad.clone()
+    s = torch.randn(B, 7, M, generator=g, requires_grad=True)
+    inv = 1.0 / torch.clamp(nd, min=1e-10)
+    w = inv / inv.sum(2, keepdim=True)
+    it = ref_mods._F.feature_interpolate(s, ni, w)
+    wsum2 = torch.randn(it.shape, generator=g)
+    (it * wsum2).sum().backward()
+    np.savez_compressed(os.path.join(OUT, "ref_py_grads_small.npz"), x=x.detach().numpy(), wsum=wsum.numpy(),
+                        g_group=g_group.numpy(), s=s.detach().numpy(), w=w.numpy(), wsum2=wsum2.numpy(),
+                        interp=it.detach().numpy(), g_interp=s.grad.numpy(),
+                        meta=np.array("uses bq / nn / nnd of ref_py_modules_small.npz"))
+    print("grad golden ok")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    ScoreNetwork, ref_mods = import_reference()
+    gen_modules(ref_mods)
+    gen_scorenet(ScoreNetwork)
