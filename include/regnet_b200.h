@@ -1,0 +1,157 @@
+/*
+ * regnet_b200.h -- C ABI of libregnet_b200.so: REGNet's point-cloud hot path as sm_100a CUDA.
+ *
+ * Plain pointers and sizes only (no torch types).  All pointers are DEVICE pointers unless stated otherwise;
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Every function returns 0 on
+ * success and a non-zero REGNET_E* code on failure; regnet_last_error() then returns a thread-local message.
+ * Outputs are caller-allocated (the reference allocates inside the op: sampling_kernel.cu:140,
+ * ball_query_kernel.cu:107-109, interpolate_kernel.cu:109-110,196,301, grouping_kernel.cu:122 -- the Python
+ * shim regnet_for_3d_grasping_b200/pn2_ext.py allocates with torch so the caching allocator / stream
+ * semantics are kept).  Inputs are borrowed and never written.
+ *
+ * Section 1 replaces, one entry point each, the 7 functions of the reference's pybind module `pn2_ext`
+ * (multi_model/utils/pn2_utils/csrc/main.cpp:6-14) and the 2 of `dgcnn_ext`
+ * (multi_model/utils/pn2_utils/functions/csrc/main.cpp:3-6).  Tensors that the reference takes as
+ * (B, 3, N) "any stride" at::Tensors are passed as base pointer + three element strides, so the permuted
+ * views REGNet actually passes (score_network.py:46, pointnet2.py:89-90) need no copy.
+ *
+ * Section 2 is the fused path behind the module-level drop-in (multi_model.score_network.ScoreNetwork):
+ * a native plan that runs the whole PointNet2Seg forward (utils/pointnet2.py:86-121) on device.
+ *
+ * Paths cited are relative to /root/reference/multi_model/utils/pn2_utils/ unless they start elsewhere.
+ */
+#ifndef REGNET_B200_H_
+#define REGNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REGNET_OK 0
+#define REGNET_EINVAL 1   /* bad argument (the reference's TORCH_CHECK / CHECK_EQ failures) */
+#define REGNET_ECUDA 2    /* CUDA runtime / launch error */
+#define REGNET_ELIMIT 3   /* size outside what this build supports (message says which) */
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+const char* regnet_last_error(void);          /* thread-local, valid until the next failing call */
+int regnet_abi_version(void);                 /* bumped on any signature change */
+int regnet_device_arch(int* sm_major, int* sm_minor, int* sm_count);  /* of the current device */
+/* The reference device-asserts on out-of-range gather/scatter indices (grouping_kernel.cu:89,
+ * interpolate_kernel.cu:168,278).  Here such elements are skipped and a device flag is raised; this call
+ * synchronises, returns REGNET_EINVAL if the flag was raised since the last call, and clears it. */
+int regnet_check_index_errors(void);
+
+/* ---- 1. pn2_ext operator ABI --------------------------------------------------------------------------- */
+
+/* csrc/sampling.h:7-9 FarthestPointSample (kernel csrc/sampling_kernel.cu:47-117).
+ * points: logical (B,3,N) fp32 with element strides (sb,sc,sn).  index: (B,M) int64, first pick = 0.
+ * new_xyz (optional, may be NULL): (B,3,M) contiguous, the sampled coordinates (function.py:11-26 gather_points
+ * fused).  Bit-exact with the reference including its tie rule.  EINVAL unless 0 < M <= N. */
+int regnet_farthest_point_sample(const float* points, int64_t sb, int64_t sc, int64_t sn, int B, int N, int M,
+                                 int64_t* index, float* new_xyz, void* stream);
+/* same, with explicit tuning (cluster_size in {0=auto,1,2,4,8}, threads in {0=auto,512,1024}) and an
+ * optional int32 copy of the indices for the fused path */
+int regnet_farthest_point_sample_ex(const float* points, int64_t sb, int64_t sc, int64_t sn, int B, int N, int M,
+                                    int64_t* index64, int32_t* index32, float* new_xyz, int cluster_size,
+                                    int threads, void* stream);
+
+/* csrc/ball_query.h:7-11 BallQuery (kernel csrc/ball_query_kernel.cu:31-74).
+ * points (B,3,N), centroids (B,3,M) strided as above; radius is a C float squared in fp32; strict d < r*r;
+ * first K hits in ascending index order, first hit replicated into unused slots, no hit -> zeros.
+ * index (B,M,K) int64, count (B,M) int64; index32 (optional) int32 copy.  K <= 128. */
+int regnet_ball_query(const float* points, int64_t psb, int64_t psc, int64_t psn, const float* centroids,
+                      int64_t csb, int64_t csc, int64_t csn, int B, int N, int M, float radius, int K,
+                      int64_t* index, int64_t* count, int32_t* index32, void* stream);
+
+/* csrc/grouping.h:7-14 GroupPointsForward / GroupPointsBackward (csrc/grouping_kernel.cu:29-51, 54-149).
+ * input (B,C,N) strided; index (B,M,K) int64 contiguous; out (B,C,M,K) contiguous.
+ * backward: grad_out (B,C,M,K) contiguous -> grad_in (B,C,N) contiguous, zero-filled then scatter-added. */
+int regnet_group_points_forward(const float* input, int64_t sb, int64_t sc, int64_t sn, const int64_t* index,
+                                int B, int C, int N, int M, int K, float* out, void* stream);
+int regnet_group_points_backward(const float* grad_out, const int64_t* index, int B, int C, int N, int M, int K,
+                                 float* grad_in, void* stream);
+
+/* csrc/interpolate.h:8-22 PointSearch (kernel csrc/interpolate_kernel.cu:28-77): exact 3-NN, strict '<'
+ * insertion (earliest index wins ties), distances SQUARED.  EINVAL unless k == 3 and Nk >= 3.
+ * index (B,Nq,3) int64, distance (B,Nq,3) fp32. */
+int regnet_point_search(const float* query, int64_t qsb, int64_t qsc, int64_t qsn, const float* key, int64_t ksb,
+                        int64_t ksc, int64_t ksn, int B, int Nq, int Nk, int k, int64_t* index, float* distance,
+                        void* stream);
+
+/* InterpolateForward / InterpolateBackward (csrc/interpolate_kernel.cu:134-232, 239-337).
+ * input (B,C,Ns) strided, index/weight (B,Nd,3) contiguous -> out (B,C,Nd) contiguous;
+ * backward: grad_out (B,C,Nd) contiguous -> grad_in (B,C,Ns) contiguous. */
+int regnet_interpolate_forward(const float* input, int64_t sb, int64_t sc, int64_t sn, const int64_t* index,
+                               const float* weight, int B, int C, int Ns, int Nd, float* out, void* stream);
+int regnet_interpolate_backward(const float* grad_out, const int64_t* index, const float* weight, int B, int C,
+                                int Ns, int Nd, float* grad_in, void* stream);
+
+/* dgcnn_ext (functions/csrc/gather_knn.h:7-13): same maths as group_points with N' == N. */
+int regnet_gather_knn_forward(const float* input, int64_t sb, int64_t sc, int64_t sn, const int64_t* index, int B,
+                              int C, int N, int M, int K, float* out, void* stream);
+int regnet_gather_knn_backward(const float* grad_out, const int64_t* index, int B, int C, int N, int M, int K,
+                               float* grad_in, void* stream);
+
+/* ---- 2. fused ScoreNet forward -------------------------------------------------------------------------- */
+
+/* Engine of the shared-MLP contraction (nn/modules/mlp.py:55-106 = chained 1x1 conv + BN + ReLU):
+ *   REGNET_ENGINE_TC    tcgen05 tensor cores, operands split into bf16 hi+lo planes, 3 products, fp32 accumulate
+ *                       in TMEM (the product path)
+ *   REGNET_ENGINE_SIMT  fp32 FFMA tiles (bring-up / cross-check engine, also CUDA, never a CPU path) */
+#define REGNET_ENGINE_TC 0
+#define REGNET_ENGINE_SIMT 1
+
+#define REGNET_MAX_LAYERS 4
+
+typedef struct regnet_scorenet_config {
+  int32_t batch;               /* B */
+  int32_t num_points;          /* N (25600 in REGNet, train.py:70) */
+  int32_t num_centroids[3];    /* utils/pointnet2.py:40  (5120,1024,256) */
+  float radius[3];             /* utils/pointnet2.py:41  (0.02,0.08,0.32) */
+  int32_t num_neighbours[3];   /* utils/pointnet2.py:42  (64,64,64); must be 64 for the pooled epilogue */
+  int32_t engine;              /* REGNET_ENGINE_* */
+  int32_t use_side_stream;     /* 1: geometry chain (FPS/ball query/3-NN) on an internal second stream */
+} regnet_scorenet_config;
+
+typedef struct regnet_scorenet regnet_scorenet;   /* opaque plan */
+
+/* Create / destroy a plan.  The plan owns its workspace (cudaMalloc) and prepared weights. */
+int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** out);
+int regnet_scorenet_destroy(regnet_scorenet* plan);
+int64_t regnet_scorenet_workspace_bytes(const regnet_scorenet* plan);
+
+/* Fold + upload one conv/BN layer (eval mode: y = relu(scale * (W x) + shift)).
+ * stage: 0-2 = sa_modules[i], 3-5 = fp_modules[i-3], 6 = seg mlp, 7 = score head (conv_score+bn_score, sigmoid).
+ * weight: DEVICE fp32 (cout, cin) row-major (the conv weight with its trailing 1x1 dims dropped);
+ * scale/shift: DEVICE fp32 (cout) = gamma/sqrt(var+eps), beta - mean*scale (+ scale*bias for the score head). */
+int regnet_scorenet_set_layer(regnet_scorenet* plan, int stage, int layer, int cin, int cout, const float* weight,
+                              const float* scale, const float* shift, void* stream);
+
+/* Run the forward.  pc: (B,N,6) fp32 contiguous (xyz,rgb), as score_network.py:31-46 receives it.
+ * all_feature: (B,N,256) fp32 contiguous (= the reference's all_feature values; the reference returns them as a
+ * transposed view of (B,256,N), score_network.py:48).  score: (B,N) fp32.  Asynchronous on `stream`. */
+int regnet_scorenet_forward(regnet_scorenet* plan, const float* pc, float* all_feature, float* score, void* stream);
+
+/* Read back intermediates of the last forward for parity tests (device pointers into the plan's workspace,
+ * valid until the next forward).  what: "fps0".."fps2" int32 (B,M_i); "bq0".."bq2" int32 (B,M_i,64);
+ * "nn0".."nn2" int32 (B,Nd_i,3); "sa0".."sa2" fp32 (B,M_i,C) point-major; "fp0".."fp2" fp32 point-major. */
+int regnet_scorenet_intermediate(regnet_scorenet* plan, const char* what, void** ptr, int64_t* numel);
+
+/* Number of kernels launched by the last regnet_scorenet_forward (for bench.py's gpu_launches). */
+int regnet_scorenet_launch_count(const regnet_scorenet* plan);
+
+/* ---- 3. building blocks exposed for tests / micro-benchmarks ------------------------------------------- */
+
+/* Y = act(scale * (X W^T) + shift), X (P,cin) fp32 row-major, W (cout,cin) fp32 row-major.
+ * pool == 0: Y (P,cout) fp32 row-major.  pool > 0 (must be 64): Y (P/pool,cout) = max over each run of `pool` rows.
+ * act: 0 none, 1 relu, 2 sigmoid.  engine as above.  Stand-alone (allocates + frees scratch internally; not for
+ * hot loops -- the plan uses pre-split operands). */
+int regnet_mlp_layer(const float* X, const float* W, const float* scale, const float* shift, int64_t P, int cin,
+                     int cout, int pool, int act, int engine, float* Y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGNET_B200_H_ */

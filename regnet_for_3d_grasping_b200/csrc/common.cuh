@@ -1,0 +1,70 @@
+// Shared device/host helpers for libregnet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/regnet_b200.h"
+
+namespace regnet {
+
+// ---- error plumbing ---------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define RN_CHECK_ARG(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ::regnet::set_error(__VA_ARGS__);         \
+      return REGNET_EINVAL;                     \
+    }                                           \
+  } while (0)
+
+#define RN_CUDA(call)                                            \
+  do {                                                           \
+    cudaError_t e__ = (call);                                    \
+    if (e__ != cudaSuccess) return ::regnet::cuda_fail(e__, #call); \
+  } while (0)
+
+#define RN_LAUNCH_CHECK(name)                                    \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return ::regnet::cuda_fail(e__, name); \
+  } while (0)
+
+#define RN_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != REGNET_OK) return rc__; \
+  } while (0)
+
+// ---- the reference's squared distance, rounding pinned ------------------------------------------------------
+// nvcc -O2 compiles (x2-x1)*(x2-x1)+(y2-y1)*(y2-y1)+(z2-z1)*(z2-z1) (sampling_kernel.cu:82,
+// ball_query_kernel.cu:60, interpolate_kernel.cu:56) to FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.)
+// (oracle/_ref/pn2_ext_ref.sass.txt).  Intrinsics keep that order whatever this translation unit's flags are.
+__device__ __forceinline__ float sqdist_ref(float x1, float y1, float z1, float x2, float y2, float z2) {
+  const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
+  float t = __fmul_rn(dy, dy);
+  t = __fmaf_rn(dx, dx, t);
+  t = __fmaf_rn(dz, dz, t);
+  return t;
+}
+
+// ---- split-bf16 operand format --------------------------------------------------------------------------------
+// x ~= hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi): 16 significant bits, fp32 range.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(__fsub_rn(x, __bfloat162float(hi)));
+}
+
+__host__ __device__ __forceinline__ int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+__host__ __device__ __forceinline__ int round_up(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+struct Strides3 {
+  int64_t b, c, n;
+};
+
+}  // namespace regnet

@@ -1,0 +1,41 @@
+// Shared-MLP layer contraction: Y = act(scale * (X W^T) + shift) [+ max over runs of 64 rows].
+// One description, two engines (gemm_simt.cu: fp32 FFMA tiles; gemm_tc.cu: tcgen05 split-bf16).
+//
+// This is the reference's Conv1d/Conv2d(k=1, bias=False) + BatchNorm + ReLU of
+// multi_model/utils/pn2_utils/nn/modules/conv.py:24-36,64-76 (eval mode: BN folded to scale/shift), and with
+// pool = 64 also the `torch.max(new_feature, 3)` of pn2_utils/modules.py:245 fused into the epilogue.
+// Rows are positions (point-major), columns are channels.
+#pragma once
+#include "common.cuh"
+
+namespace regnet {
+
+struct Epilogue {
+  const float* scale = nullptr;   // (cout) or nullptr = 1
+  const float* shift = nullptr;   // (cout) or nullptr = 0
+  int act = 1;                    // 0 none, 1 relu, 2 sigmoid
+  int pool = 0;                   // 0, or 64: rows are reduced by max in runs of 64 (P % 64 == 0)
+  float* out_f32 = nullptr;       // (P or P/pool, ld_f32) fp32
+  int ld_f32 = 0;
+  __nv_bfloat16* out_hi = nullptr;  // (P, ld_split) bf16 planes of the same values (pool == 0 only)
+  __nv_bfloat16* out_lo = nullptr;
+  int ld_split = 0;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-v)));
+  return v;
+}
+
+// X (P, ldx) fp32 with columns >= K zero, W (cout, ldw) fp32 with columns >= K zero; kpad = padded K (mult of 16)
+int gemm_simt_launch(const float* X, int ldx, const float* W, int ldw, int64_t P, int kpad, int cout,
+                     const Epilogue& ep, cudaStream_t stream);
+
+// X as bf16 hi/lo planes (P, ldx), W as bf16 hi/lo planes (cout, ldw); ldx, ldw multiples of 8; K = logical depth
+int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, const __nv_bfloat16* Whi,
+                   const __nv_bfloat16* Wlo, int ldw, int64_t P, int K, int cout, const Epilogue& ep,
+                   cudaStream_t stream);
+int gemm_tc_supported(void);  // 1 when the driver entry point for tensor maps is available on this box
+
+}  // namespace regnet

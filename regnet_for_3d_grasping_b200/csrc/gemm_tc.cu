@@ -1,0 +1,444 @@
+// tcgen05 engine for the shared-MLP layer (see gemm.cuh): Y = act(scale * (X W^T) + shift) [+ 64-row max-pool].
+//
+// fp32 parity (<= 1e-4 rel, BASELINE.json north_star) on bf16 tensor cores: every fp32 operand is carried as two
+// bf16 planes x = hi + lo (16 significant bits, fp32 exponent range) and each k-block issues three products into
+// the SAME fp32 TMEM accumulator:  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term is ~2^-18 relative).
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer : cp.async.bulk.tensor (128B swizzle) of X_hi/X_lo [128 x 64] and W_hi/W_lo [BN x 64]
+//                              tiles into a STAGES-deep shared-memory ring, completion on `full` mbarriers
+//   warp 1      MMA issuer   : one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16), 12 per
+//                              k-block; tcgen05.commit releases the stage (`empty`) and publishes the accumulator
+//                              (`tmem_full`).  Also owns the TMEM allocation (2 x BN fp32 columns, double buffered
+//                              so the epilogue of tile i overlaps the main loop of tile i+1)
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32 (thread = one position row, 32 channels per load), BN
+//                              scale/shift + activation in registers, then either vectorised fp32 / bf16 hi+lo
+//                              row stores, or the 64-row max-pool via redux.sync on an order-preserving integer
+//                              image of the floats (one instruction per channel per warp)
+// Rows (positions) live on the 128 TMEM lanes, channels on the columns, so a tile is 128 positions x BN channels
+// and both operands are K-major -- the canonical TMA/UMMA SWIZZLE_128B layout.
+#include <cuda.h>
+
+#include "gemm.cuh"
+
+namespace regnet {
+
+namespace {
+
+constexpr int BM = 128;      // positions per tile = TMEM lanes
+constexpr int BK = 64;       // bf16 per k-block row = 128 bytes = one swizzle span
+constexpr int NTHREADS = 192;
+constexpr int EPI_THREADS = 128;
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;              // one plane of X
+  static constexpr int B_BYTES = BN * BK * 2;              // one plane of W
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = BN == 128 ? 3 : 2;         // shared-memory ring depth (192 KB of tiles)
+  static constexpr int OFF_BAR = STAGES * STAGE_BYTES;     // mbarriers + tmem pointer
+  static constexpr int OFF_SCALE = OFF_BAR + 128;          // scale[BN], shift[BN]
+  static constexpr int OFF_PART = OFF_SCALE + 2 * BN * 4;  // pooled partials [4][BN] as uint32
+  static constexpr int SMEM_BYTES = OFF_PART + 4 * BN * 4 + 1024;  // + slack for manual 1024B alignment
+  static constexpr int TMEM_COLS = 2 * BN;                 // 256 or 512: power of two >= 32
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch error surfaced to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s at 2 GHz
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+// start address >> 4 in [0,14), LBO (ignored for swizzled K-major) = 1 in [16,30), SBO = 1024 B >> 4 in [32,46)
+// (8 rows x 128 B per swizzle atom), version = 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// A,B K-major (bits 15,16 = 0), N>>3 in [17,23), M>>4 in [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t order_bits(float v) {  // unsigned order == float order
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unorder_bits(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
+               const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo, int64_t P,
+               int K, int cout, Epilogue ep) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  // bars[0..STAGES) full, [STAGES..2*STAGES) empty, then tmem_full[2], tmem_empty[2]
+  const uint32_t bar_full = smem_base + C::OFF_BAR;
+  const uint32_t bar_empty = bar_full + 8 * STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 8 * (2 * STAGES + 4));
+  float* s_scale = reinterpret_cast<float*>(smem + C::OFF_SCALE);
+  float* s_shift = s_scale + BN;
+  uint32_t* s_part = reinterpret_cast<uint32_t*>(smem + C::OFF_PART);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ctile = (cout + BN - 1) / BN;
+  const int64_t n_ptile = (P + BM - 1) / BM;
+  const int64_t n_tiles = n_ptile * n_ctile;
+  const int n_kblk = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&map_xhi);
+    tma_prefetch_desc(&map_xlo);
+    tma_prefetch_desc(&map_whi);
+    tma_prefetch_desc(&map_wlo);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_holder), C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  (void)bars;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = (int)((tile / n_ctile) * BM);
+        const int col0 = (int)(tile % n_ctile) * BN;
+        for (int kb = 0; kb < n_kblk; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_arrive_expect_tx(full, C::STAGE_BYTES);
+          tma_load_2d(sA, &map_xhi, full, kb * BK, row0);
+          tma_load_2d(sA + C::A_BYTES, &map_xlo, full, kb * BK, row0);
+          tma_load_2d(sA + 2 * C::A_BYTES, &map_whi, full, kb * BK, col0);
+          tma_load_2d(sA + 2 * C::A_BYTES + C::B_BYTES, &map_wlo, full, kb * BK, col0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      uint32_t stage = 0, phase = 0;
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < n_kblk; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
+          const uint64_t a_hi = make_sdesc(sA), a_lo = make_sdesc(sA + C::A_BYTES);
+          const uint64_t b_hi = make_sdesc(sA + 2 * C::A_BYTES), b_lo = make_sdesc(sA + 2 * C::A_BYTES + C::B_BYTES);
+          const int rem = K - kb * BK;
+          const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
+          for (int k = 0; k < ksteps; ++k) {  // +2 per k-step: 32 bytes >> 4 inside the 128B swizzle span
+            umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+          }
+          for (int k = 0; k < ksteps; ++k) umma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+          for (int k = 0; k < ksteps; ++k) umma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+          umma_commit(bar_empty + 8 * stage);            // stage reusable once these MMAs have read it
+          if (kb == n_kblk - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;  // 0..127
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      const int64_t row0 = (tile / n_ctile) * BM;
+      const int col0 = (int)(tile % n_ctile) * BN;
+      // stage this channel tile's scale / shift (previous tile's readers are past the trailing barrier)
+      for (int c = et; c < BN; c += EPI_THREADS) {
+        const int gc = col0 + c;
+        s_scale[c] = (ep.scale && gc < cout) ? ep.scale[gc] : 1.f;
+        s_shift[c] = (ep.shift && gc < cout) ? ep.shift[gc] : 0.f;
+      }
+      epi_bar_sync();
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int64_t row = row0 + q * 32 + lane;
+      const bool row_ok = row < P;
+      uint32_t keep[BN / 32];
+#pragma unroll
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32, v);
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          y[j] = apply_act(fmaf(__uint_as_float(v[j]), s_scale[ch * 32 + j], s_shift[ch * 32 + j]), ep.act);
+        const int c0 = col0 + ch * 32;
+        if (ep.pool) {
+          uint32_t mine = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t m = __reduce_max_sync(FULL, order_bits(y[j]));
+            if (lane == j) mine = m;
+          }
+          keep[ch] = mine;
+        } else if (row_ok) {
+          if (c0 + 32 <= cout) {
+            if (ep.out_f32) {
+              float4* dst = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ld_f32 + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            }
+            if (ep.out_hi) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(y[2 * j], h0, l0);
+                split_bf16(y[2 * j + 1], h1, l1);
+                __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
+                hi[j] = *reinterpret_cast<uint32_t*>(&hh);
+                lo[j] = *reinterpret_cast<uint32_t*>(&ll);
+              }
+              uint4* dh = reinterpret_cast<uint4*>(ep.out_hi + row * ep.ld_split + c0);
+              uint4* dl = reinterpret_cast<uint4*>(ep.out_lo + row * ep.ld_split + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (c0 + j < cout) {
+                if (ep.out_f32) ep.out_f32[row * ep.ld_f32 + c0 + j] = y[j];
+                if (ep.out_hi) {
+                  __nv_bfloat16 h, l;
+                  split_bf16(y[j], h, l);
+                  ep.out_hi[row * ep.ld_split + c0 + j] = h;
+                  ep.out_lo[row * ep.ld_split + c0 + j] = l;
+                }
+              }
+            }
+          }
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (ep.pool) {
+#pragma unroll
+        for (int ch = 0; ch < BN / 32; ++ch) s_part[q * BN + ch * 32 + lane] = keep[ch];
+        epi_bar_sync();
+        for (int e = et; e < 2 * BN; e += EPI_THREADS) {
+          const int g = e / BN, c = e - g * BN;
+          const int64_t grow = row0 / 64 + g;
+          if (grow * 64 < P && col0 + c < cout) {
+            const uint32_t m = max(s_part[(2 * g) * BN + c], s_part[(2 * g + 1) * BN + c]);
+            ep.out_f32[grow * ep.ld_f32 + col0 + c] = unorder_bits(m);
+          }
+        }
+      }
+      epi_bar_sync();  // s_scale / s_part free for the next tile
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled is not available from this driver");
+    return REGNET_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%d ld=%d)", (int)r,
+              (long long)rows, cols, ld);
+    return REGNET_ECUDA;
+  }
+  return REGNET_OK;
+}
+
+template <int BN>
+int launch(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl, int64_t P,
+           int K, int cout, const Epilogue& ep, cudaStream_t stream) {
+  int dev = 0, sms = 0;
+  RN_CUDA(cudaGetDevice(&dev));
+  RN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  RN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+  const int64_t n_tiles = ((P + BM - 1) / BM) * ((cout + BN - 1) / BN);
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, P, K, cout, ep);
+  RN_LAUNCH_CHECK("gemm_tc_kernel");
+  return REGNET_OK;
+}
+
+}  // namespace
+
+int gemm_tc_supported(void) { return encode_fn() != nullptr; }
+
+int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, const __nv_bfloat16* Whi,
+                   const __nv_bfloat16* Wlo, int ldw, int64_t P, int K, int cout, const Epilogue& ep,
+                   cudaStream_t stream) {
+  RN_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= K && ldw >= K,
+               "gemm_tc: leading dimensions must be multiples of 8 and >= K (K=%d ldx=%d ldw=%d)", K, ldx, ldw);
+  RN_CHECK_ARG(ep.pool == 0 || (ep.pool == 64 && P % 64 == 0 && ep.out_f32 && !ep.out_hi),
+               "gemm_tc: pooled epilogue needs pool == 64, P %% 64 == 0 and an fp32 output");
+  RN_CHECK_ARG(!ep.out_f32 || ep.pool || ep.ld_f32 % 4 == 0, "gemm_tc: fp32 output leading dimension must be a multiple of 4");
+  RN_CHECK_ARG(!ep.out_hi || ep.ld_split % 8 == 0, "gemm_tc: split output leading dimension must be a multiple of 8");
+  RN_CHECK_ARG(P < (1LL << 31), "gemm_tc: too many rows");
+  if (P == 0) return REGNET_OK;
+  const int bn = cout > 128 ? 256 : 128;
+  CUtensorMap mxh, mxl, mwh, mwl;
+  RN_TRY(make_map(&mxh, Xhi, P, K, ldx, BM));
+  RN_TRY(make_map(&mxl, Xlo, P, K, ldx, BM));
+  RN_TRY(make_map(&mwh, Whi, cout, K, ldw, bn));
+  RN_TRY(make_map(&mwl, Wlo, cout, K, ldw, bn));
+  if (bn == 256) return launch<256>(mxh, mxl, mwh, mwl, P, K, cout, ep, stream);
+  return launch<128>(mxh, mxl, mwh, mwl, P, K, cout, ep, stream);
+}
+
+}  // namespace regnet

@@ -1,0 +1,38 @@
+// Internal launch functions shared between translation units of libregnet_b200.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace regnet {
+
+int fps_block_log2(int N);
+int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx64, int32_t* idx32, float* new_xyz,
+               int cluster_size, int threads, cudaStream_t stream);
+int ball_query_launch(const float* pts, Strides3 pst, const float* ctr, Strides3 cst, int B, int N, int M,
+                      float radius, int K, int64_t* index, int64_t* count, int32_t* index32, cudaStream_t stream);
+int three_nn_launch(const float* qry, Strides3 qst, const float* key, Strides3 kst, int B, int Nq, int Nk,
+                    int64_t* index, float* dist, int32_t* index32, float* weight, cudaStream_t stream);
+
+int group_forward_launch(const float* in, Strides3 st, const int64_t* index, int B, int C, int N, int M, int K,
+                         float* out, int* d_oob, cudaStream_t stream);
+int group_backward_launch(const float* gout, const int64_t* index, int B, int C, int N, int M, int K, float* gin,
+                          int* d_oob, cudaStream_t stream);
+int interp_forward_launch(const float* in, Strides3 st, const int64_t* index, const float* weight, int B, int C,
+                          int Ns, int Nd, float* out, int* d_oob, cudaStream_t stream);
+int interp_backward_launch(const float* gout, const int64_t* index, const float* weight, int B, int C, int Ns,
+                           int Nd, float* gin, int* d_oob, cudaStream_t stream);
+
+int sa_operand_launch(const float* xyz, Strides3 xst, const float* new_xyz, const float* feat, int64_t feat_bstride,
+                      int feat_ld, int C, const int32_t* nbr, int B, int N, int M, int K, int kpad, float* out_f32,
+                      __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);
+int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld, int C2, const float* dense,
+                      int64_t dense_bstride, int dense_ld, int C1, const int32_t* idx, const float* w, int B, int Nd,
+                      int kpad, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);
+int split_rows_launch(const float* src, int64_t rows, int cols, int ld_src, int kpad, __nv_bfloat16* hi,
+                      __nv_bfloat16* lo, float* f32, cudaStream_t stream);
+int score_head_launch(const float* X, int ldx, const float* w, const float* scale, const float* shift, int64_t P,
+                      int cin, float* score, cudaStream_t stream);
+
+int* oob_flag();  // per-device lazily allocated device int, set by kernels that meet an out-of-range index
+
+}  // namespace regnet

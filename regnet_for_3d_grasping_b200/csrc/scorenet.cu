@@ -1,0 +1,406 @@
+// Native plan for the whole ScoreNet (PointNet2Seg) forward -- section 2 of include/regnet_b200.h.
+//
+// Restates, B200-first, the call chain of /root/reference/multi_model/utils/pointnet2.py:86-121 :
+//   3 x PointNetSAModule (pn2_utils/modules.py:210-246): FPS -> gather -> ball query -> group/concat -> SharedMLP -> max
+//   3 x PointnetFPModule (pn2_utils/modules.py:500-509, 104-131): 3-NN -> weights -> interpolate/concat -> SharedMLP
+//   seg SharedMLP + conv_score/bn_score/sigmoid (pointnet2.py:116-119)
+// Differences from the reference's execution (not its results):
+//   * activations are point-major (rows = points/positions, channels contiguous) so every gather reads a row;
+//   * the geometry chain (FPS / ball query / 3-NN depends on xyz only) runs on a second stream, overlapped with
+//     the MLP GEMMs of the previous level;
+//   * group+concat and interpolate+concat write the GEMM operand once, already split for the tensor-core engine;
+//   * BN (eval) + ReLU + the 64-neighbour max-pool are GEMM epilogues; nothing else touches the activations.
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "internal.cuh"
+
+using namespace regnet;
+
+namespace {
+
+const int SA_CH[3][3] = {{128, 128, 256}, {256, 256, 512}, {512, 512, 1024}};  // pointnet2.py:43
+const int FP_CH[3][3] = {{1024, 1024, 0}, {512, 512, 0}, {256, 256, 256}};       // pointnet2.py:44
+const int FP_NL[3] = {2, 2, 3};
+const int SEG_CH[4] = {512, 256, 256, 128};                                       // pointnet2.py:46
+
+struct Layer {
+  int cin = 0, cout = 0, kpad = 0;
+  float* w_f32 = nullptr;           // (cout, kpad) zero padded
+  __nv_bfloat16* w_hi = nullptr;    // (cout, kpad)
+  __nv_bfloat16* w_lo = nullptr;
+  float* scale = nullptr;
+  float* shift = nullptr;
+  bool set = false;
+};
+
+struct Act {  // an activation matrix (rows, ld) in the layout of the selected engine
+  float* f32 = nullptr;
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int ld = 0;
+};
+
+}  // namespace
+
+struct regnet_scorenet {
+  regnet_scorenet_config cfg;
+  int B = 0, N = 0;
+  int M[3] = {0, 0, 0};
+  Layer layers[8][REGNET_MAX_LAYERS];
+  int nlayers[8] = {3, 3, 3, 2, 2, 3, 4, 1};
+  // geometry
+  int32_t* fps_idx[3] = {nullptr, nullptr, nullptr};
+  float* new_xyz[3] = {nullptr, nullptr, nullptr};   // (B,3,M_i) planar
+  int32_t* nbr[3] = {nullptr, nullptr, nullptr};     // (B,M_i,64)
+  int32_t* nn_idx[3] = {nullptr, nullptr, nullptr};  // (B,Nd_i,3)
+  float* nn_w[3] = {nullptr, nullptr, nullptr};
+  // features (fp32, point-major)
+  float* sa_out[3] = {nullptr, nullptr, nullptr};    // (B,M_i,C_i)
+  float* fp_out[2] = {nullptr, nullptr};             // fp0 (B,M1,1024), fp1 (B,M0,512); fp2 is the caller's buffer
+  float* last_allfeat = nullptr;
+  // ping-pong activation arenas
+  unsigned char* arena[2] = {nullptr, nullptr};
+  size_t arena_bytes = 0;
+  std::vector<void*> allocs;
+  size_t total_bytes = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_bq[3] = {nullptr, nullptr, nullptr}, ev_nn = nullptr;
+  int launches = 0;
+};
+
+namespace {
+
+int dalloc(regnet_scorenet* p, void** out, size_t bytes) {
+  bytes = (bytes + 255) / 256 * 256;
+  RN_CUDA(cudaMalloc(out, bytes));
+  p->allocs.push_back(*out);
+  p->total_bytes += bytes;
+  return REGNET_OK;
+}
+
+Act make_act(const regnet_scorenet* p, int which, int64_t rows, int ld) {
+  Act a;
+  a.ld = ld;
+  if (p->cfg.engine == REGNET_ENGINE_SIMT) {
+    a.f32 = reinterpret_cast<float*>(p->arena[which]);
+  } else {
+    a.hi = reinterpret_cast<__nv_bfloat16*>(p->arena[which]);
+    a.lo = a.hi + (size_t)rows * ld;
+  }
+  return a;
+}
+
+// one conv+BN+act layer: in -> (out_act and/or out_f32), optional 64-row pooling
+int run_layer(regnet_scorenet* p, const Layer& L, const Act& in, int64_t P, int act, int pool, const Act* out_act,
+              float* out_f32, int ld_f32, cudaStream_t s) {
+  if (!L.set) {
+    set_error("scorenet: a layer (cin=%d) was never given weights (regnet_scorenet_set_layer)", L.cin);
+    return REGNET_EINVAL;
+  }
+  Epilogue ep;
+  ep.scale = L.scale; ep.shift = L.shift; ep.act = act; ep.pool = pool;
+  ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
+  ++p->launches;
+  if (p->cfg.engine == REGNET_ENGINE_SIMT) {
+    if (out_act) {
+      if (out_f32 && out_f32 != out_act->f32) {
+        set_error("scorenet: SIMT engine cannot write two fp32 outputs");
+        return REGNET_EINVAL;
+      }
+      ep.out_f32 = out_act->f32; ep.ld_f32 = out_act->ld;
+    }
+    return gemm_simt_launch(in.f32, in.ld, L.w_f32, L.kpad, P, L.kpad, L.cout, ep, s);
+  }
+  if (out_act) { ep.out_hi = out_act->hi; ep.out_lo = out_act->lo; ep.ld_split = out_act->ld; }
+  return gemm_tc_launch(in.hi, in.lo, in.ld, L.w_hi, L.w_lo, L.kpad, P, L.cin, L.cout, ep, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** out) {
+  RN_CHECK_ARG(cfg && out, "scorenet_create: null argument");
+  RN_CHECK_ARG(cfg->batch > 0 && cfg->num_points > 0, "scorenet_create: empty batch");
+  RN_CHECK_ARG(cfg->engine == REGNET_ENGINE_TC || cfg->engine == REGNET_ENGINE_SIMT, "scorenet_create: unknown engine");
+  int prev = cfg->num_points;
+  for (int i = 0; i < 3; ++i) {
+    RN_CHECK_ARG(cfg->num_centroids[i] > 0 && cfg->num_centroids[i] <= prev,
+                 "scorenet_create: num_centroids[%d]=%d must be in (0, %d]", i, cfg->num_centroids[i], prev);
+    RN_CHECK_ARG(cfg->num_neighbours[i] == 64, "scorenet_create: num_neighbours must be 64 (pooled epilogue)");
+    RN_CHECK_ARG(cfg->radius[i] > 0.f, "scorenet_create: radius must be > 0");
+    prev = cfg->num_centroids[i];
+  }
+  RN_CHECK_ARG(cfg->num_centroids[2] >= 3, "scorenet_create: the coarsest level needs >= 3 points for 3-NN");
+  if (cfg->engine == REGNET_ENGINE_TC && !gemm_tc_supported()) {
+    set_error("scorenet_create: tensor-map driver entry point unavailable; the tcgen05 engine cannot run here");
+    return REGNET_ECUDA;
+  }
+  regnet_scorenet* p = new regnet_scorenet();
+  p->cfg = *cfg;
+  p->B = cfg->batch;
+  p->N = cfg->num_points;
+  for (int i = 0; i < 3; ++i) p->M[i] = cfg->num_centroids[i];
+  const int B = p->B, N = p->N;
+  const int* M = p->M;
+  int rc = REGNET_OK;
+  auto A = [&](void** ptr, size_t bytes) { if (!rc) rc = dalloc(p, ptr, bytes); };
+  for (int i = 0; i < 3; ++i) {
+    A((void**)&p->fps_idx[i], sizeof(int32_t) * (size_t)B * M[i]);
+    A((void**)&p->new_xyz[i], sizeof(float) * (size_t)B * 3 * M[i]);
+    A((void**)&p->nbr[i], sizeof(int32_t) * (size_t)B * M[i] * 64);
+    A((void**)&p->sa_out[i], sizeof(float) * (size_t)B * M[i] * SA_CH[i][2]);
+  }
+  const int nd[3] = {M[1], M[0], N};  // dense point counts of fp0, fp1, fp2
+  for (int i = 0; i < 3; ++i) {
+    A((void**)&p->nn_idx[i], sizeof(int32_t) * (size_t)B * nd[i] * 3);
+    A((void**)&p->nn_w[i], sizeof(float) * (size_t)B * nd[i] * 3);
+  }
+  A((void**)&p->fp_out[0], sizeof(float) * (size_t)B * M[1] * 1024);
+  A((void**)&p->fp_out[1], sizeof(float) * (size_t)B * M[0] * 512);
+  // activation arenas: the widest (rows x ld) any layer reads or writes, 4 bytes per element in both engines
+  size_t need = 0;
+  auto upd = [&](int64_t rows, int ld) { need = std::max(need, (size_t)rows * (size_t)ld * 4); };
+  for (int i = 0; i < 3; ++i) {
+    const int64_t P = (int64_t)B * M[i] * 64;
+    const int cin = (i == 0 ? 3 : SA_CH[i - 1][2]) + 3;
+    upd(P, round_up(cin, 16));
+    upd(P, SA_CH[i][0]);
+    upd(P, SA_CH[i][1]);
+  }
+  upd((int64_t)B * M[1], 1536); upd((int64_t)B * M[1], 1024);
+  upd((int64_t)B * M[0], 1280); upd((int64_t)B * M[0], 512);
+  upd((int64_t)B * N, round_up(515, 16)); upd((int64_t)B * N, 512);
+  p->arena_bytes = need;
+  A((void**)&p->arena[0], need);
+  A((void**)&p->arena[1], need);
+  if (!rc && cfg->use_side_stream) {
+    cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming);
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p->ev_bq[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_nn, cudaEventDisableTiming);
+    if (e != cudaSuccess) rc = cuda_fail(e, "stream/event creation");
+  }
+  if (rc) {
+    regnet_scorenet_destroy(p);
+    return rc;
+  }
+  *out = p;
+  return REGNET_OK;
+}
+
+int regnet_scorenet_destroy(regnet_scorenet* p) {
+  if (!p) return REGNET_OK;
+  for (void* a : p->allocs) cudaFree(a);
+  if (p->ev_start) cudaEventDestroy(p->ev_start);
+  for (int i = 0; i < 3; ++i) if (p->ev_bq[i]) cudaEventDestroy(p->ev_bq[i]);
+  if (p->ev_nn) cudaEventDestroy(p->ev_nn);
+  if (p->side) cudaStreamDestroy(p->side);
+  delete p;
+  return REGNET_OK;
+}
+
+int64_t regnet_scorenet_workspace_bytes(const regnet_scorenet* p) { return p ? (int64_t)p->total_bytes : 0; }
+
+int regnet_scorenet_launch_count(const regnet_scorenet* p) { return p ? p->launches : 0; }
+
+int regnet_scorenet_set_layer(regnet_scorenet* p, int stage, int layer, int cin, int cout, const float* weight,
+                              const float* scale, const float* shift, void* stream_) {
+  cudaStream_t s = (cudaStream_t)stream_;
+  RN_CHECK_ARG(p && weight && scale && shift, "scorenet_set_layer: null argument");
+  RN_CHECK_ARG(stage >= 0 && stage < 8 && layer >= 0 && layer < p->nlayers[stage],
+               "scorenet_set_layer: no layer %d in stage %d", layer, stage);
+  int ecin, ecout;
+  if (stage < 3) {
+    ecin = layer == 0 ? (stage == 0 ? 3 : SA_CH[stage - 1][2]) + 3 : SA_CH[stage][layer - 1];
+    ecout = SA_CH[stage][layer];
+  } else if (stage < 6) {
+    const int f = stage - 3;
+    const int sparse_c = f == 0 ? SA_CH[2][2] : FP_CH[f - 1][FP_NL[f - 1] - 1];
+    const int dense_c = f == 0 ? SA_CH[1][2] : f == 1 ? SA_CH[0][2] : 3;
+    ecin = layer == 0 ? sparse_c + dense_c : FP_CH[f][layer - 1];
+    ecout = FP_CH[f][layer];
+  } else if (stage == 6) {
+    ecin = layer == 0 ? 256 : SEG_CH[layer - 1];
+    ecout = SEG_CH[layer];
+  } else {
+    ecin = 128;
+    ecout = 1;
+  }
+  RN_CHECK_ARG(cin == ecin && cout == ecout, "scorenet_set_layer: stage %d layer %d expects (%d -> %d), got (%d -> %d)",
+               stage, layer, ecin, ecout, cin, cout);
+  Layer& L = p->layers[stage][layer];
+  if (!L.w_f32) {
+    L.cin = cin; L.cout = cout; L.kpad = round_up(cin, 16);
+    RN_TRY(dalloc(p, (void**)&L.w_f32, sizeof(float) * (size_t)cout * L.kpad));
+    RN_TRY(dalloc(p, (void**)&L.w_hi, sizeof(__nv_bfloat16) * (size_t)cout * L.kpad));
+    RN_TRY(dalloc(p, (void**)&L.w_lo, sizeof(__nv_bfloat16) * (size_t)cout * L.kpad));
+    RN_TRY(dalloc(p, (void**)&L.scale, sizeof(float) * cout));
+    RN_TRY(dalloc(p, (void**)&L.shift, sizeof(float) * cout));
+  }
+  RN_TRY(split_rows_launch(weight, cout, cin, cin, L.kpad, L.w_hi, L.w_lo, L.w_f32, s));
+  RN_CUDA(cudaMemcpyAsync(L.scale, scale, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
+  RN_CUDA(cudaMemcpyAsync(L.shift, shift, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
+  L.set = true;
+  return REGNET_OK;
+}
+
+int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feature, float* score, void* stream_) {
+  cudaStream_t ms = (cudaStream_t)stream_;
+  RN_CHECK_ARG(p && pc && all_feature && score, "scorenet_forward: null argument");
+  const int B = p->B, N = p->N;
+  const int* M = p->M;
+  const bool fork = p->side != nullptr;
+  cudaStream_t gs = fork ? p->side : ms;  // geometry stream
+  p->launches = 0;
+  p->last_allfeat = all_feature;
+  if (fork) {
+    RN_CUDA(cudaEventRecord(p->ev_start, ms));
+    RN_CUDA(cudaStreamWaitEvent(gs, p->ev_start, 0));
+  }
+  // ---- geometry chain (xyz only) ------------------------------------------------------------------------
+  const Strides3 st0{(int64_t)N * 6, 1, 6};  // pc (B,N,6): the (B,3,N) view of score_network.py:46 without a copy
+  const float* lvl_xyz[4] = {pc, p->new_xyz[0], p->new_xyz[1], p->new_xyz[2]};
+  Strides3 lvl_st[4] = {st0, {(int64_t)3 * M[0], M[0], 1}, {(int64_t)3 * M[1], M[1], 1}, {(int64_t)3 * M[2], M[2], 1}};
+  const int lvl_n[4] = {N, M[0], M[1], M[2]};
+  for (int i = 0; i < 3; ++i) {
+    RN_TRY(fps_launch(lvl_xyz[i], lvl_st[i], B, lvl_n[i], M[i], nullptr, p->fps_idx[i], p->new_xyz[i], 0, 0, gs));
+    RN_TRY(ball_query_launch(lvl_xyz[i], lvl_st[i], lvl_xyz[i + 1], lvl_st[i + 1], B, lvl_n[i], M[i],
+                             p->cfg.radius[i], 64, nullptr, nullptr, p->nbr[i], gs));
+    p->launches += 2;
+    if (fork) RN_CUDA(cudaEventRecord(p->ev_bq[i], gs));
+  }
+  for (int f = 0; f < 3; ++f) {  // fp f: dense level 2-f, sparse level 3-f
+    const int dl = 2 - f, sl = 3 - f;
+    RN_TRY(three_nn_launch(lvl_xyz[dl], lvl_st[dl], lvl_xyz[sl], lvl_st[sl], B, lvl_n[dl], lvl_n[sl], nullptr, nullptr,
+                           p->nn_idx[f], p->nn_w[f], gs));
+    ++p->launches;
+  }
+  if (fork) RN_CUDA(cudaEventRecord(p->ev_nn, gs));
+
+  // ---- set abstraction MLPs -----------------------------------------------------------------------------
+  const float* feat = pc + 3;      // level-0 features = rgb, rows of stride 6
+  int64_t feat_bs = (int64_t)N * 6;
+  int feat_ld = 6, feat_c = 3;
+  for (int i = 0; i < 3; ++i) {
+    if (fork) RN_CUDA(cudaStreamWaitEvent(ms, p->ev_bq[i], 0));
+    const int64_t P = (int64_t)B * M[i] * 64;
+    const int kpad = round_up(feat_c + 3, 16);
+    Act a0 = make_act(p, 0, P, kpad);
+    RN_TRY(sa_operand_launch(lvl_xyz[i], lvl_st[i], p->new_xyz[i], feat, feat_bs, feat_ld, feat_c, p->nbr[i], B,
+                             lvl_n[i], M[i], 64, kpad, a0.f32, a0.hi, a0.lo, ms));
+    ++p->launches;
+    Act a1 = make_act(p, 1, P, SA_CH[i][0]);
+    RN_TRY(run_layer(p, p->layers[i][0], a0, P, 1, 0, &a1, nullptr, 0, ms));
+    Act a2 = make_act(p, 0, P, SA_CH[i][1]);
+    RN_TRY(run_layer(p, p->layers[i][1], a1, P, 1, 0, &a2, nullptr, 0, ms));
+    RN_TRY(run_layer(p, p->layers[i][2], a2, P, 1, 64, nullptr, p->sa_out[i], SA_CH[i][2], ms));
+    feat = p->sa_out[i];
+    feat_c = feat_ld = SA_CH[i][2];
+    feat_bs = (int64_t)M[i] * feat_c;
+  }
+  // ---- feature propagation --------------------------------------------------------------------------------
+  if (fork) RN_CUDA(cudaStreamWaitEvent(ms, p->ev_nn, 0));
+  const float* sparse = p->sa_out[2];
+  int sparse_c = SA_CH[2][2];
+  int sparse_n = M[2];
+  Act seg_in;
+  for (int f = 0; f < 3; ++f) {
+    const int dl = 2 - f;
+    const int nd = lvl_n[dl];
+    const float* dense = dl == 0 ? pc + 3 : p->sa_out[dl - 1];
+    const int dense_c = dl == 0 ? 3 : SA_CH[dl - 1][2];
+    const int dense_ld = dl == 0 ? 6 : dense_c;
+    const int64_t dense_bs = (int64_t)nd * dense_ld;
+    const int64_t P = (int64_t)B * nd;
+    const int kpad = round_up(sparse_c + dense_c, 16);
+    Act cur = make_act(p, 0, P, kpad);
+    RN_TRY(fp_operand_launch(sparse, (int64_t)sparse_n * sparse_c, sparse_c, sparse_c, dense, dense_bs, dense_ld, dense_c,
+                             p->nn_idx[f], p->nn_w[f], B, nd, kpad, cur.f32, cur.hi, cur.lo, ms));
+    ++p->launches;
+    int which = 1;
+    for (int l = 0; l < FP_NL[f]; ++l) {
+      const bool last = l == FP_NL[f] - 1;
+      const int cout = FP_CH[f][l];
+      if (!last) {
+        Act nxt = make_act(p, which, P, cout);
+        RN_TRY(run_layer(p, p->layers[3 + f][l], cur, P, 1, 0, &nxt, nullptr, 0, ms));
+        cur = nxt;
+        which ^= 1;
+      } else if (f < 2) {
+        RN_TRY(run_layer(p, p->layers[3 + f][l], cur, P, 1, 0, nullptr, p->fp_out[f], cout, ms));
+        sparse = p->fp_out[f];
+      } else {
+        // fp2's last layer: all_feature for the caller, and the seg head's operand
+        if (p->cfg.engine == REGNET_ENGINE_SIMT) {
+          RN_TRY(run_layer(p, p->layers[3 + f][l], cur, P, 1, 0, nullptr, all_feature, cout, ms));
+          seg_in.f32 = all_feature;
+          seg_in.ld = cout;
+        } else {
+          seg_in = make_act(p, which, P, cout);
+          RN_TRY(run_layer(p, p->layers[3 + f][l], cur, P, 1, 0, &seg_in, all_feature, cout, ms));
+          which ^= 1;
+        }
+      }
+    }
+    sparse_c = FP_CH[f][FP_NL[f] - 1];
+    sparse_n = nd;
+  }
+  // ---- seg head + score -------------------------------------------------------------------------------------
+  {
+    const int64_t P = (int64_t)B * N;
+    Act cur = seg_in;
+    int which = (cur.hi == reinterpret_cast<__nv_bfloat16*>(p->arena[0]) || cur.f32 == reinterpret_cast<float*>(p->arena[0])) ? 1 : 0;
+    for (int l = 0; l < 3; ++l) {
+      Act nxt = make_act(p, which, P, SEG_CH[l]);
+      RN_TRY(run_layer(p, p->layers[6][l], cur, P, 1, 0, &nxt, nullptr, 0, ms));
+      cur = nxt;
+      which ^= 1;
+    }
+    float* last = reinterpret_cast<float*>(p->arena[which]);  // (P,128) fp32
+    if (p->cfg.engine == REGNET_ENGINE_SIMT) {
+      Act o; o.f32 = last; o.ld = 128;
+      RN_TRY(run_layer(p, p->layers[6][3], cur, P, 1, 0, &o, nullptr, 0, ms));
+    } else {
+      RN_TRY(run_layer(p, p->layers[6][3], cur, P, 1, 0, nullptr, last, 128, ms));
+    }
+    const Layer& H = p->layers[7][0];
+    if (!H.set) {
+      set_error("scorenet: score head weights were never set");
+      return REGNET_EINVAL;
+    }
+    RN_TRY(score_head_launch(last, 128, H.w_f32, H.scale, H.shift, P, 128, score, ms));
+    ++p->launches;
+  }
+  return REGNET_OK;
+}
+
+int regnet_scorenet_intermediate(regnet_scorenet* p, const char* what, void** ptr, int64_t* numel) {
+  RN_CHECK_ARG(p && what && ptr && numel, "scorenet_intermediate: null argument");
+  const size_t n = strlen(what);
+  RN_CHECK_ARG(n >= 3, "scorenet_intermediate: unknown name '%s'", what);
+  const int i = what[n - 1] - '0';
+  RN_CHECK_ARG(i >= 0 && i < 3, "scorenet_intermediate: unknown name '%s'", what);
+  const std::string k(what, n - 1);
+  const int B = p->B;
+  const int nd[3] = {p->M[1], p->M[0], p->N};
+  if (k == "fps") { *ptr = p->fps_idx[i]; *numel = (int64_t)B * p->M[i]; }
+  else if (k == "xyz") { *ptr = p->new_xyz[i]; *numel = (int64_t)B * 3 * p->M[i]; }
+  else if (k == "bq") { *ptr = p->nbr[i]; *numel = (int64_t)B * p->M[i] * 64; }
+  else if (k == "nn") { *ptr = p->nn_idx[i]; *numel = (int64_t)B * nd[i] * 3; }
+  else if (k == "nnw") { *ptr = p->nn_w[i]; *numel = (int64_t)B * nd[i] * 3; }
+  else if (k == "sa") { *ptr = p->sa_out[i]; *numel = (int64_t)B * p->M[i] * SA_CH[i][2]; }
+  else if (k == "fp" && i < 2) { *ptr = p->fp_out[i]; *numel = (int64_t)B * nd[i] * (i == 0 ? 1024 : 512); }
+  else if (k == "fp" && i == 2) { *ptr = p->last_allfeat; *numel = (int64_t)B * p->N * 256; }
+  else {
+    set_error("scorenet_intermediate: unknown name '%s'", what);
+    return REGNET_EINVAL;
+  }
+  return REGNET_OK;
+}
+
+}  // extern "C"

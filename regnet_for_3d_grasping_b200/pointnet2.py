@@ -1,0 +1,106 @@
+"""PointNet2Seg -- the ScoreNet body (multi_model/utils/pointnet2.py:12-121), same constructor, attribute names
+and state-dict keys.
+
+forward():
+  * eval mode  -> one call into the native plan (csrc/scorenet.cu): FPS, ball query, grouping, tcgen05 MLPs with
+                  fused BN/ReLU/max-pool, 3-NN interpolation, seg head and score, all on device;
+  * train mode -> the op-by-op module path (modules.py) so BatchNorm sees batch statistics, dropout is applied
+                  and autograd records the graph; the point operators underneath are still this package's kernels.
+Both return what the reference returns: (sparse_feature (B,256,N), x_score (B,N)); in eval mode sparse_feature is
+a transposed view of the plan's point-major (B,N,256) buffer, so ScoreNetwork's `.transpose(2,1)` hands the
+caller a contiguous (B,N,256) tensor.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .modules import PointNetSAModule, PointnetFPModule
+from .nn_layers import SharedMLP
+from .scorenet import NUM_CENTROIDS, NUM_NEIGHBOURS, RADIUS, ScoreNetPlan
+
+SA_CHANNELS = ((128, 128, 256), (256, 256, 512), (512, 512, 1024))
+FP_CHANNELS = ((1024, 1024), (512, 512), (256, 256, 256))
+SEG_CHANNELS = (512, 256, 256, 128)
+
+
+class PointNet2Seg(nn.Module):
+    _SA_MODULE = PointNetSAModule
+    _FP_MODULE = PointnetFPModule
+
+    def __init__(self, input_chann=3, k_score=1, k_obj=2, add_channel_flag=False, dropout_prob=0.5):
+        super().__init__()
+        self.k_score = k_score
+        feat = input_chann - 3
+        skip = [feat]
+        self.sa_modules = nn.ModuleList()
+        for i, widths in enumerate(SA_CHANNELS):
+            self.sa_modules.append(self._SA_MODULE(in_channels=feat, mlp_channels=widths, num_centroids=NUM_CENTROIDS[i],
+                                                   radius=RADIUS[i], num_neighbours=NUM_NEIGHBOURS[i], use_xyz=True))
+            feat = widths[-1]
+            skip.append(feat)
+        self.fp_modules = nn.ModuleList()
+        for i, widths in enumerate(FP_CHANNELS):
+            self.fp_modules.append(self._FP_MODULE(in_channels=feat + skip[-2 - i], mlp_channels=widths, num_neighbors=3))
+            feat = widths[-1]
+        self.mlp = SharedMLP(feat * (3 if add_channel_flag else 1), SEG_CHANNELS, ndim=1, dropout_prob=dropout_prob)
+        self.conv_score = nn.Conv1d(SEG_CHANNELS[-1], self.k_score, 1)
+        self.bn_score = nn.BatchNorm1d(self.k_score)
+        self.sigmoid = nn.Sigmoid()
+        self._fusable = (input_chann == 6 and k_score == 1 and not add_channel_flag)
+        self._plans = {}
+        self.engine = None  # None = library default (tcgen05); tests may force _lib.ENGINE_SIMT
+
+    # -- op-by-op path (training) ---------------------------------------------------------------------------
+    def _forward_modules(self, points, add_channel1=None, add_channel2=None):
+        B, _, N = points.size()
+        xyz, feature = points[:, :3, :], points[:, 3:6, :]
+        level_xyz, level_feature = [xyz], [feature]
+        for sa in self.sa_modules:
+            xyz, feature = sa(xyz, feature)
+            level_xyz.append(xyz)
+            level_feature.append(feature)
+        sparse_xyz, sparse_feature = xyz, feature
+        for i, fp in enumerate(self.fp_modules):
+            dense_xyz, dense_feature = level_xyz[-2 - i], level_feature[-2 - i]
+            sparse_feature = fp(dense_xyz, sparse_xyz, dense_feature, sparse_feature)
+            sparse_xyz = dense_xyz
+        if add_channel1 is not None and add_channel2 is not None:
+            c = sparse_feature.shape[1]
+            extra = [a.view(B, 1, N).repeat(1, c, 1).float() for a in (add_channel1, add_channel2)]
+            sparse_feature = torch.cat([sparse_feature] + extra, dim=1)
+        x = self.mlp(sparse_feature)
+        x_score = self.bn_score(self.conv_score(x)).transpose(2, 1).contiguous()
+        return sparse_feature, self.sigmoid(x_score).view(B, N)
+
+    # -- fused path (eval) ---------------------------------------------------------------------------------------
+    def _state_key(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _plan_for(self, B, N, device):
+        key = (B, N, str(device), self.engine)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = ScoreNetPlan(B, N, device, engine=self.engine)
+            self._plans[key] = plan
+        sd = {"x." + k: v for k, v in self.state_dict().items()}
+        plan.bind_state(sd, root="x.", key=self._state_key())
+        return plan
+
+    def _forward_fused(self, points):
+        B, _, N = points.size()
+        pc = points.permute(0, 2, 1)  # (B,N,6); contiguous again if it came from ScoreNetwork's permute
+        plan = self._plan_for(B, N, points.device)
+        all_feature, score = plan.forward(pc.float())
+        return all_feature.transpose(1, 2), score
+
+    def forward(self, points, add_channel1=None, add_channel2=None):
+        fused = (not self.training and self._fusable and add_channel1 is None and points.is_cuda
+                 and points.size(2) >= NUM_CENTROIDS[0])
+        if fused:
+            return self._forward_fused(points)
+        return self._forward_modules(points, add_channel1, add_channel2)
+
+    def __getstate__(self):  # plans hold native handles: never pickle them (torch.save(model), train.py:175-178)
+        state = self.__dict__.copy()
+        state["_plans"] = {}
+        return state

@@ -1,0 +1,29 @@
+"""Shared parity definitions."""
+import numpy as np
+import torch
+
+REL_TOL = 1e-4  # BASELINE.json north_star: MLP / pooled features within 1e-4 relative
+
+
+def assert_features_close(got, want, tol=REL_TOL, what="feature"):
+    got = torch.as_tensor(got).double().cpu()
+    want = torch.as_tensor(want).double().cpu()
+    assert got.shape == want.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(want.shape)}"
+    err = (got - want).abs()
+    peak = want.abs().max().item()
+    rms = want.pow(2).mean().sqrt().item()
+    assert err.max().item() <= tol * max(peak, 1e-30), f"{what}: max err {err.max().item():.3e} vs {tol}*peak {peak:.3e}"
+    bound = tol * want.abs() + tol * rms
+    worst = (err - bound).max().item()
+    assert worst <= 0, f"{what}: elementwise rtol/atol violated by {worst:.3e} (rms {rms:.3e})"
+
+
+def rel_err(got, want):
+    got = torch.as_tensor(got).double().cpu()
+    want = torch.as_tensor(want).double().cpu()
+    return ((got - want).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+
+def bq_rowhash(bq, K):
+    w = (np.arange(K, dtype=np.int64) * 2654435761 % 1000003 + 1)
+    return (np.asarray(bq, dtype=np.int64) * w).sum(-1)

@@ -1,0 +1,119 @@
+"""CPU suite, part 3: host-side mirror of the reference interface (modules, state dict, BN folding).
+
+The CUDA operators cannot run here, so the module wiring is exercised with the C oracle patched in under
+`function.pn2_ext` -- the oracle is the checker's stand-in for the kernels, the modules under test are the
+product's.  Outputs are compared with fixtures produced by the reference's own modules."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+
+@pytest.fixture()
+def oracle_ops(oracle, monkeypatch):
+    from regnet_for_3d_grasping_b200 import function
+    monkeypatch.setattr(function, "pn2_ext", oracle.as_pn2_ext())
+    return oracle
+
+
+def test_state_dict_schema_matches_reference():
+    from oracle import ref_modules
+    from regnet_for_3d_grasping_b200.score_network import ScoreNetwork
+    net = ScoreNetwork(training=False)
+    sd = net.state_dict()
+    want = ref_modules.scorenet_state_shapes()
+    assert set(sd.keys()) == set(want.keys())
+    assert len(sd) == 127
+    for k, shape in want.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert sum(p.numel() for p in net.parameters()) == 5542531
+
+
+def test_sa_fp_modules_match_reference_outputs(oracle_ops):
+    ref = golden("ref_py_modules_small.npz")
+    from regnet_for_3d_grasping_b200.modules import PointNetSAModule, PointnetFPModule
+    sa = PointNetSAModule(in_channels=5, mlp_channels=(16, 24), num_centroids=128, radius=0.15, num_neighbours=16,
+                          use_xyz=True).eval()
+    fp = PointnetFPModule(in_channels=29, mlp_channels=(20, 12), num_neighbors=3).eval()
+    sa.load_state_dict({k[3:]: torch.from_numpy(ref[k]) for k in ref.files if k.startswith("sa.")})
+    fp.load_state_dict({k[3:]: torch.from_numpy(ref[k]) for k in ref.files if k.startswith("fp.")})
+    pc = torch.from_numpy(ref["pc"])
+    xyz = pc[:, :, :3].permute(0, 2, 1)
+    feat = torch.from_numpy(ref["feat"])
+    with torch.no_grad():
+        new_xyz, new_feat = sa(xyz, feat)
+        up = fp(xyz, new_xyz, feat, new_feat)
+    assert np.array_equal(new_xyz.numpy(), ref["new_xyz"])
+    np.testing.assert_allclose(new_feat.numpy(), ref["new_feat"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(up.numpy(), ref["up"], rtol=1e-6, atol=1e-6)
+
+
+def test_autograd_wrappers_match_reference_gradients(oracle_ops):
+    ref = golden("ref_py_grads_small.npz")
+    mods = golden("ref_py_modules_small.npz")
+    from regnet_for_3d_grasping_b200 import function as F
+    bq = torch.from_numpy(mods["bq"]).long()
+    nn = torch.from_numpy(mods["nn"]).long()
+    x = torch.from_numpy(ref["x"]).requires_grad_(True)
+    (F.group_points(x, bq) * torch.from_numpy(ref["wsum"])).sum().backward()
+    np.testing.assert_allclose(x.grad.numpy(), ref["g_group"], rtol=1e-5, atol=1e-5)
+    s = torch.from_numpy(ref["s"]).requires_grad_(True)
+    it = F.feature_interpolate(s, nn, torch.from_numpy(ref["w"]))
+    np.testing.assert_allclose(it.detach().numpy(), ref["interp"], rtol=1e-6, atol=1e-6)
+    (it * torch.from_numpy(ref["wsum2"])).sum().backward()
+    np.testing.assert_allclose(s.grad.numpy(), ref["g_interp"], rtol=1e-5, atol=1e-5)
+    # index-producing ops are non-differentiable (function.py:46-48,76-78,131-133)
+    pts = torch.rand(1, 3, 32, requires_grad=True)
+    assert not F.farthest_point_sample(pts, 8).requires_grad
+    assert not F.ball_query(pts, pts[:, :, :4], 0.5, 4)[0].requires_grad
+    assert not F.search_nn_distance(pts, pts[:, :, :8], 3)[0].requires_grad
+
+
+def test_scorenetwork_train_path_matches_reference(oracle_ops):
+    """Op-by-op path of the drop-in ScoreNetwork (module in eval() so BN/dropout are deterministic) against the
+    fixture from the reference's ScoreNetwork, including the loss."""
+    ref = golden("ref_py_scorenet_n6144.npz")
+    from oracle import ref_modules
+    from regnet_for_3d_grasping_b200 import synth
+    from regnet_for_3d_grasping_b200.score_network import ScoreNetwork
+    net = ScoreNetwork(training=True).eval()
+    net.load_state_dict(ref_modules.random_scorenet_state(seed=3))
+    pc = torch.from_numpy(synth.batch("table", [11], 6144))
+    tgt = torch.from_numpy(synth.scores_like_dataset(5, 1, 6144))
+    with torch.no_grad():
+        feat, score, loss = net(pc, tgt)      # CPU tensors -> not fusable -> module path
+    assert feat.shape == (1, 6144, 256) and score.shape == (1, 6144)
+    np.testing.assert_allclose(feat[0, ref["rows"]].numpy(), ref["all_feature_rows"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(score[0].numpy(), ref["score"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(loss.numpy(), golden("ref_py_scorenet_loss.npz")["loss"], rtol=1e-5)
+    net.is_training = False
+    with torch.no_grad():
+        assert net(pc, tgt)[2] is None
+
+
+def test_fold_bn_equals_batchnorm_eval():
+    from regnet_for_3d_grasping_b200.nn_layers import Conv1d
+    from regnet_for_3d_grasping_b200.scorenet import fold_bn
+    torch.manual_seed(0)
+    blk = Conv1d(7, 5, 1).eval()
+    with torch.no_grad():
+        blk.bn.running_mean.normal_(0, 0.3)
+        blk.bn.running_var.uniform_(0.5, 2.0)
+        blk.bn.weight.uniform_(0.5, 1.5)
+        blk.bn.bias.normal_(0, 0.2)
+        x = torch.randn(3, 7, 11)
+        want = blk(x)
+        w, scale, shift = fold_bn({"p." + k: v for k, v in blk.state_dict().items()}, "p")
+        got = torch.relu(torch.einsum("oc,bcn->bon", w, x) * scale[None, :, None] + shift[None, :, None])
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_synthetic_clouds_are_seeded_and_shaped():
+    from regnet_for_3d_grasping_b200 import synth
+    a, b = synth.table_scene(5, 25600), synth.table_scene(5, 25600)
+    assert a.shape == (25600, 6) and a.dtype == np.float32 and np.array_equal(a, b)
+    assert not np.array_equal(a, synth.table_scene(6, 25600))
+    assert 0.5 < a[:, 2].mean() < 0.8 and a[:, 3:].min() >= 0 and a[:, 3:].max() <= 1
+    lat = synth.lattice(1, 512)
+    assert len(np.unique(lat[:, :3], axis=0)) < 512   # duplicates exist: tie paths are exercised
