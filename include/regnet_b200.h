@@ -139,6 +139,13 @@ int regnet_scorenet_forward(regnet_scorenet* plan, const float* pc, float* all_f
  * "nn0".."nn2" int32 (B,Nd_i,3); "sa0".."sa2" fp32 (B,M_i,C) point-major; "fp0".."fp2" fp32 point-major. */
 int regnet_scorenet_intermediate(regnet_scorenet* plan, const char* what, void** ptr, int64_t* numel);
 
+/* Per-launch timing for bench.py's roofline block.  With profiling on, the forward runs every kernel on the
+ * caller's stream (no side stream) bracketed by CUDA events; regnet_scorenet_profile synchronises and writes one
+ * "label milliseconds\n" line per launch of the LAST forward into buf (labels: fps.i, ball_query.i, three_nn.i,
+ * sa_operand.i, fp_operand.i, gemm.<stage>.l<j>[pool], score_head). */
+int regnet_scorenet_set_profiling(regnet_scorenet* plan, int on);
+int regnet_scorenet_profile(regnet_scorenet* plan, char* buf, int64_t buf_bytes);
+
 /* Number of kernels launched by the last regnet_scorenet_forward (for bench.py's gpu_launches). */
 int regnet_scorenet_launch_count(const regnet_scorenet* plan);
 

@@ -66,6 +66,8 @@ int oracle_fps(const float* points, int64_t B, int64_t N, int64_t M, int64_t* in
   if (M <= 0 || N < M) return -1;
   const int block = oracle_fps_block_size(N);
   int err = 0;
+  /* clouds run in parallel (FPS itself is sequential; splitting one cloud's scan across threads was measured
+   * slower than serial because of the 5119 fork/joins) */
 #pragma omp parallel for schedule(dynamic, 1)
   for (int64_t b = 0; b < B; ++b) {
     const float* p = points + b * N * 3;

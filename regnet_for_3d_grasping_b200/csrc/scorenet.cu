@@ -27,6 +27,17 @@ const int FP_CH[3][3] = {{1024, 1024, 0}, {512, 512, 0}, {256, 256, 256}};      
 const int FP_NL[3] = {2, 2, 3};
 const int SEG_CH[4] = {512, 256, 256, 128};                                       // pointnet2.py:46
 
+const char* const GEMM_LABEL[7][4] = {
+    {"gemm.sa0.l0", "gemm.sa0.l1", "gemm.sa0.l2pool", ""}, {"gemm.sa1.l0", "gemm.sa1.l1", "gemm.sa1.l2pool", ""},
+    {"gemm.sa2.l0", "gemm.sa2.l1", "gemm.sa2.l2pool", ""}, {"gemm.fp0.l0", "gemm.fp0.l1", "", ""},
+    {"gemm.fp1.l0", "gemm.fp1.l1", "", ""},                {"gemm.fp2.l0", "gemm.fp2.l1", "gemm.fp2.l2", ""},
+    {"gemm.seg.l0", "gemm.seg.l1", "gemm.seg.l2", "gemm.seg.l3"}};
+const char* const FPS_LABEL[3] = {"fps.0", "fps.1", "fps.2"};
+const char* const BQ_LABEL[3] = {"ball_query.0", "ball_query.1", "ball_query.2"};
+const char* const NN_LABEL[3] = {"three_nn.0", "three_nn.1", "three_nn.2"};
+const char* const SAOP_LABEL[3] = {"sa_operand.0", "sa_operand.1", "sa_operand.2"};
+const char* const FPOP_LABEL[3] = {"fp_operand.0", "fp_operand.1", "fp_operand.2"};
+
 struct Layer {
   int cin = 0, cout = 0, kpad = 0;
   float* w_f32 = nullptr;           // (cout, kpad) zero padded
@@ -70,6 +81,11 @@ struct regnet_scorenet {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_start = nullptr, ev_bq[3] = {nullptr, nullptr, nullptr}, ev_nn = nullptr;
   int launches = 0;
+  // optional per-launch timing (regnet_scorenet_set_profiling): events around every launch, serial execution
+  bool profiling = false;
+  struct Rec { const char* label; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  size_t nrec = 0;
 };
 
 namespace {
@@ -80,6 +96,25 @@ int dalloc(regnet_scorenet* p, void** out, size_t bytes) {
   p->allocs.push_back(*out);
   p->total_bytes += bytes;
   return REGNET_OK;
+}
+
+// profiling brackets: no-ops unless enabled
+void prof_begin(regnet_scorenet* p, const char* label, cudaStream_t s) {
+  if (!p->profiling) return;
+  if (p->nrec == p->recs.size()) {
+    regnet_scorenet::Rec r;
+    r.label = label;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    p->recs.push_back(r);
+  }
+  p->recs[p->nrec].label = label;
+  cudaEventRecord(p->recs[p->nrec].a, s);
+}
+void prof_end(regnet_scorenet* p, cudaStream_t s) {
+  if (!p->profiling) return;
+  cudaEventRecord(p->recs[p->nrec].b, s);
+  ++p->nrec;
 }
 
 Act make_act(const regnet_scorenet* p, int which, int64_t rows, int ld) {
@@ -95,8 +130,19 @@ Act make_act(const regnet_scorenet* p, int which, int64_t rows, int ld) {
 }
 
 // one conv+BN+act layer: in -> (out_act and/or out_f32), optional 64-row pooling
-int run_layer(regnet_scorenet* p, const Layer& L, const Act& in, int64_t P, int act, int pool, const Act* out_act,
-              float* out_f32, int ld_f32, cudaStream_t s) {
+int run_layer_impl(regnet_scorenet* p, const Layer& L, const Act& in, int64_t P, int act, int pool, const Act* out_act,
+                   float* out_f32, int ld_f32, cudaStream_t s);
+
+int run_layer(regnet_scorenet* p, const char* label, const Layer& L, const Act& in, int64_t P, int act, int pool,
+              const Act* out_act, float* out_f32, int ld_f32, cudaStream_t s) {
+  prof_begin(p, label, s);
+  const int rc = run_layer_impl(p, L, in, P, act, pool, out_act, out_f32, ld_f32, s);
+  prof_end(p, s);
+  return rc;
+}
+
+int run_layer_impl(regnet_scorenet* p, const Layer& L, const Act& in, int64_t P, int act, int pool, const Act* out_act,
+                   float* out_f32, int ld_f32, cudaStream_t s) {
   if (!L.set) {
     set_error("scorenet: a layer (cin=%d) was never given weights (regnet_scorenet_set_layer)", L.cin);
     return REGNET_EINVAL;
@@ -200,6 +246,7 @@ int regnet_scorenet_destroy(regnet_scorenet* p) {
   for (int i = 0; i < 3; ++i) if (p->ev_bq[i]) cudaEventDestroy(p->ev_bq[i]);
   if (p->ev_nn) cudaEventDestroy(p->ev_nn);
   if (p->side) cudaStreamDestroy(p->side);
+  for (auto& r : p->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete p;
   return REGNET_OK;
 }
@@ -254,7 +301,8 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   RN_CHECK_ARG(p && pc && all_feature && score, "scorenet_forward: null argument");
   const int B = p->B, N = p->N;
   const int* M = p->M;
-  const bool fork = p->side != nullptr;
+  const bool fork = p->side != nullptr && !p->profiling;  // profiling serialises everything on `ms`
+  p->nrec = 0;
   cudaStream_t gs = fork ? p->side : ms;  // geometry stream
   p->launches = 0;
   p->last_allfeat = all_feature;
@@ -268,16 +316,22 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   Strides3 lvl_st[4] = {st0, {(int64_t)3 * M[0], M[0], 1}, {(int64_t)3 * M[1], M[1], 1}, {(int64_t)3 * M[2], M[2], 1}};
   const int lvl_n[4] = {N, M[0], M[1], M[2]};
   for (int i = 0; i < 3; ++i) {
+    prof_begin(p, FPS_LABEL[i], gs);
     RN_TRY(fps_launch(lvl_xyz[i], lvl_st[i], B, lvl_n[i], M[i], nullptr, p->fps_idx[i], p->new_xyz[i], 0, 0, gs));
+    prof_end(p, gs);
+    prof_begin(p, BQ_LABEL[i], gs);
     RN_TRY(ball_query_launch(lvl_xyz[i], lvl_st[i], lvl_xyz[i + 1], lvl_st[i + 1], B, lvl_n[i], M[i],
                              p->cfg.radius[i], 64, nullptr, nullptr, p->nbr[i], gs));
+    prof_end(p, gs);
     p->launches += 2;
     if (fork) RN_CUDA(cudaEventRecord(p->ev_bq[i], gs));
   }
   for (int f = 0; f < 3; ++f) {  // fp f: dense level 2-f, sparse level 3-f
     const int dl = 2 - f, sl = 3 - f;
+    prof_begin(p, NN_LABEL[f], gs);
     RN_TRY(three_nn_launch(lvl_xyz[dl], lvl_st[dl], lvl_xyz[sl], lvl_st[sl], B, lvl_n[dl], lvl_n[sl], nullptr, nullptr,
                            p->nn_idx[f], p->nn_w[f], gs));
+    prof_end(p, gs);
     ++p->launches;
   }
   if (fork) RN_CUDA(cudaEventRecord(p->ev_nn, gs));
@@ -291,14 +345,16 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     const int64_t P = (int64_t)B * M[i] * 64;
     const int kpad = round_up(feat_c + 3, 16);
     Act a0 = make_act(p, 0, P, kpad);
+    prof_begin(p, SAOP_LABEL[i], ms);
     RN_TRY(sa_operand_launch(lvl_xyz[i], lvl_st[i], p->new_xyz[i], feat, feat_bs, feat_ld, feat_c, p->nbr[i], B,
                              lvl_n[i], M[i], 64, kpad, a0.f32, a0.hi, a0.lo, ms));
+    prof_end(p, ms);
     ++p->launches;
     Act a1 = make_act(p, 1, P, SA_CH[i][0]);
-    RN_TRY(run_layer(p, p->layers[i][0], a0, P, 1, 0, &a1, nullptr, 0, ms));
+    RN_TRY(run_layer(p, GEMM_LABEL[i][0], p->layers[i][0], a0, P, 1, 0, &a1, nullptr, 0, ms));
     Act a2 = make_act(p, 0, P, SA_CH[i][1]);
-    RN_TRY(run_layer(p, p->layers[i][1], a1, P, 1, 0, &a2, nullptr, 0, ms));
-    RN_TRY(run_layer(p, p->layers[i][2], a2, P, 1, 64, nullptr, p->sa_out[i], SA_CH[i][2], ms));
+    RN_TRY(run_layer(p, GEMM_LABEL[i][1], p->layers[i][1], a1, P, 1, 0, &a2, nullptr, 0, ms));
+    RN_TRY(run_layer(p, GEMM_LABEL[i][2], p->layers[i][2], a2, P, 1, 64, nullptr, p->sa_out[i], SA_CH[i][2], ms));
     feat = p->sa_out[i];
     feat_c = feat_ld = SA_CH[i][2];
     feat_bs = (int64_t)M[i] * feat_c;
@@ -319,8 +375,10 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     const int64_t P = (int64_t)B * nd;
     const int kpad = round_up(sparse_c + dense_c, 16);
     Act cur = make_act(p, 0, P, kpad);
+    prof_begin(p, FPOP_LABEL[f], ms);
     RN_TRY(fp_operand_launch(sparse, (int64_t)sparse_n * sparse_c, sparse_c, sparse_c, dense, dense_bs, dense_ld, dense_c,
                              p->nn_idx[f], p->nn_w[f], B, nd, kpad, cur.f32, cur.hi, cur.lo, ms));
+    prof_end(p, ms);
     ++p->launches;
     int which = 1;
     for (int l = 0; l < FP_NL[f]; ++l) {
@@ -328,21 +386,21 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
       const int cout = FP_CH[f][l];
       if (!last) {
         Act nxt = make_act(p, which, P, cout);
-        RN_TRY(run_layer(p, p->layers[3 + f][l], cur, P, 1, 0, &nxt, nullptr, 0, ms));
+        RN_TRY(run_layer(p, GEMM_LABEL[3 + f][l], p->layers[3 + f][l], cur, P, 1, 0, &nxt, nullptr, 0, ms));
         cur = nxt;
         which ^= 1;
       } else if (f < 2) {
-        RN_TRY(run_layer(p, p->layers[3 + f][l], cur, P, 1, 0, nullptr, p->fp_out[f], cout, ms));
+        RN_TRY(run_layer(p, GEMM_LABEL[3 + f][l], p->layers[3 + f][l], cur, P, 1, 0, nullptr, p->fp_out[f], cout, ms));
         sparse = p->fp_out[f];
       } else {
         // fp2's last layer: all_feature for the caller, and the seg head's operand
         if (p->cfg.engine == REGNET_ENGINE_SIMT) {
-          RN_TRY(run_layer(p, p->layers[3 + f][l], cur, P, 1, 0, nullptr, all_feature, cout, ms));
+          RN_TRY(run_layer(p, GEMM_LABEL[3 + f][l], p->layers[3 + f][l], cur, P, 1, 0, nullptr, all_feature, cout, ms));
           seg_in.f32 = all_feature;
           seg_in.ld = cout;
         } else {
           seg_in = make_act(p, which, P, cout);
-          RN_TRY(run_layer(p, p->layers[3 + f][l], cur, P, 1, 0, &seg_in, all_feature, cout, ms));
+          RN_TRY(run_layer(p, GEMM_LABEL[3 + f][l], p->layers[3 + f][l], cur, P, 1, 0, &seg_in, all_feature, cout, ms));
           which ^= 1;
         }
       }
@@ -357,24 +415,48 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     int which = (cur.hi == reinterpret_cast<__nv_bfloat16*>(p->arena[0]) || cur.f32 == reinterpret_cast<float*>(p->arena[0])) ? 1 : 0;
     for (int l = 0; l < 3; ++l) {
       Act nxt = make_act(p, which, P, SEG_CH[l]);
-      RN_TRY(run_layer(p, p->layers[6][l], cur, P, 1, 0, &nxt, nullptr, 0, ms));
+      RN_TRY(run_layer(p, GEMM_LABEL[6][l], p->layers[6][l], cur, P, 1, 0, &nxt, nullptr, 0, ms));
       cur = nxt;
       which ^= 1;
     }
     float* last = reinterpret_cast<float*>(p->arena[which]);  // (P,128) fp32
     if (p->cfg.engine == REGNET_ENGINE_SIMT) {
       Act o; o.f32 = last; o.ld = 128;
-      RN_TRY(run_layer(p, p->layers[6][3], cur, P, 1, 0, &o, nullptr, 0, ms));
+      RN_TRY(run_layer(p, GEMM_LABEL[6][3], p->layers[6][3], cur, P, 1, 0, &o, nullptr, 0, ms));
     } else {
-      RN_TRY(run_layer(p, p->layers[6][3], cur, P, 1, 0, nullptr, last, 128, ms));
+      RN_TRY(run_layer(p, GEMM_LABEL[6][3], p->layers[6][3], cur, P, 1, 0, nullptr, last, 128, ms));
     }
     const Layer& H = p->layers[7][0];
     if (!H.set) {
       set_error("scorenet: score head weights were never set");
       return REGNET_EINVAL;
     }
+    prof_begin(p, "score_head", ms);
     RN_TRY(score_head_launch(last, 128, H.w_f32, H.scale, H.shift, P, 128, score, ms));
+    prof_end(p, ms);
     ++p->launches;
+  }
+  return REGNET_OK;
+}
+
+int regnet_scorenet_set_profiling(regnet_scorenet* p, int on) {
+  RN_CHECK_ARG(p != nullptr, "scorenet_set_profiling: null plan");
+  p->profiling = on != 0;
+  p->nrec = 0;
+  return REGNET_OK;
+}
+
+int regnet_scorenet_profile(regnet_scorenet* p, char* buf, int64_t buf_bytes) {
+  RN_CHECK_ARG(p && buf && buf_bytes > 0, "scorenet_profile: null argument");
+  RN_CUDA(cudaDeviceSynchronize());
+  int64_t off = 0;
+  buf[0] = 0;
+  for (size_t i = 0; i < p->nrec; ++i) {
+    float ms = 0.f;
+    RN_CUDA(cudaEventElapsedTime(&ms, p->recs[i].a, p->recs[i].b));
+    const int n = snprintf(buf + off, (size_t)(buf_bytes - off), "%s %.6f\n", p->recs[i].label, ms);
+    if (n < 0 || off + n >= buf_bytes) break;
+    off += n;
   }
   return REGNET_OK;
 }

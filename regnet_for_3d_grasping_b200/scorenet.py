@@ -125,6 +125,23 @@ class ScoreNetPlan:
         self._last_pc = pc  # keep the (possibly copied) input alive until the stream has consumed it
         return all_feature, score
 
+    def profile_forward(self, pc):
+        """One forward with every launch bracketed by CUDA events (serial, caller's stream).
+        Returns [(label, milliseconds), ...] in launch order."""
+        lib = _lib.load()
+        _lib.check(lib.regnet_scorenet_set_profiling(self._h, 1))
+        try:
+            self.forward(pc)
+            buf = ctypes.create_string_buffer(1 << 16)
+            _lib.check(lib.regnet_scorenet_profile(self._h, buf, len(buf)))
+        finally:
+            _lib.check(lib.regnet_scorenet_set_profiling(self._h, 0))
+        out = []
+        for line in buf.value.decode().splitlines():
+            label, ms = line.rsplit(" ", 1)
+            out.append((label, float(ms)))
+        return out
+
     def intermediate(self, name, dtype, shape):
         """Copy of an intermediate of the last forward (see regnet_scorenet_intermediate)."""
         ptr, numel = ctypes.c_void_p(), ctypes.c_int64()

@@ -1,0 +1,28 @@
+#!/bin/bash
+# Everything one gpurun call should do; each stage under its own timeout, logs into gpurun_out/.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+nvidia-smi > gpurun_out/smi.txt 2>&1
+python -c "import os; print('cores', os.cpu_count())" >> gpurun_out/smi.txt
+STAGES="${1:-golden ops mlp scorenet smoke bench sweep ncu}"
+for s in $STAGES; do
+  echo "=== stage $s $(date +%T)"
+  case $s in
+    golden)   timeout 600 python oracle/gen_golden_gpu.py gpurun_out/golden > gpurun_out/golden.log 2>&1 ;;
+    ops)      timeout 900 python -m pytest tests/test_gpu_ops.py -q -m gpu -x > gpurun_out/test_ops.log 2>&1 ;;
+    mlp)      timeout 600 python -m pytest tests/test_gpu_mlp.py -q -m gpu -s > gpurun_out/test_mlp.log 2>&1 ;;
+    scorenet) timeout 900 python -m pytest tests/test_gpu_scorenet.py -q -m gpu > gpurun_out/test_scorenet.log 2>&1 ;;
+    smoke)    timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 ;;
+    bench)    timeout 600 python bench.py --steps 5 --warmup 3 --engine simt --no-cpu-baseline > gpurun_out/bench_simt.log 2>&1
+              timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_tc.log 2>&1 ;;
+    benchref) timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1 ;;
+    sweep)    timeout 300 python scripts/fps_sweep.py > gpurun_out/fps_sweep.log 2>&1 ;;
+    ncu)      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
+                 --log-file gpurun_out/launches.csv python scripts/one_forward.py tc serial > gpurun_out/ncu_list.log 2>&1 ;;
+    ncufull)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 3 -c 3 \
+                 -o gpurun_out/prof_gemm python scripts/one_forward.py tc serial > gpurun_out/ncu_full.log 2>&1 ;;
+    alltests) timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/test_all.log 2>&1 ;;
+  esac
+  echo "    exit $?"
+done
+tail -n 5 gpurun_out/*.log

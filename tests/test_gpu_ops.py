@@ -1,0 +1,183 @@
+"""GPU parity, operators: every call goes torch tensor -> pn2_ext shim -> C ABI -> sm_100a kernel and is compared
+with the CPU oracle on the same seeded inputs (bit-exact for indices / counts / squared distances) and with the
+golden vectors recorded from the reference's own CUDA kernels."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from helpers import bq_rowhash
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ext(lib_path):
+    from regnet_for_3d_grasping_b200 import pn2_ext
+    assert torch.cuda.is_available()
+    return pn2_ext
+
+
+def _cases():
+    from oracle import gen_golden_gpu
+    return gen_golden_gpu.cases()
+
+
+@pytest.mark.parametrize("name", list(_cases().keys()))
+def test_search_ops_bit_exact_vs_oracle(ext, oracle, name):
+    c = _cases()[name]
+    pc = torch.from_numpy(c["pts"])
+    xyz_c = pc[:, :, :3].permute(0, 2, 1)
+    xyz = pc.cuda()[:, :, :3].permute(0, 2, 1)         # non-contiguous (B,3,N) view, stride 6, like score_network.py:46
+    B = xyz.shape[0]
+    idx = ext.farthest_point_sample(xyz, c["M"])
+    want = oracle.farthest_point_sample(xyz_c, c["M"])
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (B, c["M"])
+    assert torch.equal(idx.cpu(), want), f"{name}: FPS mismatch at {(idx.cpu() != want).nonzero()[:3].tolist()}"
+    new_xyz = xyz.gather(2, idx.unsqueeze(1).expand(B, 3, c["M"]))
+    bq, cnt = ext.ball_query(xyz, new_xyz, c["radius"], c["K"])
+    wbq, wcnt = oracle.ball_query(xyz_c, new_xyz.cpu(), c["radius"], c["K"])
+    assert bq.dtype == torch.int64 and cnt.dtype == torch.int64
+    assert torch.equal(cnt.cpu(), wcnt) and torch.equal(bq.cpu(), wbq), f"{name}: ball query mismatch"
+    if c["M"] >= 3:
+        nn, nnd = ext.point_search(xyz, new_xyz, 3)
+        wnn, wnnd = oracle.point_search(xyz_c, new_xyz.cpu(), 3)
+        assert torch.equal(nn.cpu(), wnn), f"{name}: 3-NN index mismatch"
+        assert torch.equal(nnd.cpu(), wnnd), f"{name}: 3-NN squared distance mismatch (must be bit-equal)"
+
+
+def test_search_ops_vs_reference_cuda_golden(ext):
+    ref = golden("ref_cuda_ops.npz")
+    for name, c in _cases().items():
+        xyz = torch.from_numpy(c["pts"]).cuda()[:, :, :3].permute(0, 2, 1)
+        B = xyz.shape[0]
+        idx = ext.farthest_point_sample(xyz, c["M"])
+        assert np.array_equal(idx.cpu().numpy(), ref[name + ".fps"]), name
+        new_xyz = xyz.gather(2, idx.unsqueeze(1).expand(B, 3, c["M"]))
+        bq, cnt = ext.ball_query(xyz, new_xyz, c["radius"], c["K"])
+        assert np.array_equal(cnt.cpu().numpy(), ref[name + ".bqcnt"]), name
+        if name + ".bq" in ref.files:
+            assert np.array_equal(bq.cpu().numpy(), ref[name + ".bq"]), name
+        else:
+            assert np.array_equal(bq_rowhash(bq.cpu().numpy(), c["K"]), ref[name + ".bq_rowhash"]), name
+        if c["M"] >= 3:
+            nn, nnd = ext.point_search(xyz, new_xyz, 3)
+            if name + ".nn" in ref.files:
+                assert np.array_equal(nn.cpu().numpy(), ref[name + ".nn"]) and np.array_equal(nnd.cpu().numpy(), ref[name + ".nnd"]), name
+            else:
+                assert np.array_equal(nn.cpu().numpy()[:, :4096], ref[name + ".nn_head"]), name
+
+
+@pytest.mark.parametrize("cs,threads", [(1, 512), (2, 512), (4, 512), (8, 512), (1, 1024), (2, 1024), (4, 1024), (8, 1024)])
+def test_fps_every_cluster_configuration(lib_path, oracle, cs, threads):
+    """All launch shapes of the cluster kernel give the same (reference) answer, contiguous planar input too."""
+    from regnet_for_3d_grasping_b200 import _lib, synth
+    lib = _lib.load()
+    for kind, n, m in (("lattice", 5120, 700), ("table", 7000, 900), ("cube", 300, 300)):
+        pts = synth.batch(kind, [n, n + 1], n)
+        xyz_c = torch.from_numpy(pts[:, :, :3]).permute(0, 2, 1).contiguous()
+        want = oracle.farthest_point_sample(xyz_c, m)
+        x = xyz_c.cuda()
+        idx = torch.empty(2, m, dtype=torch.int64, device="cuda")
+        idx32 = torch.empty(2, m, dtype=torch.int32, device="cuda")
+        nx = torch.empty(2, 3, m, device="cuda")
+        rc = lib.regnet_farthest_point_sample_ex(ctypes.c_void_p(x.data_ptr()), x.stride(0), x.stride(1), x.stride(2), 2, n, m,
+                                                 ctypes.c_void_p(idx.data_ptr()), ctypes.c_void_p(idx32.data_ptr()),
+                                                 ctypes.c_void_p(nx.data_ptr()), cs, threads, None)
+        assert rc == 0, lib.regnet_last_error()
+        torch.cuda.synchronize()
+        assert torch.equal(idx.cpu(), want), (kind, cs, threads)
+        assert torch.equal(idx32.cpu().long(), want)
+        assert torch.equal(nx.cpu(), xyz_c.gather(2, want.unsqueeze(1).expand(2, 3, m)))
+
+
+def test_fps_full_size_cloud_matches_oracle(ext, oracle):
+    """BASELINE config size: 25 600 points -> 5 120 centroids (one cloud; the oracle needs ~2 s for it)."""
+    from regnet_for_3d_grasping_b200 import synth
+    pts = synth.batch("table", [77], 25600)
+    want = oracle.farthest_point_sample(torch.from_numpy(pts[:, :, :3]).permute(0, 2, 1), 5120)
+    got = ext.farthest_point_sample(torch.from_numpy(pts).cuda()[:, :, :3].permute(0, 2, 1), 5120)
+    assert torch.equal(got.cpu(), want)
+    assert got.unique().numel() > 5000   # FPS picks (nearly) distinct points; duplicates only where the cloud has them
+
+
+def test_group_and_interpolate_forward_backward(ext, oracle):
+    g = torch.Generator().manual_seed(5)
+    B, C, N, M, K = 2, 19, 1024, 256, 16
+    from regnet_for_3d_grasping_b200 import synth
+    pts = synth.batch("cube", [8, 9], N)
+    xyz_c = torch.from_numpy(pts[:, :, :3]).permute(0, 2, 1)
+    idx = oracle.farthest_point_sample(xyz_c, M)
+    new_xyz = xyz_c.gather(2, idx.unsqueeze(1).expand(B, 3, M))
+    bq, _ = oracle.ball_query(xyz_c, new_xyz, 0.12, K)
+    nn, nnd = oracle.point_search(xyz_c, new_xyz, 3)
+    inv = 1.0 / torch.clamp(nnd, min=1e-10)
+    w = inv / inv.sum(2, keepdim=True)
+    feat = torch.randn(B, C, N, generator=g)
+    feat_nc = torch.randn(B, N, C, generator=g).permute(0, 2, 1)      # strided input
+    for f in (feat, feat_nc):
+        got = ext.group_points_forward(f.cuda(), bq.cuda())
+        assert torch.equal(got.cpu(), oracle.group_points_forward(f, bq))
+    gout = torch.randn(B, C, M, K, generator=g)
+    np.testing.assert_allclose(ext.group_points_backward(gout.cuda(), bq.cuda(), N).cpu().numpy(),
+                               oracle.group_points_backward(gout, bq, N).numpy(), rtol=1e-5, atol=1e-5)
+    sfeat = torch.randn(B, C, M, generator=g)
+    got = ext.interpolate_forward(sfeat.cuda(), nn.cuda(), w.cuda())
+    assert torch.equal(got.cpu(), oracle.interpolate_forward(sfeat, nn, w)), "same fma chain => bit equal"
+    iout = torch.randn(B, C, N, generator=g)
+    np.testing.assert_allclose(ext.interpolate_backward(iout.cuda(), nn.cuda(), w.cuda(), M).cpu().numpy(),
+                               oracle.interpolate_backward(iout, nn, w, M).numpy(), rtol=1e-5, atol=1e-5)
+    ext.check_index_errors()
+    bad = bq.clone()
+    bad[0, 0, 0] = N + 5
+    ext.group_points_forward(feat.cuda(), bad.cuda())
+    with pytest.raises(RuntimeError, match="out of range"):
+        ext.check_index_errors()
+
+
+def test_autograd_functions_on_gpu(ext, oracle):
+    from regnet_for_3d_grasping_b200 import function as F
+    g = torch.Generator().manual_seed(9)
+    xyz = torch.rand(2, 3, 256, generator=g).cuda()
+    feat = torch.randn(2, 6, 256, generator=g).cuda().requires_grad_(True)
+    idx = F.farthest_point_sample(xyz, 64)
+    new_xyz = F.gather_points(xyz, idx)
+    nbr, _ = F.ball_query(xyz, new_xyz, 0.3, 8)
+    grouped = F.group_points(feat, nbr)
+    grouped.square().sum().backward()
+    ref = torch.zeros_like(feat)
+    ref.scatter_add_(2, nbr.view(2, 1, -1).expand(2, 6, -1), (2 * grouped.detach()).view(2, 6, -1))
+    np.testing.assert_allclose(feat.grad.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_error_behaviour_matches_reference(ext):
+    x = torch.rand(1, 3, 10, device="cuda")
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(x, 11)
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(x, 0)
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(torch.rand(1, 4, 10, device="cuda"), 2)
+    with pytest.raises(RuntimeError):
+        ext.point_search(x, x, 2)
+    with pytest.raises(RuntimeError):
+        ext.point_search(x, x[:, :, :2], 3)
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(x.double(), 2)
+    idx, cnt = ext.ball_query(x, x + 10.0, 0.1, 4)
+    assert idx.abs().sum().item() == 0 and cnt.sum().item() == 0
+    assert ext.farthest_point_sample(torch.rand(0, 3, 10, device="cuda"), 2).shape == (0, 2)
+
+
+def test_dgcnn_alias(ext):
+    from regnet_for_3d_grasping_b200 import dgcnn_ext
+    torch.manual_seed(1)
+    feat = torch.rand(2, 4, 5, device="cuda")
+    knn = torch.randint(0, 5, (2, 5, 3), device="cuda")
+    want = torch.gather(feat.unsqueeze(2).expand(2, 4, 5, 5), 3, knn.unsqueeze(1).expand(2, 4, 5, 3))
+    assert torch.equal(dgcnn_ext.gather_knn_forward(feat, knn), want)        # functions/gather_knn.py:26-55 self-check
+    g = dgcnn_ext.gather_knn_backward(torch.ones(2, 4, 5, 3, device="cuda"), knn)
+    ref = torch.zeros(2, 4, 5, device="cuda").scatter_add_(2, knn.view(2, 1, 15).expand(2, 4, 15), torch.ones(2, 4, 15, device="cuda"))
+    assert torch.allclose(g, ref)

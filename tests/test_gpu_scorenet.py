@@ -1,0 +1,147 @@
+"""GPU parity, the fused ScoreNet forward (native plan) against the oracle restatement of the reference
+(oracle/ref_modules.py, CPU fp64 features / fp32 search ops) and the committed golden fixture."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from helpers import assert_features_close
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(num_centroids=(512, 128, 32), radius=(0.05, 0.12, 0.4))
+
+
+def _oracle_forward(oracle, sd, pc, **arch):
+    from oracle import ref_modules
+    with torch.no_grad():
+        return ref_modules.scorenet_forward(sd, pc, oracle.as_pn2_ext(), dtype=torch.float64, keep=True, **arch)
+
+
+@pytest.mark.parametrize("engine", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("kind", ["table", "lattice"])
+def test_plan_small_cloud_every_stage(lib_path, oracle, engine, kind):
+    from oracle import ref_modules
+    from regnet_for_3d_grasping_b200 import synth
+    from regnet_for_3d_grasping_b200.scorenet import ScoreNetPlan
+    B, N = 2, 2048
+    pc = torch.from_numpy(synth.batch(kind, [31, 32], N))
+    if kind == "lattice":
+        pc[:, :, :3] *= 4.0
+    sd = ref_modules.random_scorenet_state(seed=5)
+    feat, score, dbg = _oracle_forward(oracle, sd, pc, **SMALL)
+    plan = ScoreNetPlan(B, N, "cuda", engine=engine, **SMALL)
+    plan.bind_state(sd)
+    got_feat, got_score = plan.forward(pc.cuda())
+    torch.cuda.synchronize()
+    M = SMALL["num_centroids"]
+    nd = (M[1], M[0], N)
+    for i in range(3):
+        assert torch.equal(plan.intermediate(f"fps{i}", torch.int32, (B, M[i])).cpu().long(), dbg[f"fps{i}"]), f"fps{i}"
+        assert torch.equal(plan.intermediate(f"bq{i}", torch.int32, (B, M[i], 64)).cpu().long(), dbg[f"bq{i}"]), f"bq{i}"
+        assert torch.equal(plan.intermediate(f"nn{i}", torch.int32, (B, nd[i], 3)).cpu().long(), dbg[f"nn{i}"]), f"nn{i}"
+    for i, c in enumerate((256, 512, 1024)):
+        assert_features_close(plan.intermediate(f"sa{i}", torch.float32, (B, M[i], c)), dbg[f"sa{i}"].transpose(1, 2), what=f"sa{i}")
+    for i, c in enumerate((1024, 512)):
+        assert_features_close(plan.intermediate(f"fp{i}", torch.float32, (B, nd[i], c)), dbg[f"fp{i}"].transpose(1, 2), what=f"fp{i}")
+    assert_features_close(got_feat, feat, what="all_feature")
+    assert_features_close(got_score, score, what="score")
+    assert plan.launch_count > 30
+    # same input again -> identical bits (no atomics / races in the forward)
+    f2, s2 = plan.forward(pc.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(f2, got_feat) and torch.equal(s2, got_score)
+    plan.close()
+
+
+def test_plan_vs_reference_python_golden(lib_path):
+    """N=6144 with the reference's real architecture constants, against outputs of the reference's own modules."""
+    ref = golden("ref_py_scorenet_n6144.npz")
+    from oracle import ref_modules
+    from regnet_for_3d_grasping_b200 import synth
+    from regnet_for_3d_grasping_b200.scorenet import ScoreNetPlan
+    pc = torch.from_numpy(synth.batch("table", [11], 6144)).cuda()
+    plan = ScoreNetPlan(1, 6144, "cuda")
+    plan.bind_state(ref_modules.random_scorenet_state(seed=3))
+    feat, score = plan.forward(pc)
+    torch.cuda.synchronize()
+    for i, m in enumerate((5120, 1024, 256)):
+        assert np.array_equal(plan.intermediate(f"fps{i}", torch.int32, (1, m)).cpu().numpy()[0], ref[f"fps{i}"])
+        assert np.array_equal(plan.intermediate(f"bq{i}", torch.int32, (1, m, 64)).cpu().numpy()[0].sum(1), ref[f"bq{i}_sum"])
+    assert np.array_equal(plan.intermediate("nn2", torch.int32, (1, 6144, 3)).cpu().numpy()[0, ::13], ref["nn2"])
+    assert_features_close(feat[0, torch.from_numpy(ref["rows"]).long().cuda()], ref["all_feature_rows"], what="all_feature rows")
+    assert_features_close(score[0], ref["score"], what="score")
+
+
+def test_dropin_scorenetwork_fused_equals_module_path(lib_path):
+    """multi_model.score_network.ScoreNetwork drop-in: eval-mode fused plan == its own op-by-op module path
+    (torch conv/BN over this package's point operators) == golden; loss path as in the reference."""
+    ref = golden("ref_py_scorenet_n6144.npz")
+    from oracle import ref_modules
+    from regnet_for_3d_grasping_b200 import synth
+    from regnet_for_3d_grasping_b200.score_network import ScoreNetwork
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net = ScoreNetwork(training=True).cuda().eval()
+    net.load_state_dict(ref_modules.random_scorenet_state(seed=3))
+    pc = torch.from_numpy(synth.batch("table", [11], 6144)).cuda()
+    tgt = torch.from_numpy(synth.scores_like_dataset(5, 1, 6144)).cuda()
+    with torch.no_grad():
+        feat, score, loss = net(pc, tgt)
+        body = net.extrat_featurePN2
+        f2, s2 = body._forward_modules(pc[:, :, :6].permute(0, 2, 1))
+    assert feat.shape == (1, 6144, 256) and score.shape == (1, 6144)
+    assert_features_close(feat, f2.transpose(2, 1), what="fused vs module path: all_feature")
+    assert_features_close(score, s2, what="fused vs module path: score")
+    assert_features_close(score[0], ref["score"], what="score vs golden")
+    np.testing.assert_allclose(loss.item(), golden("ref_py_scorenet_loss.npz")["loss"], rtol=1e-4)
+    # parameters change -> the plan re-folds them
+    with torch.no_grad():
+        net.extrat_featurePN2.bn_score.bias.add_(0.5)
+        _, s3, _ = net(pc)
+    assert (s3 - score).abs().max().item() > 1e-3
+
+
+def test_train_mode_step_runs_and_updates(lib_path):
+    """train.py --mode pretrain_score shape of a step (train.py:143-149): forward, MSE loss, backward, Adam."""
+    from regnet_for_3d_grasping_b200 import synth
+    from regnet_for_3d_grasping_b200.score_network import ScoreNetwork
+    torch.manual_seed(0)
+    net = ScoreNetwork(training=True).cuda().train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    pc = torch.from_numpy(synth.batch("table", [1], 5632)).cuda()
+    tgt = torch.from_numpy(synth.scores_like_dataset(2, 1, 5632)).cuda()
+    before = net.extrat_featurePN2.sa_modules[0].mlp[0].conv.weight.detach().clone()
+    _, score, loss = net(pc, tgt)
+    loss.sum().backward()
+    opt.step()
+    assert torch.isfinite(loss).all() and score.shape == (1, 5632)
+    assert (net.extrat_featurePN2.sa_modules[0].mlp[0].conv.weight.detach() - before).abs().max().item() > 0
+
+
+def test_full_size_batch_properties(lib_path, oracle):
+    """BASELINE config 2 (B=15 x 25 600): size-independent properties + exact FPS parity on one of the clouds."""
+    from oracle import ref_modules
+    from regnet_for_3d_grasping_b200 import synth
+    from regnet_for_3d_grasping_b200.scorenet import ScoreNetPlan
+    B, N = 15, 25600
+    pts = synth.batch("table", range(100, 100 + B), N)
+    pc = torch.from_numpy(pts).cuda()
+    plan = ScoreNetPlan(B, N, "cuda")
+    plan.bind_state(ref_modules.random_scorenet_state(seed=0))
+    feat, score = plan.forward(pc)
+    torch.cuda.synchronize()
+    assert torch.isfinite(feat).all() and torch.isfinite(score).all()
+    assert (score > 0).all() and (score < 1).all() and (feat >= 0).all()       # sigmoid / ReLU ranges
+    fps0 = plan.intermediate("fps0", torch.int32, (B, 5120)).cpu()
+    assert (fps0[:, 0] == 0).all() and fps0.min() >= 0 and fps0.max() < N
+    want = oracle.farthest_point_sample(torch.from_numpy(pts[7:8, :, :3]).permute(0, 2, 1), 5120)
+    assert torch.equal(fps0[7:8].long(), want)
+    bq0 = plan.intermediate("bq0", torch.int32, (B, 5120, 64)).cpu()
+    assert (bq0[:, :, 0] >= 0).all() and (bq0[:, :, 1:] >= bq0[:, :, :1]).all()   # first hit is the smallest index
+    # clouds are independent units: cloud 3 alone gives the same rows (batch-axis sharding is exact)
+    plan1 = ScoreNetPlan(1, N, "cuda")
+    plan1.bind_state(ref_modules.random_scorenet_state(seed=0))
+    f1, s1 = plan1.forward(pc[3:4].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(f1[0], feat[3]) and torch.equal(s1[0], score[3])
