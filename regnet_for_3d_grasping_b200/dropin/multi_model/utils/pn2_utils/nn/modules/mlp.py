@@ -1,0 +1,3 @@
+"""reference: pn2_utils/nn/modules/mlp.py"""
+import _bootstrap  # noqa: F401
+from regnet_for_3d_grasping_b200.nn_layers import SharedMLP  # noqa: F401

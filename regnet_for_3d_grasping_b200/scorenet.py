@@ -43,6 +43,8 @@ class ScoreNetPlan:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("ScoreNetPlan needs a CUDA device; there is no CPU path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         if engine is None:
             engine = _lib.ENGINE_TC
         self.engine = engine
