@@ -51,7 +51,8 @@ int regnet_check_index_errors(void);
  * fused).  Bit-exact with the reference including its tie rule.  EINVAL unless 0 < M <= N. */
 int regnet_farthest_point_sample(const float* points, int64_t sb, int64_t sc, int64_t sn, int B, int N, int M,
                                  int64_t* index, float* new_xyz, void* stream);
-/* same, with explicit tuning (cluster_size in {0=auto,1,2,4,8}, threads in {0=auto,512,1024}) and an
+/* same, with explicit tuning (cluster_size in {0=auto,1,2,4,8}, threads in {0=auto,256,512,1024}; a negative
+ * thread count selects the barrier.cluster exchange instead of st.async+mbarrier, for A/B measurements) and an
  * optional int32 copy of the indices for the fused path */
 int regnet_farthest_point_sample_ex(const float* points, int64_t sb, int64_t sc, int64_t sn, int B, int N, int M,
                                     int64_t* index64, int32_t* index32, float* new_xyz, int cluster_size,

@@ -1,5 +1,6 @@
 // Farthest point sampling for sm_100a: one thread-block CLUSTER per cloud, points and running min-distances
-// resident in registers for the whole kernel, argmax by redux.sync + DSMEM exchange.
+// resident in registers for the whole kernel, argmax by redux.sync, cluster-wide exchange through distributed
+// shared memory with st.async + mbarrier (no barrier.cluster on the critical path).
 //
 // Replaces csrc/sampling_kernel.cu:47-170 of the reference (grid = B blocks of <= 512 threads, min-distance
 // array in global memory, 10-level shared-memory tree per iteration).  Results are bit-identical, including the
@@ -8,7 +9,16 @@
 //   the smallest bit-reversed value (log2(block) bits), and within a slot the smallest j;
 //   block = min(nextpow2(N), 512), at least 16;  if the maximum is 0 the previous pick is repeated.
 // That rule is folded into one 32-bit key  tie(j) = brev(j mod block) | (j div block)  so that the argmax is
-// (max distance bits, min tie) -- two redux.sync per level instead of a 64-bit shuffle tree.
+// (max distance bits, min tie): one redux.sync.max per level, plus a redux.sync.min only when two lanes tie.
+//
+// Per iteration (i = 1 .. M-1), every thread:
+//   1. updates min-distance of its PPT register-resident points against the current centroid, keeps its best;
+//   2. warp argmax -> the winning lane writes {dist bits} and {tie,x,y,z} for its warp to shared memory;
+//   3. __syncthreads; every warp reduces the W warp records redundantly (no second barrier, records are
+//      double-buffered by iteration parity);
+//   4. (cluster only) lanes 0..CS-1 of warp 0 push the CTA record into every peer's shared memory with
+//      st.async.mbarrier::complete_tx; all threads wait on the local mbarrier of this parity, reduce the CS
+//      records.  The winner's coordinates travel with the record, so no global load sits on the critical path.
 #include "common.cuh"
 
 namespace regnet {
@@ -16,15 +26,7 @@ namespace regnet {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-
-struct __align__(16) FpsRecord {
-  uint32_t dbits;  // bits of the (non-negative) distance: unsigned order == float order
-  uint32_t tie;    // smaller wins
-  float x, y;
-  float z;
-  uint32_t pad[3];
-};
-static_assert(sizeof(FpsRecord) == 32, "record is two 16-byte words");
+constexpr uint32_t NO_TIE = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -37,37 +39,70 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t a) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
+__device__ __forceinline__ void st_async_v4(uint32_t addr, uint4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_u32(uint32_t addr, uint32_t a, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(addr), "r"(a), "r"(mbar) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-
-// Warp-wide argmax of (dbits, -tie); on return every lane holds the winner's key and coordinates.
-__device__ __forceinline__ void warp_pick(uint32_t& dbits, uint32_t& tie, float& x, float& y, float& z) {
-  const uint32_t wmax = __reduce_max_sync(FULL, dbits);
-  const uint32_t mine = (dbits == wmax) ? tie : 0xffffffffu;
-  const uint32_t wtie = __reduce_min_sync(FULL, mine);
-  const unsigned vote = __ballot_sync(FULL, dbits == wmax && mine == wtie);
-  const int src = __ffs(vote) - 1;
-  x = __shfl_sync(FULL, x, src);
-  y = __shfl_sync(FULL, y, src);
-  z = __shfl_sync(FULL, z, src);
-  dbits = wmax;
-  tie = wtie;
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arm(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();  // protocol bug: fail the launch instead of hanging the GPU
+  }
 }
 
-template <int CS, int T, int PPT>
+// Lane holding the warp-wide winner of (max d, min tie); `wmax` = the maximum on return (all lanes).
+__device__ __forceinline__ int pick_lane(uint32_t d, uint32_t tie, uint32_t& wmax) {
+  wmax = __reduce_max_sync(FULL, d);
+  unsigned vote = __ballot_sync(FULL, d == wmax);
+  if (vote & (vote - 1)) {  // several lanes attain the maximum: apply the reference's tie order
+    const uint32_t mine = (d == wmax) ? tie : NO_TIE;
+    const uint32_t wtie = __reduce_min_sync(FULL, mine);
+    vote = __ballot_sync(FULL, d == wmax && mine == wtie);
+  }
+  return __ffs(vote) - 1;
+}
+
+template <int CS, int T, int PPT, bool MBAR>
 __global__ void __launch_bounds__(T, 1)
 fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, int64_t* __restrict__ idx64,
            int32_t* __restrict__ idx32, float* __restrict__ new_xyz) {
   constexpr int W = T / 32;
-  __shared__ FpsRecord warp_rec[2][W];
-  __shared__ FpsRecord cta_rec[2][CS];  // slot r is written by cluster rank r (through DSMEM when r != me)
+  __shared__ uint32_t warp_d[2][W];
+  __shared__ __align__(16) uint4 warp_r[2][W];  // {tie, x, y, z}
+  __shared__ uint32_t cta_d[2][8];               // slot r is written by cluster rank r (DSMEM)
+  __shared__ __align__(16) uint4 cta_r[2][8];
+  __shared__ __align__(8) uint64_t bars[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t rank = (CS > 1) ? cluster_ctarank() : 0u;
@@ -102,7 +137,17 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
       o[0] = cx; o[M] = cy; o[2 * (int64_t)M] = cz;
     }
   }
-  if (CS > 1) cluster_sync_all();  // peers' shared memory must exist before the first remote store
+  constexpr uint32_t TX_BYTES = CS * 20;  // per iteration each peer sends 16 + 4 bytes
+  if (CS > 1) {
+    if (MBAR && tid == 0) {
+      mbar_init(smem_u32(&bars[0]), 1);
+      mbar_init(smem_u32(&bars[1]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_arm(smem_u32(&bars[1]), TX_BYTES);           // iteration 1 (odd parity slot)
+      if (M > 2) mbar_arm(smem_u32(&bars[0]), TX_BYTES);  // iteration 2
+    }
+    cluster_sync_all();  // peers' shared memory and barriers exist before the first remote store
+  }
 
   for (int i = 1; i < M; ++i) {
     const int par = i & 1;
@@ -115,39 +160,47 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
       md[k] = m;
       if (m > best) { best = m; bj = jbase + k * CS * T; bx = px[k]; by = py[k]; bz = pz[k]; }
     }
-    uint32_t dbits = __float_as_uint(best);
-    uint32_t tie = (bj < 0) ? 0xffffffffu : (__brev((uint32_t)bj & mask) | ((uint32_t)bj >> nbits));
-    warp_pick(dbits, tie, bx, by, bz);
-    if (lane == 0) {
-      FpsRecord r;
-      r.dbits = dbits; r.tie = tie; r.x = bx; r.y = by; r.z = bz; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-      warp_rec[par][warp] = r;
+    const uint32_t tie = (bj < 0) ? NO_TIE : (__brev((uint32_t)bj & mask) | ((uint32_t)bj >> nbits));
+    uint32_t dmax;
+    // -- warp level
+    const int src1 = pick_lane(__float_as_uint(best), tie, dmax);
+    if (lane == src1) {
+      warp_d[par][warp] = dmax;
+      warp_r[par][warp] = make_uint4(tie, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz));
     }
     __syncthreads();
-    {
-      FpsRecord r;
-      if (lane < W) r = warp_rec[par][lane];
-      else { r.dbits = 0; r.tie = 0xffffffffu; r.x = r.y = r.z = 0.f; }
-      dbits = r.dbits; tie = r.tie; bx = r.x; by = r.y; bz = r.z;
-      warp_pick(dbits, tie, bx, by, bz);
-    }
+    // -- CTA level (every warp, redundantly)
+    const int src2 = pick_lane(lane < W ? warp_d[par][lane] : 0u, lane < W ? warp_r[par][lane].x : NO_TIE, dmax);
+    uint4 win = warp_r[par][src2];
+    // -- cluster level
     if (CS > 1) {
       if (warp == 0 && lane < CS) {
-        const uint32_t dst = mapa_u32(smem_u32(&cta_rec[par][rank]), (uint32_t)lane);
-        st_cluster_v4(dst, dbits, tie, __float_as_uint(bx), __float_as_uint(by));
-        st_cluster_u32(dst + 16, __float_as_uint(bz));
+        const uint32_t dst_r = mapa_u32(smem_u32(&cta_r[par][rank]), (uint32_t)lane);
+        const uint32_t dst_d = mapa_u32(smem_u32(&cta_d[par][rank]), (uint32_t)lane);
+        if (MBAR) {
+          const uint32_t dst_bar = mapa_u32(smem_u32(&bars[par]), (uint32_t)lane);
+          st_async_v4(dst_r, win, dst_bar);
+          st_async_u32(dst_d, dmax, dst_bar);
+        } else {
+          st_cluster_v4(dst_r, win);
+          st_cluster_u32(dst_d, dmax);
+        }
       }
-      cluster_sync_all();
-      FpsRecord r;
-      if (lane < CS) r = cta_rec[par][lane];
-      else { r.dbits = 0; r.tie = 0xffffffffu; r.x = r.y = r.z = 0.f; }
-      dbits = r.dbits; tie = r.tie; bx = r.x; by = r.y; bz = r.z;
-      warp_pick(dbits, tie, bx, by, bz);
+      if (MBAR) {
+        mbar_wait_cluster(smem_u32(&bars[par]), (uint32_t)((i - 1) >> 1) & 1u);  // k-th use of this parity's barrier
+        // re-arm this parity's barrier for iteration i+2: no peer can send that record before it has received
+        // this CTA's record of iteration i+1, which is sent after the next __syncthreads
+        if (tid == 0 && i + 2 < M) mbar_arm(smem_u32(&bars[par]), TX_BYTES);
+      } else {
+        cluster_sync_all();
+      }
+      const int src3 = pick_lane(lane < CS ? cta_d[par][lane] : 0u, lane < CS ? cta_r[par][lane].x : NO_TIE, dmax);
+      win = cta_r[par][src3];
     }
-    if (dbits != 0u) {  // otherwise every remaining distance is 0: the reference repeats the previous pick
-      const uint32_t t = __brev(tie) & mask;
-      cur = (int)(((tie & ((1u << (32 - nbits)) - 1u)) << nbits) | t);
-      cx = bx; cy = by; cz = bz;
+    if (dmax != 0u) {  // otherwise every remaining distance is 0: the reference repeats the previous pick
+      const uint32_t t = __brev(win.x) & mask;
+      cur = (int)(((win.x & ((1u << (32 - nbits)) - 1u)) << nbits) | t);
+      cx = __uint_as_float(win.y); cy = __uint_as_float(win.z); cz = __uint_as_float(win.w);
     }
     if (rank == 0 && tid == 0) {
       if (idx64) idx64[(int64_t)cloud * M + i] = cur;
@@ -158,11 +211,12 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
       }
     }
   }
+  if (CS > 1) cluster_sync_all();  // no CTA leaves while a peer may still address its shared memory
 }
 
 template <int CS, int T, int PPT>
 int launch_fps(const float* pts, Strides3 st, int B, int N, int M, int nbits, int64_t* idx64, int32_t* idx32,
-               float* new_xyz, cudaStream_t stream) {
+               float* new_xyz, bool mbar, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * CS));
   cfg.blockDim = dim3(T);
@@ -175,19 +229,23 @@ int launch_fps(const float* pts, Strides3 st, int B, int N, int M, int nbits, in
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RN_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CS, T, PPT>, pts, st, N, M, nbits, idx64, idx32, new_xyz));
+  if (mbar || CS == 1) {
+    RN_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CS, T, PPT, true>, pts, st, N, M, nbits, idx64, idx32, new_xyz));
+  } else {
+    RN_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CS, T, PPT, false>, pts, st, N, M, nbits, idx64, idx32, new_xyz));
+  }
   return REGNET_OK;
 }
 
 template <int CS, int T>
 int dispatch_ppt(int ppt, const float* pts, Strides3 st, int B, int N, int M, int nbits, int64_t* idx64,
-                 int32_t* idx32, float* new_xyz, cudaStream_t stream) {
-  if (ppt <= 1) return launch_fps<CS, T, 1>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, stream);
-  if (ppt <= 2) return launch_fps<CS, T, 2>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, stream);
-  if (ppt <= 4) return launch_fps<CS, T, 4>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, stream);
-  if (ppt <= 8) return launch_fps<CS, T, 8>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, stream);
-  if constexpr (T == 512) {
-    if (ppt <= 16) return launch_fps<CS, T, 16>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, stream);
+                 int32_t* idx32, float* new_xyz, bool mbar, cudaStream_t stream) {
+  if (ppt <= 1) return launch_fps<CS, T, 1>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
+  if (ppt <= 2) return launch_fps<CS, T, 2>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
+  if (ppt <= 4) return launch_fps<CS, T, 4>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
+  if (ppt <= 8) return launch_fps<CS, T, 8>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
+  if constexpr (T <= 512) {
+    if (ppt <= 16) return launch_fps<CS, T, 16>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
   }
   set_error("farthest_point_sample: %d points per thread exceeds the register-resident limit", ppt);
   return REGNET_ELIMIT;
@@ -204,19 +262,24 @@ int fps_block_log2(int N) {  // sampling_kernel.cu:32-40 get_block + the switch'
   return cnt;
 }
 
+// `threads` selects the CTA size (0 = auto); a NEGATIVE value selects the barrier.cluster exchange variant with
+// |threads| threads (kept for A/B measurements against the st.async + mbarrier exchange).
 int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx64, int32_t* idx32, float* new_xyz,
                int cluster_size, int threads, cudaStream_t stream) {
   RN_CHECK_ARG(B > 0 && N > 0, "farthest_point_sample: empty input (B=%d, N=%d)", B, N);
   RN_CHECK_ARG(M > 0, "farthest_point_sample: num_centroids must be > 0 (got %d)", M);
   RN_CHECK_ARG(N >= M, "farthest_point_sample: num_points (%d) must be >= num_centroids (%d)", N, M);
   RN_CHECK_ARG(idx64 || idx32, "farthest_point_sample: no index output");
-  if (cluster_size == 0) cluster_size = (N > 8192) ? 8 : (N > 2048) ? 4 : (N > 1024) ? 2 : 1;
+  bool mbar = true;
+  if (threads < 0) { mbar = false; threads = -threads; }
+  if (cluster_size == 0) cluster_size = (N > 8192) ? 8 : (N > 6144) ? 2 : 1;
   if (threads == 0) threads = 512;
   RN_CHECK_ARG(cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8,
                "farthest_point_sample: cluster_size must be 1, 2, 4 or 8");
-  RN_CHECK_ARG(threads == 512 || threads == 1024, "farthest_point_sample: threads must be 512 or 1024");
+  RN_CHECK_ARG(threads == 256 || threads == 512 || threads == 1024,
+               "farthest_point_sample: threads must be 256, 512 or 1024");
   // grow the cluster until the cloud fits in registers
-  const int max_ppt = threads == 512 ? 16 : 8;
+  const int max_ppt = threads <= 512 ? 16 : 8;
   while (cluster_size < 8 && ceil_div(N, cluster_size * threads) > max_ppt) cluster_size *= 2;
   const int ppt = ceil_div(N, cluster_size * threads);
   if (ppt > max_ppt) {
@@ -225,9 +288,10 @@ int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx6
     return REGNET_ELIMIT;
   }
   const int nbits = fps_block_log2(N);
-#define RN_FPS_CASE(CS, T)                                                                        \
-  if (cluster_size == CS && threads == T)                                                         \
-    return dispatch_ppt<CS, T>(ppt, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, stream);
+#define RN_FPS_CASE(CS, T)                                                                              \
+  if (cluster_size == CS && threads == T)                                                               \
+    return dispatch_ppt<CS, T>(ppt, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
+  RN_FPS_CASE(1, 256) RN_FPS_CASE(2, 256) RN_FPS_CASE(4, 256) RN_FPS_CASE(8, 256)
   RN_FPS_CASE(1, 512) RN_FPS_CASE(2, 512) RN_FPS_CASE(4, 512) RN_FPS_CASE(8, 512)
   RN_FPS_CASE(1, 1024) RN_FPS_CASE(2, 1024) RN_FPS_CASE(4, 1024) RN_FPS_CASE(8, 1024)
 #undef RN_FPS_CASE

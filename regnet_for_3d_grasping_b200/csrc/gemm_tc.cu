@@ -40,7 +40,9 @@ struct Cfg {
   static constexpr int OFF_BAR = STAGES * STAGE_BYTES;     // mbarriers + tmem pointer
   static constexpr int OFF_SCALE = OFF_BAR + 128;          // scale[BN], shift[BN]
   static constexpr int OFF_PART = OFF_SCALE + 2 * BN * 4;  // pooled partials [4][BN] as uint32
-  static constexpr int SMEM_BYTES = OFF_PART + 4 * BN * 4 + 1024;  // + slack for manual 1024B alignment
+  static constexpr int OFF_STAGE = (OFF_PART + 4 * BN * 4 + 1023) / 1024 * 1024;  // epilogue store staging:
+  static constexpr int STAGE_OUT_BYTES = 4 * 2 * 2048;     //   4 warps x {hi, lo} x [32 rows x 64 B], 64B-swizzled
+  static constexpr int SMEM_BYTES = OFF_STAGE + STAGE_OUT_BYTES + 1024;  // + slack for manual 1024B alignment
   static constexpr int TMEM_COLS = 2 * BN;                 // 256 or 512: power of two >= 32
 };
 
@@ -87,6 +89,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -154,7 +167,8 @@ __device__ __forceinline__ float unorder_bits(uint32_t u) {
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
-               const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo, int64_t P,
+               const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
+               const __grid_constant__ CUtensorMap map_ohi, const __grid_constant__ CUtensorMap map_olo, int64_t P,
                int K, int cout, Epilogue ep) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
@@ -279,8 +293,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32, v);
         float y[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          y[j] = apply_act(fmaf(__uint_as_float(v[j]), s_scale[ch * 32 + j], s_shift[ch * 32 + j]), ep.act);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + ch * 32 + 4 * j4);
+          const float4 sh = *reinterpret_cast<const float4*>(s_shift + ch * 32 + 4 * j4);
+          y[4 * j4 + 0] = apply_act(fmaf(__uint_as_float(v[4 * j4 + 0]), sc.x, sh.x), ep.act);
+          y[4 * j4 + 1] = apply_act(fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y), ep.act);
+          y[4 * j4 + 2] = apply_act(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z), ep.act);
+          y[4 * j4 + 3] = apply_act(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w), ep.act);
+        }
         const int c0 = col0 + ch * 32;
         if (ep.pool) {
           uint32_t mine = 0;
@@ -290,44 +310,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
             if (lane == j) mine = m;
           }
           keep[ch] = mine;
-        } else if (row_ok) {
-          if (c0 + 32 <= cout) {
-            if (ep.out_f32) {
+        } else {
+          if (ep.out_hi && c0 < cout) {
+            // bf16 hi/lo planes: stage this warp's [32 rows x 32 ch] block in shared memory (64B-swizzled rows,
+            // conflict-free STS.128) and let TMA write full lines; rows >= P / channels >= cout are clipped by TMA
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat16 h0, l0, h1, l1;
+              split_bf16(y[2 * j], h0, l0);
+              split_bf16(y[2 * j + 1], h1, l1);
+              __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
+              hi[j] = *reinterpret_cast<uint32_t*>(&hh);
+              lo[j] = *reinterpret_cast<uint32_t*>(&ll);
+            }
+            const uint32_t st_hi = smem_base + C::OFF_STAGE + (warp - 2) * 4096, st_lo = st_hi + 2048;
+            if (lane == 0) bulk_wait_read();  // the previous block's TMA stores have finished reading the staging
+            __syncwarp();
+            const uint32_t swz = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t off = (uint32_t)lane * 64u + (((uint32_t)j ^ swz) << 4);
+              sts_v4(st_hi + off, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              sts_v4(st_lo + off, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_ohi, st_hi, c0, (int)(row0 + q * 32));
+              tma_store_2d(&map_olo, st_lo, c0, (int)(row0 + q * 32));
+              bulk_commit();
+            }
+          }
+          if (ep.out_f32 && row_ok) {
+            if (c0 + 32 <= cout) {
               float4* dst = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ld_f32 + c0);
 #pragma unroll
               for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-            }
-            if (ep.out_hi) {
-              uint32_t hi[16], lo[16];
+            } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(y[2 * j], h0, l0);
-                split_bf16(y[2 * j + 1], h1, l1);
-                __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
-                hi[j] = *reinterpret_cast<uint32_t*>(&hh);
-                lo[j] = *reinterpret_cast<uint32_t*>(&ll);
-              }
-              uint4* dh = reinterpret_cast<uint4*>(ep.out_hi + row * ep.ld_split + c0);
-              uint4* dl = reinterpret_cast<uint4*>(ep.out_lo + row * ep.ld_split + c0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (c0 + j < cout) {
-                if (ep.out_f32) ep.out_f32[row * ep.ld_f32 + c0 + j] = y[j];
-                if (ep.out_hi) {
-                  __nv_bfloat16 h, l;
-                  split_bf16(y[j], h, l);
-                  ep.out_hi[row * ep.ld_split + c0 + j] = h;
-                  ep.out_lo[row * ep.ld_split + c0 + j] = l;
-                }
-              }
+              for (int j = 0; j < 32; ++j)
+                if (c0 + j < cout) ep.out_f32[row * ep.ld_f32 + c0 + j] = y[j];
             }
           }
         }
@@ -350,6 +373,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
       }
       epi_bar_sync();  // s_scale / s_part free for the next tile
     }
+    if (lane == 0) bulk_wait_all();  // outstanding TMA stores complete before the CTA (and its smem) goes away
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -381,7 +406,8 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld, int box_rows) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld, int box_rows, int box_cols = BK,
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("gemm_tc: cuTensorMapEncodeTiled is not available from this driver");
@@ -389,10 +415,10 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld,
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%d ld=%d)", (int)r,
@@ -403,15 +429,16 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld,
 }
 
 template <int BN>
-int launch(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl, int64_t P,
-           int K, int cout, const Epilogue& ep, cudaStream_t stream) {
+int launch(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl,
+           const CUtensorMap& moh, const CUtensorMap& mol, int64_t P, int K, int cout, const Epilogue& ep,
+           cudaStream_t stream) {
   int dev = 0, sms = 0;
   RN_CUDA(cudaGetDevice(&dev));
   RN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   RN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
   const int64_t n_tiles = ((P + BM - 1) / BM) * ((cout + BN - 1) / BN);
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, P, K, cout, ep);
+  gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep);
   RN_LAUNCH_CHECK("gemm_tc_kernel");
   return REGNET_OK;
 }
@@ -437,8 +464,13 @@ int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, 
   RN_TRY(make_map(&mxl, Xlo, P, K, ldx, BM));
   RN_TRY(make_map(&mwh, Whi, cout, K, ldw, bn));
   RN_TRY(make_map(&mwl, Wlo, cout, K, ldw, bn));
-  if (bn == 256) return launch<256>(mxh, mxl, mwh, mwl, P, K, cout, ep, stream);
-  return launch<128>(mxh, mxl, mwh, mwl, P, K, cout, ep, stream);
+  CUtensorMap moh = mxh, mol = mxl;  // placeholders when there is no split output
+  if (ep.out_hi) {
+    RN_TRY(make_map(&moh, ep.out_hi, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    RN_TRY(make_map(&mol, ep.out_lo, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
+  if (bn == 256) return launch<256>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+  return launch<128>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
 }
 
 }  // namespace regnet

@@ -32,14 +32,17 @@ __device__ __forceinline__ void stage_points(float4* tile, const float* __restri
 
 // index (B,M,K): first K hits ascending, first hit replicated into the unused slots, zeros if none.
 // hits[k * (BQ_THREADS+1) + tid] keeps the per-thread list conflict-free for both the scan (column access)
-// and the coalesced write-out (row access).
+// and the coalesced write-out (row access).  HitT = uint16_t when N <= 65536 (halves shared memory => 6 CTAs/SM).
+// The scan is unrolled by 4 with the (rare) hit handling kept in index order, so the common path is four
+// independent LDS.128 + distance chains per trip.
+template <typename HitT>
 __global__ void __launch_bounds__(BQ_THREADS)
 ball_query_kernel(const float* __restrict__ pts, Strides3 pst, const float* __restrict__ ctr, Strides3 cst, int N,
                   int M, float radius, int K, int64_t* __restrict__ index, int64_t* __restrict__ count,
                   int32_t* __restrict__ index32) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* tile = reinterpret_cast<float4*>(smem_raw);
-  int* hits = reinterpret_cast<int*>(smem_raw + sizeof(float4) * TILE_PTS);
+  HitT* hits = reinterpret_cast<HitT*>(smem_raw + sizeof(float4) * TILE_PTS);
   constexpr int LD = BQ_THREADS + 1;
 
   const int b = blockIdx.y;
@@ -55,27 +58,37 @@ ball_query_kernel(const float* __restrict__ pts, Strides3 pst, const float* __re
     y1 = c[(int64_t)m * cst.n + cst.c];
     z1 = c[(int64_t)m * cst.n + 2 * cst.c];
   }
-  int cnt = live ? 0 : K;  // dead threads count as full so the warp can leave early
+  int cnt = live ? 0 : K;  // dead threads count as full so the block can leave early
   for (int base = 0; base < N; base += TILE_PTS) {
     const int n = min(TILE_PTS, N - base);
     __syncthreads();
     stage_points(tile, p, pst, base, n, N);
-    __syncthreads();
-    // whole block leaves once every centroid is full (checked per tile; cheap and keeps barriers uniform)
+    // whole block leaves once every centroid is full (checked per tile; also the barrier after staging)
     if (__syncthreads_and(cnt >= K)) break;
     if (cnt < K) {
-      for (int t = 0; t < n; ++t) {
-        const float4 q = tile[t];
-        const float d = sqdist_ref(x1, y1, z1, q.x, q.y, q.z);
-        if (d < r2) {
-          hits[cnt * LD + threadIdx.x] = base + t;
-          if (++cnt >= K) break;
+      int t = 0;
+      for (; t + 4 <= n; t += 4) {
+        const float4 q0 = tile[t], q1 = tile[t + 1], q2 = tile[t + 2], q3 = tile[t + 3];
+        const bool h0 = sqdist_ref(x1, y1, z1, q0.x, q0.y, q0.z) < r2;
+        const bool h1 = sqdist_ref(x1, y1, z1, q1.x, q1.y, q1.z) < r2;
+        const bool h2 = sqdist_ref(x1, y1, z1, q2.x, q2.y, q2.z) < r2;
+        const bool h3 = sqdist_ref(x1, y1, z1, q3.x, q3.y, q3.z) < r2;
+        if (h0 | h1 | h2 | h3) {
+          if (h0 && cnt < K) hits[(cnt++) * LD + threadIdx.x] = (HitT)(base + t);
+          if (h1 && cnt < K) hits[(cnt++) * LD + threadIdx.x] = (HitT)(base + t + 1);
+          if (h2 && cnt < K) hits[(cnt++) * LD + threadIdx.x] = (HitT)(base + t + 2);
+          if (h3 && cnt < K) hits[(cnt++) * LD + threadIdx.x] = (HitT)(base + t + 3);
+          if (cnt >= K) break;
         }
+      }
+      for (; t < n && cnt < K; ++t) {
+        const float4 q = tile[t];
+        if (sqdist_ref(x1, y1, z1, q.x, q.y, q.z) < r2) hits[(cnt++) * LD + threadIdx.x] = (HitT)(base + t);
       }
     }
   }
   if (live) {
-    const int first = cnt > 0 ? hits[threadIdx.x] : 0;
+    const HitT first = cnt > 0 ? hits[threadIdx.x] : (HitT)0;
     for (int k = cnt; k < K; ++k) hits[k * LD + threadIdx.x] = first;
     if (count) count[(int64_t)b * M + m] = cnt;
   }
@@ -83,7 +96,7 @@ ball_query_kernel(const float* __restrict__ pts, Strides3 pst, const float* __re
   const int rows = min(BQ_THREADS, M - m0);
   for (int e = threadIdx.x; e < rows * K; e += BQ_THREADS) {
     const int r = e / K, k = e - r * K;
-    const int v = hits[k * LD + r];
+    const int v = (int)hits[k * LD + r];
     const int64_t o = ((int64_t)b * M + m0 + r) * K + k;
     if (index) index[o] = v;
     if (index32) index32[o] = v;
@@ -117,19 +130,40 @@ three_nn_kernel(const float* __restrict__ qry, Strides3 qst, const float* __rest
     stage_points(tile, kp, kst, base, n, Nk);
     __syncthreads();
     if (live) {
-#pragma unroll 4
-      for (int t = 0; t < n; ++t) {
-        const float4 c = tile[t];
-        const float d = sqdist_ref(x1, y1, z1, c.x, c.y, c.z);
-        if (d < d2) {                 // fast reject: d2 is the current 3rd best once the list is warm
-          if (d < d0) { d2 = d1; i2 = i1; d1 = d0; i1 = i0; d0 = d; i0 = base + t; }
-          else if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = base + t; }
-          else { d2 = d; i2 = base + t; }
+      auto insert = [&](float d, int j) {
+        if (d < d2) {                 // d2 is the current 3rd best once the list is warm
+          if (d < d0) { d2 = d1; i2 = i1; d1 = d0; i1 = i0; d0 = d; i0 = j; }
+          else if (d < d1) { d2 = d1; i2 = i1; d1 = d; i1 = j; }
+          else { d2 = d; i2 = j; }
         } else if (d < d0) {          // only reachable while the bogus zeros of the initialiser are present
-          d2 = d1; i2 = i1; d1 = d0; i1 = i0; d0 = d; i0 = base + t;
+          d2 = d1; i2 = i1; d1 = d0; i1 = i0; d0 = d; i0 = j;
         } else if (d < d1) {
-          d2 = d1; i2 = i1; d1 = d; i1 = base + t;
+          d2 = d1; i2 = i1; d1 = d; i1 = j;
         }
+      };
+      int t = 0;
+      if (base == 0) {                // first three keys flush the initialiser; after that d0 <= d1 <= d2 holds
+        for (; t < 3 && t < n; ++t) {
+          const float4 c = tile[t];
+          insert(sqdist_ref(x1, y1, z1, c.x, c.y, c.z), t);
+        }
+      }
+      for (; t + 4 <= n; t += 4) {
+        const float4 c0 = tile[t], c1 = tile[t + 1], c2 = tile[t + 2], c3 = tile[t + 3];
+        const float e0 = sqdist_ref(x1, y1, z1, c0.x, c0.y, c0.z);
+        const float e1 = sqdist_ref(x1, y1, z1, c1.x, c1.y, c1.z);
+        const float e2 = sqdist_ref(x1, y1, z1, c2.x, c2.y, c2.z);
+        const float e3 = sqdist_ref(x1, y1, z1, c3.x, c3.y, c3.z);
+        if (fminf(fminf(e0, e1), fminf(e2, e3)) < d2) {   // sorted list: nothing below d2 => nothing to insert
+          insert(e0, base + t);
+          insert(e1, base + t + 1);
+          insert(e2, base + t + 2);
+          insert(e3, base + t + 3);
+        }
+      }
+      for (; t < n; ++t) {
+        const float4 c = tile[t];
+        insert(sqdist_ref(x1, y1, z1, c.x, c.y, c.z), base + t);
       }
     }
   }
@@ -160,12 +194,19 @@ int ball_query_launch(const float* pts, Strides3 pst, const float* ctr, Strides3
     set_error("ball_query: num_neighbours=%d exceeds the supported maximum of 128", K);
     return REGNET_ELIMIT;
   }
-  const size_t smem = sizeof(float4) * TILE_PTS + sizeof(int) * (size_t)K * (BQ_THREADS + 1);
-  // per-device attribute; cheap enough to set on every launch (keeps multi-device processes correct)
-  RN_CUDA(cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(sizeof(float4) * TILE_PTS + sizeof(int) * 128 * (BQ_THREADS + 1))));
   dim3 grid(ceil_div(M, BQ_THREADS), B);
-  ball_query_kernel<<<grid, BQ_THREADS, smem, stream>>>(pts, pst, ctr, cst, N, M, radius, K, index, count, index32);
+  // per-device attribute; cheap enough to set on every launch (keeps multi-device processes correct)
+  if (N <= 65536) {
+    const size_t smem = sizeof(float4) * TILE_PTS + sizeof(uint16_t) * (size_t)K * (BQ_THREADS + 1);
+    RN_CUDA(cudaFuncSetAttribute(ball_query_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(float4) * TILE_PTS + sizeof(uint16_t) * 128 * (BQ_THREADS + 1))));
+    ball_query_kernel<uint16_t><<<grid, BQ_THREADS, smem, stream>>>(pts, pst, ctr, cst, N, M, radius, K, index, count, index32);
+  } else {
+    const size_t smem = sizeof(float4) * TILE_PTS + sizeof(int) * (size_t)K * (BQ_THREADS + 1);
+    RN_CUDA(cudaFuncSetAttribute(ball_query_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(float4) * TILE_PTS + sizeof(int) * 128 * (BQ_THREADS + 1))));
+    ball_query_kernel<int><<<grid, BQ_THREADS, smem, stream>>>(pts, pst, ctr, cst, N, M, radius, K, index, count, index32);
+  }
   RN_LAUNCH_CHECK("ball_query_kernel");
   return REGNET_OK;
 }
