@@ -272,7 +272,14 @@ int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx6
   RN_CHECK_ARG(idx64 || idx32, "farthest_point_sample: no index output");
   bool mbar = true;
   if (threads < 0) { mbar = false; threads = -threads; }
-  if (cluster_size == 0) cluster_size = (N > 8192) ? 8 : (N > 6144) ? 2 : 1;
+  // auto policy from the B=15 sweep on B200 (profiles/r01_fps_sweep.txt): the per-iteration cost is latency, not
+  // arithmetic, so small clouds stay in one CTA (no DSMEM round trip) and large ones spread over 8 CTAs
+  if (cluster_size == 0 && threads == 0) {
+    if (N <= 2048) { cluster_size = 1; threads = 256; }
+    else if (N <= 12288) { cluster_size = 8; threads = 256; }
+    else { cluster_size = 8; threads = 512; }
+  }
+  if (cluster_size == 0) cluster_size = (N > 2048) ? 8 : 1;
   if (threads == 0) threads = 512;
   RN_CHECK_ARG(cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8,
                "farthest_point_sample: cluster_size must be 1, 2, 4 or 8");

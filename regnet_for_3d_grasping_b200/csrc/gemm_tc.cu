@@ -164,7 +164,16 @@ __device__ __forceinline__ float unorder_bits(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-template <int BN>
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+  if (ACT == 1) return fmaxf(v, 0.f);
+  if (ACT == 2) return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-v)));
+  return v;
+}
+
+// POOL / ACT are compile-time so that each instance carries only its own epilogue (a runtime switch inlined the
+// sigmoid's division subroutine 256 times and the unrolled epilogue overflowed the instruction cache).
+template <int BN, bool POOL, int ACT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
                const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
@@ -286,8 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
       tc_fence_after();
       const int64_t row = row0 + q * 32 + lane;
       const bool row_ok = row < P;
-      uint32_t keep[BN / 32];
-#pragma unroll
+#pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32, v);
@@ -296,20 +304,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 sc = *reinterpret_cast<const float4*>(s_scale + ch * 32 + 4 * j4);
           const float4 sh = *reinterpret_cast<const float4*>(s_shift + ch * 32 + 4 * j4);
-          y[4 * j4 + 0] = apply_act(fmaf(__uint_as_float(v[4 * j4 + 0]), sc.x, sh.x), ep.act);
-          y[4 * j4 + 1] = apply_act(fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y), ep.act);
-          y[4 * j4 + 2] = apply_act(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z), ep.act);
-          y[4 * j4 + 3] = apply_act(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w), ep.act);
+          y[4 * j4 + 0] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 0]), sc.x, sh.x));
+          y[4 * j4 + 1] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y));
+          y[4 * j4 + 2] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z));
+          y[4 * j4 + 3] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w));
         }
         const int c0 = col0 + ch * 32;
-        if (ep.pool) {
+        if (POOL) {
           uint32_t mine = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const uint32_t m = __reduce_max_sync(FULL, order_bits(y[j]));
             if (lane == j) mine = m;
           }
-          keep[ch] = mine;
+          s_part[q * BN + ch * 32 + lane] = mine;
         } else {
           if (ep.out_hi && c0 < cout) {
             // bf16 hi/lo planes: stage this warp's [32 rows x 32 ch] block in shared memory (64B-swizzled rows,
@@ -358,9 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      if (ep.pool) {
-#pragma unroll
-        for (int ch = 0; ch < BN / 32; ++ch) s_part[q * BN + ch * 32 + lane] = keep[ch];
+      if (POOL) {
         epi_bar_sync();
         for (int e = et; e < 2 * BN; e += EPI_THREADS) {
           const int g = e / BN, c = e - g * BN;
@@ -428,19 +434,35 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld,
   return REGNET_OK;
 }
 
-template <int BN>
+template <int BN, bool POOL, int ACT>
 int launch(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl,
            const CUtensorMap& moh, const CUtensorMap& mol, int64_t P, int K, int cout, const Epilogue& ep,
            cudaStream_t stream) {
   int dev = 0, sms = 0;
   RN_CUDA(cudaGetDevice(&dev));
   RN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  RN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+  RN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, POOL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               Cfg<BN>::SMEM_BYTES));
   const int64_t n_tiles = ((P + BM - 1) / BM) * ((cout + BN - 1) / BN);
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  gemm_tc_kernel<BN><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep);
+  gemm_tc_kernel<BN, POOL, ACT><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, moh, mol, P, K,
+                                                                                  cout, ep);
   RN_LAUNCH_CHECK("gemm_tc_kernel");
   return REGNET_OK;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl,
+              const CUtensorMap& moh, const CUtensorMap& mol, int64_t P, int K, int cout, const Epilogue& ep,
+              cudaStream_t stream) {
+  if (ep.pool) {
+    if (ep.act == 1) return launch<BN, true, 1>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+    if (ep.act == 0) return launch<BN, true, 0>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+    return launch<BN, true, 2>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+  }
+  if (ep.act == 1) return launch<BN, false, 1>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+  if (ep.act == 0) return launch<BN, false, 0>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+  return launch<BN, false, 2>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
 }
 
 }  // namespace
@@ -457,6 +479,7 @@ int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, 
   RN_CHECK_ARG(!ep.out_f32 || ep.pool || ep.ld_f32 % 4 == 0, "gemm_tc: fp32 output leading dimension must be a multiple of 4");
   RN_CHECK_ARG(!ep.out_hi || ep.ld_split % 8 == 0, "gemm_tc: split output leading dimension must be a multiple of 8");
   RN_CHECK_ARG(P < (1LL << 31), "gemm_tc: too many rows");
+  RN_CHECK_ARG(ep.act >= 0 && ep.act <= 2, "gemm_tc: unknown activation %d", ep.act);
   if (P == 0) return REGNET_OK;
   const int bn = cout > 128 ? 256 : 128;
   CUtensorMap mxh, mxl, mwh, mwl;
@@ -469,8 +492,8 @@ int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, 
     RN_TRY(make_map(&moh, ep.out_hi, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
     RN_TRY(make_map(&mol, ep.out_lo, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   }
-  if (bn == 256) return launch<256>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
-  return launch<128>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+  if (bn == 256) return launch_bn<256>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+  return launch_bn<128>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
 }
 
 }  // namespace regnet
