@@ -135,6 +135,13 @@ int regnet_scorenet_set_layer(regnet_scorenet* plan, int stage, int layer, int c
  * transposed view of (B,256,N), score_network.py:48).  score: (B,N) fp32.  Asynchronous on `stream`. */
 int regnet_scorenet_forward(regnet_scorenet* plan, const float* pc, float* all_feature, float* score, void* stream);
 
+/* Optional software pipelining across forwards (throughput mode).  The geometry chain of a forward (FPS, ball query,
+ * 3-NN: xyz only, ~40 % of a step, dominated by FPS's sequential dependency) is enqueued on the plan's side stream for
+ * the NEXT input while the MLPs of the current one run: call prefetch(pc_next) BEFORE forward(pc_current); the
+ * following forward(pc_next) finds its geometry ready.  `pc` must stay valid and unchanged until that forward has
+ * completed.  At most two prefetches may be outstanding.  Without a prefetch, forward computes the geometry itself. */
+int regnet_scorenet_prefetch(regnet_scorenet* plan, const float* pc, void* stream);
+
 /* Read back intermediates of the last forward for parity tests (device pointers into the plan's workspace,
  * valid until the next forward).  what: "fps0".."fps2" int32 (B,M_i); "bq0".."bq2" int32 (B,M_i,64);
  * "nn0".."nn2" int32 (B,Nd_i,3); "sa0".."sa2" fp32 (B,M_i,C) point-major; "fp0".."fp2" fp32 point-major. */

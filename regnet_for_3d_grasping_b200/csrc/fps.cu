@@ -285,6 +285,10 @@ int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx6
                "farthest_point_sample: cluster_size must be 1, 2, 4 or 8");
   RN_CHECK_ARG(threads == 256 || threads == 512 || threads == 1024,
                "farthest_point_sample: threads must be 256, 512 or 1024");
+  // the in-thread tie order relies on CS*T being a multiple of the reference block size (<= 512): only
+  // CS=1,T=256 with more than 256 points violates it
+  const int nbits = fps_block_log2(N);
+  if ((cluster_size * threads) % (1 << nbits) != 0) threads = 512;
   // grow the cluster until the cloud fits in registers
   const int max_ppt = threads <= 512 ? 16 : 8;
   while (cluster_size < 8 && ceil_div(N, cluster_size * threads) > max_ppt) cluster_size *= 2;
@@ -294,7 +298,6 @@ int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx6
               8 * threads * max_ppt);
     return REGNET_ELIMIT;
   }
-  const int nbits = fps_block_log2(N);
 #define RN_FPS_CASE(CS, T)                                                                              \
   if (cluster_size == CS && threads == T)                                                               \
     return dispatch_ppt<CS, T>(ppt, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);

@@ -63,12 +63,20 @@ struct regnet_scorenet {
   int M[3] = {0, 0, 0};
   Layer layers[8][REGNET_MAX_LAYERS];
   int nlayers[8] = {3, 3, 3, 2, 2, 3, 4, 1};
-  // geometry
-  int32_t* fps_idx[3] = {nullptr, nullptr, nullptr};
-  float* new_xyz[3] = {nullptr, nullptr, nullptr};   // (B,3,M_i) planar
-  int32_t* nbr[3] = {nullptr, nullptr, nullptr};     // (B,M_i,64)
-  int32_t* nn_idx[3] = {nullptr, nullptr, nullptr};  // (B,Nd_i,3)
-  float* nn_w[3] = {nullptr, nullptr, nullptr};
+  // geometry results, double buffered: geometry of forward i+1 (side stream) may run while the MLPs of forward i
+  // (caller's stream) still read slot i%2 -- see regnet_scorenet_prefetch
+  struct Geom {
+    int32_t* fps_idx[3] = {nullptr, nullptr, nullptr};
+    float* new_xyz[3] = {nullptr, nullptr, nullptr};   // (B,3,M_i) planar
+    int32_t* nbr[3] = {nullptr, nullptr, nullptr};     // (B,M_i,64)
+    int32_t* nn_idx[3] = {nullptr, nullptr, nullptr};  // (B,Nd_i,3)
+    float* nn_w[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_bq[3] = {nullptr, nullptr, nullptr}, ev_nn = nullptr;
+    const float* pc = nullptr;   // input this slot was computed for (prefetched and not yet consumed)
+    bool pending = false;
+  } geom[2];
+  int next_slot = 0;   // slot the next geometry pass writes
+  int last_slot = 0;   // slot the last forward consumed (regnet_scorenet_intermediate)
   // features (fp32, point-major)
   float* sa_out[3] = {nullptr, nullptr, nullptr};    // (B,M_i,C_i)
   float* fp_out[2] = {nullptr, nullptr};             // fp0 (B,M1,1024), fp1 (B,M0,512); fp2 is the caller's buffer
@@ -79,8 +87,9 @@ struct regnet_scorenet {
   std::vector<void*> allocs;
   size_t total_bytes = 0;
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_start = nullptr, ev_bq[3] = {nullptr, nullptr, nullptr}, ev_nn = nullptr;
+  cudaEvent_t ev_start = nullptr;
   int launches = 0;
+  int prefetch_launches = 0;
   // optional per-launch timing (regnet_scorenet_set_profiling): events around every launch, serial execution
   bool profiling = false;
   struct Rec { const char* label; cudaEvent_t a, b; };
@@ -195,17 +204,18 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   const int* M = p->M;
   int rc = REGNET_OK;
   auto A = [&](void** ptr, size_t bytes) { if (!rc) rc = dalloc(p, ptr, bytes); };
-  for (int i = 0; i < 3; ++i) {
-    A((void**)&p->fps_idx[i], sizeof(int32_t) * (size_t)B * M[i]);
-    A((void**)&p->new_xyz[i], sizeof(float) * (size_t)B * 3 * M[i]);
-    A((void**)&p->nbr[i], sizeof(int32_t) * (size_t)B * M[i] * 64);
-    A((void**)&p->sa_out[i], sizeof(float) * (size_t)B * M[i] * SA_CH[i][2]);
-  }
   const int nd[3] = {M[1], M[0], N};  // dense point counts of fp0, fp1, fp2
-  for (int i = 0; i < 3; ++i) {
-    A((void**)&p->nn_idx[i], sizeof(int32_t) * (size_t)B * nd[i] * 3);
-    A((void**)&p->nn_w[i], sizeof(float) * (size_t)B * nd[i] * 3);
+  for (int g = 0; g < 2; ++g) {
+    regnet_scorenet::Geom& G = p->geom[g];
+    for (int i = 0; i < 3; ++i) {
+      A((void**)&G.fps_idx[i], sizeof(int32_t) * (size_t)B * M[i]);
+      A((void**)&G.new_xyz[i], sizeof(float) * (size_t)B * 3 * M[i]);
+      A((void**)&G.nbr[i], sizeof(int32_t) * (size_t)B * M[i] * 64);
+      A((void**)&G.nn_idx[i], sizeof(int32_t) * (size_t)B * nd[i] * 3);
+      A((void**)&G.nn_w[i], sizeof(float) * (size_t)B * nd[i] * 3);
+    }
   }
+  for (int i = 0; i < 3; ++i) A((void**)&p->sa_out[i], sizeof(float) * (size_t)B * M[i] * SA_CH[i][2]);
   A((void**)&p->fp_out[0], sizeof(float) * (size_t)B * M[1] * 1024);
   A((void**)&p->fp_out[1], sizeof(float) * (size_t)B * M[0] * 512);
   // activation arenas: the widest (rows x ld) any layer reads or writes, 4 bytes per element in both engines
@@ -227,8 +237,11 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   if (!rc && cfg->use_side_stream) {
     cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming);
-    for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&p->ev_bq[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_nn, cudaEventDisableTiming);
+    for (int g = 0; g < 2; ++g) {
+      for (int i = 0; i < 3 && e == cudaSuccess; ++i)
+        e = cudaEventCreateWithFlags(&p->geom[g].ev_bq[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->geom[g].ev_nn, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) rc = cuda_fail(e, "stream/event creation");
   }
   if (rc) {
@@ -243,8 +256,10 @@ int regnet_scorenet_destroy(regnet_scorenet* p) {
   if (!p) return REGNET_OK;
   for (void* a : p->allocs) cudaFree(a);
   if (p->ev_start) cudaEventDestroy(p->ev_start);
-  for (int i = 0; i < 3; ++i) if (p->ev_bq[i]) cudaEventDestroy(p->ev_bq[i]);
-  if (p->ev_nn) cudaEventDestroy(p->ev_nn);
+  for (int g = 0; g < 2; ++g) {
+    for (int i = 0; i < 3; ++i) if (p->geom[g].ev_bq[i]) cudaEventDestroy(p->geom[g].ev_bq[i]);
+    if (p->geom[g].ev_nn) cudaEventDestroy(p->geom[g].ev_nn);
+  }
   if (p->side) cudaStreamDestroy(p->side);
   for (auto& r : p->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete p;
@@ -296,57 +311,107 @@ int regnet_scorenet_set_layer(regnet_scorenet* p, int stage, int layer, int cin,
   return REGNET_OK;
 }
 
-int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feature, float* score, void* stream_) {
-  cudaStream_t ms = (cudaStream_t)stream_;
-  RN_CHECK_ARG(p && pc && all_feature && score, "scorenet_forward: null argument");
+// Geometry chain of one forward (depends on xyz only): FPS -> ball query per level, then the three 3-NN searches.
+// Runs on the side stream when there is one (after everything already queued on `ms`, which orders it behind the
+// previous reader of this slot), else on `ms`.
+static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaStream_t ms) {
   const int B = p->B, N = p->N;
   const int* M = p->M;
+  regnet_scorenet::Geom& G = p->geom[slot];
   const bool fork = p->side != nullptr && !p->profiling;  // profiling serialises everything on `ms`
-  p->nrec = 0;
-  cudaStream_t gs = fork ? p->side : ms;  // geometry stream
-  p->launches = 0;
-  p->last_allfeat = all_feature;
+  cudaStream_t gs = fork ? p->side : ms;
   if (fork) {
     RN_CUDA(cudaEventRecord(p->ev_start, ms));
     RN_CUDA(cudaStreamWaitEvent(gs, p->ev_start, 0));
   }
-  // ---- geometry chain (xyz only) ------------------------------------------------------------------------
   const Strides3 st0{(int64_t)N * 6, 1, 6};  // pc (B,N,6): the (B,3,N) view of score_network.py:46 without a copy
-  const float* lvl_xyz[4] = {pc, p->new_xyz[0], p->new_xyz[1], p->new_xyz[2]};
+  const float* lvl_xyz[4] = {pc, G.new_xyz[0], G.new_xyz[1], G.new_xyz[2]};
   Strides3 lvl_st[4] = {st0, {(int64_t)3 * M[0], M[0], 1}, {(int64_t)3 * M[1], M[1], 1}, {(int64_t)3 * M[2], M[2], 1}};
   const int lvl_n[4] = {N, M[0], M[1], M[2]};
   for (int i = 0; i < 3; ++i) {
     prof_begin(p, FPS_LABEL[i], gs);
-    RN_TRY(fps_launch(lvl_xyz[i], lvl_st[i], B, lvl_n[i], M[i], nullptr, p->fps_idx[i], p->new_xyz[i], 0, 0, gs));
+    RN_TRY(fps_launch(lvl_xyz[i], lvl_st[i], B, lvl_n[i], M[i], nullptr, G.fps_idx[i], G.new_xyz[i], 0, 0, gs));
     prof_end(p, gs);
     prof_begin(p, BQ_LABEL[i], gs);
     RN_TRY(ball_query_launch(lvl_xyz[i], lvl_st[i], lvl_xyz[i + 1], lvl_st[i + 1], B, lvl_n[i], M[i],
-                             p->cfg.radius[i], 64, nullptr, nullptr, p->nbr[i], gs));
+                             p->cfg.radius[i], 64, nullptr, nullptr, G.nbr[i], gs));
     prof_end(p, gs);
     p->launches += 2;
-    if (fork) RN_CUDA(cudaEventRecord(p->ev_bq[i], gs));
+    if (fork) RN_CUDA(cudaEventRecord(G.ev_bq[i], gs));
   }
   for (int f = 0; f < 3; ++f) {  // fp f: dense level 2-f, sparse level 3-f
     const int dl = 2 - f, sl = 3 - f;
     prof_begin(p, NN_LABEL[f], gs);
     RN_TRY(three_nn_launch(lvl_xyz[dl], lvl_st[dl], lvl_xyz[sl], lvl_st[sl], B, lvl_n[dl], lvl_n[sl], nullptr, nullptr,
-                           p->nn_idx[f], p->nn_w[f], gs));
+                           G.nn_idx[f], G.nn_w[f], gs));
     prof_end(p, gs);
     ++p->launches;
   }
-  if (fork) RN_CUDA(cudaEventRecord(p->ev_nn, gs));
+  if (fork) RN_CUDA(cudaEventRecord(G.ev_nn, gs));
+  return REGNET_OK;
+}
+
+int regnet_scorenet_prefetch(regnet_scorenet* p, const float* pc, void* stream_) {
+  RN_CHECK_ARG(p && pc, "scorenet_prefetch: null argument");
+  const int slot = p->next_slot;
+  if (p->geom[slot].pending) {
+    set_error("scorenet_prefetch: both geometry slots hold unconsumed prefetches; call regnet_scorenet_forward first");
+    return REGNET_EINVAL;
+  }
+  const int saved = p->launches;
+  p->launches = 0;
+  RN_TRY(geometry_enqueue(p, pc, slot, (cudaStream_t)stream_));
+  p->prefetch_launches = p->launches;
+  p->launches = saved;
+  p->geom[slot].pc = pc;
+  p->geom[slot].pending = true;
+  p->next_slot ^= 1;
+  return REGNET_OK;
+}
+
+int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feature, float* score, void* stream_) {
+  cudaStream_t ms = (cudaStream_t)stream_;
+  RN_CHECK_ARG(p && pc && all_feature && score, "scorenet_forward: null argument");
+  const int B = p->B, N = p->N;
+  const int* M = p->M;
+  const bool fork = p->side != nullptr && !p->profiling;
+  p->nrec = 0;
+  p->launches = 0;
+  p->last_allfeat = all_feature;
+  // geometry: consume the oldest prefetch if it was made for this input, otherwise compute it now
+  int slot = p->next_slot;
+  const int oldest = p->geom[p->next_slot].pending ? p->next_slot : (p->next_slot ^ 1);
+  if (p->geom[oldest].pending && p->geom[oldest].pc == pc && !p->profiling) {
+    slot = oldest;
+    p->launches = p->prefetch_launches;
+  } else {
+    if (p->geom[slot].pending) slot ^= 1;
+    if (p->geom[slot].pending) {
+      set_error("scorenet_forward: input does not match the pending prefetches");
+      return REGNET_EINVAL;
+    }
+    RN_TRY(geometry_enqueue(p, pc, slot, ms));
+    if (slot == p->next_slot) p->next_slot ^= 1;
+  }
+  regnet_scorenet::Geom& G = p->geom[slot];
+  G.pending = false;
+  p->last_slot = slot;
+  const Strides3 st0{(int64_t)N * 6, 1, 6};
+  const float* lvl_xyz[4] = {pc, G.new_xyz[0], G.new_xyz[1], G.new_xyz[2]};
+  Strides3 lvl_st[4] = {st0, {(int64_t)3 * M[0], M[0], 1}, {(int64_t)3 * M[1], M[1], 1}, {(int64_t)3 * M[2], M[2], 1}};
+  const int lvl_n[4] = {N, M[0], M[1], M[2]};
 
   // ---- set abstraction MLPs -----------------------------------------------------------------------------
   const float* feat = pc + 3;      // level-0 features = rgb, rows of stride 6
   int64_t feat_bs = (int64_t)N * 6;
   int feat_ld = 6, feat_c = 3;
   for (int i = 0; i < 3; ++i) {
-    if (fork) RN_CUDA(cudaStreamWaitEvent(ms, p->ev_bq[i], 0));
+    if (fork) RN_CUDA(cudaStreamWaitEvent(ms, G.ev_bq[i], 0));
     const int64_t P = (int64_t)B * M[i] * 64;
     const int kpad = round_up(feat_c + 3, 16);
     Act a0 = make_act(p, 0, P, kpad);
     prof_begin(p, SAOP_LABEL[i], ms);
-    RN_TRY(sa_operand_launch(lvl_xyz[i], lvl_st[i], p->new_xyz[i], feat, feat_bs, feat_ld, feat_c, p->nbr[i], B,
+    RN_TRY(sa_operand_launch(lvl_xyz[i], lvl_st[i], G.new_xyz[i], feat, feat_bs, feat_ld, feat_c, G.nbr[i], B,
                              lvl_n[i], M[i], 64, kpad, a0.f32, a0.hi, a0.lo, ms));
     prof_end(p, ms);
     ++p->launches;
@@ -360,7 +425,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     feat_bs = (int64_t)M[i] * feat_c;
   }
   // ---- feature propagation --------------------------------------------------------------------------------
-  if (fork) RN_CUDA(cudaStreamWaitEvent(ms, p->ev_nn, 0));
+  if (fork) RN_CUDA(cudaStreamWaitEvent(ms, G.ev_nn, 0));
   const float* sparse = p->sa_out[2];
   int sparse_c = SA_CH[2][2];
   int sparse_n = M[2];
@@ -377,7 +442,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     Act cur = make_act(p, 0, P, kpad);
     prof_begin(p, FPOP_LABEL[f], ms);
     RN_TRY(fp_operand_launch(sparse, (int64_t)sparse_n * sparse_c, sparse_c, sparse_c, dense, dense_bs, dense_ld, dense_c,
-                             p->nn_idx[f], p->nn_w[f], B, nd, kpad, cur.f32, cur.hi, cur.lo, ms));
+                             G.nn_idx[f], G.nn_w[f], B, nd, kpad, cur.f32, cur.hi, cur.lo, ms));
     prof_end(p, ms);
     ++p->launches;
     int which = 1;
@@ -470,11 +535,12 @@ int regnet_scorenet_intermediate(regnet_scorenet* p, const char* what, void** pt
   const std::string k(what, n - 1);
   const int B = p->B;
   const int nd[3] = {p->M[1], p->M[0], p->N};
-  if (k == "fps") { *ptr = p->fps_idx[i]; *numel = (int64_t)B * p->M[i]; }
-  else if (k == "xyz") { *ptr = p->new_xyz[i]; *numel = (int64_t)B * 3 * p->M[i]; }
-  else if (k == "bq") { *ptr = p->nbr[i]; *numel = (int64_t)B * p->M[i] * 64; }
-  else if (k == "nn") { *ptr = p->nn_idx[i]; *numel = (int64_t)B * nd[i] * 3; }
-  else if (k == "nnw") { *ptr = p->nn_w[i]; *numel = (int64_t)B * nd[i] * 3; }
+  const regnet_scorenet::Geom& G = p->geom[p->last_slot];
+  if (k == "fps") { *ptr = G.fps_idx[i]; *numel = (int64_t)B * p->M[i]; }
+  else if (k == "xyz") { *ptr = G.new_xyz[i]; *numel = (int64_t)B * 3 * p->M[i]; }
+  else if (k == "bq") { *ptr = G.nbr[i]; *numel = (int64_t)B * p->M[i] * 64; }
+  else if (k == "nn") { *ptr = G.nn_idx[i]; *numel = (int64_t)B * nd[i] * 3; }
+  else if (k == "nnw") { *ptr = G.nn_w[i]; *numel = (int64_t)B * nd[i] * 3; }
   else if (k == "sa") { *ptr = p->sa_out[i]; *numel = (int64_t)B * p->M[i] * SA_CH[i][2]; }
   else if (k == "fp" && i < 2) { *ptr = p->fp_out[i]; *numel = (int64_t)B * nd[i] * (i == 0 ? 1024 : 512); }
   else if (k == "fp" && i == 2) { *ptr = p->last_allfeat; *numel = (int64_t)B * p->N * 256; }

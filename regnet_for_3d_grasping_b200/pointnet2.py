@@ -93,6 +93,14 @@ class PointNet2Seg(nn.Module):
         all_feature, score = plan.forward(pc.float())
         return all_feature.transpose(1, 2), score
 
+    def prefetch(self, pc):
+        """Throughput mode (eval only): start the geometry chain for a future batch `pc` (B,N,6) now, overlapped with
+        the forward issued next.  Later call forward on the same tensor."""
+        if self.training or not self._fusable:
+            return
+        plan = self._plan_for(pc.size(0), pc.size(1), pc.device)
+        plan.prefetch(pc)
+
     def forward(self, points, add_channel1=None, add_channel2=None):
         fused = (not self.training and self._fusable and add_channel1 is None and points.is_cuda
                  and points.size(2) >= NUM_CENTROIDS[0])

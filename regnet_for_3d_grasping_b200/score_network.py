@@ -18,6 +18,12 @@ class ScoreNetwork(nn.Module):
         """MSE between predicted and target per-point grasp score, both (B,N)."""
         return self.criterion_reg(pscore, tscore.float())
 
+    def prefetch(self, pc):
+        """Optional (not in the reference): announce the NEXT batch so its FPS / ball-query / 3-NN chain overlaps the
+        MLPs of the batch whose forward() is called next.  `pc` must be a contiguous (B,N,6) float32 CUDA tensor and
+        the same tensor must be passed to forward() afterwards."""
+        self.extrat_featurePN2.prefetch(pc)
+
     def forward(self, pc, pc_score=None, pc_label=None):
         """pc (B,N,>=6) [, pc_score (B,N)] -> (all_feature (B,N,256), output_score (B,N), loss | None).
         all_feature is the 256-channel output of the last feature-propagation layer (pointnet2.py:121), not the

@@ -127,6 +127,15 @@ class ScoreNetPlan:
         self._last_pc = pc  # keep the (possibly copied) input alive until the stream has consumed it
         return all_feature, score
 
+    def prefetch(self, pc):
+        """Enqueue the geometry chain (FPS / ball query / 3-NN) of a FUTURE forward(pc) on the plan's side stream so
+        that it overlaps the MLPs of the forward issued next.  `pc` must be the very tensor (contiguous (B,N,6) fp32)
+        later passed to forward() and must not change in between."""
+        if pc.device != self.device or pc.dtype != torch.float32 or not pc.is_contiguous() or tuple(pc.shape) != (self.batch, self.num_points, 6):
+            raise RuntimeError("prefetch needs the contiguous (B, N, 6) float32 tensor that forward() will receive")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().regnet_scorenet_prefetch(self._h, _p(pc), _lib.current_stream_ptr()))
+
     def profile_forward(self, pc):
         """One forward with every launch bracketed by CUDA events (serial, caller's stream).
         Returns [(label, milliseconds), ...] in launch order."""

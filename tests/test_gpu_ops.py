@@ -76,7 +76,8 @@ def test_fps_every_cluster_configuration(lib_path, oracle, cs, threads):
     """All launch shapes of the cluster kernel give the same (reference) answer, contiguous planar input too."""
     from regnet_for_3d_grasping_b200 import _lib, synth
     lib = _lib.load()
-    for kind, n, m in (("lattice", 5120, 700), ("table", 7000, 900), ("cube", 300, 300)):
+    for kind, n, m in (("lattice", 5120, 700), ("table", 7000, 900), ("cube", 300, 300), ("lattice", 1500, 400),
+                       ("lattice", 300, 120)):
         pts = synth.batch(kind, [n, n + 1], n)
         xyz_c = torch.from_numpy(pts[:, :, :3]).permute(0, 2, 1).contiguous()
         want = oracle.farthest_point_sample(xyz_c, m)

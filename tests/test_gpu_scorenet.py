@@ -145,3 +145,46 @@ def test_full_size_batch_properties(lib_path, oracle):
     f1, s1 = plan1.forward(pc[3:4].contiguous())
     torch.cuda.synchronize()
     assert torch.equal(f1[0], feat[3]) and torch.equal(s1[0], score[3])
+
+
+def test_prefetch_pipeline_equals_plain_forward(lib_path):
+    """Software-pipelined throughput mode (prefetch geometry of batch i+1 during the MLPs of batch i) returns
+    exactly what independent forwards return, for alternating different inputs and both slot orders."""
+    from regnet_for_3d_grasping_b200 import synth, weights
+    from regnet_for_3d_grasping_b200.scorenet import ScoreNetPlan
+    B, N = 2, 6144
+    sd = weights.random_scorenet_state(seed=4)
+    batches = [torch.from_numpy(synth.batch("table", [50 + 2 * k, 51 + 2 * k], N)).cuda() for k in range(3)]
+    plain = ScoreNetPlan(B, N, "cuda")
+    plain.bind_state(sd)
+    want = []
+    for pc in batches:
+        f, s = plain.forward(pc)
+        torch.cuda.synchronize()
+        want.append((f.clone(), s.clone()))
+    plan = ScoreNetPlan(B, N, "cuda")
+    plan.bind_state(sd)
+    order = [0, 1, 2, 1, 0, 0, 2]
+    plan.prefetch(batches[order[0]])
+    got = []
+    for i, k in enumerate(order):
+        if i + 1 < len(order):
+            plan.prefetch(batches[order[i + 1]])
+        f, s = plan.forward(batches[k])
+        got.append((k, f, s))          # fresh output tensors per call
+    torch.cuda.synchronize()
+    for k, f, s in got:
+        assert torch.equal(f, want[k][0]) and torch.equal(s, want[k][1]), f"pipelined result differs for batch {k}"
+    # a forward without matching prefetch still works (computes geometry inline) ...
+    f, s = plan.forward(batches[1])
+    torch.cuda.synchronize()
+    assert torch.equal(s, want[1][1])
+    # ... and a third outstanding prefetch is refused
+    plan.prefetch(batches[0])
+    plan.prefetch(batches[1])
+    with pytest.raises(RuntimeError, match="prefetch"):
+        plan.prefetch(batches[2])
+    f, s = plan.forward(batches[0])
+    f2, s2 = plan.forward(batches[1])
+    torch.cuda.synchronize()
+    assert torch.equal(s, want[0][1]) and torch.equal(s2, want[1][1])
