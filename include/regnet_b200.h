@@ -113,7 +113,8 @@ typedef struct regnet_scorenet_config {
   float radius[3];             /* utils/pointnet2.py:41  (0.02,0.08,0.32) */
   int32_t num_neighbours[3];   /* utils/pointnet2.py:42  (64,64,64); must be 64 for the pooled epilogue */
   int32_t engine;              /* REGNET_ENGINE_* */
-  int32_t use_side_stream;     /* 1: geometry chain (FPS/ball query/3-NN) on an internal second stream */
+  int32_t use_side_stream;     /* 0: one stream; 1: geometry chain (FPS/ball query/3-NN) on an internal second stream;
+                                  2: only FPS there (co-resides with the GEMM CTAs), the rest on the caller's stream */
 } regnet_scorenet_config;
 
 typedef struct regnet_scorenet regnet_scorenet;   /* opaque plan */
@@ -157,7 +158,39 @@ int regnet_scorenet_profile(regnet_scorenet* plan, char* buf, int64_t buf_bytes)
 /* Number of kernels launched by the last regnet_scorenet_forward (for bench.py's gpu_launches). */
 int regnet_scorenet_launch_count(const regnet_scorenet* plan);
 
-/* ---- 3. building blocks exposed for tests / micro-benchmarks ------------------------------------------- */
+/* ---- 3. region stage ----------------------------------------------------- */
+
+/* dataset_utils/get_regiondataset.py:354-434 _select_score_center, on device and batched.
+ * pc (B,N,6), score (B,N).  Per cloud: positives = score > score_thre; more than center_num of them -> farthest point
+ * sampling over the positives in index order (bit-exact with the reference's per-cloud pn2_ext call), mapped back to
+ * cloud indices; 1..center_num -> all of them, then uniform repeats; none -> center_num distinct random points.
+ * center_index (B,center_num) int64; center_pc (B,center_num,6); positive_count (B) int32, optional.
+ * workspace: regnet_select_score_center_workspace(B,N,center_num) bytes of device scratch. */
+int64_t regnet_select_score_center_workspace(int B, int N, int center_num);
+int regnet_select_score_center(const float* pc, const float* score, int B, int N, int center_num, float score_thre,
+                               uint64_t seed, int64_t* center_index, float* center_pc, int32_t* positive_count,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
+/* get_regiondataset.py:279-352 _get_local_points_batch + _get_group_pc: for every centre the points with
+ * sqrt(dx^2+dy^2+dz^2) <= radius (non-strict, products rounded separately as torch does), then exactly group_num of
+ * them: without replacement when count >= group_num, with replacement when 0 < count < group_num, -1 rows when empty.
+ * index (B,NC,G) int64, group (B,NC,G,6) fp32, count (B,NC) int32 optional (number of points inside each ball). */
+int regnet_ball_crop_sample(const float* pc, const float* center_pc, int B, int N, int NC, float radius, int group_num,
+                            uint64_t seed, int64_t* index, float* group, int32_t* count, void* stream);
+
+/* multi_model/gripper_region_network.py:532-544: per-row sampler over a (rows,G) byte mask: more than K set -> K
+ * without replacement (ascending), more than min_count -> K with replacement, else the row is rejected (-1).
+ * index (rows,K) int64; count (rows) int32 optional. */
+int regnet_mask_sample(const uint8_t* mask, int rows, int G, int K, int min_count, uint64_t seed, int64_t* index,
+                       int32_t* count, void* stream);
+
+/* gripper_region_network.py:389-395 + utils/pointnet2.py:161,167,223,232: out[b,c,:] = max over the G rows
+ * feat[idx[b,c,g] + b*N, :] of a point-major (B*N, C) feature tensor (negative indices wrap as in the reference).
+ * index (B,NC,G) int64; out (B,NC,C).  C % 4 == 0. */
+int regnet_gather_max(const float* feat, const int64_t* index, int B, int N, int NC, int G, int C, float* out,
+                      void* stream);
+
+/* ---- 4. building blocks exposed for tests / micro-benchmarks ------------------------------------------- */
 
 /* Y = act(scale * (X W^T) + shift), X (P,cin) fp32 row-major, W (cout,cin) fp32 row-major.
  * pool == 0: Y (P,cout) fp32 row-major.  pool > 0 (must be 64): Y (P/pool,cout) = max over each run of `pool` rows.

@@ -96,8 +96,14 @@ __device__ __forceinline__ int pick_lane(uint32_t d, uint32_t tie, uint32_t& wma
 template <int CS, int T, int PPT, bool MBAR>
 __global__ void __launch_bounds__(T, 1)
 fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, int64_t* __restrict__ idx64,
-           int32_t* __restrict__ idx32, float* __restrict__ new_xyz) {
+           int32_t* __restrict__ idx32, float* __restrict__ new_xyz, const int32_t* __restrict__ n_var) {
   constexpr int W = T / 32;
+  if (n_var) {  // per-cloud point count (region stage: FPS over each cloud's positive points)
+    N = n_var[blockIdx.x / CS];
+    if (N <= M) return;  // not enough points: the caller does not use FPS for this cloud (whole cluster leaves)
+    nbits = N <= 1 ? 0 : 32 - __clz(N - 1);
+    nbits = min(9, max(4, nbits));
+  }
   __shared__ uint32_t warp_d[2][W];
   __shared__ __align__(16) uint4 warp_r[2][W];  // {tie, x, y, z}
   __shared__ uint32_t cta_d[2][8];               // slot r is written by cluster rank r (DSMEM)
@@ -216,7 +222,7 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
 
 template <int CS, int T, int PPT>
 int launch_fps(const float* pts, Strides3 st, int B, int N, int M, int nbits, int64_t* idx64, int32_t* idx32,
-               float* new_xyz, bool mbar, cudaStream_t stream) {
+               float* new_xyz, const int32_t* n_var, bool mbar, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * CS));
   cfg.blockDim = dim3(T);
@@ -230,22 +236,22 @@ int launch_fps(const float* pts, Strides3 st, int B, int N, int M, int nbits, in
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (mbar || CS == 1) {
-    RN_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CS, T, PPT, true>, pts, st, N, M, nbits, idx64, idx32, new_xyz));
+    RN_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CS, T, PPT, true>, pts, st, N, M, nbits, idx64, idx32, new_xyz, n_var));
   } else {
-    RN_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CS, T, PPT, false>, pts, st, N, M, nbits, idx64, idx32, new_xyz));
+    RN_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CS, T, PPT, false>, pts, st, N, M, nbits, idx64, idx32, new_xyz, n_var));
   }
   return REGNET_OK;
 }
 
 template <int CS, int T>
 int dispatch_ppt(int ppt, const float* pts, Strides3 st, int B, int N, int M, int nbits, int64_t* idx64,
-                 int32_t* idx32, float* new_xyz, bool mbar, cudaStream_t stream) {
-  if (ppt <= 1) return launch_fps<CS, T, 1>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
-  if (ppt <= 2) return launch_fps<CS, T, 2>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
-  if (ppt <= 4) return launch_fps<CS, T, 4>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
-  if (ppt <= 8) return launch_fps<CS, T, 8>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
+                 int32_t* idx32, float* new_xyz, const int32_t* n_var, bool mbar, cudaStream_t stream) {
+  if (ppt <= 1) return launch_fps<CS, T, 1>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
+  if (ppt <= 2) return launch_fps<CS, T, 2>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
+  if (ppt <= 4) return launch_fps<CS, T, 4>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
+  if (ppt <= 8) return launch_fps<CS, T, 8>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
   if constexpr (T <= 512) {
-    if (ppt <= 16) return launch_fps<CS, T, 16>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
+    if (ppt <= 16) return launch_fps<CS, T, 16>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
   }
   set_error("farthest_point_sample: %d points per thread exceeds the register-resident limit", ppt);
   return REGNET_ELIMIT;
@@ -264,11 +270,26 @@ int fps_block_log2(int N) {  // sampling_kernel.cu:32-40 get_block + the switch'
 
 // `threads` selects the CTA size (0 = auto); a NEGATIVE value selects the barrier.cluster exchange variant with
 // |threads| threads (kept for A/B measurements against the st.async + mbarrier exchange).
+static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx64, int32_t* idx32,
+                           float* new_xyz, const int32_t* n_var, int cluster_size, int threads, cudaStream_t stream);
+
 int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx64, int32_t* idx32, float* new_xyz,
                int cluster_size, int threads, cudaStream_t stream) {
+  RN_CHECK_ARG(N >= M, "farthest_point_sample: num_points (%d) must be >= num_centroids (%d)", N, M);
+  return fps_launch_impl(pts, st, B, N, M, idx64, idx32, new_xyz, nullptr, cluster_size, threads, stream);
+}
+
+// per-cloud point counts n_per_cloud[b] <= Nmax (device array); clouds with n <= M are skipped (output untouched)
+int fps_launch_var(const float* pts, Strides3 st, int B, int Nmax, int M, const int32_t* n_per_cloud, int32_t* idx32,
+                   cudaStream_t stream) {
+  RN_CHECK_ARG(n_per_cloud != nullptr, "farthest_point_sample: null per-cloud counts");
+  return fps_launch_impl(pts, st, B, Nmax, M, nullptr, idx32, nullptr, n_per_cloud, 0, 0, stream);
+}
+
+static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx64, int32_t* idx32,
+                           float* new_xyz, const int32_t* n_var, int cluster_size, int threads, cudaStream_t stream) {
   RN_CHECK_ARG(B > 0 && N > 0, "farthest_point_sample: empty input (B=%d, N=%d)", B, N);
   RN_CHECK_ARG(M > 0, "farthest_point_sample: num_centroids must be > 0 (got %d)", M);
-  RN_CHECK_ARG(N >= M, "farthest_point_sample: num_points (%d) must be >= num_centroids (%d)", N, M);
   RN_CHECK_ARG(idx64 || idx32, "farthest_point_sample: no index output");
   bool mbar = true;
   if (threads < 0) { mbar = false; threads = -threads; }
@@ -300,7 +321,7 @@ int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx6
   }
 #define RN_FPS_CASE(CS, T)                                                                              \
   if (cluster_size == CS && threads == T)                                                               \
-    return dispatch_ppt<CS, T>(ppt, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, mbar, stream);
+    return dispatch_ppt<CS, T>(ppt, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
   RN_FPS_CASE(1, 256) RN_FPS_CASE(2, 256) RN_FPS_CASE(4, 256) RN_FPS_CASE(8, 256)
   RN_FPS_CASE(1, 512) RN_FPS_CASE(2, 512) RN_FPS_CASE(4, 512) RN_FPS_CASE(8, 512)
   RN_FPS_CASE(1, 1024) RN_FPS_CASE(2, 1024) RN_FPS_CASE(4, 1024) RN_FPS_CASE(8, 1024)

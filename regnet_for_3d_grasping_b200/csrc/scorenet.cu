@@ -314,39 +314,70 @@ int regnet_scorenet_set_layer(regnet_scorenet* p, int stage, int layer, int cin,
 // Geometry chain of one forward (depends on xyz only): FPS -> ball query per level, then the three 3-NN searches.
 // Runs on the side stream when there is one (after everything already queued on `ms`, which orders it behind the
 // previous reader of this slot), else on `ms`.
-static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaStream_t ms) {
-  const int B = p->B, N = p->N;
+// Level tables of one forward: xyz pointer / strides / point count of levels 0..3 for geometry slot G.
+struct Levels {
+  const float* xyz[4];
+  Strides3 st[4];
+  int n[4];
+};
+static Levels make_levels(const regnet_scorenet* p, const regnet_scorenet::Geom& G, const float* pc) {
+  const int N = p->N;
   const int* M = p->M;
+  Levels L;
+  L.xyz[0] = pc; L.xyz[1] = G.new_xyz[0]; L.xyz[2] = G.new_xyz[1]; L.xyz[3] = G.new_xyz[2];
+  L.st[0] = Strides3{(int64_t)N * 6, 1, 6};  // pc (B,N,6): the (B,3,N) view of score_network.py:46 without a copy
+  for (int i = 0; i < 3; ++i) L.st[i + 1] = Strides3{(int64_t)3 * M[i], M[i], 1};
+  L.n[0] = N; L.n[1] = M[0]; L.n[2] = M[1]; L.n[3] = M[2];
+  return L;
+}
+
+static int ball_query_level(regnet_scorenet* p, regnet_scorenet::Geom& G, const Levels& L, int i, cudaStream_t s) {
+  prof_begin(p, BQ_LABEL[i], s);
+  RN_TRY(ball_query_launch(L.xyz[i], L.st[i], L.xyz[i + 1], L.st[i + 1], p->B, L.n[i], p->M[i], p->cfg.radius[i], 64,
+                           nullptr, nullptr, G.nbr[i], s));
+  prof_end(p, s);
+  ++p->launches;
+  return REGNET_OK;
+}
+
+static int three_nn_all(regnet_scorenet* p, regnet_scorenet::Geom& G, const Levels& L, cudaStream_t s) {
+  for (int f = 0; f < 3; ++f) {  // fp f: dense level 2-f, sparse level 3-f
+    const int dl = 2 - f, sl = 3 - f;
+    prof_begin(p, NN_LABEL[f], s);
+    RN_TRY(three_nn_launch(L.xyz[dl], L.st[dl], L.xyz[sl], L.st[sl], p->B, L.n[dl], L.n[sl], nullptr, nullptr,
+                           G.nn_idx[f], G.nn_w[f], s));
+    prof_end(p, s);
+    ++p->launches;
+  }
+  return REGNET_OK;
+}
+
+// Side-stream part of one forward's geometry (depends on xyz only).
+//   use_side_stream == 1: the whole chain (FPS -> ball query per level, then the 3-NN searches) runs on the side stream;
+//   use_side_stream == 2: only the three FPS launches do (register-resident, ~1 KB of shared memory: they co-reside
+//                         with the one-CTA-per-SM GEMM kernels); ball query / 3-NN need tens of KB of shared memory
+//                         per CTA, cannot share an SM with a GEMM CTA and stay on the caller's stream;
+//   no side stream / profiling: everything on `ms`.
+// It is ordered behind everything already queued on `ms`, i.e. behind the previous reader of this slot.
+static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaStream_t ms) {
   regnet_scorenet::Geom& G = p->geom[slot];
   const bool fork = p->side != nullptr && !p->profiling;  // profiling serialises everything on `ms`
+  const bool fps_only = fork && p->cfg.use_side_stream == 2;
   cudaStream_t gs = fork ? p->side : ms;
   if (fork) {
     RN_CUDA(cudaEventRecord(p->ev_start, ms));
     RN_CUDA(cudaStreamWaitEvent(gs, p->ev_start, 0));
   }
-  const Strides3 st0{(int64_t)N * 6, 1, 6};  // pc (B,N,6): the (B,3,N) view of score_network.py:46 without a copy
-  const float* lvl_xyz[4] = {pc, G.new_xyz[0], G.new_xyz[1], G.new_xyz[2]};
-  Strides3 lvl_st[4] = {st0, {(int64_t)3 * M[0], M[0], 1}, {(int64_t)3 * M[1], M[1], 1}, {(int64_t)3 * M[2], M[2], 1}};
-  const int lvl_n[4] = {N, M[0], M[1], M[2]};
+  const Levels L = make_levels(p, G, pc);
   for (int i = 0; i < 3; ++i) {
     prof_begin(p, FPS_LABEL[i], gs);
-    RN_TRY(fps_launch(lvl_xyz[i], lvl_st[i], B, lvl_n[i], M[i], nullptr, G.fps_idx[i], G.new_xyz[i], 0, 0, gs));
-    prof_end(p, gs);
-    prof_begin(p, BQ_LABEL[i], gs);
-    RN_TRY(ball_query_launch(lvl_xyz[i], lvl_st[i], lvl_xyz[i + 1], lvl_st[i + 1], B, lvl_n[i], M[i],
-                             p->cfg.radius[i], 64, nullptr, nullptr, G.nbr[i], gs));
-    prof_end(p, gs);
-    p->launches += 2;
-    if (fork) RN_CUDA(cudaEventRecord(G.ev_bq[i], gs));
-  }
-  for (int f = 0; f < 3; ++f) {  // fp f: dense level 2-f, sparse level 3-f
-    const int dl = 2 - f, sl = 3 - f;
-    prof_begin(p, NN_LABEL[f], gs);
-    RN_TRY(three_nn_launch(lvl_xyz[dl], lvl_st[dl], lvl_xyz[sl], lvl_st[sl], B, lvl_n[dl], lvl_n[sl], nullptr, nullptr,
-                           G.nn_idx[f], G.nn_w[f], gs));
+    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], 0, 0, gs));
     prof_end(p, gs);
     ++p->launches;
+    if (!fps_only) RN_TRY(ball_query_level(p, G, L, i, gs));
+    if (fork) RN_CUDA(cudaEventRecord(G.ev_bq[i], gs));  // level i ready (FPS only, or FPS + ball query)
   }
+  if (!fps_only) RN_TRY(three_nn_all(p, G, L, gs));
   if (fork) RN_CUDA(cudaEventRecord(G.ev_nn, gs));
   return REGNET_OK;
 }
@@ -396,10 +427,11 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   regnet_scorenet::Geom& G = p->geom[slot];
   G.pending = false;
   p->last_slot = slot;
-  const Strides3 st0{(int64_t)N * 6, 1, 6};
-  const float* lvl_xyz[4] = {pc, G.new_xyz[0], G.new_xyz[1], G.new_xyz[2]};
-  Strides3 lvl_st[4] = {st0, {(int64_t)3 * M[0], M[0], 1}, {(int64_t)3 * M[1], M[1], 1}, {(int64_t)3 * M[2], M[2], 1}};
-  const int lvl_n[4] = {N, M[0], M[1], M[2]};
+  const bool fps_only = fork && p->cfg.use_side_stream == 2;
+  const Levels L = make_levels(p, G, pc);
+  const float* const* lvl_xyz = L.xyz;
+  const Strides3* lvl_st = L.st;
+  const int* lvl_n = L.n;
 
   // ---- set abstraction MLPs -----------------------------------------------------------------------------
   const float* feat = pc + 3;      // level-0 features = rgb, rows of stride 6
@@ -407,6 +439,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   int feat_ld = 6, feat_c = 3;
   for (int i = 0; i < 3; ++i) {
     if (fork) RN_CUDA(cudaStreamWaitEvent(ms, G.ev_bq[i], 0));
+    if (fps_only) RN_TRY(ball_query_level(p, G, L, i, ms));
     const int64_t P = (int64_t)B * M[i] * 64;
     const int kpad = round_up(feat_c + 3, 16);
     Act a0 = make_act(p, 0, P, kpad);
@@ -426,6 +459,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   }
   // ---- feature propagation --------------------------------------------------------------------------------
   if (fork) RN_CUDA(cudaStreamWaitEvent(ms, G.ev_nn, 0));
+  if (fps_only) RN_TRY(three_nn_all(p, G, L, ms));
   const float* sparse = p->sa_out[2];
   int sparse_c = SA_CH[2][2];
   int sparse_n = M[2];

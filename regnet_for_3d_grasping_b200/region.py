@@ -1,0 +1,133 @@
+"""Region stage of REGNet on device: grasp-centre selection and region cropping,
+plus the grouped max-pool (R3) and the per-row masked sampler of the closing-box crop (R6).
+
+`get_grasp_allobj` keeps the signature and return tuple of dataset_utils/get_regiondataset.py:13-42 so that
+train.py:237 / test.py:135 can call it unchanged; the implementation is three batched kernel launches instead of
+B*N_C Python iterations with host synchronisation (csrc/region.cu, C ABI in include/regnet_b200.h section 3).
+
+Random draws come from a counter-based device generator seeded from torch's CPU generator (`torch.manual_seed`
+makes them reproducible); the reference draws from numpy's global state seeded with the wall clock
+(train.py:59, test.py:56), so only the distributions -- not the streams -- can be matched.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _seed(seed):
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return ctypes.c_uint64(seed & (2 ** 64 - 1))
+
+
+def _need(t, name, dtype=torch.float32):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (the region stage has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}")
+
+
+def select_score_center(pc, pre_score, center_num, score_thre, seed=None, return_count=False):
+    """get_regiondataset.py:354-434.  pc (B,N,6), pre_score (B,N) -> center_pc (B,center_num,6),
+    center_pc_index (B,center_num) int64."""
+    _need(pc, "pc")
+    _need(pre_score, "pre_score")
+    B, N, C = pc.shape
+    if C != 6:
+        pc = pc[:, :, :6]
+    pc = pc.contiguous()
+    score = pre_score.contiguous().view(B, N)
+    lib = _lib.load()
+    center_index = torch.empty(B, center_num, dtype=torch.int64, device=pc.device)
+    center_pc = torch.empty(B, center_num, 6, dtype=torch.float32, device=pc.device)
+    count = torch.empty(B, dtype=torch.int32, device=pc.device)
+    ws_bytes = lib.regnet_select_score_center_workspace(B, N, center_num)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=pc.device)
+    with torch.cuda.device(pc.device):
+        _lib.check(lib.regnet_select_score_center(_p(pc), _p(score), B, N, int(center_num), float(score_thre), _seed(seed),
+                                                  _p(center_index), _p(center_pc), _p(count), _p(ws), ws_bytes,
+                                                  _lib.current_stream_ptr()))
+    if return_count:
+        return center_pc, center_index, count
+    return center_pc, center_index
+
+
+def get_group_pc(pc, center_pc, center_pc_index, group_num, width, height, depth, r_time, seed=None, return_count=False):
+    """get_regiondataset.py:311-352.  -> pc_group_index (B,N_C,group_num) int64, pc_group (B,N_C,group_num,6)."""
+    _need(pc, "pc")
+    _need(center_pc, "center_pc")
+    B, N, C = pc.shape
+    if C != 6:
+        pc = pc[:, :, :6]
+    pc = pc.contiguous()
+    center_pc = center_pc.contiguous()
+    NC = center_pc.shape[1]
+    radius = max(width, height, depth) * r_time            # python double, rounded to fp32 at the comparison
+    index = torch.empty(B, NC, group_num, dtype=torch.int64, device=pc.device)
+    group = torch.empty(B, NC, group_num, 6, dtype=torch.float32, device=pc.device)
+    count = torch.empty(B, NC, dtype=torch.int32, device=pc.device)
+    with torch.cuda.device(pc.device):
+        _lib.check(_lib.load().regnet_ball_crop_sample(_p(pc), _p(center_pc), B, N, NC, float(radius), int(group_num),
+                                                       _seed(seed), _p(index), _p(group), _p(count),
+                                                       _lib.current_stream_ptr()))
+    if return_count:
+        return index, group, count
+    return index, group
+
+
+def get_grasp_allobj(pc, predict_score, params, data_paths, use_theta=True, seed=None):
+    """Drop-in for dataset_utils.get_regiondataset.get_grasp_allobj (get_regiondataset.py:13-42).
+
+    Returns (center_pc, center_pc_index, pc_group_index, pc_group, pc_group_more_index, pc_group_more, grasp_labels).
+    grasp_labels needs the scene files on disk (_get_center_grasp, :45-134); that lookup is a later row of the
+    scope table and is not provided: pass data_paths=[] (the inference path of test.py:135)."""
+    (center_num, score_thre, group_num, r_time_group, group_num_more, r_time_group_more, width, height, depth) = params
+    s = None if seed is None else int(seed)
+    center_pc, center_pc_index = select_score_center(pc, predict_score, center_num, score_thre, seed=s)
+    pc_group_index, pc_group = get_group_pc(pc, center_pc, center_pc_index, group_num, width, height, depth, r_time_group,
+                                            seed=None if s is None else s + 1)
+    pc_group_more_index, pc_group_more = get_group_pc(pc, center_pc, center_pc_index, group_num_more, width, height, depth,
+                                                      r_time_group_more, seed=None if s is None else s + 2)
+    if len(data_paths) > 0:
+        raise NotImplementedError("grasp label lookup (_get_center_grasp) is not part of this round's scope; "
+                                  "call with data_paths=[]")
+    return center_pc, center_pc_index, pc_group_index, pc_group, pc_group_more_index, pc_group_more, None
+
+
+def sample_mask_rows(mask, num, min_count=5, seed=None, return_count=False):
+    """gripper_region_network.py:532-544: for each row of a (rows,G) boolean mask pick `num` column indices:
+    more than `num` set -> without replacement; more than `min_count` -> with replacement; else -1 (row rejected)."""
+    if not mask.is_cuda:
+        raise RuntimeError("mask must be a CUDA tensor")
+    m = mask.to(torch.uint8).contiguous()
+    rows, G = m.shape
+    index = torch.empty(rows, num, dtype=torch.int64, device=m.device)
+    count = torch.empty(rows, dtype=torch.int32, device=m.device)
+    with torch.cuda.device(m.device):
+        _lib.check(_lib.load().regnet_mask_sample(_p(m), rows, G, int(num), int(min_count), _seed(seed), _p(index), _p(count),
+                                                  _lib.current_stream_ptr()))
+    if return_count:
+        return index, count
+    return index
+
+
+def gather_max(all_feature, index):
+    """max over each group's feature rows: all_feature (B,N,C) point-major contiguous, index (B,N_C,G) int64
+    -> (B,N_C,C).  Equals MaxPool1d(G)(all_feature.view(-1,C)[index + b*N].permute(0,2,1)) of
+    gripper_region_network.py:389-395 + utils/pointnet2.py:161,167."""
+    _need(all_feature, "all_feature")
+    _need(index, "index", torch.int64)
+    f = all_feature.contiguous()
+    B, N, C = f.shape
+    ix = index.contiguous()
+    _, NC, G = ix.shape
+    out = torch.empty(B, NC, C, dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        _lib.check(_lib.load().regnet_gather_max(_p(f), _p(ix), B, N, NC, G, C, _p(out), _lib.current_stream_ptr()))
+    return out

@@ -38,7 +38,7 @@ def fold_bn(sd, prefix, eps=BN_EPS):
 
 class ScoreNetPlan:
     def __init__(self, batch, num_points, device, engine=None, num_centroids=NUM_CENTROIDS, radius=RADIUS,
-                 side_stream=True):
+                 side_stream=2):
         lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -57,7 +57,8 @@ class ScoreNetPlan:
             cfg.radius[i] = float(radius[i])
             cfg.num_neighbours[i] = NUM_NEIGHBOURS[i]
         cfg.engine = engine
-        cfg.use_side_stream = 1 if side_stream else 0
+        # 0: single stream; 1: whole geometry chain on the side stream; 2: only FPS on the side stream (default)
+        cfg.use_side_stream = int(side_stream)
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(lib.regnet_scorenet_create(ctypes.byref(cfg), ctypes.byref(self._h)))

