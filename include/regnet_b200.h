@@ -150,8 +150,10 @@ int regnet_scorenet_intermediate(regnet_scorenet* plan, const char* what, void**
 
 /* Per-launch timing for bench.py's roofline block.  With profiling on, the forward runs every kernel on the
  * caller's stream (no side stream) bracketed by CUDA events; regnet_scorenet_profile synchronises and writes one
- * "label milliseconds\n" line per launch of the LAST forward into buf (labels: fps.i, ball_query.i, three_nn.i,
+ * "label milliseconds start_offset_ms\n" line per launch of the LAST forward into buf (labels: fps.i, ball_query.i, three_nn.i,
  * sa_operand.i, fp_operand.i, gemm.<stage>.l<j>[pool], score_head). */
+/* on = 1: as above.  on = 2: timeline mode -- streams and prefetch stay as configured, events are recorded around
+ * every launch and accumulate over forwards until regnet_scorenet_profile reads them (overlap diagnostics). */
 int regnet_scorenet_set_profiling(regnet_scorenet* plan, int on);
 int regnet_scorenet_profile(regnet_scorenet* plan, char* buf, int64_t buf_bytes);
 

@@ -19,6 +19,8 @@
 //   4. (cluster only) lanes 0..CS-1 of warp 0 push the CTA record into every peer's shared memory with
 //      st.async.mbarrier::complete_tx; all threads wait on the local mbarrier of this parity, reduce the CS
 //      records.  The winner's coordinates travel with the record, so no global load sits on the critical path.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace regnet {
@@ -295,6 +297,13 @@ static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, i
   if (threads < 0) { mbar = false; threads = -threads; }
   // auto policy from the B=15 sweep on B200 (profiles/r01_fps_sweep.txt): the per-iteration cost is latency, not
   // arithmetic, so small clouds stay in one CTA (no DSMEM round trip) and large ones spread over 8 CTAs
+  if (cluster_size == 0 && threads == 0) {
+    // debug knob for overlap experiments: REGNET_FPS_FORCE="<cluster>,<threads>" (negative threads = barrier variant)
+    if (const char* f = getenv("REGNET_FPS_FORCE")) {
+      int c = 0, t = 0;
+      if (sscanf(f, "%d,%d", &c, &t) == 2 && N > 2048) { cluster_size = c; threads = t; if (t < 0) { mbar = false; threads = -t; } }
+    }
+  }
   if (cluster_size == 0 && threads == 0) {
     if (N <= 2048) { cluster_size = 1; threads = 256; }
     else if (N <= 12288) { cluster_size = 8; threads = 256; }

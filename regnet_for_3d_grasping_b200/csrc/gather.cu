@@ -97,96 +97,175 @@ interp_backward_kernel(const float* __restrict__ gout, const int64_t* __restrict
 }
 
 // ---- fused operand producers ----------------------------------------------------------------------------------
-// Output row r (one grouped position / one dense point) has `kpad` columns; two adjacent columns per thread.
+// Output row r (one grouped position / one dense point) has `kpad` columns; FOUR adjacent columns per thread so that
+// feature rows move as 16-byte vectors and enough bytes are in flight per thread to cover the gather latency.
 struct OperandOut {
   float* f32;            // (rows, kpad) fp32, or nullptr
   __nv_bfloat16* hi;     // (rows, kpad) bf16 planes, or nullptr
   __nv_bfloat16* lo;
 };
 
-__device__ __forceinline__ void store_pair(const OperandOut& o, int64_t off, float a, float b) {
-  if (o.f32) *reinterpret_cast<float2*>(o.f32 + off) = make_float2(a, b);
+__device__ __forceinline__ void store_quad(const OperandOut& o, int64_t off, float4 v) {
+  if (o.f32) *reinterpret_cast<float4*>(o.f32 + off) = v;
   if (o.hi) {
-    __nv_bfloat16 ah, al, bh, bl;
-    split_bf16(a, ah, al);
-    split_bf16(b, bh, bl);
-    *reinterpret_cast<__nv_bfloat162*>(o.hi + off) = __halves2bfloat162(ah, bh);
-    *reinterpret_cast<__nv_bfloat162*>(o.lo + off) = __halves2bfloat162(al, bl);
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]);
+    split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]);
+    split_bf16(v.w, h[3], l[3]);
+    __nv_bfloat162 h01 = __halves2bfloat162(h[0], h[1]), h23 = __halves2bfloat162(h[2], h[3]);
+    __nv_bfloat162 l01 = __halves2bfloat162(l[0], l[1]), l23 = __halves2bfloat162(l[2], l[3]);
+    uint2 ph, pl;
+    ph.x = *reinterpret_cast<uint32_t*>(&h01); ph.y = *reinterpret_cast<uint32_t*>(&h23);
+    pl.x = *reinterpret_cast<uint32_t*>(&l01); pl.y = *reinterpret_cast<uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(o.hi + off) = ph;
+    *reinterpret_cast<uint2*>(o.lo + off) = pl;
   }
 }
 
-// SA operand: row (b,m,k) = [ xyz[j]-new_xyz[m] (3) | feat[j, 0..C) | 0 ... ], j = nbr[b,m,k]      (modules.py:44-52)
+// SA operand: row (b,m,k) = [ feat[j, 0..C) | xyz[j]-new_xyz[m] (3) | 0 ... ], j = nbr[b,m,k].
+// The reference concatenates [xyz_rel, feature] (modules.py:44-52); the rotation by three columns is folded into the
+// first layer's weights when they are uploaded (regnet_scorenet_set_layer), which keeps feature quads 16-byte aligned.
 __global__ void __launch_bounds__(THREADS)
 sa_operand_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __restrict__ new_xyz,
-                  const float* __restrict__ feat, int64_t feat_bstride, int feat_ld, int C,
-                  const int32_t* __restrict__ nbr, int N, int M, int K, int kpad, int64_t total_pairs, OperandOut out) {
-  const int half = kpad >> 1;
-  for (int64_t e = blockIdx.x * (int64_t)THREADS + threadIdx.x; e < total_pairs; e += (int64_t)gridDim.x * THREADS) {
-    const int cp = (int)(e % half);
-    const int64_t row = e / half;
+                  const float* __restrict__ feat, int64_t feat_bstride, int feat_ld, int C, int vec_ok,
+                  const int32_t* __restrict__ nbr, int M, int K, int kpad, int64_t total_quads, OperandOut out) {
+  const int quads = kpad >> 2;
+  for (int64_t e = blockIdx.x * (int64_t)THREADS + threadIdx.x; e < total_quads; e += (int64_t)gridDim.x * THREADS) {
+    const int q = (int)(e % quads);
+    const int64_t row = e / quads;
     const int64_t bm = row / K;
     const int m = (int)(bm % M);
     const int64_t b = bm / M;
     const int j = nbr[row];
-    float v[2];
+    const int c0 = q * 4;
+    float4 v;
+    if (vec_ok && c0 + 4 <= C) {
+      v = *reinterpret_cast<const float4*>(feat + b * feat_bstride + (int64_t)j * feat_ld + c0);
+    } else {
+      float t[4];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int col = cp * 2 + t;
-      float x = 0.f;
-      if (col < 3) {
-        x = __fsub_rn(xyz[b * xst.b + col * xst.c + (int64_t)j * xst.n], new_xyz[(b * 3 + col) * M + m]);
-      } else if (col < 3 + C) {
-        x = feat[b * feat_bstride + (int64_t)j * feat_ld + (col - 3)];
+      for (int u = 0; u < 4; ++u) {
+        const int col = c0 + u;
+        float x = 0.f;
+        if (col < C) {
+          x = feat[b * feat_bstride + (int64_t)j * feat_ld + col];
+        } else if (col < C + 3) {
+          const int a = col - C;
+          x = __fsub_rn(xyz[b * xst.b + a * xst.c + (int64_t)j * xst.n], new_xyz[(b * 3 + a) * M + m]);
+        }
+        t[u] = x;
       }
-      v[t] = x;
+      v = make_float4(t[0], t[1], t[2], t[3]);
     }
-    store_pair(out, row * kpad + cp * 2, v[0], v[1]);
+    store_quad(out, row * kpad + c0, v);
   }
-  (void)N;
+}
+
+// SA level 0 with its first MLP layer fused: the grouped input has only 6 channels (rgb + xyz_rel), so the layer
+// 6 -> COUT is ~770 FMAs per position -- cheaper on the SIMT pipes than a tensor-core launch whose epilogue has to
+// write the same 128-channel activation anyway.  One thread = (position, 4 output channels); its 24 weights and
+// scale/shift stay in registers (the quad index is constant per thread because THREADS % (COUT/4) == 0).
+// y = relu(scale * (W v) + shift), v = [feat[j,0..3) | xyz[j]-new_xyz[m]] (the rotated order of sa_operand_kernel).
+template <int COUT>
+__global__ void __launch_bounds__(THREADS)
+sa0_fused_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __restrict__ new_xyz,
+                 const float* __restrict__ feat, int64_t feat_bstride, int feat_ld, const int32_t* __restrict__ nbr,
+                 const float* __restrict__ W, int ldw, const float* __restrict__ scale, const float* __restrict__ shift,
+                 int M, int K, int64_t rows, OperandOut out, int ld_out) {
+  constexpr int QUADS = COUT / 4;
+  static_assert(THREADS % QUADS == 0, "quad index must be constant per thread");
+  const int q = threadIdx.x % QUADS;
+  float w[4][6], sc[4], sh[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) w[u][c] = W[(q * 4 + u) * ldw + c];
+    sc[u] = scale[q * 4 + u];
+    sh[u] = shift[q * 4 + u];
+  }
+  const int64_t rows_per_pass = (int64_t)gridDim.x * (THREADS / QUADS);
+  for (int64_t row = (int64_t)blockIdx.x * (THREADS / QUADS) + threadIdx.x / QUADS; row < rows; row += rows_per_pass) {
+    const int64_t bm = row / K;
+    const int m = (int)(bm % M);
+    const int64_t b = bm / M;
+    const int j = nbr[row];
+    float v[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = feat[b * feat_bstride + (int64_t)j * feat_ld + c];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      v[3 + a] = __fsub_rn(xyz[b * xst.b + a * xst.c + (int64_t)j * xst.n], new_xyz[(b * 3 + a) * M + m]);
+    float y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) acc = fmaf(w[u][c], v[c], acc);
+      y[u] = fmaxf(fmaf(acc, sc[u], sh[u]), 0.f);
+    }
+    store_quad(out, row * ld_out + q * 4, make_float4(y[0], y[1], y[2], y[3]));
+  }
 }
 
 // FP operand: row (b,n) = [ sum_k w[b,n,k]*sparse[idx[b,n,k], 0..C2) | dense[n, 0..C1) | 0 ... ]   (modules.py:117-127)
 __global__ void __launch_bounds__(THREADS)
 fp_operand_kernel(const float* __restrict__ sparse, int64_t sparse_bstride, int sparse_ld, int C2,
-                  const float* __restrict__ dense, int64_t dense_bstride, int dense_ld, int C1,
-                  const int32_t* __restrict__ idx, const float* __restrict__ w, int Nd, int kpad, int64_t total_pairs,
-                  OperandOut out) {
-  const int half = kpad >> 1;
-  for (int64_t e = blockIdx.x * (int64_t)THREADS + threadIdx.x; e < total_pairs; e += (int64_t)gridDim.x * THREADS) {
-    const int cp = (int)(e % half);
-    const int64_t row = e / half;
+                  const float* __restrict__ dense, int64_t dense_bstride, int dense_ld, int C1, int sparse_vec,
+                  int dense_vec, const int32_t* __restrict__ idx, const float* __restrict__ w, int Nd, int kpad,
+                  int64_t total_quads, OperandOut out) {
+  const int quads = kpad >> 2;
+  for (int64_t e = blockIdx.x * (int64_t)THREADS + threadIdx.x; e < total_quads; e += (int64_t)gridDim.x * THREADS) {
+    const int q = (int)(e % quads);
+    const int64_t row = e / quads;
     const int n = (int)(row % Nd);
     const int64_t b = row / Nd;
-    const int i0 = idx[row * 3], i1 = idx[row * 3 + 1], i2 = idx[row * 3 + 2];
-    const float w0 = w[row * 3], w1 = w[row * 3 + 1], w2 = w[row * 3 + 2];
-    const float* __restrict__ sp = sparse + b * sparse_bstride;
-    float v[2];
+    const int c0 = q * 4;
+    float4 v;
+    if (sparse_vec && c0 + 4 <= C2) {
+      const int i0 = idx[row * 3], i1 = idx[row * 3 + 1], i2 = idx[row * 3 + 2];
+      const float w0 = w[row * 3], w1 = w[row * 3 + 1], w2 = w[row * 3 + 2];
+      const float* __restrict__ sp = sparse + b * sparse_bstride + c0;
+      const float4 a0 = *reinterpret_cast<const float4*>(sp + (int64_t)i0 * sparse_ld);
+      const float4 a1 = *reinterpret_cast<const float4*>(sp + (int64_t)i1 * sparse_ld);
+      const float4 a2 = *reinterpret_cast<const float4*>(sp + (int64_t)i2 * sparse_ld);
+      v.x = __fmaf_rn(a2.x, w2, __fmaf_rn(a1.x, w1, __fmaf_rn(a0.x, w0, 0.f)));   // k = 0,1,2 in order, as the
+      v.y = __fmaf_rn(a2.y, w2, __fmaf_rn(a1.y, w1, __fmaf_rn(a0.y, w0, 0.f)));   // reference's fma chain
+      v.z = __fmaf_rn(a2.z, w2, __fmaf_rn(a1.z, w1, __fmaf_rn(a0.z, w0, 0.f)));
+      v.w = __fmaf_rn(a2.w, w2, __fmaf_rn(a1.w, w1, __fmaf_rn(a0.w, w0, 0.f)));
+    } else if (dense_vec && c0 >= C2 && c0 + 4 <= C2 + C1) {
+      v = *reinterpret_cast<const float4*>(dense + b * dense_bstride + (int64_t)n * dense_ld + (c0 - C2));
+    } else {
+      float t[4];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int col = cp * 2 + t;
-      float x = 0.f;
-      if (col < C2) {
-        x = __fmaf_rn(sp[(int64_t)i0 * sparse_ld + col], w0, 0.f);
-        x = __fmaf_rn(sp[(int64_t)i1 * sparse_ld + col], w1, x);
-        x = __fmaf_rn(sp[(int64_t)i2 * sparse_ld + col], w2, x);
-      } else if (col < C2 + C1) {
-        x = dense[b * dense_bstride + (int64_t)n * dense_ld + (col - C2)];
+      for (int u = 0; u < 4; ++u) {
+        const int col = c0 + u;
+        float x = 0.f;
+        if (col < C2) {
+          const float* __restrict__ sp = sparse + b * sparse_bstride + col;
+          x = __fmaf_rn(sp[(int64_t)idx[row * 3] * sparse_ld], w[row * 3], 0.f);
+          x = __fmaf_rn(sp[(int64_t)idx[row * 3 + 1] * sparse_ld], w[row * 3 + 1], x);
+          x = __fmaf_rn(sp[(int64_t)idx[row * 3 + 2] * sparse_ld], w[row * 3 + 2], x);
+        } else if (col < C2 + C1) {
+          x = dense[b * dense_bstride + (int64_t)n * dense_ld + (col - C2)];
+        }
+        t[u] = x;
       }
-      v[t] = x;
+      v = make_float4(t[0], t[1], t[2], t[3]);
     }
-    store_pair(out, row * kpad + cp * 2, v[0], v[1]);
+    store_quad(out, row * kpad + c0, v);
   }
 }
 
 // fp32 rows -> bf16 hi/lo planes (used for weights and by regnet_mlp_layer)
 __global__ void __launch_bounds__(THREADS)
-split_rows_kernel(const float* __restrict__ src, int64_t rows, int cols, int ld_src, int kpad,
+split_rows_kernel(const float* __restrict__ src, int64_t rows, int cols, int ld_src, int kpad, int rot,
                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ f32) {
   const int64_t total = rows * kpad;
   for (int64_t e = blockIdx.x * (int64_t)THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * THREADS) {
     const int col = (int)(e % kpad);
     const int64_t r = e / kpad;
-    const float x = col < cols ? src[r * ld_src + col] : 0.f;
+    const float x = col < cols ? src[r * ld_src + (col + rot) % cols] : 0.f;   // dst col c <- src col (c+rot) mod cols
     if (f32) f32[e] = x;
     if (hi) {
       __nv_bfloat16 h, l;
@@ -242,32 +321,50 @@ int interp_backward_launch(const float* gout, const int64_t* index, const float*
 int sa_operand_launch(const float* xyz, Strides3 xst, const float* new_xyz, const float* feat, int64_t feat_bstride,
                       int feat_ld, int C, const int32_t* nbr, int B, int N, int M, int K, int kpad, float* out_f32,
                       __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream) {
-  RN_CHECK_ARG(kpad % 2 == 0 && kpad >= 3 + C, "sa_operand: bad kpad %d for C=%d", kpad, C);
-  const int64_t total = (int64_t)B * M * K * (kpad / 2);
+  RN_CHECK_ARG(kpad % 4 == 0 && kpad >= 3 + C, "sa_operand: bad kpad %d for C=%d", kpad, C);
+  const int64_t total = (int64_t)B * M * K * (kpad / 4);
   OperandOut o{out_f32, out_hi, out_lo};
-  sa_operand_kernel<<<grid_for(total), THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, C, nbr, N,
-                                                             M, K, kpad, total, o);
+  const int vec_ok = (feat_ld % 4 == 0) && (feat_bstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
+  sa_operand_kernel<<<grid_for(total), THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, C, vec_ok,
+                                                             nbr, M, K, kpad, total, o);
   RN_LAUNCH_CHECK("sa_operand_kernel");
+  (void)N;
+  return REGNET_OK;
+}
+
+int sa0_fused_launch(const float* xyz, Strides3 xst, const float* new_xyz, const float* feat, int64_t feat_bstride,
+                     int feat_ld, const int32_t* nbr, const float* W, int ldw, const float* scale, const float* shift,
+                     int cout, int B, int M, int K, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                     int ld_out, cudaStream_t stream) {
+  RN_CHECK_ARG(cout == 128 && ld_out % 4 == 0, "sa0_fused: only the 6 -> 128 layer of the reference architecture");
+  const int64_t rows = (int64_t)B * M * K;
+  OperandOut o{out_f32, out_hi, out_lo};
+  sa0_fused_kernel<128><<<grid_for(rows * 32), THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, nbr, W,
+                                                                    ldw, scale, shift, M, K, rows, o, ld_out);
+  RN_LAUNCH_CHECK("sa0_fused_kernel");
   return REGNET_OK;
 }
 
 int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld, int C2, const float* dense,
                       int64_t dense_bstride, int dense_ld, int C1, const int32_t* idx, const float* w, int B, int Nd,
                       int kpad, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream) {
-  RN_CHECK_ARG(kpad % 2 == 0 && kpad >= C1 + C2, "fp_operand: bad kpad %d for C1+C2=%d", kpad, C1 + C2);
-  const int64_t total = (int64_t)B * Nd * (kpad / 2);
+  RN_CHECK_ARG(kpad % 4 == 0 && kpad >= C1 + C2, "fp_operand: bad kpad %d for C1+C2=%d", kpad, C1 + C2);
+  const int64_t total = (int64_t)B * Nd * (kpad / 4);
   OperandOut o{out_f32, out_hi, out_lo};
-  fp_operand_kernel<<<grid_for(total), THREADS, 0, stream>>>(sparse, sparse_bstride, sparse_ld, C2, dense,
-                                                             dense_bstride, dense_ld, C1, idx, w, Nd, kpad, total, o);
+  const int sparse_vec = (sparse_ld % 4 == 0) && (sparse_bstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(sparse) & 15) == 0);
+  const int dense_vec = (dense_ld % 4 == 0) && (dense_bstride % 4 == 0) && (C2 % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
+  fp_operand_kernel<<<grid_for(total), THREADS, 0, stream>>>(sparse, sparse_bstride, sparse_ld, C2, dense, dense_bstride,
+                                                             dense_ld, C1, sparse_vec, dense_vec, idx, w, Nd, kpad, total, o);
   RN_LAUNCH_CHECK("fp_operand_kernel");
   return REGNET_OK;
 }
 
 int split_rows_launch(const float* src, int64_t rows, int cols, int ld_src, int kpad, __nv_bfloat16* hi,
-                      __nv_bfloat16* lo, float* f32, cudaStream_t stream) {
+                      __nv_bfloat16* lo, float* f32, cudaStream_t stream, int rot) {
   const int64_t total = rows * kpad;
   if (total == 0) return REGNET_OK;
-  split_rows_kernel<<<grid_for(total), THREADS, 0, stream>>>(src, rows, cols, ld_src, kpad, hi, lo, f32);
+  split_rows_kernel<<<grid_for(total), THREADS, 0, stream>>>(src, rows, cols, ld_src, kpad, rot, hi, lo, f32);
   RN_LAUNCH_CHECK("split_rows_kernel");
   return REGNET_OK;
 }

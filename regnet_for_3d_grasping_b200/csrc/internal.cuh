@@ -25,11 +25,16 @@ int interp_backward_launch(const float* gout, const int64_t* index, const float*
 int sa_operand_launch(const float* xyz, Strides3 xst, const float* new_xyz, const float* feat, int64_t feat_bstride,
                       int feat_ld, int C, const int32_t* nbr, int B, int N, int M, int K, int kpad, float* out_f32,
                       __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);
+int sa0_fused_launch(const float* xyz, Strides3 xst, const float* new_xyz, const float* feat, int64_t feat_bstride,
+                     int feat_ld, const int32_t* nbr, const float* W, int ldw, const float* scale, const float* shift,
+                     int cout, int B, int M, int K, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                     int ld_out, cudaStream_t stream);
 int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld, int C2, const float* dense,
                       int64_t dense_bstride, int dense_ld, int C1, const int32_t* idx, const float* w, int B, int Nd,
                       int kpad, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);
+// dst[:, c] = src[:, (c + rot) mod cols] for c < cols, zero padding up to kpad
 int split_rows_launch(const float* src, int64_t rows, int cols, int ld_src, int kpad, __nv_bfloat16* hi,
-                      __nv_bfloat16* lo, float* f32, cudaStream_t stream);
+                      __nv_bfloat16* lo, float* f32, cudaStream_t stream, int rot = 0);
 int score_head_launch(const float* X, int ldx, const float* w, const float* scale, const float* shift, int64_t P,
                       int cin, float* score, cudaStream_t stream);
 

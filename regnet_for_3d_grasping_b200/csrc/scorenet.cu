@@ -10,6 +10,7 @@
 //     the MLP GEMMs of the previous level;
 //   * group+concat and interpolate+concat write the GEMM operand once, already split for the tensor-core engine;
 //   * BN (eval) + ReLU + the 64-neighbour max-pool are GEMM epilogues; nothing else touches the activations.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -58,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  regnet_scorenet_config cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 1; } cfg;
   int B = 0, N = 0;
   int M[3] = {0, 0, 0};
   Layer layers[8][REGNET_MAX_LAYERS];
@@ -91,7 +92,7 @@ struct regnet_scorenet {
   int launches = 0;
   int prefetch_launches = 0;
   // optional per-launch timing (regnet_scorenet_set_profiling): events around every launch, serial execution
-  bool profiling = false;
+  int profiling = 0;   // 0 off; 1 serial per-launch timing; 2 timeline (keeps streams / prefetch, records events)
   struct Rec { const char* label; cudaEvent_t a, b; };
   std::vector<Rec> recs;
   size_t nrec = 0;
@@ -196,7 +197,8 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
     return REGNET_ECUDA;
   }
   regnet_scorenet* p = new regnet_scorenet();
-  p->cfg = *cfg;
+  static_cast<regnet_scorenet_config&>(p->cfg) = *cfg;
+  if (const char* e = getenv("REGNET_FUSE_SA0")) p->cfg.fuse_sa0 = atoi(e);
   p->B = cfg->batch;
   p->N = cfg->num_points;
   for (int i = 0; i < 3; ++i) p->M[i] = cfg->num_centroids[i];
@@ -304,7 +306,9 @@ int regnet_scorenet_set_layer(regnet_scorenet* p, int stage, int layer, int cin,
     RN_TRY(dalloc(p, (void**)&L.scale, sizeof(float) * cout));
     RN_TRY(dalloc(p, (void**)&L.shift, sizeof(float) * cout));
   }
-  RN_TRY(split_rows_launch(weight, cout, cin, cin, L.kpad, L.w_hi, L.w_lo, L.w_f32, s));
+  // SA first layers: the operand is [feature | xyz_rel] (gather.cu), the reference's conv weight is [xyz_rel | feature]
+  const int rot = (stage < 3 && layer == 0) ? 3 : 0;
+  RN_TRY(split_rows_launch(weight, cout, cin, cin, L.kpad, L.w_hi, L.w_lo, L.w_f32, s, rot));
   RN_CUDA(cudaMemcpyAsync(L.scale, scale, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
   RN_CUDA(cudaMemcpyAsync(L.shift, shift, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
   L.set = true;
@@ -361,7 +365,7 @@ static int three_nn_all(regnet_scorenet* p, regnet_scorenet::Geom& G, const Leve
 // It is ordered behind everything already queued on `ms`, i.e. behind the previous reader of this slot.
 static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaStream_t ms) {
   regnet_scorenet::Geom& G = p->geom[slot];
-  const bool fork = p->side != nullptr && !p->profiling;  // profiling serialises everything on `ms`
+  const bool fork = p->side != nullptr && p->profiling != 1;  // serial profiling puts everything on `ms`
   const bool fps_only = fork && p->cfg.use_side_stream == 2;
   cudaStream_t gs = fork ? p->side : ms;
   if (fork) {
@@ -405,14 +409,14 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   RN_CHECK_ARG(p && pc && all_feature && score, "scorenet_forward: null argument");
   const int B = p->B, N = p->N;
   const int* M = p->M;
-  const bool fork = p->side != nullptr && !p->profiling;
-  p->nrec = 0;
+  const bool fork = p->side != nullptr && p->profiling != 1;
+  if (p->profiling != 2) p->nrec = 0;  // timeline mode accumulates across forwards until read
   p->launches = 0;
   p->last_allfeat = all_feature;
   // geometry: consume the oldest prefetch if it was made for this input, otherwise compute it now
   int slot = p->next_slot;
   const int oldest = p->geom[p->next_slot].pending ? p->next_slot : (p->next_slot ^ 1);
-  if (p->geom[oldest].pending && p->geom[oldest].pc == pc && !p->profiling) {
+  if (p->geom[oldest].pending && p->geom[oldest].pc == pc && p->profiling != 1) {
     slot = oldest;
     p->launches = p->prefetch_launches;
   } else {
@@ -442,14 +446,28 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     if (fps_only) RN_TRY(ball_query_level(p, G, L, i, ms));
     const int64_t P = (int64_t)B * M[i] * 64;
     const int kpad = round_up(feat_c + 3, 16);
-    Act a0 = make_act(p, 0, P, kpad);
-    prof_begin(p, SAOP_LABEL[i], ms);
-    RN_TRY(sa_operand_launch(lvl_xyz[i], lvl_st[i], G.new_xyz[i], feat, feat_bs, feat_ld, feat_c, G.nbr[i], B,
-                             lvl_n[i], M[i], 64, kpad, a0.f32, a0.hi, a0.lo, ms));
-    prof_end(p, ms);
-    ++p->launches;
     Act a1 = make_act(p, 1, P, SA_CH[i][0]);
-    RN_TRY(run_layer(p, GEMM_LABEL[i][0], p->layers[i][0], a0, P, 1, 0, &a1, nullptr, 0, ms));
+    if (i == 0 && p->cfg.fuse_sa0) {
+      // level 0: gather + centre + first layer (6 -> 128) in one SIMT pass, no 6-channel operand round trip
+      const Layer& L0 = p->layers[0][0];
+      if (!L0.set) {
+        set_error("scorenet: sa_modules.0.mlp.0 was never given weights");
+        return REGNET_EINVAL;
+      }
+      prof_begin(p, "sa0_fused", ms);
+      RN_TRY(sa0_fused_launch(lvl_xyz[0], lvl_st[0], G.new_xyz[0], feat, feat_bs, feat_ld, G.nbr[0], L0.w_f32, L0.kpad,
+                              L0.scale, L0.shift, L0.cout, B, M[0], 64, a1.f32, a1.hi, a1.lo, a1.ld, ms));
+      prof_end(p, ms);
+      ++p->launches;
+    } else {
+      Act a0 = make_act(p, 0, P, kpad);
+      prof_begin(p, SAOP_LABEL[i], ms);
+      RN_TRY(sa_operand_launch(lvl_xyz[i], lvl_st[i], G.new_xyz[i], feat, feat_bs, feat_ld, feat_c, G.nbr[i], B,
+                               lvl_n[i], M[i], 64, kpad, a0.f32, a0.hi, a0.lo, ms));
+      prof_end(p, ms);
+      ++p->launches;
+      RN_TRY(run_layer(p, GEMM_LABEL[i][0], p->layers[i][0], a0, P, 1, 0, &a1, nullptr, 0, ms));
+    }
     Act a2 = make_act(p, 0, P, SA_CH[i][1]);
     RN_TRY(run_layer(p, GEMM_LABEL[i][1], p->layers[i][1], a1, P, 1, 0, &a2, nullptr, 0, ms));
     RN_TRY(run_layer(p, GEMM_LABEL[i][2], p->layers[i][2], a2, P, 1, 64, nullptr, p->sa_out[i], SA_CH[i][2], ms));
@@ -540,7 +558,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
 
 int regnet_scorenet_set_profiling(regnet_scorenet* p, int on) {
   RN_CHECK_ARG(p != nullptr, "scorenet_set_profiling: null plan");
-  p->profiling = on != 0;
+  p->profiling = on;
   p->nrec = 0;
   return REGNET_OK;
 }
@@ -551,9 +569,10 @@ int regnet_scorenet_profile(regnet_scorenet* p, char* buf, int64_t buf_bytes) {
   int64_t off = 0;
   buf[0] = 0;
   for (size_t i = 0; i < p->nrec; ++i) {
-    float ms = 0.f;
+    float ms = 0.f, t0 = 0.f;
     RN_CUDA(cudaEventElapsedTime(&ms, p->recs[i].a, p->recs[i].b));
-    const int n = snprintf(buf + off, (size_t)(buf_bytes - off), "%s %.6f\n", p->recs[i].label, ms);
+    RN_CUDA(cudaEventElapsedTime(&t0, p->recs[0].a, p->recs[i].a));
+    const int n = snprintf(buf + off, (size_t)(buf_bytes - off), "%s %.6f %.6f\n", p->recs[i].label, ms, t0);
     if (n < 0 || off + n >= buf_bytes) break;
     off += n;
   }

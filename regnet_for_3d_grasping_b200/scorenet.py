@@ -148,11 +148,28 @@ class ScoreNetPlan:
             _lib.check(lib.regnet_scorenet_profile(self._h, buf, len(buf)))
         finally:
             _lib.check(lib.regnet_scorenet_set_profiling(self._h, 0))
+        return [(label, ms) for label, ms, _ in self._parse_profile(buf)]
+
+    @staticmethod
+    def _parse_profile(buf):
         out = []
         for line in buf.value.decode().splitlines():
-            label, ms = line.rsplit(" ", 1)
-            out.append((label, float(ms)))
+            label, ms, t0 = line.rsplit(" ", 2)
+            out.append((label, float(ms), float(t0)))
         return out
+
+    def timeline(self, fn):
+        """Run fn() (any sequence of prefetch()/forward() calls) with an event pair around every launch but WITHOUT
+        serialising the streams; returns [(label, duration_ms, start_ms_since_first_launch), ...]."""
+        lib = _lib.load()
+        _lib.check(lib.regnet_scorenet_set_profiling(self._h, 2))
+        try:
+            fn()
+            buf = ctypes.create_string_buffer(1 << 20)
+            _lib.check(lib.regnet_scorenet_profile(self._h, buf, len(buf)))
+        finally:
+            _lib.check(lib.regnet_scorenet_set_profiling(self._h, 0))
+        return self._parse_profile(buf)
 
     def intermediate(self, name, dtype, shape):
         """Copy of an intermediate of the last forward (see regnet_scorenet_intermediate)."""
