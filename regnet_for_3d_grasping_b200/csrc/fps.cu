@@ -237,9 +237,16 @@ int launch_fps(const float* pts, Strides3 st, int B, int N, int M, int nbits, in
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // Ask for the maximum shared-memory carve-out although this kernel needs ~2 KB: the L1/shared split of an SM can
+  // only change while the SM is empty, and the tcgen05 GEMM CTAs that should share the SM with this (latency-bound,
+  // minutes-of-cycles-long) kernel need ~217 KB.  With the default small carve-out they could not become resident.
   if (mbar || CS == 1) {
+    RN_CUDA(cudaFuncSetAttribute(fps_kernel<CS, T, PPT, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared));
     RN_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CS, T, PPT, true>, pts, st, N, M, nbits, idx64, idx32, new_xyz, n_var));
   } else {
+    RN_CUDA(cudaFuncSetAttribute(fps_kernel<CS, T, PPT, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 (int)cudaSharedmemCarveoutMaxShared));
     RN_CUDA(cudaLaunchKernelEx(&cfg, fps_kernel<CS, T, PPT, false>, pts, st, N, M, nbits, idx64, idx32, new_xyz, n_var));
   }
   return REGNET_OK;
@@ -254,6 +261,9 @@ int dispatch_ppt(int ppt, const float* pts, Strides3 st, int B, int N, int M, in
   if (ppt <= 8) return launch_fps<CS, T, 8>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
   if constexpr (T <= 512) {
     if (ppt <= 16) return launch_fps<CS, T, 16>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
+  }
+  if constexpr (T <= 128) {
+    if (ppt <= 32) return launch_fps<CS, T, 32>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
   }
   set_error("farthest_point_sample: %d points per thread exceeds the register-resident limit", ppt);
   return REGNET_ELIMIT;
@@ -313,14 +323,14 @@ static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, i
   if (threads == 0) threads = 512;
   RN_CHECK_ARG(cluster_size == 1 || cluster_size == 2 || cluster_size == 4 || cluster_size == 8,
                "farthest_point_sample: cluster_size must be 1, 2, 4 or 8");
-  RN_CHECK_ARG(threads == 256 || threads == 512 || threads == 1024,
-               "farthest_point_sample: threads must be 256, 512 or 1024");
+  RN_CHECK_ARG(threads == 128 || threads == 256 || threads == 512 || threads == 1024,
+               "farthest_point_sample: threads must be 128, 256, 512 or 1024");
   // the in-thread tie order relies on CS*T being a multiple of the reference block size (<= 512): only
   // CS=1,T=256 with more than 256 points violates it
   const int nbits = fps_block_log2(N);
   if ((cluster_size * threads) % (1 << nbits) != 0) threads = 512;
   // grow the cluster until the cloud fits in registers
-  const int max_ppt = threads <= 512 ? 16 : 8;
+  const int max_ppt = threads <= 128 ? 32 : threads <= 512 ? 16 : 8;
   while (cluster_size < 8 && ceil_div(N, cluster_size * threads) > max_ppt) cluster_size *= 2;
   const int ppt = ceil_div(N, cluster_size * threads);
   if (ppt > max_ppt) {
@@ -331,6 +341,7 @@ static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, i
 #define RN_FPS_CASE(CS, T)                                                                              \
   if (cluster_size == CS && threads == T)                                                               \
     return dispatch_ppt<CS, T>(ppt, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
+  RN_FPS_CASE(1, 128) RN_FPS_CASE(2, 128) RN_FPS_CASE(4, 128) RN_FPS_CASE(8, 128)
   RN_FPS_CASE(1, 256) RN_FPS_CASE(2, 256) RN_FPS_CASE(4, 256) RN_FPS_CASE(8, 256)
   RN_FPS_CASE(1, 512) RN_FPS_CASE(2, 512) RN_FPS_CASE(4, 512) RN_FPS_CASE(8, 512)
   RN_FPS_CASE(1, 1024) RN_FPS_CASE(2, 1024) RN_FPS_CASE(4, 1024) RN_FPS_CASE(8, 1024)

@@ -18,7 +18,7 @@ for s in $STAGES; do
     benchref) timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1 ;;
     sweep)    timeout 300 python scripts/fps_sweep.py > gpurun_out/fps_sweep.log 2>&1 ;;
     timeline) timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2.log 2>&1
-              REGNET_FPS_FORCE=8,-512 timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2_barrier.log 2>&1
+              REGNET_FPS_FORCE=8,128 timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2_t128.log 2>&1
               REGNET_FPS_FORCE=8,256 timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2_t256.log 2>&1 ;;
     ab)       timeout 300 python scripts/pipeline_ab.py > gpurun_out/pipeline_ab.log 2>&1 ;;
     region)   timeout 600 python -m pytest tests/test_gpu_region.py -q -m gpu > gpurun_out/test_region.log 2>&1 ;;

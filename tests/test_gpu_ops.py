@@ -70,7 +70,7 @@ def test_search_ops_vs_reference_cuda_golden(ext):
                 assert np.array_equal(nn.cpu().numpy()[:, :4096], ref[name + ".nn_head"]), name
 
 
-@pytest.mark.parametrize("cs,threads", [(1, 256), (2, 256), (4, 256), (8, 256), (1, 512), (2, 512), (4, 512), (8, 512),
+@pytest.mark.parametrize("cs,threads", [(1, 128), (4, 128), (8, 128), (1, 256), (2, 256), (4, 256), (8, 256), (1, 512), (2, 512), (4, 512), (8, 512),
                                         (1, 1024), (2, 1024), (4, 1024), (8, 1024), (2, -512), (8, -256)])
 def test_fps_every_cluster_configuration(lib_path, oracle, cs, threads):
     """All launch shapes of the cluster kernel give the same (reference) answer, contiguous planar input too."""
