@@ -168,7 +168,7 @@ sa_operand_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __re
 // scale/shift stay in registers (the quad index is constant per thread because THREADS % (COUT/4) == 0).
 // y = relu(scale * (W v) + shift), v = [feat[j,0..3) | xyz[j]-new_xyz[m]] (the rotated order of sa_operand_kernel).
 template <int COUT>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 sa0_fused_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __restrict__ new_xyz,
                  const float* __restrict__ feat, int64_t feat_bstride, int feat_ld, const int32_t* __restrict__ nbr,
                  const float* __restrict__ W, int ldw, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -184,27 +184,45 @@ sa0_fused_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __res
     sc[u] = scale[q * 4 + u];
     sh[u] = shift[q * 4 + u];
   }
-  const int64_t rows_per_pass = (int64_t)gridDim.x * (THREADS / QUADS);
-  for (int64_t row = (int64_t)blockIdx.x * (THREADS / QUADS) + threadIdx.x / QUADS; row < rows; row += rows_per_pass) {
-    const int64_t bm = row / K;
-    const int m = (int)(bm % M);
-    const int64_t b = bm / M;
-    const int j = nbr[row];
-    float v[6];
+  // R rows per thread per trip, all their gathers issued before any arithmetic: the kernel is bound by the latency of
+  // the dependent index -> point loads, so the number of rows in flight per warp is what sets its speed
+  constexpr int R = 4;
+  constexpr int ROWS_PER_BLOCK = (THREADS / QUADS) * R;
+  const int sub = threadIdx.x / QUADS;
+  for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_BLOCK; base < rows; base += (int64_t)gridDim.x * ROWS_PER_BLOCK) {
+    int j[R];
+    int64_t row[R];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) v[c] = feat[b * feat_bstride + (int64_t)j * feat_ld + c];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-      v[3 + a] = __fsub_rn(xyz[b * xst.b + a * xst.c + (int64_t)j * xst.n], new_xyz[(b * 3 + a) * M + m]);
-    float y[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float acc = 0.f;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) acc = fmaf(w[u][c], v[c], acc);
-      y[u] = fmaxf(fmaf(acc, sc[u], sh[u]), 0.f);
+    for (int r = 0; r < R; ++r) {
+      row[r] = base + r * (THREADS / QUADS) + sub;
+      j[r] = row[r] < rows ? nbr[row[r]] : 0;
     }
-    store_quad(out, row * ld_out + q * 4, make_float4(y[0], y[1], y[2], y[3]));
+    float v[R][6];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t rr = row[r] < rows ? row[r] : 0;
+      const int64_t bm = rr / K;
+      const int m = (int)(bm % M);
+      const int64_t b = bm / M;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[r][c] = feat[b * feat_bstride + (int64_t)j[r] * feat_ld + c];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        v[r][3 + a] = __fsub_rn(xyz[b * xst.b + a * xst.c + (int64_t)j[r] * xst.n], new_xyz[(b * 3 + a) * M + m]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (row[r] >= rows) continue;
+      float y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) acc = fmaf(w[u][c], v[r][c], acc);
+        y[u] = fmaxf(fmaf(acc, sc[u], sh[u]), 0.f);
+      }
+      store_quad(out, row[r] * ld_out + q * 4, make_float4(y[0], y[1], y[2], y[3]));
+    }
   }
 }
 
@@ -339,7 +357,7 @@ int sa0_fused_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
   RN_CHECK_ARG(cout == 128 && ld_out % 4 == 0, "sa0_fused: only the 6 -> 128 layer of the reference architecture");
   const int64_t rows = (int64_t)B * M * K;
   OperandOut o{out_f32, out_hi, out_lo};
-  sa0_fused_kernel<128><<<grid_for(rows * 32), THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, nbr, W,
+  sa0_fused_kernel<128><<<grid_for(rows * 8), THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, nbr, W,
                                                                     ldw, scale, shift, M, K, rows, o, ld_out);
   RN_LAUNCH_CHECK("sa0_fused_kernel");
   return REGNET_OK;

@@ -20,6 +20,7 @@ struct Epilogue {
   __nv_bfloat16* out_hi = nullptr;  // (P, ld_split) bf16 planes of the same values (pool == 0 only)
   __nv_bfloat16* out_lo = nullptr;
   int ld_split = 0;
+  unsigned int* tile_counter = nullptr;  // tcgen05 engine: zeroed device counter => dynamic tile scheduling
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -38,7 +38,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = BN == 128 ? 3 : 2;         // shared-memory ring depth (192 KB of tiles)
   static constexpr int OFF_BAR = STAGES * STAGE_BYTES;     // mbarriers + tmem pointer
-  static constexpr int OFF_SCALE = OFF_BAR + 128;          // scale[BN], shift[BN]
+  static constexpr int OFF_SCALE = OFF_BAR + 256;          // scale[BN], shift[BN]
   static constexpr int OFF_PART = OFF_SCALE + 2 * BN * 4;  // pooled partials [4][BN] as uint32
   static constexpr int OFF_STAGE = (OFF_PART + 4 * BN * 4 + 1023) / 1024 * 1024;  // epilogue store staging:
   static constexpr int STAGE_OUT_BYTES = 4 * 2 * 2048;     //   4 warps x {hi, lo} x [32 rows x 64 B], 64B-swizzled
@@ -190,7 +190,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
   const uint32_t bar_empty = bar_full + 8 * STAGES;
   const uint32_t bar_tfull = bar_empty + 8 * STAGES;
   const uint32_t bar_tempty = bar_tfull + 16;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 8 * (2 * STAGES + 4));
+  const uint32_t bar_sfull = bar_tempty + 16;   // tile-scheduler ring: 4 slots, producer -> {MMA, epilogue}
+  const uint32_t bar_sempty = bar_sfull + 32;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + C::OFF_BAR + 8 * (2 * STAGES + 4 + 8));
+  volatile int* sched_ring = reinterpret_cast<volatile int*>(tmem_holder + 1);
   float* s_scale = reinterpret_cast<float*>(smem + C::OFF_SCALE);
   float* s_shift = s_scale + BN;
   uint32_t* s_part = reinterpret_cast<uint32_t*>(smem + C::OFF_PART);
@@ -210,6 +213,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 4);
     }
+    for (int r = 0; r < 4; ++r) {
+      mbar_init(bar_sfull + 8 * r, 1);
+      mbar_init(bar_sempty + 8 * r, 5);   // MMA lane + one lane of each epilogue warp
+    }
     fence_barrier_init();
     tma_prefetch_desc(&map_xhi);
     tma_prefetch_desc(&map_xlo);
@@ -223,13 +230,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
   const uint32_t tmem_base = *tmem_holder;
   (void)bars;
 
+  // Tile scheduling.  With ep.tile_counter the CTAs draw tiles from a global counter (a CTA that becomes resident
+  // late, or shares its SM with another kernel, simply takes fewer tiles); the producer lane draws, and hands the
+  // tile index to the MMA lane and the epilogue warps through a 4-slot shared-memory ring.  Without it: static
+  // round-robin over gridDim.x.  -1 ends the loop.
+  unsigned int* const tile_counter = ep.tile_counter;
+  auto draw_tile = [&](uint32_t it) -> int {        // producer lane only
+    int64_t t;
+    if (tile_counter) {
+      const uint32_t slot = it & 3;
+      if (it >= 4) mbar_wait(bar_sempty + 8 * slot, ((it >> 2) - 1) & 1);
+      t = (int64_t)atomicAdd(tile_counter, 1u);
+      sched_ring[slot] = t < n_tiles ? (int)t : -1;
+      mbar_arrive(bar_sfull + 8 * slot);
+    } else {
+      t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+    }
+    return t < n_tiles ? (int)t : -1;
+  };
+  auto take_tile = [&](uint32_t it, bool release) -> int {   // MMA lane / every epilogue thread
+    if (!tile_counter) {
+      const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+      return t < n_tiles ? (int)t : -1;
+    }
+    const uint32_t slot = it & 3;
+    mbar_wait(bar_sfull + 8 * slot, (it >> 2) & 1);
+    const int t = sched_ring[slot];
+    if (release) mbar_arrive(bar_sempty + 8 * slot);
+    return t;
+  };
+
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int row0 = (int)((tile / n_ctile) * BM);
-        const int col0 = (int)(tile % n_ctile) * BN;
+      for (uint32_t pit = 0;; ++pit) {
+        const int tile = draw_tile(pit);
+        if (tile < 0) break;
+        const int row0 = (tile / n_ctile) * BM;
+        const int col0 = (tile % n_ctile) * BN;
         for (int kb = 0; kb < n_kblk; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
@@ -249,8 +288,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       uint32_t stage = 0, phase = 0;
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      for (uint32_t it = 0;; ++it) {
+        if (take_tile(it, true) < 0) break;
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
@@ -279,11 +318,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
     // ================= epilogue (warps 2..5; TMEM lane quarter = warp % 4) =================
     const int q = warp & 3;
     const int et = threadIdx.x - 64;  // 0..127
-    uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t it = 0;; ++it) {
+      const int tile = take_tile(it, false);
+      __syncwarp();
+      if (tile_counter && lane == 0) mbar_arrive(bar_sempty + 8 * (it & 3));
+      if (tile < 0) break;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int64_t row0 = (tile / n_ctile) * BM;
-      const int col0 = (int)(tile % n_ctile) * BN;
+      const int64_t row0 = (int64_t)(tile / n_ctile) * BM;
+      const int col0 = (tile % n_ctile) * BN;
       // stage this channel tile's scale / shift (previous tile's readers are past the trailing barrier)
       for (int c = et; c < BN; c += EPI_THREADS) {
         const int gc = col0 + c;

@@ -59,7 +59,9 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 1; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 1; int dynamic_tiles = 1; } cfg;
+  unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
+  int gemm_idx = 0;
   int B = 0, N = 0;
   int M[3] = {0, 0, 0};
   Layer layers[8][REGNET_MAX_LAYERS];
@@ -172,6 +174,7 @@ int run_layer_impl(regnet_scorenet* p, const Layer& L, const Act& in, int64_t P,
     return gemm_simt_launch(in.f32, in.ld, L.w_f32, L.kpad, P, L.kpad, L.cout, ep, s);
   }
   if (out_act) { ep.out_hi = out_act->hi; ep.out_lo = out_act->lo; ep.ld_split = out_act->ld; }
+  if (p->cfg.dynamic_tiles && p->gemm_idx < 64) ep.tile_counter = p->tile_counters + (p->gemm_idx++);
   return gemm_tc_launch(in.hi, in.lo, in.ld, L.w_hi, L.w_lo, L.kpad, P, L.cin, L.cout, ep, s);
 }
 
@@ -199,6 +202,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   regnet_scorenet* p = new regnet_scorenet();
   static_cast<regnet_scorenet_config&>(p->cfg) = *cfg;
   if (const char* e = getenv("REGNET_FUSE_SA0")) p->cfg.fuse_sa0 = atoi(e);
+  if (const char* e = getenv("REGNET_DYNAMIC_TILES")) p->cfg.dynamic_tiles = atoi(e);
   p->B = cfg->batch;
   p->N = cfg->num_points;
   for (int i = 0; i < 3; ++i) p->M[i] = cfg->num_centroids[i];
@@ -218,6 +222,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
     }
   }
   for (int i = 0; i < 3; ++i) A((void**)&p->sa_out[i], sizeof(float) * (size_t)B * M[i] * SA_CH[i][2]);
+  A((void**)&p->tile_counters, sizeof(unsigned int) * 64);
   A((void**)&p->fp_out[0], sizeof(float) * (size_t)B * M[1] * 1024);
   A((void**)&p->fp_out[1], sizeof(float) * (size_t)B * M[0] * 512);
   // activation arenas: the widest (rows x ld) any layer reads or writes, 4 bytes per element in both engines
@@ -363,7 +368,7 @@ static int three_nn_all(regnet_scorenet* p, regnet_scorenet::Geom& G, const Leve
 //                         per CTA, cannot share an SM with a GEMM CTA and stay on the caller's stream;
 //   no side stream / profiling: everything on `ms`.
 // It is ordered behind everything already queued on `ms`, i.e. behind the previous reader of this slot.
-static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaStream_t ms) {
+static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaStream_t ms, bool overlapped) {
   regnet_scorenet::Geom& G = p->geom[slot];
   const bool fork = p->side != nullptr && p->profiling != 1;  // serial profiling puts everything on `ms`
   const bool fps_only = fork && p->cfg.use_side_stream == 2;
@@ -375,7 +380,11 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
   const Levels L = make_levels(p, G, pc);
   for (int i = 0; i < 3; ++i) {
     prof_begin(p, FPS_LABEL[i], gs);
-    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], 0, 0, gs));
+    // a prefetched FPS shares its SMs with the previous step's GEMM CTAs: 4 warps (one per scheduler partition,
+    // 227 registers) is the shape whose register-file footprint leaves room for them (profiles/README.md)
+    const bool corun = overlapped && fork && L.n[i] > 12288;
+    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], corun ? 8 : 0,
+                      corun ? 128 : 0, gs));
     prof_end(p, gs);
     ++p->launches;
     if (!fps_only) RN_TRY(ball_query_level(p, G, L, i, gs));
@@ -395,7 +404,7 @@ int regnet_scorenet_prefetch(regnet_scorenet* p, const float* pc, void* stream_)
   }
   const int saved = p->launches;
   p->launches = 0;
-  RN_TRY(geometry_enqueue(p, pc, slot, (cudaStream_t)stream_));
+  RN_TRY(geometry_enqueue(p, pc, slot, (cudaStream_t)stream_, true));
   p->prefetch_launches = p->launches;
   p->launches = saved;
   p->geom[slot].pc = pc;
@@ -425,12 +434,15 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
       set_error("scorenet_forward: input does not match the pending prefetches");
       return REGNET_EINVAL;
     }
-    RN_TRY(geometry_enqueue(p, pc, slot, ms));
+    RN_TRY(geometry_enqueue(p, pc, slot, ms, false));
     if (slot == p->next_slot) p->next_slot ^= 1;
   }
   regnet_scorenet::Geom& G = p->geom[slot];
   G.pending = false;
   p->last_slot = slot;
+  p->gemm_idx = 0;
+  if (p->cfg.engine == REGNET_ENGINE_TC && p->cfg.dynamic_tiles)
+    RN_CUDA(cudaMemsetAsync(p->tile_counters, 0, sizeof(unsigned int) * 64, ms));
   const bool fps_only = fork && p->cfg.use_side_stream == 2;
   const Levels L = make_levels(p, G, pc);
   const float* const* lvl_xyz = L.xyz;
