@@ -123,25 +123,29 @@ __device__ __forceinline__ void store_quad(const OperandOut& o, int64_t off, flo
   }
 }
 
-// SA operand: row (b,m,k) = [ feat[j, 0..C) | xyz[j]-new_xyz[m] (3) | 0 ... ], j = nbr[b,m,k].
+// Index arithmetic in these producers is 32-bit with power-of-two splits: a first version used 64-bit '/' and '%' by
+// run-time divisors per element and spent more instructions on (software) division than on the data.
+//   block = 256 threads = (256/TQ) rows x TQ quads;  grid.x over row groups (grid-stride), grid.y over quad tiles.
+
+// SA operand: row (b,m,k) = [ feat[j, 0..C) | xyz[j]-new_xyz[m] (3) | 0 ... ], j = nbr[b,m,k], K = 64 neighbours.
 // The reference concatenates [xyz_rel, feature] (modules.py:44-52); the rotation by three columns is folded into the
 // first layer's weights when they are uploaded (regnet_scorenet_set_layer), which keeps feature quads 16-byte aligned.
+template <int TQ>
 __global__ void __launch_bounds__(THREADS)
 sa_operand_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __restrict__ new_xyz,
                   const float* __restrict__ feat, int64_t feat_bstride, int feat_ld, int C, int vec_ok,
-                  const int32_t* __restrict__ nbr, int M, int K, int kpad, int64_t total_quads, OperandOut out) {
-  const int quads = kpad >> 2;
-  for (int64_t e = blockIdx.x * (int64_t)THREADS + threadIdx.x; e < total_quads; e += (int64_t)gridDim.x * THREADS) {
-    const int q = (int)(e % quads);
-    const int64_t row = e / quads;
-    const int64_t bm = row / K;
-    const int m = (int)(bm % M);
-    const int64_t b = bm / M;
+                  const int32_t* __restrict__ nbr, uint32_t M, int kpad, uint32_t rows, OperandOut out) {
+  constexpr uint32_t RPB = THREADS / TQ;
+  const uint32_t q = blockIdx.y * TQ + (threadIdx.x % TQ);
+  if ((int)(q * 4) >= kpad) return;
+  const int c0 = (int)q * 4;
+  for (uint32_t row = blockIdx.x * RPB + threadIdx.x / TQ; row < rows; row += gridDim.x * RPB) {
+    const uint32_t bm = row >> 6;             // K == 64
+    const uint32_t b = bm / M, m = bm - b * M;
     const int j = nbr[row];
-    const int c0 = q * 4;
     float4 v;
     if (vec_ok && c0 + 4 <= C) {
-      v = *reinterpret_cast<const float4*>(feat + b * feat_bstride + (int64_t)j * feat_ld + c0);
+      v = *reinterpret_cast<const float4*>(feat + (int64_t)b * feat_bstride + (int64_t)j * feat_ld + c0);
     } else {
       float t[4];
 #pragma unroll
@@ -149,16 +153,16 @@ sa_operand_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __re
         const int col = c0 + u;
         float x = 0.f;
         if (col < C) {
-          x = feat[b * feat_bstride + (int64_t)j * feat_ld + col];
+          x = feat[(int64_t)b * feat_bstride + (int64_t)j * feat_ld + col];
         } else if (col < C + 3) {
           const int a = col - C;
-          x = __fsub_rn(xyz[b * xst.b + a * xst.c + (int64_t)j * xst.n], new_xyz[(b * 3 + a) * M + m]);
+          x = __fsub_rn(xyz[(int64_t)b * xst.b + a * xst.c + (int64_t)j * xst.n], new_xyz[((int64_t)b * 3 + a) * M + m]);
         }
         t[u] = x;
       }
       v = make_float4(t[0], t[1], t[2], t[3]);
     }
-    store_quad(out, row * kpad + c0, v);
+    store_quad(out, (int64_t)row * kpad + c0, v);
   }
 }
 
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(THREADS, 3)
 sa0_fused_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __restrict__ new_xyz,
                  const float* __restrict__ feat, int64_t feat_bstride, int feat_ld, const int32_t* __restrict__ nbr,
                  const float* __restrict__ W, int ldw, const float* __restrict__ scale, const float* __restrict__ shift,
-                 int M, int K, int64_t rows, OperandOut out, int ld_out) {
+                 uint32_t M, uint32_t rows, OperandOut out, int ld_out) {
   constexpr int QUADS = COUT / 4;
   static_assert(THREADS % QUADS == 0, "quad index must be constant per thread");
   const int q = threadIdx.x % QUADS;
@@ -184,31 +188,29 @@ sa0_fused_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __res
     sc[u] = scale[q * 4 + u];
     sh[u] = shift[q * 4 + u];
   }
-  // R rows per thread per trip, all their gathers issued before any arithmetic: the kernel is bound by the latency of
-  // the dependent index -> point loads, so the number of rows in flight per warp is what sets its speed
+  // R rows per thread per trip, all their gathers issued before any arithmetic (latency of index -> point loads)
   constexpr int R = 4;
-  constexpr int ROWS_PER_BLOCK = (THREADS / QUADS) * R;
-  const int sub = threadIdx.x / QUADS;
-  for (int64_t base = (int64_t)blockIdx.x * ROWS_PER_BLOCK; base < rows; base += (int64_t)gridDim.x * ROWS_PER_BLOCK) {
+  constexpr uint32_t RPB = THREADS / QUADS;
+  const uint32_t sub = threadIdx.x / QUADS;
+  for (uint32_t base = blockIdx.x * RPB * R; base < rows; base += gridDim.x * RPB * R) {
     int j[R];
-    int64_t row[R];
+    uint32_t row[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      row[r] = base + r * (THREADS / QUADS) + sub;
+      row[r] = base + r * RPB + sub;
       j[r] = row[r] < rows ? nbr[row[r]] : 0;
     }
     float v[R][6];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int64_t rr = row[r] < rows ? row[r] : 0;
-      const int64_t bm = rr / K;
-      const int m = (int)(bm % M);
-      const int64_t b = bm / M;
+      const uint32_t bm = (row[r] < rows ? row[r] : 0u) >> 6;   // K == 64
+      const uint32_t b = bm / M, m = bm - b * M;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) v[r][c] = feat[b * feat_bstride + (int64_t)j[r] * feat_ld + c];
+      for (int c = 0; c < 3; ++c) v[r][c] = feat[(int64_t)b * feat_bstride + (int64_t)j[r] * feat_ld + c];
 #pragma unroll
       for (int a = 0; a < 3; ++a)
-        v[r][3 + a] = __fsub_rn(xyz[b * xst.b + a * xst.c + (int64_t)j[r] * xst.n], new_xyz[(b * 3 + a) * M + m]);
+        v[r][3 + a] = __fsub_rn(xyz[(int64_t)b * xst.b + a * xst.c + (int64_t)j[r] * xst.n],
+                                new_xyz[((int64_t)b * 3 + a) * M + m]);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -221,7 +223,7 @@ sa0_fused_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __res
         for (int c = 0; c < 6; ++c) acc = fmaf(w[u][c], v[r][c], acc);
         y[u] = fmaxf(fmaf(acc, sc[u], sh[u]), 0.f);
       }
-      store_quad(out, row[r] * ld_out + q * 4, make_float4(y[0], y[1], y[2], y[3]));
+      store_quad(out, (int64_t)row[r] * ld_out + q * 4, make_float4(y[0], y[1], y[2], y[3]));
     }
   }
 }
@@ -230,20 +232,19 @@ sa0_fused_kernel(const float* __restrict__ xyz, Strides3 xst, const float* __res
 __global__ void __launch_bounds__(THREADS)
 fp_operand_kernel(const float* __restrict__ sparse, int64_t sparse_bstride, int sparse_ld, int C2,
                   const float* __restrict__ dense, int64_t dense_bstride, int dense_ld, int C1, int sparse_vec,
-                  int dense_vec, const int32_t* __restrict__ idx, const float* __restrict__ w, int Nd, int kpad,
-                  int64_t total_quads, OperandOut out) {
-  const int quads = kpad >> 2;
-  for (int64_t e = blockIdx.x * (int64_t)THREADS + threadIdx.x; e < total_quads; e += (int64_t)gridDim.x * THREADS) {
-    const int q = (int)(e % quads);
-    const int64_t row = e / quads;
-    const int n = (int)(row % Nd);
-    const int64_t b = row / Nd;
-    const int c0 = q * 4;
+                  int dense_vec, const int32_t* __restrict__ idx, const float* __restrict__ w, uint32_t Nd, int kpad,
+                  uint32_t rows, OperandOut out) {
+  constexpr uint32_t TQ = 32, RPB = THREADS / TQ;
+  const uint32_t q = blockIdx.y * TQ + (threadIdx.x % TQ);
+  if ((int)(q * 4) >= kpad) return;
+  const int c0 = (int)q * 4;
+  for (uint32_t row = blockIdx.x * RPB + threadIdx.x / TQ; row < rows; row += gridDim.x * RPB) {
+    const uint32_t b = row / Nd, n = row - b * Nd;
     float4 v;
     if (sparse_vec && c0 + 4 <= C2) {
       const int i0 = idx[row * 3], i1 = idx[row * 3 + 1], i2 = idx[row * 3 + 2];
       const float w0 = w[row * 3], w1 = w[row * 3 + 1], w2 = w[row * 3 + 2];
-      const float* __restrict__ sp = sparse + b * sparse_bstride + c0;
+      const float* __restrict__ sp = sparse + (int64_t)b * sparse_bstride + c0;
       const float4 a0 = *reinterpret_cast<const float4*>(sp + (int64_t)i0 * sparse_ld);
       const float4 a1 = *reinterpret_cast<const float4*>(sp + (int64_t)i1 * sparse_ld);
       const float4 a2 = *reinterpret_cast<const float4*>(sp + (int64_t)i2 * sparse_ld);
@@ -252,7 +253,7 @@ fp_operand_kernel(const float* __restrict__ sparse, int64_t sparse_bstride, int 
       v.z = __fmaf_rn(a2.z, w2, __fmaf_rn(a1.z, w1, __fmaf_rn(a0.z, w0, 0.f)));
       v.w = __fmaf_rn(a2.w, w2, __fmaf_rn(a1.w, w1, __fmaf_rn(a0.w, w0, 0.f)));
     } else if (dense_vec && c0 >= C2 && c0 + 4 <= C2 + C1) {
-      v = *reinterpret_cast<const float4*>(dense + b * dense_bstride + (int64_t)n * dense_ld + (c0 - C2));
+      v = *reinterpret_cast<const float4*>(dense + (int64_t)b * dense_bstride + (int64_t)n * dense_ld + (c0 - C2));
     } else {
       float t[4];
 #pragma unroll
@@ -260,18 +261,18 @@ fp_operand_kernel(const float* __restrict__ sparse, int64_t sparse_bstride, int 
         const int col = c0 + u;
         float x = 0.f;
         if (col < C2) {
-          const float* __restrict__ sp = sparse + b * sparse_bstride + col;
+          const float* __restrict__ sp = sparse + (int64_t)b * sparse_bstride + col;
           x = __fmaf_rn(sp[(int64_t)idx[row * 3] * sparse_ld], w[row * 3], 0.f);
           x = __fmaf_rn(sp[(int64_t)idx[row * 3 + 1] * sparse_ld], w[row * 3 + 1], x);
           x = __fmaf_rn(sp[(int64_t)idx[row * 3 + 2] * sparse_ld], w[row * 3 + 2], x);
         } else if (col < C2 + C1) {
-          x = dense[b * dense_bstride + (int64_t)n * dense_ld + (col - C2)];
+          x = dense[(int64_t)b * dense_bstride + (int64_t)n * dense_ld + (col - C2)];
         }
         t[u] = x;
       }
       v = make_float4(t[0], t[1], t[2], t[3]);
     }
-    store_quad(out, row * kpad + c0, v);
+    store_quad(out, (int64_t)row * kpad + c0, v);
   }
 }
 
@@ -336,15 +337,34 @@ int interp_backward_launch(const float* gout, const int64_t* index, const float*
   return REGNET_OK;
 }
 
+static inline unsigned row_grid(uint32_t rows, uint32_t rows_per_block, unsigned ytiles) {
+  uint64_t g = ((uint64_t)rows + rows_per_block - 1) / rows_per_block;
+  const uint64_t cap = (148ull * 16 + ytiles - 1) / ytiles;   // ~16 resident blocks per SM overall, then grid-stride
+  if (g > cap) g = cap;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
 int sa_operand_launch(const float* xyz, Strides3 xst, const float* new_xyz, const float* feat, int64_t feat_bstride,
                       int feat_ld, int C, const int32_t* nbr, int B, int N, int M, int K, int kpad, float* out_f32,
                       __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream) {
   RN_CHECK_ARG(kpad % 4 == 0 && kpad >= 3 + C, "sa_operand: bad kpad %d for C=%d", kpad, C);
-  const int64_t total = (int64_t)B * M * K * (kpad / 4);
+  RN_CHECK_ARG(K == 64, "sa_operand: 64 neighbours per centroid expected");
+  const int64_t rows64 = (int64_t)B * M * K;
+  RN_CHECK_ARG(rows64 < (1LL << 31), "sa_operand: too many positions");
+  const uint32_t rows = (uint32_t)rows64;
   OperandOut o{out_f32, out_hi, out_lo};
   const int vec_ok = (feat_ld % 4 == 0) && (feat_bstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
-  sa_operand_kernel<<<grid_for(total), THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, C, vec_ok,
-                                                             nbr, M, K, kpad, total, o);
+  const int quads = kpad / 4;
+  if (quads <= 4) {
+    dim3 grid(row_grid(rows, THREADS / 4, 1), 1);
+    sa_operand_kernel<4><<<grid, THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, C, vec_ok, nbr,
+                                                       (uint32_t)M, kpad, rows, o);
+  } else {
+    const unsigned yt = (unsigned)ceil_div(quads, 32);
+    dim3 grid(row_grid(rows, THREADS / 32, yt), yt);
+    sa_operand_kernel<32><<<grid, THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, C, vec_ok, nbr,
+                                                        (uint32_t)M, kpad, rows, o);
+  }
   RN_LAUNCH_CHECK("sa_operand_kernel");
   (void)N;
   return REGNET_OK;
@@ -354,11 +374,13 @@ int sa0_fused_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
                      int feat_ld, const int32_t* nbr, const float* W, int ldw, const float* scale, const float* shift,
                      int cout, int B, int M, int K, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
                      int ld_out, cudaStream_t stream) {
-  RN_CHECK_ARG(cout == 128 && ld_out % 4 == 0, "sa0_fused: only the 6 -> 128 layer of the reference architecture");
-  const int64_t rows = (int64_t)B * M * K;
+  RN_CHECK_ARG(cout == 128 && ld_out % 4 == 0 && K == 64, "sa0_fused: only the 6 -> 128 layer of the reference architecture");
+  const int64_t rows64 = (int64_t)B * M * K;
+  RN_CHECK_ARG(rows64 < (1LL << 31), "sa0_fused: too many positions");
   OperandOut o{out_f32, out_hi, out_lo};
-  sa0_fused_kernel<128><<<grid_for(rows * 8), THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, nbr, W,
-                                                                    ldw, scale, shift, M, K, rows, o, ld_out);
+  const unsigned grid = row_grid((uint32_t)rows64, (THREADS / 32) * 4, 1);
+  sa0_fused_kernel<128><<<grid, THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, nbr, W, ldw, scale,
+                                                     shift, (uint32_t)M, (uint32_t)rows64, o, ld_out);
   RN_LAUNCH_CHECK("sa0_fused_kernel");
   return REGNET_OK;
 }
@@ -367,13 +389,16 @@ int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld
                       int64_t dense_bstride, int dense_ld, int C1, const int32_t* idx, const float* w, int B, int Nd,
                       int kpad, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream) {
   RN_CHECK_ARG(kpad % 4 == 0 && kpad >= C1 + C2, "fp_operand: bad kpad %d for C1+C2=%d", kpad, C1 + C2);
-  const int64_t total = (int64_t)B * Nd * (kpad / 4);
+  const int64_t rows64 = (int64_t)B * Nd;
+  RN_CHECK_ARG(rows64 * 3 < (1LL << 31), "fp_operand: too many points");
   OperandOut o{out_f32, out_hi, out_lo};
   const int sparse_vec = (sparse_ld % 4 == 0) && (sparse_bstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(sparse) & 15) == 0);
   const int dense_vec = (dense_ld % 4 == 0) && (dense_bstride % 4 == 0) && (C2 % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
-  fp_operand_kernel<<<grid_for(total), THREADS, 0, stream>>>(sparse, sparse_bstride, sparse_ld, C2, dense, dense_bstride,
-                                                             dense_ld, C1, sparse_vec, dense_vec, idx, w, Nd, kpad, total, o);
+  const unsigned yt = (unsigned)ceil_div(kpad / 4, 32);
+  dim3 grid(row_grid((uint32_t)rows64, THREADS / 32, yt), yt);
+  fp_operand_kernel<<<grid, THREADS, 0, stream>>>(sparse, sparse_bstride, sparse_ld, C2, dense, dense_bstride, dense_ld,
+                                                  C1, sparse_vec, dense_vec, idx, w, (uint32_t)Nd, kpad, (uint32_t)rows64, o);
   RN_LAUNCH_CHECK("fp_operand_kernel");
   return REGNET_OK;
 }

@@ -59,7 +59,8 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 1; int dynamic_tiles = 1; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 1; int dynamic_tiles = 1; int use_grid = 1; } cfg;
+  void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
   int B = 0, N = 0;
@@ -203,6 +204,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   static_cast<regnet_scorenet_config&>(p->cfg) = *cfg;
   if (const char* e = getenv("REGNET_FUSE_SA0")) p->cfg.fuse_sa0 = atoi(e);
   if (const char* e = getenv("REGNET_DYNAMIC_TILES")) p->cfg.dynamic_tiles = atoi(e);
+  if (const char* e = getenv("REGNET_USE_GRID")) p->cfg.use_grid = atoi(e);
   p->B = cfg->batch;
   p->N = cfg->num_points;
   for (int i = 0; i < 3; ++i) p->M[i] = cfg->num_centroids[i];
@@ -223,6 +225,8 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   }
   for (int i = 0; i < 3; ++i) A((void**)&p->sa_out[i], sizeof(float) * (size_t)B * M[i] * SA_CH[i][2]);
   A((void**)&p->tile_counters, sizeof(unsigned int) * 64);
+  A(&p->grid_ws[0], (size_t)grid_workspace_bytes(B, N));
+  A(&p->grid_ws[1], (size_t)grid_workspace_bytes(B, M[0]));
   A((void**)&p->fp_out[0], sizeof(float) * (size_t)B * M[1] * 1024);
   A((void**)&p->fp_out[1], sizeof(float) * (size_t)B * M[0] * 512);
   // activation arenas: the widest (rows x ld) any layer reads or writes, 4 bytes per element in both engines
@@ -341,9 +345,22 @@ static Levels make_levels(const regnet_scorenet* p, const regnet_scorenet::Geom&
 }
 
 static int ball_query_level(regnet_scorenet* p, regnet_scorenet::Geom& G, const Levels& L, int i, cudaStream_t s) {
+  const float r = p->cfg.radius[i];
+  if (p->cfg.use_grid && i < 2 && L.n[i] <= 65536) {
+    // levels 0 and 1: bin the points into an (x,y) grid of cell edge >= r, then look at 3x3 cells per centroid
+    prof_begin(p, i == 0 ? "grid_build.0" : "grid_build.1", s);
+    RN_TRY(grid_build_launch(L.xyz[i], L.st[i], p->B, L.n[i], r * 1.001f + 1e-7f, p->grid_ws[i], s));
+    prof_end(p, s);
+    prof_begin(p, BQ_LABEL[i], s);
+    RN_TRY(ball_query_grid_launch(L.xyz[i], L.st[i], L.xyz[i + 1], L.st[i + 1], p->B, L.n[i], p->M[i], r, p->grid_ws[i],
+                                  G.nbr[i], s));
+    prof_end(p, s);
+    p->launches += 2;
+    return REGNET_OK;
+  }
   prof_begin(p, BQ_LABEL[i], s);
-  RN_TRY(ball_query_launch(L.xyz[i], L.st[i], L.xyz[i + 1], L.st[i + 1], p->B, L.n[i], p->M[i], p->cfg.radius[i], 64,
-                           nullptr, nullptr, G.nbr[i], s));
+  RN_TRY(ball_query_launch(L.xyz[i], L.st[i], L.xyz[i + 1], L.st[i + 1], p->B, L.n[i], p->M[i], r, 64, nullptr, nullptr,
+                           G.nbr[i], s));
   prof_end(p, s);
   ++p->launches;
   return REGNET_OK;
@@ -352,6 +369,18 @@ static int ball_query_level(regnet_scorenet* p, regnet_scorenet::Geom& G, const 
 static int three_nn_all(regnet_scorenet* p, regnet_scorenet::Geom& G, const Levels& L, cudaStream_t s) {
   for (int f = 0; f < 3; ++f) {  // fp f: dense level 2-f, sparse level 3-f
     const int dl = 2 - f, sl = 3 - f;
+    if (p->cfg.use_grid && f == 2) {
+      // the big one (N queries against M0 keys): finest grid the cell budget allows over the keys
+      prof_begin(p, "grid_build.nn", s);
+      RN_TRY(grid_build_launch(L.xyz[sl], L.st[sl], p->B, L.n[sl], 0.f, p->grid_ws[1], s));
+      prof_end(p, s);
+      prof_begin(p, NN_LABEL[f], s);
+      RN_TRY(three_nn_grid_launch(L.xyz[dl], L.st[dl], L.xyz[sl], L.st[sl], p->B, L.n[dl], L.n[sl], p->grid_ws[1],
+                                  G.nn_idx[f], G.nn_w[f], s));
+      prof_end(p, s);
+      p->launches += 2;
+      continue;
+    }
     prof_begin(p, NN_LABEL[f], s);
     RN_TRY(three_nn_launch(L.xyz[dl], L.st[dl], L.xyz[sl], L.st[sl], p->B, L.n[dl], L.n[sl], nullptr, nullptr,
                            G.nn_idx[f], G.nn_w[f], s));
