@@ -37,6 +37,13 @@ int gemm_simt_launch(const float* X, int ldx, const float* W, int ldw, int64_t P
 int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, const __nv_bfloat16* Whi,
                    const __nv_bfloat16* Wlo, int ldw, int64_t P, int K, int cout, const Epilogue& ep,
                    cudaStream_t stream);
-int gemm_tc_supported(void);  // 1 when the driver entry point for tensor maps is available on this box
+int gemm_tc_supported(void);
+
+// 2-D bf16 tensor map over a (rows, cols) row-major matrix with leading dimension ld (elements); box = box_cols x
+// box_rows, swizzle_bytes in {64, 128}.  CUtensorMap is passed opaquely so that this header needs no <cuda.h>.
+struct CUtensorMap_st;
+int tc_make_map(CUtensorMap_st* map, const void* base, int64_t rows, int cols, int ld, int box_rows, int box_cols,
+                int swizzle_bytes);
+int tc_driver_ok(void);  // 1 when the driver entry point for tensor maps is available on this box
 
 }  // namespace regnet

@@ -58,7 +58,7 @@ __device__ __forceinline__ float act_fn(float v) {
 // POOL / ACT are compile-time so that each instance carries only its own epilogue (a runtime switch inlined the
 // sigmoid's division subroutine 256 times and the unrolled epilogue overflowed the instruction cache).
 template <int BN, bool POOL, int ACT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __maxnreg__(88)   // one CTA per SM by shared memory; 88 registers leave room for a co-resident FPS CTA
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
                const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
                const __grid_constant__ CUtensorMap map_ohi, const __grid_constant__ CUtensorMap map_olo, int64_t P,
@@ -223,71 +223,82 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
       const bool row_ok = row < P;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32, v);
-        float y[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 sc = *reinterpret_cast<const float4*>(s_scale + ch * 32 + 4 * j4);
-          const float4 sh = *reinterpret_cast<const float4*>(s_shift + ch * 32 + 4 * j4);
-          y[4 * j4 + 0] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 0]), sc.x, sh.x));
-          y[4 * j4 + 1] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y));
-          y[4 * j4 + 2] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z));
-          y[4 * j4 + 3] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w));
-        }
+        // 32 channels per trip, as two 16-column TMEM loads: keeps the epilogue at ~80 registers so that the
+        // register-resident FPS kernel of the next step fits on the same SM (profiles/README.md)
         const int c0 = col0 + ch * 32;
-        if (POOL) {
-          uint32_t mine = 0;
+        const uint32_t st_hi = smem_base + C::OFF_STAGE + (warp - 2) * 4096, st_lo = st_hi + 2048;
+        const bool stage_out = !POOL && ep.out_hi && c0 < cout;
+        uint32_t mine = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const uint32_t m = __reduce_max_sync(FULL, order_bits(y[j]));
-            if (lane == j) mine = m;
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32 + half * 16, v);
+          float y[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + ch * 32 + half * 16 + 4 * j4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + ch * 32 + half * 16 + 4 * j4);
+            y[4 * j4 + 0] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 0]), sc.x, sh.x));
+            y[4 * j4 + 1] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y));
+            y[4 * j4 + 2] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z));
+            y[4 * j4 + 3] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w));
           }
-          s_part[q * BN + ch * 32 + lane] = mine;
-        } else {
-          if (ep.out_hi && c0 < cout) {
-            // bf16 hi/lo planes: stage this warp's [32 rows x 32 ch] block in shared memory (64B-swizzled rows,
-            // conflict-free STS.128) and let TMA write full lines; rows >= P / channels >= cout are clipped by TMA
-            uint32_t hi[16], lo[16];
+          if (POOL) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(y[2 * j], h0, l0);
-              split_bf16(y[2 * j + 1], h1, l1);
-              __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
-              hi[j] = *reinterpret_cast<uint32_t*>(&hh);
-              lo[j] = *reinterpret_cast<uint32_t*>(&ll);
+              const uint32_t m = __reduce_max_sync(FULL, order_bits(y[j]));
+              if (lane == half * 16 + j) mine = m;
             }
-            const uint32_t st_hi = smem_base + C::OFF_STAGE + (warp - 2) * 4096, st_lo = st_hi + 2048;
-            if (lane == 0) bulk_wait_read();  // the previous block's TMA stores have finished reading the staging
-            __syncwarp();
-            const uint32_t swz = (uint32_t)(lane >> 1) & 3u;
+          } else {
+            if (stage_out) {
+              // bf16 hi/lo planes: stage this warp's [32 rows x 32 ch] block in shared memory (64B-swizzled rows,
+              // conflict-free STS.128) and let TMA write full lines; rows >= P / channels >= cout are clipped by TMA
+              uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t off = (uint32_t)lane * 64u + (((uint32_t)j ^ swz) << 4);
-              sts_v4(st_hi + off, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              sts_v4(st_lo + off, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(y[2 * j], h0, l0);
+                split_bf16(y[2 * j + 1], h1, l1);
+                __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
+                hi[j] = *reinterpret_cast<uint32_t*>(&hh);
+                lo[j] = *reinterpret_cast<uint32_t*>(&ll);
+              }
+              if (half == 0) {
+                if (lane == 0) bulk_wait_read();  // the previous block's TMA stores have finished reading the staging
+                __syncwarp();
+              }
+              const uint32_t swz = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t off = (uint32_t)lane * 64u + (((uint32_t)(half * 2 + j) ^ swz) << 4);
+                sts_v4(st_hi + off, hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                sts_v4(st_lo + off, lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+              if (half == 1) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&map_ohi, st_hi, c0, (int)(row0 + q * 32));
+                  tma_store_2d(&map_olo, st_lo, c0, (int)(row0 + q * 32));
+                  bulk_commit();
+                }
+              }
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&map_ohi, st_hi, c0, (int)(row0 + q * 32));
-              tma_store_2d(&map_olo, st_lo, c0, (int)(row0 + q * 32));
-              bulk_commit();
-            }
-          }
-          if (ep.out_f32 && row_ok) {
-            if (c0 + 32 <= cout) {
-              float4* dst = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ld_f32 + c0);
+            if (ep.out_f32 && row_ok) {
+              const int ch0 = c0 + half * 16;
+              if (ch0 + 16 <= cout) {
+                float4* dst = reinterpret_cast<float4*>(ep.out_f32 + row * ep.ld_f32 + ch0);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-            } else {
+                for (int j = 0; j < 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+              } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c0 + j < cout) ep.out_f32[row * ep.ld_f32 + c0 + j] = y[j];
+                for (int j = 0; j < 16; ++j)
+                  if (ch0 + j < cout) ep.out_f32[row * ep.ld_f32 + ch0 + j] = y[j];
+              }
             }
           }
         }
+        if (POOL) s_part[q * BN + ch * 32 + lane] = mine;
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
@@ -318,6 +329,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
+}  // namespace (kernels)
+
+namespace {
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -338,8 +353,11 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld, int box_rows, int box_cols = BK,
-             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+}  // namespace
+
+int tc_make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld, int box_rows, int box_cols,
+                int swizzle_bytes) {
+  const CUtensorMapSwizzle swizzle = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("gemm_tc: cuTensorMapEncodeTiled is not available from this driver");
@@ -359,6 +377,11 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld,
   }
   return REGNET_OK;
 }
+
+int tc_driver_ok(void) { return encode_fn() != nullptr; }
+
+namespace {
+
 
 template <int BN, bool POOL, int ACT>
 int launch(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl,
@@ -393,7 +416,7 @@ int launch_bn(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap&
 
 }  // namespace
 
-int gemm_tc_supported(void) { return encode_fn() != nullptr; }
+int gemm_tc_supported(void) { return tc_driver_ok(); }
 
 int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, const __nv_bfloat16* Whi,
                    const __nv_bfloat16* Wlo, int ldw, int64_t P, int K, int cout, const Epilogue& ep,
@@ -409,14 +432,14 @@ int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, 
   if (P == 0) return REGNET_OK;
   const int bn = cout > 128 ? 256 : 128;
   CUtensorMap mxh, mxl, mwh, mwl;
-  RN_TRY(make_map(&mxh, Xhi, P, K, ldx, BM));
-  RN_TRY(make_map(&mxl, Xlo, P, K, ldx, BM));
-  RN_TRY(make_map(&mwh, Whi, cout, K, ldw, bn));
-  RN_TRY(make_map(&mwl, Wlo, cout, K, ldw, bn));
+  RN_TRY(tc_make_map(&mxh, Xhi, P, K, ldx, BM));
+  RN_TRY(tc_make_map(&mxl, Xlo, P, K, ldx, BM));
+  RN_TRY(tc_make_map(&mwh, Whi, cout, K, ldw, bn));
+  RN_TRY(tc_make_map(&mwl, Wlo, cout, K, ldw, bn));
   CUtensorMap moh = mxh, mol = mxl;  // placeholders when there is no split output
   if (ep.out_hi) {
-    RN_TRY(make_map(&moh, ep.out_hi, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-    RN_TRY(make_map(&mol, ep.out_lo, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    RN_TRY(tc_make_map(&moh, ep.out_hi, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    RN_TRY(tc_make_map(&mol, ep.out_lo, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
   }
   if (bn == 256) return launch_bn<256>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
   return launch_bn<128>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);

@@ -59,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 1; int dynamic_tiles = 1; int use_grid = 1; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
@@ -205,6 +205,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   if (const char* e = getenv("REGNET_FUSE_SA0")) p->cfg.fuse_sa0 = atoi(e);
   if (const char* e = getenv("REGNET_DYNAMIC_TILES")) p->cfg.dynamic_tiles = atoi(e);
   if (const char* e = getenv("REGNET_USE_GRID")) p->cfg.use_grid = atoi(e);
+  if (const char* e = getenv("REGNET_FPS_CORUN")) sscanf(e, "%d,%d", &p->cfg.corun_cs, &p->cfg.corun_threads);
   p->B = cfg->batch;
   p->N = cfg->num_points;
   for (int i = 0; i < 3; ++i) p->M[i] = cfg->num_centroids[i];
@@ -412,8 +413,8 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
     // a prefetched FPS shares its SMs with the previous step's GEMM CTAs: 4 warps (one per scheduler partition,
     // 227 registers) is the shape whose register-file footprint leaves room for them (profiles/README.md)
     const bool corun = overlapped && fork && L.n[i] > 12288;
-    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], corun ? 8 : 0,
-                      corun ? 128 : 0, gs));
+    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i],
+                      corun ? p->cfg.corun_cs : 0, corun ? p->cfg.corun_threads : 0, gs));
     prof_end(p, gs);
     ++p->launches;
     if (!fps_only) RN_TRY(ball_query_level(p, G, L, i, gs));

@@ -20,6 +20,7 @@ for s in $STAGES; do
     timeline) timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2.log 2>&1
               REGNET_FPS_FORCE=8,128 timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2_t128.log 2>&1
               REGNET_FPS_FORCE=8,256 timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2_t256.log 2>&1 ;;
+    corun)    for v in 8,128 8,256 8,512; do REGNET_FPS_CORUN=$v timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_corun_${v/,/_}.log 2>&1; done ;;
     ab)       timeout 300 python scripts/pipeline_ab.py > gpurun_out/pipeline_ab.log 2>&1 ;;
     region)   timeout 600 python -m pytest tests/test_gpu_region.py -q -m gpu > gpurun_out/test_region.log 2>&1 ;;
     ncu)      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
