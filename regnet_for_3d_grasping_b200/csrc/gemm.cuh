@@ -8,6 +8,8 @@
 #pragma once
 #include "common.cuh"
 
+struct CUtensorMap_st;  // <cuda.h>
+
 namespace regnet {
 
 struct Epilogue {
@@ -41,8 +43,7 @@ int gemm_tc_supported(void);
 
 // 2-D bf16 tensor map over a (rows, cols) row-major matrix with leading dimension ld (elements); box = box_cols x
 // box_rows, swizzle_bytes in {64, 128}.  CUtensorMap is passed opaquely so that this header needs no <cuda.h>.
-struct CUtensorMap_st;
-int tc_make_map(CUtensorMap_st* map, const void* base, int64_t rows, int cols, int ld, int box_rows, int box_cols,
+int tc_make_map(::CUtensorMap_st* map, const void* base, int64_t rows, int cols, int ld, int box_rows, int box_cols,
                 int swizzle_bytes);
 int tc_driver_ok(void);  // 1 when the driver entry point for tensor maps is available on this box
 

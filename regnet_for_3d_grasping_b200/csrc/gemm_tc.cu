@@ -432,14 +432,14 @@ int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, 
   if (P == 0) return REGNET_OK;
   const int bn = cout > 128 ? 256 : 128;
   CUtensorMap mxh, mxl, mwh, mwl;
-  RN_TRY(tc_make_map(&mxh, Xhi, P, K, ldx, BM));
-  RN_TRY(tc_make_map(&mxl, Xlo, P, K, ldx, BM));
-  RN_TRY(tc_make_map(&mwh, Whi, cout, K, ldw, bn));
-  RN_TRY(tc_make_map(&mwl, Wlo, cout, K, ldw, bn));
+  RN_TRY(tc_make_map(&mxh, Xhi, P, K, ldx, BM, BK, 128));
+  RN_TRY(tc_make_map(&mxl, Xlo, P, K, ldx, BM, BK, 128));
+  RN_TRY(tc_make_map(&mwh, Whi, cout, K, ldw, bn, BK, 128));
+  RN_TRY(tc_make_map(&mwl, Wlo, cout, K, ldw, bn, BK, 128));
   CUtensorMap moh = mxh, mol = mxl;  // placeholders when there is no split output
   if (ep.out_hi) {
-    RN_TRY(tc_make_map(&moh, ep.out_hi, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
-    RN_TRY(tc_make_map(&mol, ep.out_lo, P, cout, ep.ld_split, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+    RN_TRY(tc_make_map(&moh, ep.out_hi, P, cout, ep.ld_split, 32, 32, 64));
+    RN_TRY(tc_make_map(&mol, ep.out_lo, P, cout, ep.ld_split, 32, 32, 64));
   }
   if (bn == 256) return launch_bn<256>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
   return launch_bn<128>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);

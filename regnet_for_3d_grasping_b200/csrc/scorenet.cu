@@ -59,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 2; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
@@ -489,7 +489,25 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     const int64_t P = (int64_t)B * M[i] * 64;
     const int kpad = round_up(feat_c + 3, 16);
     Act a1 = make_act(p, 1, P, SA_CH[i][0]);
-    if (i == 0 && p->cfg.fuse_sa0) {
+    Act a2 = make_act(p, 0, P, SA_CH[i][1]);
+    bool need_l1 = true;
+    if (i == 0 && p->cfg.fuse_sa0 >= 2 && p->cfg.engine == REGNET_ENGINE_TC) {
+      // level 0: gather + centre + layers 0 and 1 (6 -> 128 -> 128) in one kernel; the first activation stays on chip
+      const Layer& L0 = p->layers[0][0];
+      const Layer& L1 = p->layers[0][1];
+      if (!L0.set || !L1.set) {
+        set_error("scorenet: sa_modules.0.mlp.{0,1} were never given weights");
+        return REGNET_EINVAL;
+      }
+      unsigned int* counter = (p->cfg.dynamic_tiles && p->gemm_idx < 64) ? p->tile_counters + (p->gemm_idx++) : nullptr;
+      prof_begin(p, "sa0_front", ms);
+      RN_TRY(sa0_front_launch(lvl_xyz[0], lvl_st[0], G.new_xyz[0], feat, feat_bs, feat_ld, G.nbr[0], L0.w_f32, L0.kpad,
+                              L0.scale, L0.shift, L1.w_hi, L1.w_lo, L1.kpad, L1.scale, L1.shift, B, M[0], a2.hi, a2.lo,
+                              a2.ld, counter, ms));
+      prof_end(p, ms);
+      ++p->launches;
+      need_l1 = false;
+    } else if (i == 0 && p->cfg.fuse_sa0) {
       // level 0: gather + centre + first layer (6 -> 128) in one SIMT pass, no 6-channel operand round trip
       const Layer& L0 = p->layers[0][0];
       if (!L0.set) {
@@ -510,8 +528,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
       ++p->launches;
       RN_TRY(run_layer(p, GEMM_LABEL[i][0], p->layers[i][0], a0, P, 1, 0, &a1, nullptr, 0, ms));
     }
-    Act a2 = make_act(p, 0, P, SA_CH[i][1]);
-    RN_TRY(run_layer(p, GEMM_LABEL[i][1], p->layers[i][1], a1, P, 1, 0, &a2, nullptr, 0, ms));
+    if (need_l1) RN_TRY(run_layer(p, GEMM_LABEL[i][1], p->layers[i][1], a1, P, 1, 0, &a2, nullptr, 0, ms));
     RN_TRY(run_layer(p, GEMM_LABEL[i][2], p->layers[i][2], a2, P, 1, 64, nullptr, p->sa_out[i], SA_CH[i][2], ms));
     feat = p->sa_out[i];
     feat_c = feat_ld = SA_CH[i][2];
