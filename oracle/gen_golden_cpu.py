@@ -127,8 +127,39 @@ def gen_modules(ref_mods):
     print("grad golden ok")
 
 
+def gen_heads():
+    """Region / refine heads (utils/pointnet2.py:123-254) of the reference on seeded inputs, eval mode."""
+    from multi_model.utils.pointnet2 import PointNet2Refine, PointNet2TwoStage
+    g = torch.Generator().manual_seed(17)
+
+    from regnet_for_3d_grasping_b200.weights import seeded_state_like
+
+    def randomize(mod):
+        mod.load_state_dict(seeded_state_like(mod.state_dict(), seed=17), strict=True)
+
+    two = PointNet2TwoStage(num_points=16, input_chann=6, k_cls=4, k_reg=40, k_reg_theta=4).eval()
+    ref = PointNet2Refine(num_points=8, input_chann=6, k_cls=2, k_reg=10).eval()
+    randomize(two)
+    randomize(ref)
+    x = torch.randn(12, 256, 16, generator=g)
+    gf = torch.randn(7, 256, 8, generator=g)
+    grp = torch.randn(7, 128, generator=g)
+    with torch.no_grad():
+        cls, reg, mp = two(x, None)
+        rcls, rreg = ref(gf, grp)
+    out = {"x": x.numpy(), "gf": gf.numpy(), "grp": grp.numpy(), "cls": cls.numpy(), "reg": reg.numpy(),
+           "mp": mp.numpy(), "rcls": rcls.numpy(), "rreg": rreg.numpy(),
+           "meta": np.array("PointNet2TwoStage(16,6,4,40,4) / PointNet2Refine(8,6,2,10), eval; weights = weights.seeded_state_like(state_dict, seed=17)")}
+    np.savez_compressed(os.path.join(OUT, "ref_py_heads.npz"), **out)
+    print("heads golden ok", cls.shape, reg.shape, rcls.shape)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ScoreNetwork, ref_mods = import_reference()
+    if "heads" in sys.argv:
+        gen_heads()
+        sys.exit(0)
     gen_modules(ref_mods)
     gen_scorenet(ScoreNetwork)
+    gen_heads()

@@ -1,7 +1,4 @@
-"""reference: multi_model/utils/pointnet2.py -> PointNet2Seg (ScoreNet body) and the region / refine heads"""
+"""reference: multi_model/utils/pointnet2.py -> PointNet2Seg (ScoreNet body), PointNet2TwoStage / PointNet2Refine heads"""
 import _bootstrap  # noqa: F401
 from regnet_for_3d_grasping_b200.pointnet2 import PointNet2Seg  # noqa: F401
-try:
-    from regnet_for_3d_grasping_b200.region_heads import PointNet2Refine, PointNet2TwoStage  # noqa: F401
-except ImportError:  # region stage not built yet
-    pass
+from regnet_for_3d_grasping_b200.region_heads import PointNet2Refine, PointNet2TwoStage  # noqa: F401

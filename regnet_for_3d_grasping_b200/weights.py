@@ -78,3 +78,28 @@ def random_scorenet_state(seed=0, randomize_bn=True, dtype=torch.float32):
         else:  # pragma: no cover
             raise KeyError(name)
     return sd
+
+
+def seeded_state_like(state, seed=0):
+    """Deterministic values for every tensor of a state dict, derived from (seed, key name) only -- independent of module
+    registration order, so a fixture generator and a test can agree on weights without storing them.
+    Conv/linear weights ~ U(-1/sqrt(fan_in), 1/sqrt(fan_in)); biases small; BN gamma in [0.5,1.5], var in [0.5,1.5]."""
+    import zlib
+    out = {}
+    for name, ref in state.items():
+        g = torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ (seed * 2654435761)) & 0x7fffffff)
+        shape = tuple(ref.shape)
+        if name.endswith("num_batches_tracked"):
+            v = torch.zeros(shape, dtype=ref.dtype)
+        elif name.endswith("running_var"):
+            v = torch.rand(shape, generator=g) + 0.5
+        elif name.endswith("running_mean"):
+            v = torch.randn(shape, generator=g) * 0.1
+        elif name.endswith(".weight") and len(shape) == 1:
+            v = torch.rand(shape, generator=g) + 0.5
+        elif name.endswith(".weight"):
+            v = (torch.rand(shape, generator=g) * 2 - 1) / shape[1] ** 0.5
+        else:
+            v = torch.randn(shape, generator=g) * 0.05
+        out[name] = v.to(ref.dtype)
+    return out

@@ -117,3 +117,29 @@ def test_synthetic_clouds_are_seeded_and_shaped():
     assert 0.5 < a[:, 2].mean() < 0.8 and a[:, 3:].min() >= 0 and a[:, 3:].max() <= 1
     lat = synth.lattice(1, 512)
     assert len(np.unique(lat[:, :3], axis=0)) < 512   # duplicates exist: tie paths are exercised
+
+
+def test_region_heads_match_reference_outputs():
+    """PointNet2TwoStage / PointNet2Refine mirrors (rows R4, R7): same state-dict keys, same outputs as the fixture
+    produced by the reference's classes; forward_pooled (the gather-max entry point) equals forward."""
+    ref = golden("ref_py_heads.npz")
+    from regnet_for_3d_grasping_b200.region_heads import PointNet2Refine, PointNet2TwoStage
+    two = PointNet2TwoStage(num_points=16, input_chann=6, k_cls=4, k_reg=40, k_reg_theta=4).eval()
+    rf = PointNet2Refine(num_points=8, input_chann=6, k_cls=2, k_reg=10).eval()
+    from regnet_for_3d_grasping_b200.weights import seeded_state_like
+    two.load_state_dict(seeded_state_like(two.state_dict(), seed=17), strict=True)   # same keys => same weights as the
+    rf.load_state_dict(seeded_state_like(rf.state_dict(), seed=17), strict=True)      # fixture generator used
+    x, gf, grp = (torch.from_numpy(ref[k]) for k in ("x", "gf", "grp"))
+    with torch.no_grad():
+        cls, reg, mp = two(x, None)
+        cls2, reg2, mp2 = two.forward_pooled(x.max(dim=2)[0])
+        rcls, rreg = rf(gf, grp)
+        rcls2, rreg2 = rf.forward_pooled(gf.max(dim=2)[0], grp)
+    np.testing.assert_allclose(cls.numpy(), ref["cls"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(reg.numpy(), ref["reg"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(mp.numpy(), ref["mp"], rtol=0, atol=0)
+    np.testing.assert_allclose(rcls.numpy(), ref["rcls"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rreg.numpy(), ref["rreg"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(cls, cls2) and torch.equal(reg, reg2) and torch.equal(mp, mp2)
+    assert torch.equal(rcls, rcls2) and torch.equal(rreg, rreg2)
+    assert tuple(reg.shape) == (12, 4, 10) and (reg[:, :, 7:] > 0).all() and (reg[:, :, 7:] < 1).all()
