@@ -126,6 +126,7 @@ def cpu_reference_run(steps, warmup, clouds_per_step=1):
     pn2_oracle.build()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    pn2_oracle.set_threads(cores)
     ext = pn2_oracle.as_pn2_ext()
     sd = ref_modules.random_scorenet_state(seed=0)
     pc = torch.from_numpy(synth.batch("table", range(clouds_per_step), N_POINTS))

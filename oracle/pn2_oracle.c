@@ -250,6 +250,14 @@ int oracle_group_bw(const float* grad_out, const int64_t* index, int64_t B, int6
   return 0;
 }
 
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

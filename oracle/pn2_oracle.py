@@ -72,6 +72,13 @@ def num_threads():
     return lib().oracle_num_threads()
 
 
+def set_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline should use every host core."""
+    lib().oracle_set_threads.argtypes = [ctypes.c_int]
+    lib().oracle_set_threads.restype = None
+    lib().oracle_set_threads(int(n))
+
+
 def farthest_point_sample(points, num_centroids):
     p = _aos(points)
     B, N, _ = p.shape
