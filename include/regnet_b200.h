@@ -201,6 +201,18 @@ int regnet_gather_max(const float* feat, const int64_t* index, int B, int N, int
 int regnet_mlp_layer(const float* X, const float* W, const float* scale, const float* shift, int64_t P, int cin,
                      int cout, int pool, int act, int engine, float* Y, void* stream);
 
+/* Set-abstraction level 0 as ONE kernel (csrc/sa0_chain.cu): group rgb / xyz by `nbr`, subtract the centroid, the three
+ * 1x1 conv + BN + ReLU blocks 6 -> 128 -> 128 -> 256 and the max over each centroid's 64 neighbours
+ * (pn2_utils/modules.py:44-52,241-245 with the channel plan of pointnet2.py:43).  pc (B,N,6) fp32 [xyz|rgb];
+ * new_xyz (B,3,M) planar; nbr (B,M,64) int32; W0 (128,6) in OPERAND order [rgb | xyz - centroid], W1 (128,128),
+ * W2 (256,128) row-major fp32; scale/shift = folded BatchNorm; out (B*M,256).  dbg: NULL, or (B*M*64, 256) receiving the
+ * raw accumulators of layers 0 and 1 (tests).  variant: 0 (operand-layout experiments otherwise).  Stand-alone and
+ * synchronising (tests); the plan calls the kernel with pre-split weights. */
+int regnet_sa0_chain(const float* pc, const float* new_xyz, const int32_t* nbr, int B, int N, int M, const float* W0,
+                     const float* scale0, const float* shift0, const float* W1, const float* scale1,
+                     const float* shift1, const float* W2, const float* scale2, const float* shift2, float* out,
+                     float* dbg, int variant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,4 +213,31 @@ int regnet_mlp_layer(const float* X, const float* W, const float* scale, const f
   return rc;
 }
 
+int regnet_sa0_chain(const float* pc, const float* new_xyz, const int32_t* nbr, int B, int N, int M, const float* W0,
+                     const float* scale0, const float* shift0, const float* W1, const float* scale1,
+                     const float* shift1, const float* W2, const float* scale2, const float* shift2, float* out,
+                     float* dbg, int variant, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RN_CHECK_ARG(pc && new_xyz && nbr && W0 && W1 && W2 && out, "sa0_chain: null argument");
+  RN_CHECK_ARG(B > 0 && N > 0 && M > 0, "sa0_chain: empty problem");
+  RN_CHECK_ARG(gemm_tc_supported(), "sa0_chain: tensor maps are not available from this driver");
+  void* scratch = nullptr;
+  const size_t nw = (size_t)(128 + 256) * 128;
+  RN_CUDA(cudaMalloc(&scratch, 2 * sizeof(__nv_bfloat16) * nw));
+  __nv_bfloat16* w1h = (__nv_bfloat16*)scratch;
+  __nv_bfloat16* w1l = w1h + 128 * 128;
+  __nv_bfloat16* w2h = w1l + 128 * 128;
+  __nv_bfloat16* w2l = w2h + 256 * 128;
+  int rc = split_rows_launch(W1, 128, 128, 128, 128, w1h, w1l, nullptr, stream);
+  if (!rc) rc = split_rows_launch(W2, 256, 128, 128, 128, w2h, w2l, nullptr, stream);
+  if (!rc)
+    rc = sa0_chain_launch(pc, Strides3{(int64_t)N * 6, 1, 6}, new_xyz, pc + 3, (int64_t)N * 6, 6, nbr, W0, 6, scale0,
+                          shift0, w1h, w1l, 128, scale1, shift1, w2h, w2l, 128, scale2, shift2, B, M, out, 256, dbg,
+                          nullptr, variant, stream);
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (!rc && e != cudaSuccess) rc = cuda_fail(e, "sa0_chain kernel");
+  cudaFree(scratch);
+  return rc;
+}
+
 }  // extern "C"

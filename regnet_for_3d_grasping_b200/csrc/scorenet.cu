@@ -59,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 2; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 2; int sa0_variant = 0; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
@@ -203,6 +203,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   regnet_scorenet* p = new regnet_scorenet();
   static_cast<regnet_scorenet_config&>(p->cfg) = *cfg;
   if (const char* e = getenv("REGNET_FUSE_SA0")) p->cfg.fuse_sa0 = atoi(e);
+  if (const char* e = getenv("REGNET_SA0_VARIANT")) p->cfg.sa0_variant = atoi(e);
   if (const char* e = getenv("REGNET_DYNAMIC_TILES")) p->cfg.dynamic_tiles = atoi(e);
   if (const char* e = getenv("REGNET_USE_GRID")) p->cfg.use_grid = atoi(e);
   if (const char* e = getenv("REGNET_FPS_CORUN")) sscanf(e, "%d,%d", &p->cfg.corun_cs, &p->cfg.corun_threads);
@@ -491,6 +492,28 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     Act a1 = make_act(p, 1, P, SA_CH[i][0]);
     Act a2 = make_act(p, 0, P, SA_CH[i][1]);
     bool need_l1 = true;
+    if (i == 0 && p->cfg.fuse_sa0 >= 3 && p->cfg.engine == REGNET_ENGINE_TC) {
+      // level 0: the whole chain (gather, 6 -> 128 -> 128 -> 256, max-pool) in one kernel, activations chained through TMEM
+      const Layer& L0 = p->layers[0][0];
+      const Layer& L1 = p->layers[0][1];
+      const Layer& L2 = p->layers[0][2];
+      if (!L0.set || !L1.set || !L2.set) {
+        set_error("scorenet: sa_modules.0.mlp.{0,1,2} were never given weights");
+        return REGNET_EINVAL;
+      }
+      unsigned int* counter = (p->cfg.dynamic_tiles && p->gemm_idx < 64) ? p->tile_counters + (p->gemm_idx++) : nullptr;
+      prof_begin(p, "sa0_chain", ms);
+      RN_TRY(sa0_chain_launch(lvl_xyz[0], lvl_st[0], G.new_xyz[0], feat, feat_bs, feat_ld, G.nbr[0], L0.w_f32, L0.kpad,
+                              L0.scale, L0.shift, L1.w_hi, L1.w_lo, L1.kpad, L1.scale, L1.shift, L2.w_hi, L2.w_lo, L2.kpad,
+                              L2.scale, L2.shift, B, M[0], p->sa_out[0], SA_CH[0][2], nullptr, counter,
+                              p->cfg.sa0_variant, ms));
+      prof_end(p, ms);
+      ++p->launches;
+      feat = p->sa_out[i];
+      feat_c = feat_ld = SA_CH[i][2];
+      feat_bs = (int64_t)M[i] * feat_c;
+      continue;
+    }
     if (i == 0 && p->cfg.fuse_sa0 >= 2 && p->cfg.engine == REGNET_ENGINE_TC) {
       // level 0: gather + centre + layers 0 and 1 (6 -> 128 -> 128) in one kernel; the first activation stays on chip
       const Layer& L0 = p->layers[0][0];

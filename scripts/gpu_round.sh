@@ -31,6 +31,8 @@ for s in $STAGES; do
                  -o gpurun_out/prof_sa0front python scripts/one_forward.py tc serial > gpurun_out/ncu_full_sa0.log 2>&1
               timeout 600 ncu --set full --clock-control none --import-source on -k regex:fps_kernel -s 3 -c 1 \
                  -o gpurun_out/prof_fps python scripts/one_forward.py tc serial > gpurun_out/ncu_full_fps.log 2>&1 ;;
+    sa0chk)   timeout 600 python scripts/sa0_chain_check.py > gpurun_out/sa0_chain_check.log 2>&1 ;;
+    bench3)   REGNET_FUSE_SA0=3 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_chain.log 2>&1 ;;
     alltests) timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/test_all.log 2>&1 ;;
   esac
   echo "    exit $?"
