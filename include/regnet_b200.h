@@ -206,8 +206,9 @@ int regnet_mlp_layer(const float* X, const float* W, const float* scale, const f
  * (pn2_utils/modules.py:44-52,241-245 with the channel plan of pointnet2.py:43).  pc (B,N,6) fp32 [xyz|rgb];
  * new_xyz (B,3,M) planar; nbr (B,M,64) int32; W0 (128,6) in OPERAND order [rgb | xyz - centroid], W1 (128,128),
  * W2 (256,128) row-major fp32; scale/shift = folded BatchNorm; out (B*M,256).  dbg: NULL, or (B*M*64, 256) receiving the
- * raw accumulators of layers 0 and 1 (tests).  variant: 0 (operand-layout experiments otherwise).  Stand-alone and
- * synchronising (tests); the plan calls the kernel with pre-split weights. */
+ * raw accumulators of layers 0 and 1 when variant == 1 (tests), or (148,5,8) int64 wait counters when variant == 2
+ * (scripts/sa0_chain_timing.py); variant 0 = production instance.  Stand-alone and synchronising (tests); the plan
+ * calls the kernel with pre-split weights. */
 int regnet_sa0_chain(const float* pc, const float* new_xyz, const int32_t* nbr, int B, int N, int M, const float* W0,
                      const float* scale0, const float* shift0, const float* W1, const float* scale1,
                      const float* shift1, const float* W2, const float* scale2, const float* shift2, float* out,

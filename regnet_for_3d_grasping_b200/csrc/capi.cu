@@ -174,6 +174,15 @@ int regnet_mlp_layer(const float* X, const float* W, const float* scale, const f
   const int kpad = round_up(cin, 16);
   Epilogue ep;
   ep.scale = scale; ep.shift = shift; ep.act = act; ep.pool = pool;
+  // pooled epilogues need scale >= 0: negate the weight rows whose scale is negative (same products, see internal.cuh)
+  float* abs_scale = nullptr;
+  const float* row_sign = (pool && scale) ? scale : nullptr;
+  if (row_sign) {
+    RN_CUDA(cudaMalloc(&abs_scale, sizeof(float) * cout));
+    int rc0 = abs_copy_launch(scale, abs_scale, cout, stream);
+    if (rc0) { cudaFree(abs_scale); return rc0; }
+    ep.scale = abs_scale;
+  }
   const int ldo = round_up(cout, 4);
   float* ytmp = nullptr;  // padded output when cout % 4 != 0
   const int64_t out_rows = pool ? P / pool : P;
@@ -188,7 +197,7 @@ int regnet_mlp_layer(const float* X, const float* W, const float* scale, const f
     float* Xp = (float*)scratch;
     float* Wp = Xp + (size_t)P * kpad;
     rc = split_rows_launch(X, P, cin, cin, kpad, nullptr, nullptr, Xp, stream);
-    if (!rc) rc = split_rows_launch(W, cout, cin, cin, kpad, nullptr, nullptr, Wp, stream);
+    if (!rc) rc = split_rows_launch(W, cout, cin, cin, kpad, nullptr, nullptr, Wp, stream, 0, row_sign);
     if (!rc) rc = gemm_simt_launch(Xp, kpad, Wp, kpad, P, kpad, cout, ep, stream);
   } else {
     const size_t bytes = 2 * sizeof(__nv_bfloat16) * ((size_t)P + cout) * kpad;
@@ -198,7 +207,7 @@ int regnet_mlp_layer(const float* X, const float* W, const float* scale, const f
     __nv_bfloat16* Wh = Xl + (size_t)P * kpad;
     __nv_bfloat16* Wl = Wh + (size_t)cout * kpad;
     rc = split_rows_launch(X, P, cin, cin, kpad, Xh, Xl, nullptr, stream);
-    if (!rc) rc = split_rows_launch(W, cout, cin, cin, kpad, Wh, Wl, nullptr, stream);
+    if (!rc) rc = split_rows_launch(W, cout, cin, cin, kpad, Wh, Wl, nullptr, stream, 0, row_sign);
     if (!rc) rc = gemm_tc_launch(Xh, Xl, kpad, Wh, Wl, kpad, P, cin, cout, ep, stream);
   }
   if (!rc && ytmp) {
@@ -210,6 +219,7 @@ int regnet_mlp_layer(const float* X, const float* W, const float* scale, const f
   if (!rc && e != cudaSuccess) rc = cuda_fail(e, "mlp_layer kernels");
   if (scratch) cudaFree(scratch);
   if (ytmp) cudaFree(ytmp);
+  if (abs_scale) cudaFree(abs_scale);
   return rc;
 }
 
@@ -223,16 +233,18 @@ int regnet_sa0_chain(const float* pc, const float* new_xyz, const int32_t* nbr, 
   RN_CHECK_ARG(gemm_tc_supported(), "sa0_chain: tensor maps are not available from this driver");
   void* scratch = nullptr;
   const size_t nw = (size_t)(128 + 256) * 128;
-  RN_CUDA(cudaMalloc(&scratch, 2 * sizeof(__nv_bfloat16) * nw));
+  RN_CUDA(cudaMalloc(&scratch, 2 * sizeof(__nv_bfloat16) * nw + sizeof(float) * 256));
+  float* abs2 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 2 * sizeof(__nv_bfloat16) * nw);
   __nv_bfloat16* w1h = (__nv_bfloat16*)scratch;
   __nv_bfloat16* w1l = w1h + 128 * 128;
   __nv_bfloat16* w2h = w1l + 128 * 128;
   __nv_bfloat16* w2l = w2h + 256 * 128;
   int rc = split_rows_launch(W1, 128, 128, 128, 128, w1h, w1l, nullptr, stream);
-  if (!rc) rc = split_rows_launch(W2, 256, 128, 128, 128, w2h, w2l, nullptr, stream);
+  if (!rc) rc = split_rows_launch(W2, 256, 128, 128, 128, w2h, w2l, nullptr, stream, 0, scale2);   // pooled layer: scale >= 0
+  if (!rc) rc = abs_copy_launch(scale2, abs2, 256, stream);
   if (!rc)
     rc = sa0_chain_launch(pc, Strides3{(int64_t)N * 6, 1, 6}, new_xyz, pc + 3, (int64_t)N * 6, 6, nbr, W0, 6, scale0,
-                          shift0, w1h, w1l, 128, scale1, shift1, w2h, w2l, 128, scale2, shift2, B, M, out, 256, dbg,
+                          shift0, w1h, w1l, 128, scale1, shift1, w2h, w2l, 128, abs2, shift2, B, M, out, 256, dbg,
                           nullptr, variant, stream);
   cudaError_t e = cudaStreamSynchronize(stream);
   if (!rc && e != cudaSuccess) rc = cuda_fail(e, "sa0_chain kernel");

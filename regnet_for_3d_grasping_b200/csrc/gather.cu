@@ -279,12 +279,14 @@ fp_operand_kernel(const float* __restrict__ sparse, int64_t sparse_bstride, int 
 // fp32 rows -> bf16 hi/lo planes (used for weights and by regnet_mlp_layer)
 __global__ void __launch_bounds__(THREADS)
 split_rows_kernel(const float* __restrict__ src, int64_t rows, int cols, int ld_src, int kpad, int rot,
-                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ f32) {
+                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, float* __restrict__ f32,
+                  const float* __restrict__ row_sign) {
   const int64_t total = rows * kpad;
   for (int64_t e = blockIdx.x * (int64_t)THREADS + threadIdx.x; e < total; e += (int64_t)gridDim.x * THREADS) {
     const int col = (int)(e % kpad);
     const int64_t r = e / kpad;
-    const float x = col < cols ? src[r * ld_src + (col + rot) % cols] : 0.f;   // dst col c <- src col (c+rot) mod cols
+    float x = col < cols ? src[r * ld_src + (col + rot) % cols] : 0.f;   // dst col c <- src col (c+rot) mod cols
+    if (row_sign && row_sign[r] < 0.f) x = -x;   // rows whose BN scale is negative are negated (the scale's sign too)
     if (f32) f32[e] = x;
     if (hi) {
       __nv_bfloat16 h, l;
@@ -404,11 +406,25 @@ int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld
 }
 
 int split_rows_launch(const float* src, int64_t rows, int cols, int ld_src, int kpad, __nv_bfloat16* hi,
-                      __nv_bfloat16* lo, float* f32, cudaStream_t stream, int rot) {
+                      __nv_bfloat16* lo, float* f32, cudaStream_t stream, int rot, const float* row_sign) {
   const int64_t total = rows * kpad;
   if (total == 0) return REGNET_OK;
-  split_rows_kernel<<<grid_for(total), THREADS, 0, stream>>>(src, rows, cols, ld_src, kpad, rot, hi, lo, f32);
+  split_rows_kernel<<<grid_for(total), THREADS, 0, stream>>>(src, rows, cols, ld_src, kpad, rot, hi, lo, f32, row_sign);
   RN_LAUNCH_CHECK("split_rows_kernel");
+  return REGNET_OK;
+}
+
+namespace {
+__global__ void abs_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = fabsf(src[i]);
+}
+}  // namespace
+
+int abs_copy_launch(const float* src, float* dst, int n, cudaStream_t stream) {
+  if (n <= 0) return REGNET_OK;
+  abs_copy_kernel<<<(n + 255) / 256, 256, 0, stream>>>(src, dst, n);
+  RN_LAUNCH_CHECK("abs_copy_kernel");
   return REGNET_OK;
 }
 

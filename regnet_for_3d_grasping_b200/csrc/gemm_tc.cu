@@ -221,14 +221,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
       tc_fence_after();
       const int64_t row = row0 + q * 32 + lane;
       const bool row_ok = row < P;
+      if (POOL) {
+        // 64-row max-pool.  The BN scale of a pooled layer is made non-negative when the weights are uploaded
+        // (split_rows_launch row_sign), and every activation is non-decreasing, so act(scale * max(acc) + shift) ==
+        // max(act(scale * acc + shift)): the max is taken on the RAW accumulators (4 rows per thread in registers, then
+        // 3 shuffle levels -- tc_ptx.cuh), the affine map and the activation are applied once per pooled value below.
+        const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, t_hi = t_lo + (16u << 16);
+        const int my_col = colmax_column(lane);
+        uint32_t va[16], vb[16];
+        tmem_ld_16x256b_x4_async(t_lo, va);
+        tmem_ld_16x256b_x4_async(t_hi, vb);
+        tmem_ld_wait();
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          float m[8];
+          colmax_rows4(va, vb, m);                       // 4 rows per thread, in registers
+          if (ch + 1 < BN / 32) {                        // next chunk's loads fly during the shuffles
+            tmem_ld_16x256b_x4_async(t_lo + (ch + 1) * 32, va);
+            tmem_ld_16x256b_x4_async(t_hi + (ch + 1) * 32, vb);
+          }
+          s_part[q * BN + ch * 32 + my_col] = __float_as_uint(colmax_lanes8(m, lane));
+          if (ch + 1 < BN / 32) tmem_ld_wait();
+        }
+      }
+#pragma unroll 1
+      for (int ch = 0; !POOL && ch < BN / 32; ++ch) {
         // 32 channels per trip, as two 16-column TMEM loads: keeps the epilogue at ~80 registers so that the
         // register-resident FPS kernel of the next step fits on the same SM (profiles/README.md)
         const int c0 = col0 + ch * 32;
         const uint32_t st_hi = smem_base + C::OFF_STAGE + (warp - 2) * 4096, st_lo = st_hi + 2048;
         const bool stage_out = !POOL && ep.out_hi && c0 < cout;
-        uint32_t mine = 0;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t v[16];
@@ -243,13 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
             y[4 * j4 + 2] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z));
             y[4 * j4 + 3] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w));
           }
-          if (POOL) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t m = __reduce_max_sync(FULL, order_bits(y[j]));
-              if (lane == half * 16 + j) mine = m;
-            }
-          } else {
+          {
             if (stage_out) {
               // bf16 hi/lo planes: stage this warp's [32 rows x 32 ch] block in shared memory (64B-swizzled rows,
               // conflict-free STS.128) and let TMA write full lines; rows >= P / channels >= cout are clipped by TMA
@@ -298,7 +314,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
             }
           }
         }
-        if (POOL) s_part[q * BN + ch * 32 + lane] = mine;
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
@@ -309,8 +324,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
           const int g = e / BN, c = e - g * BN;
           const int64_t grow = row0 / 64 + g;
           if (grow * 64 < P && col0 + c < cout) {
-            const uint32_t m = max(s_part[(2 * g) * BN + c], s_part[(2 * g + 1) * BN + c]);
-            ep.out_f32[grow * ep.ld_f32 + col0 + c] = unorder_bits(m);
+            const float m = fmaxf(__uint_as_float(s_part[(2 * g) * BN + c]), __uint_as_float(s_part[(2 * g + 1) * BN + c]));
+            ep.out_f32[grow * ep.ld_f32 + col0 + c] = act_fn<ACT>(fmaf(m, s_scale[c], s_shift[c]));
           }
         }
       }

@@ -45,9 +45,12 @@ int sa0_chain_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
 int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld, int C2, const float* dense,
                       int64_t dense_bstride, int dense_ld, int C1, const int32_t* idx, const float* w, int B, int Nd,
                       int kpad, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);
-// dst[:, c] = src[:, (c + rot) mod cols] for c < cols, zero padding up to kpad
+// dst[:, c] = src[:, (c + rot) mod cols] for c < cols, zero padding up to kpad.  row_sign (optional, one per row):
+// rows with row_sign[r] < 0 are negated -- used with abs_copy_launch to make the BN scale of a max-pooled layer
+// non-negative (scale * (w . x) == |scale| * ((sign(scale) w) . x)), so that the max can be taken on raw accumulators
 int split_rows_launch(const float* src, int64_t rows, int cols, int ld_src, int kpad, __nv_bfloat16* hi,
-                      __nv_bfloat16* lo, float* f32, cudaStream_t stream, int rot = 0);
+                      __nv_bfloat16* lo, float* f32, cudaStream_t stream, int rot = 0, const float* row_sign = nullptr);
+int abs_copy_launch(const float* src, float* dst, int n, cudaStream_t stream);
 int score_head_launch(const float* X, int ldx, const float* w, const float* scale, const float* shift, int64_t P,
                       int cin, float* score, cudaStream_t stream);
 

@@ -18,13 +18,14 @@
 // TMEM map (512 columns, all of it):  X = [0,128)  acc0 -> A1     Y = [128,256)  acc1 -> A2     Z = [256,512)  acc2
 //
 // Warp roles (448 threads, one CTA per SM, tiles of 128 positions = 2 centroids drawn from a global counter):
-//   warp 0       scheduler + one-time TMA load of W1 / W2
+//   warp 0       scheduler + producer: draws the tile, gathers its 128 rows (neighbour index -> rgb, xyz - centroid) as
+//                bf16 hi/lo into the A0 stage, up to two tiles ahead; one-time TMA load of W1 / W2
 //   warp 1       MMA issuer (one lane); issue order L1(i), L0(i+1), L2(i) keeps the tensor pipe busy while the
 //                converters work on the other region; hazards on X / Y are ordered by the pipe itself
-//   warps 2..5   converters: acc0 -> A1, acc1 -> A2, in four 32-channel chunks, each chunk released to the MMA lane
-//                as soon as it is written (the next layer starts after a quarter of the conversion)
+//   warps 2..5   converters acc0 -> A1, warps 10..13 converters acc1 -> A2: four 32-channel chunks, each released to the
+//                MMA lane as soon as it is written (the next layer starts after a quarter of the conversion); TMEM
+//                loads are software pipelined (load of k-step ks+1 in flight while ks is converted)
 //   warps 6..9   pool epilogue: acc2 -> BN + ReLU -> max over the 64 rows of each centroid -> (B*M, 256) fp32
-//   warps 10..13 producers: neighbour index -> rgb, xyz - centroid -> bf16 hi/lo rows of A0 (prefetched one tile ahead)
 #include <cuda.h>
 
 #include "gemm.cuh"
@@ -56,20 +57,19 @@ constexpr int NTHREADS = 448;
 constexpr uint32_t TM_X = 0, TM_Y = 128, TM_Z = 256;
 static_assert(SMEM_BYTES <= 232448, "sa0_chain: shared memory budget");
 
-// K-major operand with 32-byte rows (K = 16 bf16).  variant bit 0 = 0: SWIZZLE_32B canonical layout
-// ((8,n),2):((2,SBO),1) in 16-byte units, 16-byte chunk index XOR bit 2 of the row; = 1: no swizzle ("interleave"),
-// core matrices of 8 rows x 16 bytes, the two K chunks LBO = 128 bytes apart, 8-row groups SBO = 256 bytes apart.
-__device__ __forceinline__ uint32_t k16_offset(uint32_t row, uint32_t chunk, int noswz) {
-  if (noswz) return (row >> 3) * 256u + chunk * 128u + (row & 7u) * 16u;
+// K-major operand with 32-byte rows (K = 16 bf16): the canonical SWIZZLE_32B layout ((8,n),2):((2,SBO),1) in 16-byte
+// units -- row r at r * 32 bytes, 16-byte chunk index XOR bit 2 of the row, 8-row groups SBO = 256 bytes apart.
+// (The un-swizzled "interleave" layout with LBO = 128 B was verified to work as well during bring-up.)
+__device__ __forceinline__ uint32_t k16_offset(uint32_t row, uint32_t chunk) {
   return row * 32u + ((chunk ^ ((row >> 2) & 1u)) << 4);
 }
-__device__ __forceinline__ uint64_t make_sdesc_k16(uint32_t smem_addr, int noswz) {
+__device__ __forceinline__ uint64_t make_sdesc_k16(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)(noswz ? (128 >> 4) : 1) << 16;   // LBO
-  d |= (uint64_t)(256 >> 4) << 32;                 // SBO
+  d |= (uint64_t)1 << 16;             // LBO (unused: one swizzle span per row)
+  d |= (uint64_t)(256 >> 4) << 32;    // SBO
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(noswz ? 0 : 6) << 61;            // SWIZZLE_NONE / SWIZZLE_32B
+  d |= (uint64_t)6 << 61;             // SWIZZLE_32B
   return d;
 }
 
@@ -92,16 +92,34 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// two fp32 -> one packed bf16x2 hi word + one lo word (same rounding as split_bf16: hi = rn(x), lo = rn(x - hi))
-__device__ __forceinline__ void split_pair(float y0, float y1, uint32_t& hi, uint32_t& lo, int swap) {
-  if (swap) { const float t = y0; y0 = y1; y1 = t; }
+// two fp32 -> one packed bf16x2 hi word + one lo word (same rounding as split_bf16: hi = rn(x), lo = rn(x - hi));
+// the even element sits in the low half of the word = the lower k index of the TMEM / shared-memory operand
+__device__ __forceinline__ void split_pair(float y0, float y1, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);   // .x (low half) = y0
   hi = *reinterpret_cast<const uint32_t*>(&h);
   const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
   const __nv_bfloat162 l = __floats2bfloat162_rn(__fsub_rn(y0, h0), __fsub_rn(y1, h1));
   lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// ReLU folded into the conversions: hi = bf16_rz(max(y, 0)) -- rounding toward zero keeps y - hi >= 0 for y >= 0, so the
+// second relu-conversion lo = bf16_rn(max(y - hi, 0)) is exact for y >= 0 and gives hi = lo = 0 for y < 0.  No FMNMX;
+// hi + lo still carries 16 significant bits (residual <= 2^-17 |y|).
+__device__ __forceinline__ void relu_split_pair(float y0, float y1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y1), "f"(y0));   // d = {hi half: a, lo half: b}
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(__fsub_rn(y1, h1)), "f"(__fsub_rn(y0, h0)));
 }
 
 struct Sa0ChainArgs {
@@ -112,18 +130,23 @@ struct Sa0ChainArgs {
   const float* W0; int ldw0;                       // (128, >= 6) fp32, operand order [feature(3) | xyz_rel(3)]
   const float* scale0; const float* shift0;
   const float* scale1; const float* shift1;
-  const float* scale2; const float* shift2;
+  const float* scale2; const float* shift2;        // scale2 must be >= 0 (see the pool epilogue)
   float* out; int ld_out;                          // (rows / 64, 256)
-  float* dbg;                                      // optional (rows, 256): raw acc0 | raw acc1
+  float* dbg;                                      // MODE 1: (rows, 256): raw acc0 | raw acc1
   uint32_t M, rows;
   unsigned int* tile_counter;
   int variant;
+  unsigned long long* timing;                      // TIMING kernels: (grid, 5 roles, 8 counters)
 };
 
-__global__ void __maxnreg__(64)
+// MODE 0: production.  1: also dumps the raw accumulators of layers 0 and 1 to a.dbg (tests).  2: per-role wait
+// counters (clock64 around every mbarrier wait) to a.timing (scripts/sa0_chain_timing.py).
+template <int MODE>
+__global__ void __maxnreg__(72)   // 448 x 72 registers leave room for the co-resident FPS CTA of the next step (4 warps x 227)
 sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_constant__ CUtensorMap map_w1lo,
                  const __grid_constant__ CUtensorMap map_w2hi, const __grid_constant__ CUtensorMap map_w2lo,
                  const Sa0ChainArgs a) {
+  constexpr bool TIMING = MODE == 2;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const uint32_t sb = smem_u32(smem);
@@ -146,12 +169,11 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_tiles = (a.rows + BM - 1) / BM;
-  const int noswz = a.variant & 1, swap = (a.variant >> 1) & 1;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_a0full + 8 * s, 128);
+      mbar_init(bar_a0full + 8 * s, 32);
       mbar_init(bar_a0empty + 8 * s, 1);
     }
     mbar_init(bar_acc0, 1);
@@ -180,8 +202,8 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
     uint32_t hi[3], lo[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      split_pair(a.W0[c * a.ldw0 + 2 * j], a.W0[c * a.ldw0 + 2 * j + 1], hi[j], lo[j], 0);
-    const uint32_t off = k16_offset((uint32_t)c, 0, noswz);
+      split_pair(a.W0[c * a.ldw0 + 2 * j], a.W0[c * a.ldw0 + 2 * j + 1], hi[j], lo[j]);
+    const uint32_t off = k16_offset((uint32_t)c, 0);
     *reinterpret_cast<uint4*>(smem + OFF_W0 + off) = make_uint4(hi[0], hi[1], hi[2], 0u);
     *reinterpret_cast<uint4*>(smem + OFF_W0 + A0_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], 0u);
     s_sc[c] = a.scale0[c];
@@ -200,14 +222,34 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
+  unsigned long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_begin = TIMING ? clock64() : 0;
+  auto wait_t = [&](uint32_t bar, uint32_t parity, int k) {   // mbar_wait, accounted to counter k when TIMING
+    if (TIMING) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      tw[k] += (unsigned long long)(clock64() - t0);
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
+  auto flush_t = [&](int role) {
+    if (TIMING && lane == 0 && a.timing) {
+      tw[7] = (unsigned long long)(clock64() - t_begin);
+      for (int k = 0; k < 8; ++k) a.timing[((size_t)blockIdx.x * 5 + role) * 8 + k] = tw[k];
+    }
+  };
   auto take_tile = [&](uint32_t it) -> int {
     const uint32_t slot = it & 3;
-    mbar_wait(bar_sfull + 8 * slot, (it >> 2) & 1);
+    wait_t(bar_sfull + 8 * slot, (it >> 2) & 1, 0);
     return ring[slot];
   };
 
   if (warp == 0) {
-    // ================= scheduler + one-time weight load =================
+    // ================= scheduler + A0 producer + one-time weight load =================
+    // lane 0 draws the tile and publishes it; then the whole warp gathers the tile's 128 rows (4 per lane: neighbour
+    // index -> rgb, xyz - centroid), splits them to bf16 hi/lo and writes the A0 stage.  The ring lets this warp run
+    // up to 4 tiles ahead of the slowest consumer, the two A0 stages up to 2 tiles ahead of layer 0.
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, 4 * W1_PLANE + 4 * W2_PLANE);
       for (int kb = 0; kb < 2; ++kb) {
@@ -216,27 +258,70 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
         tma_load_2d(sb + OFF_W2 + kb * 2 * W2_PLANE, &map_w2hi, bar_w, kb * BK, 0);
         tma_load_2d(sb + OFF_W2 + kb * 2 * W2_PLANE + W2_PLANE, &map_w2lo, bar_w, kb * BK, 0);
       }
-      for (uint32_t it = 0;; ++it) {
+    }
+    for (uint32_t it = 0;; ++it) {
+      uint32_t t = 0;
+      if (lane == 0) {
         const uint32_t slot = it & 3;
-        if (it >= 4) mbar_wait(bar_sempty + 8 * slot, ((it >> 2) - 1) & 1);
-        const uint32_t t = a.tile_counter ? atomicAdd(a.tile_counter, 1u) : blockIdx.x + it * gridDim.x;
+        if (it >= 4) wait_t(bar_sempty + 8 * slot, ((it >> 2) - 1) & 1, 1);
+        t = a.tile_counter ? atomicAdd(a.tile_counter, 1u) : blockIdx.x + it * gridDim.x;
         ring[slot] = t < n_tiles ? (int)t : -1;
         mbar_arrive(bar_sfull + 8 * slot);
-        if (t >= n_tiles) break;
       }
+      t = __shfl_sync(FULL, t, 0);
+      if (t >= n_tiles) break;
+      int jn[4];
+      float c3[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t row = t * BM + u * 32 + lane;
+        const bool ok = row < a.rows;
+        const uint32_t bm = ok ? row >> 6 : 0;      // 64 neighbours per centroid
+        const uint32_t b = bm / a.M, m = bm - b * a.M;
+        jn[u] = ok ? a.nbr[row] : -1;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) c3[u][x] = a.new_xyz[((int64_t)b * 3 + x) * a.M + m];
+      }
+      float v[4][6];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t row = t * BM + u * 32 + lane;
+        const uint32_t b = (row >> 6) / a.M;
+        const int j = jn[u];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[u][c] = j >= 0 ? a.feat[(int64_t)b * a.feat_bstride + (int64_t)j * a.feat_ld + c] : 0.f;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) v[u][3 + x] = j >= 0 ? a.xyz[(int64_t)b * a.xst.b + x * a.xst.c + (int64_t)j * a.xst.n] : 0.f;
+      }
+      const uint32_t s = it & 1, ph = (it >> 1) & 1;
+      wait_t(bar_a0empty + 8 * s, ph ^ 1, 2);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t hi[3], lo[3];
+        const bool ok = jn[u] >= 0;
+        split_pair(v[u][0], v[u][1], hi[0], lo[0]);
+        split_pair(v[u][2], ok ? __fsub_rn(v[u][3], c3[u][0]) : 0.f, hi[1], lo[1]);
+        split_pair(ok ? __fsub_rn(v[u][4], c3[u][1]) : 0.f, ok ? __fsub_rn(v[u][5], c3[u][2]) : 0.f, hi[2], lo[2]);
+        const uint32_t a0 = sb + OFF_A0 + s * 2 * A0_PLANE + k16_offset((uint32_t)(u * 32 + lane), 0);
+        sts_v4(a0, hi[0], hi[1], hi[2], 0u);
+        sts_v4(a0 + A0_PLANE, lo[0], lo[1], lo[2], 0u);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_a0full + 8 * s);
     }
+    flush_t(0);
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc1 = make_idesc(BM, C1), idesc2 = make_idesc(BM, C2);
-      const uint64_t w0_hi = make_sdesc_k16(sb + OFF_W0, noswz), w0_lo = make_sdesc_k16(sb + OFF_W0 + A0_PLANE, noswz);
+      const uint64_t w0_hi = make_sdesc_k16(sb + OFF_W0), w0_lo = make_sdesc_k16(sb + OFF_W0 + A0_PLANE);
       auto issue_l0 = [&](uint32_t it) {
         const uint32_t s = it & 1, ph = (it >> 1) & 1;
-        mbar_wait(bar_a0full + 8 * s, ph);
+        wait_t(bar_a0full + 8 * s, ph, 1);
         tc_fence_after();
         const uint32_t a0 = sb + OFF_A0 + s * 2 * A0_PLANE;
-        const uint64_t a_hi = make_sdesc_k16(a0, noswz), a_lo = make_sdesc_k16(a0 + A0_PLANE, noswz);
+        const uint64_t a_hi = make_sdesc_k16(a0), a_lo = make_sdesc_k16(a0 + A0_PLANE);
         umma_f16(tmem_base + TM_X, a_hi, w0_hi, idesc1, 0);
         umma_f16(tmem_base + TM_X, a_lo, w0_hi, idesc1, 1);
         umma_f16(tmem_base + TM_X, a_hi, w0_lo, idesc1, 1);
@@ -263,12 +348,12 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
       mbar_arrive(bar_sempty);
       if (tile >= 0) {
         issue_l0(0);
-        mbar_wait(bar_w, 0);
+        wait_t(bar_w, 0, 2);
       }
       for (uint32_t it = 0; tile >= 0; ++it) {
         const uint32_t ph = it & 1;
         for (int ch = 0; ch < 4; ++ch) {
-          mbar_wait(bar_a1 + 8 * ch, ph);
+          wait_t(bar_a1 + 8 * ch, ph, 3 + (ch ? 1 : 0));
           tc_fence_after();
           issue_chunk(tmem_base + TM_Y, tmem_base + TM_X, sb + OFF_W1, W1_PLANE, idesc1, ch);
         }
@@ -277,161 +362,133 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
         mbar_arrive(bar_sempty + 8 * ((it + 1) & 3));
         if (next >= 0) issue_l0(it + 1);   // overwrites X after L1(it) in pipe order
         if (it > 0) {
-          mbar_wait(bar_z_empty, (it - 1) & 1);
+          wait_t(bar_z_empty, (it - 1) & 1, 6);
           tc_fence_after();
         }
         for (int ch = 0; ch < 4; ++ch) {
-          mbar_wait(bar_a2 + 8 * ch, ph);
+          wait_t(bar_a2 + 8 * ch, ph, 5 - (ch ? 0 : 0) + 0);
           tc_fence_after();
           issue_chunk(tmem_base + TM_Z, tmem_base + TM_Y, sb + OFF_W2, W2_PLANE, idesc2, ch);
         }
         umma_commit(bar_acc2);
         tile = next;
       }
+      flush_t(1);
     }
     __syncwarp();
-  } else if (warp < 6) {
+  } else if (warp < 6 || warp >= 10) {
     // ================= converters: accumulator -> BN + ReLU -> bf16 hi/lo A operand, in place in TMEM =================
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    auto convert = [&](uint32_t region, const float* sc, const float* sh, uint32_t bar_ready, float* dbg_row) {
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+    // warps 2..5 convert acc0 (region X) for layer 1, warps 10..13 convert acc1 (region Y) for layer 2: two groups, so
+    // that the conversion of tile i+1's first layer overlaps the conversion of tile i's second layer.
+    const bool second = warp >= 10;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (second ? TM_Y : TM_X);
+    const float* sc = s_sc + (second ? 256 : 0);
+    const float* sh = sc + 128;
+    const uint32_t bar_done = second ? bar_acc1 : bar_acc0;
+    const uint32_t bar_ready = second ? bar_a2 : bar_a1;
+    for (uint32_t it = 0;; ++it) {
+      const int tile = take_tile(it);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sempty + 8 * (it & 3));
+      if (tile < 0) break;
+      const uint32_t row = (uint32_t)tile * BM + (warp & 3) * 32 + lane;
+      float* dbg_row = (MODE == 1 && a.dbg && row < a.rows) ? a.dbg + (size_t)row * 256 + (second ? 128 : 0) : nullptr;
+      wait_t(bar_done, it & 1, 1);
+      tc_fence_after();
+      // software pipelined: the TMEM load of k-step ks+1 is in flight while k-step ks is converted and stored
+      const long long tc0 = TIMING ? clock64() : 0;
+      uint32_t va[16], vb[16];
+      tmem_ld16_nowait(lane_base, va);
+      tmem_ld_wait();
+      auto convert_step = [&](int ks, uint32_t (&v)[16], uint32_t (&vn)[16], bool last) {
+        if (!last) tmem_ld16_nowait(lane_base + 16 * (ks + 1), vn);
+        if (MODE == 1 && dbg_row) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int ks = 2 * ch + h;
-          uint32_t v[16], o[16];
-          tmem_ld16(lane_base + region + 16 * ks, v);
-          if (dbg_row) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) dbg_row[16 * ks + j] = __uint_as_float(v[j]);
-          }
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(sc + 16 * ks + 4 * j4);
-            const float4 t4 = *reinterpret_cast<const float4*>(sh + 16 * ks + 4 * j4);
-            const float y0 = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 0]), s4.x, t4.x), 0.f);
-            const float y1 = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 1]), s4.y, t4.y), 0.f);
-            const float y2 = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 2]), s4.z, t4.z), 0.f);
-            const float y3 = fmaxf(fmaf(__uint_as_float(v[4 * j4 + 3]), s4.w, t4.w), 0.f);
-            split_pair(y0, y1, o[2 * j4], o[8 + 2 * j4], swap);
-            split_pair(y2, y3, o[2 * j4 + 1], o[8 + 2 * j4 + 1], swap);
-          }
-          tmem_st16(lane_base + region + 16 * ks, o);
+          for (int j = 0; j < 16; ++j) dbg_row[16 * ks + j] = __uint_as_float(v[j]);
         }
-        tmem_st_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sc + 16 * ks + 4 * j4);
+          const float4 t4 = *reinterpret_cast<const float4*>(sh + 16 * ks + 4 * j4);
+          const float y0 = fmaf(__uint_as_float(v[4 * j4 + 0]), s4.x, t4.x);
+          const float y1 = fmaf(__uint_as_float(v[4 * j4 + 1]), s4.y, t4.y);
+          const float y2 = fmaf(__uint_as_float(v[4 * j4 + 2]), s4.z, t4.z);
+          const float y3 = fmaf(__uint_as_float(v[4 * j4 + 3]), s4.w, t4.w);
+          relu_split_pair(y0, y1, o[2 * j4], o[8 + 2 * j4]);
+          relu_split_pair(y2, y3, o[2 * j4 + 1], o[8 + 2 * j4 + 1]);
+        }
+        tmem_st16(lane_base + 16 * ks, o);
+      };
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {      // one 32-channel chunk = two k-steps; the loop body stays small (I-cache)
+        convert_step(2 * ch, va, vb, false);
+        tmem_ld_wait();
+        convert_step(2 * ch + 1, vb, va, ch == 3);
+        tmem_st_wait();                     // the chunk is complete: hand it to the MMA lane
         tc_fence_before();
         mbar_arrive(bar_ready + 8 * ch);
+        if (ch < 3) tmem_ld_wait();
       }
-    };
-    for (uint32_t it = 0;; ++it) {
-      const int tile = take_tile(it);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sempty + 8 * (it & 3));
-      if (tile < 0) break;
-      const uint32_t ph = it & 1;
-      const uint32_t row = (uint32_t)tile * BM + (warp & 3) * 32 + lane;
-      float* dbg_row = (a.dbg && row < a.rows) ? a.dbg + (size_t)row * 256 : nullptr;
-      mbar_wait(bar_acc0, ph);
-      tc_fence_after();
-      convert(TM_X, s_sc, s_sc + 128, bar_a1, dbg_row);
-      mbar_wait(bar_acc1, ph);
-      tc_fence_after();
-      convert(TM_Y, s_sc + 256, s_sc + 384, bar_a2, dbg_row ? dbg_row + 128 : nullptr);
+      if (TIMING) tw[2] += (unsigned long long)(clock64() - tc0);
     }
-  } else if (warp < 10) {
-    // ================= pool epilogue: acc2 -> BN + ReLU -> max over each centroid's 64 rows =================
+    if ((warp & 3) == 0) flush_t(second ? 3 : 2);
+  } else {
+    // ================= warps 6..9: pool epilogue: acc2 -> BN + ReLU -> max over each centroid's 64 rows =================
     const int q = warp & 3;
-    const int et = threadIdx.x - 6 * 32;   // 0..127
+    const uint32_t r = threadIdx.x - 6 * 32;   // 0..127
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + TM_Z;
     for (uint32_t it = 0;; ++it) {
-      const int tile = take_tile(it);
+      const int cur = take_tile(it);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_sempty + 8 * (it & 3));
-      if (tile < 0) break;
-      mbar_wait(bar_acc2, it & 1);
+      if (cur < 0) break;
+      wait_t(bar_acc2, it & 1, 1);
       tc_fence_after();
+      // scale2 >= 0 (the launcher's contract: rows of W2 with a negative BN scale are negated when the weights are
+      // prepared), so relu(scale * max(acc) + shift) == max(relu(scale * acc + shift)): the max is taken on the raw
+      // accumulators -- 4 rows per thread in registers (16x256b TMEM loads), then 3 shuffle levels (tc_ptx.cuh) -- and
+      // the affine map + ReLU are applied once per pooled value in the combine below
+      const uint32_t t_hi = lane_base + (16u << 16);
+      const int my_col = colmax_column(lane);
+      const long long tp0 = TIMING ? clock64() : 0;
+      uint32_t va[16], vb[16];
+      tmem_ld_16x256b_x4_async(lane_base, va);
+      tmem_ld_16x256b_x4_async(t_hi, vb);
+      tmem_ld_wait();
 #pragma unroll 1
       for (int ch = 0; ch < C2 / 32; ++ch) {
-        uint32_t mine = 0;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[16];
-          tmem_ld16(lane_base + ch * 32 + half * 16, v);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(s_sc2 + ch * 32 + half * 16 + 4 * j4);
-            const float4 t4 = *reinterpret_cast<const float4*>(s_sc2 + 256 + ch * 32 + half * 16 + 4 * j4);
-            const float y[4] = {fmaf(__uint_as_float(v[4 * j4 + 0]), s4.x, t4.x), fmaf(__uint_as_float(v[4 * j4 + 1]), s4.y, t4.y),
-                                fmaf(__uint_as_float(v[4 * j4 + 2]), s4.z, t4.z), fmaf(__uint_as_float(v[4 * j4 + 3]), s4.w, t4.w)};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              // ReLU and the float order in one integer max: negative floats are negative ints, and non-negative
-              // floats order like their bit patterns
-              const int yi = max(__float_as_int(y[j]), 0);
-              const int m = __reduce_max_sync(FULL, yi);
-              if (lane == half * 16 + 4 * j4 + j) mine = (uint32_t)m;
-            }
-          }
+        float m[8];
+        colmax_rows4(va, vb, m);
+        if (ch + 1 < C2 / 32) {                          // next chunk's loads fly during the shuffles
+          tmem_ld_16x256b_x4_async(lane_base + (ch + 1) * 32, va);
+          tmem_ld_16x256b_x4_async(t_hi + (ch + 1) * 32, vb);
         }
-        s_part[q * C2 + ch * 32 + lane] = mine;
+        s_part[q * C2 + ch * 32 + my_col] = __float_as_uint(colmax_lanes8(m, lane));
+        if (ch + 1 < C2 / 32) tmem_ld_wait();
       }
+      const long long tp1 = TIMING ? clock64() : 0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_z_empty);
       asm volatile("bar.sync 2, 128;" ::: "memory");
-      for (int e = et; e < 2 * C2; e += 128) {
+      const long long tp2 = TIMING ? clock64() : 0;
+      for (int e = (int)r; e < 2 * C2; e += 128) {
         const int g = e / C2, c = e - g * C2;
-        const uint32_t grow = (uint32_t)tile * 2 + g;
+        const uint32_t grow = (uint32_t)cur * 2 + g;
         if (grow * 64u < a.rows) {
-          const uint32_t m = max(s_part[(2 * g) * C2 + c], s_part[(2 * g + 1) * C2 + c]);
-          a.out[(size_t)grow * a.ld_out + c] = __uint_as_float(m);
+          const float m = fmaxf(__uint_as_float(s_part[(2 * g) * C2 + c]), __uint_as_float(s_part[(2 * g + 1) * C2 + c]));
+          a.out[(size_t)grow * a.ld_out + c] = fmaxf(fmaf(m, s_sc2[c], s_sc2[256 + c]), 0.f);
         }
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");
-    }
-  } else {
-    // ================= producers: gather the 6 input channels of a row, bf16 hi/lo, into the A0 stage =================
-    const uint32_t r = threadIdx.x - 10 * 32;   // row of the tile
-    auto gather = [&](int tile, float (&v)[6]) {
-      const uint32_t row = (uint32_t)tile * BM + r;
-      if (row < a.rows) {
-        const uint32_t bm = row >> 6;         // 64 neighbours per centroid
-        const uint32_t b = bm / a.M, m = bm - b * a.M;
-        const int j = a.nbr[row];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = a.feat[(int64_t)b * a.feat_bstride + (int64_t)j * a.feat_ld + c];
-#pragma unroll
-        for (int x = 0; x < 3; ++x)
-          v[3 + x] = __fsub_rn(a.xyz[(int64_t)b * a.xst.b + x * a.xst.c + (int64_t)j * a.xst.n],
-                               a.new_xyz[((int64_t)b * 3 + x) * a.M + m]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 6; ++c) v[c] = 0.f;
+      if (TIMING) {
+        tw[2] += (unsigned long long)(tp1 - tp0);
+        tw[3] += (unsigned long long)(tp2 - tp1);
+        tw[4] += (unsigned long long)(clock64() - tp2);
       }
-    };
-    const uint32_t off = k16_offset(r, 0, noswz);
-    float vn[6];
-    int tile = take_tile(0);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_sempty);
-    if (tile >= 0) gather(tile, vn);
-    for (uint32_t it = 0; tile >= 0; ++it) {
-      uint32_t hi[3], lo[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) split_pair(vn[2 * j], vn[2 * j + 1], hi[j], lo[j], 0);
-      const int next = take_tile(it + 1);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sempty + 8 * ((it + 1) & 3));
-      if (next >= 0) gather(next, vn);
-      const uint32_t s = it & 1, ph = (it >> 1) & 1;
-      mbar_wait(bar_a0empty + 8 * s, ph ^ 1);
-      const uint32_t a0 = sb + OFF_A0 + s * 2 * A0_PLANE + off;
-      sts_v4(a0, hi[0], hi[1], hi[2], 0u);
-      sts_v4(a0 + A0_PLANE, lo[0], lo[1], lo[2], 0u);
-      fence_proxy_async();
-      mbar_arrive(bar_a0full + 8 * s);
-      tile = next;
     }
+    if (q == 0) flush_t(4);
   }
 
   tc_fence_before();
@@ -461,7 +518,6 @@ int sa0_chain_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
   int dev = 0, sms = 0;
   RN_CUDA(cudaGetDevice(&dev));
   RN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  RN_CUDA(cudaFuncSetAttribute(sa0_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   Sa0ChainArgs a;
   a.xyz = xyz; a.xst = xst; a.new_xyz = new_xyz; a.feat = feat; a.feat_bstride = feat_bstride; a.feat_ld = feat_ld;
   a.nbr = nbr; a.W0 = W0; a.ldw0 = ldw0; a.scale0 = scale0; a.shift0 = shift0; a.scale1 = scale1; a.shift1 = shift1;
@@ -469,7 +525,22 @@ int sa0_chain_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
   a.rows = (uint32_t)rows64; a.tile_counter = tile_counter; a.variant = variant;
   const int64_t n_tiles = (rows64 + BM - 1) / BM;
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  sa0_chain_kernel<<<grid, NTHREADS, SMEM_BYTES, stream>>>(m1h, m1l, m2h, m2l, a);
+  // variant: 0 production; 1 = dbg receives the raw accumulators of layers 0 / 1, (rows, 256) fp32; 2 = dbg receives the
+  // per-role wait counters, (grid, 5 roles, 8) u64
+  a.timing = nullptr;
+  if (variant == 2 && dbg) {
+    a.timing = reinterpret_cast<unsigned long long*>(dbg);
+    a.dbg = nullptr;
+    RN_CUDA(cudaFuncSetAttribute(sa0_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    sa0_chain_kernel<2><<<grid, NTHREADS, SMEM_BYTES, stream>>>(m1h, m1l, m2h, m2l, a);
+  } else if (variant == 1 && dbg) {
+    RN_CUDA(cudaFuncSetAttribute(sa0_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    sa0_chain_kernel<1><<<grid, NTHREADS, SMEM_BYTES, stream>>>(m1h, m1l, m2h, m2l, a);
+  } else {
+    a.dbg = nullptr;
+    RN_CUDA(cudaFuncSetAttribute(sa0_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    sa0_chain_kernel<0><<<grid, NTHREADS, SMEM_BYTES, stream>>>(m1h, m1l, m2h, m2l, a);
+  }
   RN_LAUNCH_CHECK("sa0_chain_kernel");
   return REGNET_OK;
 }

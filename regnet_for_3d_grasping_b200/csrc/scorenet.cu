@@ -319,8 +319,12 @@ int regnet_scorenet_set_layer(regnet_scorenet* p, int stage, int layer, int cin,
   }
   // SA first layers: the operand is [feature | xyz_rel] (gather.cu), the reference's conv weight is [xyz_rel | feature]
   const int rot = (stage < 3 && layer == 0) ? 3 : 0;
-  RN_TRY(split_rows_launch(weight, cout, cin, cin, L.kpad, L.w_hi, L.w_lo, L.w_f32, s, rot));
-  RN_CUDA(cudaMemcpyAsync(L.scale, scale, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
+  // max-pooled layers (last layer of every SA stage): rows with a negative BN scale are negated together with the scale,
+  // scale * (w . x) == |scale| * ((-w) . x); with scale >= 0 the pooled epilogues take the max on raw accumulators
+  const bool pooled = stage < 3 && layer == 2;
+  RN_TRY(split_rows_launch(weight, cout, cin, cin, L.kpad, L.w_hi, L.w_lo, L.w_f32, s, rot, pooled ? scale : nullptr));
+  if (pooled) RN_TRY(abs_copy_launch(scale, L.scale, cout, s));
+  else RN_CUDA(cudaMemcpyAsync(L.scale, scale, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
   RN_CUDA(cudaMemcpyAsync(L.shift, shift, sizeof(float) * cout, cudaMemcpyDeviceToDevice, s));
   L.set = true;
   return REGNET_OK;

@@ -110,6 +110,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same load without the wait: issue, do other work, then tmem_ld_wait() before touching v
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
@@ -129,6 +140,61 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+
+// ---- 64-row max-pool of an accumulator tile -------------------------------------------------------------------
+// tcgen05.ld.16x256b.x4: the warp reads 16 TMEM lanes x 32 columns; thread t receives, for each 8-column group i,
+// v[4i+0..1] = row t/4, columns 8i + 2(t%4) + {0,1} and v[4i+2..3] = row t/4 + 8, same columns (cute
+// SM100_TMEM_LOAD_16dp256b4x: DstLayout ((4,8),(64,2,4)):((64,1024),(1,8192,256)) bits).  Two such loads (lane
+// offsets 0 and 16 of the warp's quarter) give every thread FOUR rows of 8 columns, so two of the five levels of the
+// 32-row max are plain in-thread FMNMX and only three shuffle levels remain (7 SHFL per 32 columns).
+// redux.sync.max is NOT used: measured on B200 it retires one warp instruction per ~30 cycles per scheduler
+// (scripts/ubench/tmem_ld.cu), ~7 700 cycles for a 128 x 256 tile -- more than the tile's MMA time.
+__device__ __forceinline__ void tmem_ld_16x256b_x4_async(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// in-thread part: a = rows t/4, t/4+8 (lanes 0..15 of the quarter), b = rows t/4+16, t/4+24 -> m[2i+e] = max over
+// the four rows of column 8i + 2(t%4) + e
+__device__ __forceinline__ void colmax_rows4(const uint32_t (&a)[16], const uint32_t (&b)[16], float (&m)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      m[2 * i + e] = fmaxf(fmaxf(__uint_as_float(a[4 * i + e]), __uint_as_float(a[4 * i + 2 + e])),
+                           fmaxf(__uint_as_float(b[4 * i + e]), __uint_as_float(b[4 * i + 2 + e])));
+}
+// cross-lane part: butterfly over lane bits 4, 3, 2 (the 8 lanes that hold the same columns), halving the live values
+// at every step.  Lane t ends up with the 32-row maximum of column colmax_column(t) of the 32-column chunk.
+__device__ __forceinline__ float colmax_lanes8(const float (&m)[8], int lane) {
+  float w4[4];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float keep = up ? m[4 + j] : m[j], send = up ? m[j] : m[4 + j];
+      w4[j] = fmaxf(keep, __shfl_xor_sync(FULL, send, 16));
+    }
+  }
+  float w2[2];
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float keep = up ? w4[2 + j] : w4[j], send = up ? w4[j] : w4[2 + j];
+      w2[j] = fmaxf(keep, __shfl_xor_sync(FULL, send, 8));
+    }
+  }
+  const bool up = lane & 4;
+  const float keep = up ? w2[1] : w2[0], send = up ? w2[0] : w2[1];
+  return fmaxf(keep, __shfl_xor_sync(FULL, send, 4));
+}
+// value index kept by lane t: 4 b4 + 2 b3 + b2 = 2i + e  ->  column 8i + 2(t%4) + e = 16 b4 + 8 b3 + 2 (t & 3) + b2
+__device__ __forceinline__ int colmax_column(int lane) { return (lane & 24) + 2 * (lane & 3) + ((lane >> 2) & 1); }
 
 __device__ __forceinline__ uint32_t order_bits(float v) {  // unsigned order == float order
   const uint32_t u = __float_as_uint(v);

@@ -1,9 +1,9 @@
 """Bring-up check of the TMEM-chained SA level-0 kernel (csrc/sa0_chain.cu) against a float64 torch evaluation of the
-same chain, with the raw accumulators of layers 0 and 1 dumped by the kernel.  One subprocess per operand-layout
-variant (a protocol bug traps the context, which must not take the other variants with it).
+same chain, with the raw accumulators of layers 0 and 1 dumped by the kernel's debug instance.  One subprocess per
+instance (a protocol bug traps the context, which must not take the other run with it).
 
-    python scripts/sa0_chain_check.py            # all variants
-    python scripts/sa0_chain_check.py 0          # one variant, in-process
+    python scripts/sa0_chain_check.py            # dump instance (1) and production instance (0), one subprocess each
+    python scripts/sa0_chain_check.py 0          # one instance, in-process
 """
 import ctypes
 import os
@@ -57,9 +57,13 @@ def run(variant, B=2, N=4096, M=1024):
     def err(got, ref):
         return ((got.double() - ref).abs().max() / ref.abs().max()).item()
 
-    e0, e1, e2 = err(dbg[:, :128], acc0), err(dbg[:, 128:], acc1), err(out, want)
-    print(f"variant {variant}: acc0 rel err {e0:.3e}  acc1 rel err {e1:.3e}  pooled out rel err {e2:.3e}", flush=True)
-    return e0, e1, e2
+    e2 = err(out, want)
+    if variant == 1:   # the dump instance: raw accumulators of layers 0 and 1
+        e0, e1 = err(dbg[:, :128], acc0), err(dbg[:, 128:], acc1)
+        print(f"variant {variant}: acc0 rel err {e0:.3e}  acc1 rel err {e1:.3e}  pooled out rel err {e2:.3e}", flush=True)
+    else:
+        print(f"variant {variant}: pooled out rel err {e2:.3e}", flush=True)
+    return e2
 
 
 if __name__ == "__main__":
@@ -67,7 +71,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         run(int(sys.argv[1]))
     else:
-        for v in range(4):
+        for v in (1, 0):
             r = subprocess.run([sys.executable, os.path.abspath(__file__), str(v)], capture_output=True, text=True, timeout=300)
             tail = (r.stdout + r.stderr).strip().splitlines()[-3:]
             print(f"[variant {v}] rc={r.returncode}: " + " | ".join(tail), flush=True)
