@@ -20,12 +20,12 @@
 // Warp roles (448 threads, one CTA per SM, tiles of 128 positions = 2 centroids drawn from a global counter):
 //   warp 0       scheduler + producer: draws the tile, gathers its 128 rows (neighbour index -> rgb, xyz - centroid) as
 //                bf16 hi/lo into the A0 stage, up to two tiles ahead; one-time TMA load of W1 / W2
-//   warp 1       MMA issuer (one lane); issue order L1(i), L0(i+1), L2(i) keeps the tensor pipe busy while the
-//                converters work on the other region; hazards on X / Y are ordered by the pipe itself
-//   warps 2..5   converters acc0 -> A1, warps 10..13 converters acc1 -> A2: four 32-channel chunks, each released to the
-//                MMA lane as soon as it is written (the next layer starts after a quarter of the conversion); TMEM
-//                loads are software pipelined (load of k-step ks+1 in flight while ks is converted)
-//   warps 6..9   pool epilogue: acc2 -> BN + ReLU -> max over the 64 rows of each centroid -> (B*M, 256) fp32
+//   warp 1       MMA issuer (one lane); issue order L1(i), L0(i+1), L2(i): the tensor pipe runs tile i+1's first layer
+//                and tile i's second layer while the workers drain Z of tile i-1; hazards on X / Y are ordered by the
+//                pipe itself
+//   warps 2..13  workers, three per TMEM lane quarter: conversions acc -> A (in 16-channel k-steps, each 32-channel chunk
+//                released to the MMA lane as soon as its two k-steps are written) and the pool epilogue acc2 -> max over
+//                the 64 rows of each centroid -> BN + ReLU -> (B*M, 256) fp32; TMEM loads are software pipelined
 #include <cuda.h>
 
 #include "gemm.cuh"
@@ -92,16 +92,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // two fp32 -> one packed bf16x2 hi word + one lo word (same rounding as split_bf16: hi = rn(x), lo = rn(x - hi));
@@ -120,6 +110,20 @@ __device__ __forceinline__ void relu_split_pair(float y0, float y1, uint32_t& hi
   asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y1), "f"(y0));   // d = {hi half: a, lo half: b}
   const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(__fsub_rn(y1, h1)), "f"(__fsub_rn(y0, h0)));
+}
+
+// Streaming read-only global loads that do not allocate in L1: with 231 KB of shared memory configured the L1 is ~28 KB,
+// and the 128-row gathers of every tile (~250 lines) would evict the few local-memory lines of the register-starved
+// workers (ncu: 29 % L1 hit rate on local loads before).
+__device__ __forceinline__ float ldg_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldg_stream_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 
 struct Sa0ChainArgs {
@@ -142,7 +146,7 @@ struct Sa0ChainArgs {
 // MODE 0: production.  1: also dumps the raw accumulators of layers 0 and 1 to a.dbg (tests).  2: per-role wait
 // counters (clock64 around every mbarrier wait) to a.timing (scripts/sa0_chain_timing.py).
 template <int MODE>
-__global__ void __maxnreg__(72)   // 448 x 72 registers leave room for the co-resident FPS CTA of the next step (4 warps x 227)
+__global__ void __maxnreg__(64)   // 448 x 64 registers leave room for the co-resident FPS CTA of the next step (4 warps x 227)
 sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_constant__ CUtensorMap map_w1lo,
                  const __grid_constant__ CUtensorMap map_w2hi, const __grid_constant__ CUtensorMap map_w2lo,
                  const Sa0ChainArgs a) {
@@ -155,9 +159,9 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
   const uint32_t bar_a0empty = bar_a0full + 16;   // [2] MMA -> producers
   const uint32_t bar_acc0 = bar_a0empty + 16;     // L0 complete -> converters
   const uint32_t bar_acc1 = bar_acc0 + 8;         // L1 complete -> converters
-  const uint32_t bar_acc2 = bar_acc1 + 8;         // L2 complete -> pool warps
-  const uint32_t bar_z_empty = bar_acc2 + 8;      // pool warps -> MMA
-  const uint32_t bar_a1 = bar_z_empty + 8;        // [4] converters -> MMA, per 32-channel chunk of A1
+  const uint32_t bar_acc2 = bar_acc1 + 8;         // L2 complete -> workers (pool)
+  const uint32_t bar_z_empty = bar_acc2 + 8;      // workers -> MMA: Z drained
+  const uint32_t bar_a1 = bar_z_empty + 8;        // [4] workers -> MMA, per 32-channel chunk of A1
   const uint32_t bar_a2 = bar_a1 + 32;            // [4] same for A2
   const uint32_t bar_sfull = bar_a2 + 32;         // [4] scheduler ring
   const uint32_t bar_sempty = bar_sfull + 32;     // [4]
@@ -165,7 +169,6 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
   volatile int* ring = reinterpret_cast<volatile int*>(tmem_holder + 1);
   float* s_sc = reinterpret_cast<float*>(smem + OFF_SC);   // [0,128) scale0 [128,256) shift0 [256,384) scale1 [384,512) shift1
   float* s_sc2 = s_sc + 512;                               // [0,256) scale2 [256,512) shift2
-  uint32_t* s_part = reinterpret_cast<uint32_t*>(smem + OFF_PART);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t n_tiles = (a.rows + BM - 1) / BM;
@@ -179,12 +182,12 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
     mbar_init(bar_acc0, 1);
     mbar_init(bar_acc1, 1);
     mbar_init(bar_acc2, 1);
-    mbar_init(bar_z_empty, 4);
+    mbar_init(bar_z_empty, 12);            // one lane of each worker warp
     for (int c = 0; c < 4; ++c) {
-      mbar_init(bar_a1 + 8 * c, 128);
-      mbar_init(bar_a2 + 8 * c, 128);
+      mbar_init(bar_a1 + 8 * c, 256);      // a chunk = two k-steps, converted by two different worker warps per quarter
+      mbar_init(bar_a2 + 8 * c, 256);
       mbar_init(bar_sfull + 8 * c, 1);
-      mbar_init(bar_sempty + 8 * c, 13);   // MMA lane + one lane of each converter / pool / producer warp
+      mbar_init(bar_sempty + 8 * c, 13);   // MMA lane + one lane of each worker warp
     }
     fence_barrier_init();
     tma_prefetch_desc(&map_w1hi);
@@ -278,9 +281,9 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
         const bool ok = row < a.rows;
         const uint32_t bm = ok ? row >> 6 : 0;      // 64 neighbours per centroid
         const uint32_t b = bm / a.M, m = bm - b * a.M;
-        jn[u] = ok ? a.nbr[row] : -1;
+        jn[u] = ok ? ldg_stream_s32(a.nbr + row) : -1;
 #pragma unroll
-        for (int x = 0; x < 3; ++x) c3[u][x] = a.new_xyz[((int64_t)b * 3 + x) * a.M + m];
+        for (int x = 0; x < 3; ++x) c3[u][x] = ldg_stream_f32(a.new_xyz + ((int64_t)b * 3 + x) * a.M + m);
       }
       float v[4][6];
 #pragma unroll
@@ -289,9 +292,11 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
         const uint32_t b = (row >> 6) / a.M;
         const int j = jn[u];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[u][c] = j >= 0 ? a.feat[(int64_t)b * a.feat_bstride + (int64_t)j * a.feat_ld + c] : 0.f;
+        for (int c = 0; c < 3; ++c)
+          v[u][c] = j >= 0 ? ldg_stream_f32(a.feat + (int64_t)b * a.feat_bstride + (int64_t)j * a.feat_ld + c) : 0.f;
 #pragma unroll
-        for (int x = 0; x < 3; ++x) v[u][3 + x] = j >= 0 ? a.xyz[(int64_t)b * a.xst.b + x * a.xst.c + (int64_t)j * a.xst.n] : 0.f;
+        for (int x = 0; x < 3; ++x)
+          v[u][3 + x] = j >= 0 ? ldg_stream_f32(a.xyz + (int64_t)b * a.xst.b + x * a.xst.c + (int64_t)j * a.xst.n) : 0.f;
       }
       const uint32_t s = it & 1, ph = (it >> 1) & 1;
       wait_t(bar_a0empty + 8 * s, ph ^ 1, 2);
@@ -328,7 +333,9 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
         umma_commit(bar_a0empty + 8 * s);
         umma_commit(bar_acc0);
       };
-      // one 32-channel chunk (2 k-steps) of a TS layer: A hi/lo at columns 16*ks / 16*ks + 8 of `a_region`
+      // one 32-channel chunk (2 k-steps) of a TS layer: A hi/lo at columns 16*ks / 16*ks + 8 of `a_region`.  (Layer 2
+      // stays ONE N = 256 instruction per k-step: the issue path costs ~80 cycles per tcgen05.mma -- elect + 4 R2UR --
+      // which an N = 128 instruction (64 cycles of tensor work) cannot hide.)
       auto issue_chunk = [&](uint32_t d, uint32_t a_region, uint32_t w_base, uint32_t w_plane, uint32_t idesc, int ch) {
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
@@ -366,7 +373,7 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
           tc_fence_after();
         }
         for (int ch = 0; ch < 4; ++ch) {
-          wait_t(bar_a2 + 8 * ch, ph, 5 - (ch ? 0 : 0) + 0);
+          wait_t(bar_a2 + 8 * ch, ph, 5);
           tc_fence_after();
           issue_chunk(tmem_base + TM_Z, tmem_base + TM_Y, sb + OFF_W2, W2_PLANE, idesc2, ch);
         }
@@ -376,119 +383,173 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
       flush_t(1);
     }
     __syncwarp();
-  } else if (warp < 6 || warp >= 10) {
-    // ================= converters: accumulator -> BN + ReLU -> bf16 hi/lo A operand, in place in TMEM =================
-    // warps 2..5 convert acc0 (region X) for layer 1, warps 10..13 convert acc1 (region Y) for layer 2: two groups, so
-    // that the conversion of tile i+1's first layer overlaps the conversion of tile i's second layer.
-    const bool second = warp >= 10;
-    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (second ? TM_Y : TM_X);
-    const float* sc = s_sc + (second ? 256 : 0);
-    const float* sh = sc + 128;
-    const uint32_t bar_done = second ? bar_acc1 : bar_acc0;
-    const uint32_t bar_ready = second ? bar_a2 : bar_a1;
-    for (uint32_t it = 0;; ++it) {
-      const int tile = take_tile(it);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sempty + 8 * (it & 3));
-      if (tile < 0) break;
-      const uint32_t row = (uint32_t)tile * BM + (warp & 3) * 32 + lane;
-      float* dbg_row = (MODE == 1 && a.dbg && row < a.rows) ? a.dbg + (size_t)row * 256 + (second ? 128 : 0) : nullptr;
-      wait_t(bar_done, it & 1, 1);
-      tc_fence_after();
-      // software pipelined: the TMEM load of k-step ks+1 is in flight while k-step ks is converted and stored
+  } else {
+    // ================= workers (warps 2..13): conversions and the pool epilogue =================
+    // Three warps per TMEM lane quarter q = warp % 4; worker w = 0, 1, 2 of a quarter takes the items w, w+3, w+6 of every
+    // job -- the 8 k-steps (16 channels) of a conversion, the 8 column chunks (32 channels) of the pool.  Per tile the
+    // jobs come in the order in which the tensor pipe produces their inputs:
+    //     acc1(it) -> A2 (layer 2 waits for it)   acc0(it+1) -> A1   acc2(it) -> pooled output
+    // Consecutive k-steps of a conversion belong to different workers, so the first 32-channel chunk reaches the MMA
+    // lane after ONE k-step time and every chunk barrier collects 2 x 128 arrivals.
+    // Thread coordinates are re-derived from a volatile %tid.x read inside every job instead of being kept live across
+    // the tile loop: with 64 registers (the budget that lets the next step's FPS CTA share the scheduler's register
+    // file) two loop-carried address registers were spilled, and with ~4 KB of L1 left a spill reload is an L2 round trip.
+    auto tid_now = []() -> uint32_t {
+      uint32_t t;
+      asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+      return t;
+    };
+    const int q = warp & 3;
+
+    // accumulator -> BN + ReLU -> bf16 hi/lo A operand, in place in TMEM; region X (layer 0 -> 1) or Y (layer 1 -> 2)
+    auto convert = [&](bool second, float* dbg_row) {
+      const uint32_t t = tid_now();
+      const int w = (int)((t >> 5) - 2) >> 2;
+      const uint32_t lane_base = tmem_base + ((((t >> 5) & 3u) * 32u) << 16) + (second ? TM_Y : TM_X);
+      const uint32_t sc = sb + OFF_SC + (second ? 1024 : 0), sh = sc + 512;   // byte addresses of scale / shift
+      const uint32_t bar_ready = second ? bar_a2 : bar_a1;
       const long long tc0 = TIMING ? clock64() : 0;
-      uint32_t va[16], vb[16];
-      tmem_ld16_nowait(lane_base, va);
-      tmem_ld_wait();
-      auto convert_step = [&](int ks, uint32_t (&v)[16], uint32_t (&vn)[16], bool last) {
-        if (!last) tmem_ld16_nowait(lane_base + 16 * (ks + 1), vn);
+      // No software pipelining: the three workers of a quarter hide each other's TMEM latencies.  Any second buffer
+      // (or a load issued into v while the permuted outputs are still live) spills, and with 231 KB of shared memory
+      // configured the L1 is ~28 KB: local-memory traffic goes to L2, every spill costs hundreds of cycles (ncu counted
+      // 38 M local accesses in an earlier version that was 2x slower).
+      auto convert_step = [&](int ks) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + 16 * ks, v);
         if (MODE == 1 && dbg_row) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) dbg_row[16 * ks + j] = __uint_as_float(v[j]);
         }
-        uint32_t o[16];
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(sc + 16 * ks + 4 * j4);
-          const float4 t4 = *reinterpret_cast<const float4*>(sh + 16 * ks + 4 * j4);
+        for (int j4 = 0; j4 < 4; ++j4) {     // converted in place: v[4 j4 ..] <- h h l l
+          const float4 s4 = lds_f4(sc + 4 * (16 * ks + 4 * j4));
+          const float4 t4 = lds_f4(sh + 4 * (16 * ks + 4 * j4));
           const float y0 = fmaf(__uint_as_float(v[4 * j4 + 0]), s4.x, t4.x);
           const float y1 = fmaf(__uint_as_float(v[4 * j4 + 1]), s4.y, t4.y);
           const float y2 = fmaf(__uint_as_float(v[4 * j4 + 2]), s4.z, t4.z);
           const float y3 = fmaf(__uint_as_float(v[4 * j4 + 3]), s4.w, t4.w);
-          relu_split_pair(y0, y1, o[2 * j4], o[8 + 2 * j4]);
-          relu_split_pair(y2, y3, o[2 * j4 + 1], o[8 + 2 * j4 + 1]);
+          uint32_t h0, l0, h1, l1;
+          relu_split_pair(y0, y1, h0, l0);
+          relu_split_pair(y2, y3, h1, l1);
+          v[4 * j4 + 0] = h0; v[4 * j4 + 1] = h1; v[4 * j4 + 2] = l0; v[4 * j4 + 3] = l1;
         }
+        // v = [h h l l | h h l l | h h l l | h h l l] -> the TMEM layout [8 hi words | 8 lo words]
+        const uint32_t o[16] = {v[0], v[1], v[4], v[5], v[8], v[9], v[12], v[13], v[2], v[3], v[6], v[7], v[10], v[11], v[14], v[15]};
         tmem_st16(lane_base + 16 * ks, o);
-      };
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {      // one 32-channel chunk = two k-steps; the loop body stays small (I-cache)
-        convert_step(2 * ch, va, vb, false);
-        tmem_ld_wait();
-        convert_step(2 * ch + 1, vb, va, ch == 3);
-        tmem_st_wait();                     // the chunk is complete: hand it to the MMA lane
+        tmem_st_wait();                     // this k-step is in TMEM: count it on its chunk's barrier
         tc_fence_before();
-        mbar_arrive(bar_ready + 8 * ch);
-        if (ch < 3) tmem_ld_wait();
-      }
+        mbar_arrive(bar_ready + 8 * (ks >> 1));
+      };
+      convert_step(w);
+      convert_step(w + 3);
+      if (w + 6 < 8) convert_step(w + 6);
       if (TIMING) tw[2] += (unsigned long long)(clock64() - tc0);
-    }
-    if ((warp & 3) == 0) flush_t(second ? 3 : 2);
-  } else {
-    // ================= warps 6..9: pool epilogue: acc2 -> BN + ReLU -> max over each centroid's 64 rows =================
-    const int q = warp & 3;
-    const uint32_t r = threadIdx.x - 6 * 32;   // 0..127
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + TM_Z;
-    for (uint32_t it = 0;; ++it) {
-      const int cur = take_tile(it);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_sempty + 8 * (it & 3));
-      if (cur < 0) break;
-      wait_t(bar_acc2, it & 1, 1);
-      tc_fence_after();
-      // scale2 >= 0 (the launcher's contract: rows of W2 with a negative BN scale are negated when the weights are
-      // prepared), so relu(scale * max(acc) + shift) == max(relu(scale * acc + shift)): the max is taken on the raw
-      // accumulators -- 4 rows per thread in registers (16x256b TMEM loads), then 3 shuffle levels (tc_ptx.cuh) -- and
-      // the affine map + ReLU are applied once per pooled value in the combine below
-      const uint32_t t_hi = lane_base + (16u << 16);
-      const int my_col = colmax_column(lane);
+    };
+    auto dbg_row_of = [&](int tile, bool second) -> float* {
+      if (MODE != 1) return nullptr;
+      const uint32_t row = (uint32_t)tile * BM + (tid_now() & 127u);   // quarter * 32 + lane
+      return (MODE == 1 && a.dbg && row < a.rows) ? a.dbg + (size_t)row * 256 + (second ? 128 : 0) : nullptr;
+    };
+    // acc2 -> max over each centroid's 64 rows -> BN + ReLU -> (B*M, 256) fp32.  scale2 >= 0 (the launcher's contract:
+    // rows of W2 with a negative BN scale are negated when the weights are prepared), so relu(scale * max(acc) + shift)
+    // == max(relu(scale * acc + shift)): the max is taken on the raw accumulators -- 4 rows per thread in registers
+    // (16x256b TMEM loads), then 3 shuffle levels (tc_ptx.cuh); the affine map + ReLU once per pooled value.  16 columns
+    // per item (.x2 loads): the 32-column version needs 32 live registers and spilled.
+    auto pool_drain = [&]() {
       const long long tp0 = TIMING ? clock64() : 0;
-      uint32_t va[16], vb[16];
-      tmem_ld_16x256b_x4_async(lane_base, va);
-      tmem_ld_16x256b_x4_async(t_hi, vb);
-      tmem_ld_wait();
+      const uint32_t t = tid_now();
+      const int lane = (int)(t & 31u), q = (int)((t >> 5) & 3u), w = (int)((t >> 5) - 2) >> 2;
+      const int my_col = colmax16_column(lane);
+      const uint32_t s_part_addr = sb + OFF_PART;
+      const uint32_t t_lo = tmem_base + ((uint32_t)(q * 32) << 16) + TM_Z, t_hi = t_lo + (16u << 16);
+      uint32_t va[8], vb[8];
+      tmem_ld_16x256b_x2_async(t_lo + 16 * w, va);
+      tmem_ld_16x256b_x2_async(t_hi + 16 * w, vb);
+      asm volatile("bar.sync 2, 384;" ::: "memory");   // every worker is done reading the previous tile's partials
 #pragma unroll 1
-      for (int ch = 0; ch < C2 / 32; ++ch) {
-        float m[8];
-        colmax_rows4(va, vb, m);
-        if (ch + 1 < C2 / 32) {                          // next chunk's loads fly during the shuffles
-          tmem_ld_16x256b_x4_async(lane_base + (ch + 1) * 32, va);
-          tmem_ld_16x256b_x4_async(t_hi + (ch + 1) * 32, vb);
+      for (int c = w; c < C2 / 16; c += 3) {           // this worker's items: 16 columns each (8 + 8 registers)
+        tmem_ld_wait();
+        float m[4];
+        colmax16_rows4(va, vb, m);
+        if (c + 3 < C2 / 16) {                         // next item's loads fly during the shuffles
+          tmem_ld_16x256b_x2_async(t_lo + 16 * (c + 3), va);
+          tmem_ld_16x256b_x2_async(t_hi + 16 * (c + 3), vb);
         }
-        s_part[q * C2 + ch * 32 + my_col] = __float_as_uint(colmax_lanes8(m, lane));
-        if (ch + 1 < C2 / 32) tmem_ld_wait();
+        const float r = colmax16_lanes8(m, lane);
+        if (!(lane & 4)) sts_u32(s_part_addr + 4 * (q * C2 + c * 16 + my_col), __float_as_uint(r));
       }
-      const long long tp1 = TIMING ? clock64() : 0;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_z_empty);
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (lane == 0) mbar_arrive(bar_z_empty);          // Z may be overwritten by the next tile's layer 2
+      if (TIMING) tw[3] += (unsigned long long)(clock64() - tp0);
+    };
+    // second half of the pool job, off the tensor pipe's critical path (it runs after the next tile's acc1 conversion):
+    // combine the two row-halves of each centroid, BN + ReLU, store
+    auto pool_combine = [&](int tile) {
+      const long long tp1 = TIMING ? clock64() : 0;
+      const int wt = (int)tid_now() - 64;      // 0..383 among the workers
+      const uint32_t s_sc2_addr = sb + OFF_SC + 2048, s_part_addr = sb + OFF_PART;
+      asm volatile("bar.sync 2, 384;" ::: "memory");   // all partials written
       const long long tp2 = TIMING ? clock64() : 0;
-      for (int e = (int)r; e < 2 * C2; e += 128) {
-        const int g = e / C2, c = e - g * C2;
-        const uint32_t grow = (uint32_t)cur * 2 + g;
-        if (grow * 64u < a.rows) {
-          const float m = fmaxf(__uint_as_float(s_part[(2 * g) * C2 + c]), __uint_as_float(s_part[(2 * g + 1) * C2 + c]));
-          a.out[(size_t)grow * a.ld_out + c] = fmaxf(fmaf(m, s_sc2[c], s_sc2[256 + c]), 0.f);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {           // 512 pooled values (2 centroids x 256 channels) over 384 threads
+        const int e = wt + 384 * u;
+        if (e < 2 * C2) {
+          const int g = e >> 8, c = e & (C2 - 1);
+          const uint32_t grow = (uint32_t)tile * 2 + g;
+          const float m = fmaxf(__uint_as_float(lds_u32(s_part_addr + 4 * ((2 * g) * C2 + c))),
+                                __uint_as_float(lds_u32(s_part_addr + 4 * ((2 * g + 1) * C2 + c))));
+          if (grow * 64u < a.rows)
+            a.out[(size_t)grow * a.ld_out + c] =
+                fmaxf(fmaf(m, lds_f32(s_sc2_addr + 4 * c), lds_f32(s_sc2_addr + 4 * (256 + c))), 0.f);
         }
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
       if (TIMING) {
-        tw[2] += (unsigned long long)(tp1 - tp0);
-        tw[3] += (unsigned long long)(tp2 - tp1);
-        tw[4] += (unsigned long long)(clock64() - tp2);
+        tw[4] += (unsigned long long)(tp2 - tp1);
+        tw[5] += (unsigned long long)(clock64() - tp2);
       }
+    };
+
+    // The tile number is NOT kept in a register across the iteration (it was the value the 64-register budget spilled):
+    // a worker releases ring slot `it` only after the combine of tile `it`, so the slot stays valid and the tile is simply
+    // re-read from shared memory where it is needed.  The scheduler can still run 2 tiles ahead (= the A0 stages).
+    const uint32_t ring_addr = smem_u32(const_cast<int*>(ring));
+    // `opaque` stops the compiler from pre-computing (and then spilling) values derived from the loop counter
+    auto opaque = [](uint32_t x) -> uint32_t {
+      asm volatile("" : "+r"(x));
+      return x;
+    };
+    auto tile_of = [&](uint32_t it) -> int { return (int)lds_u32(ring_addr + 4 * (opaque(it) & 3)); };
+    auto finish_tile = [&](uint32_t it) {     // combine + store tile `it`, then let the scheduler recycle its slot
+      pool_combine(tile_of(it));
+      __syncwarp();
+      if ((tid_now() & 31u) == 0) mbar_arrive(bar_sempty + 8 * (opaque(it) & 3));
+    };
+    bool have = take_tile(0) >= 0;
+    if (have) {
+      wait_t(bar_acc0, 0, 1);
+      tc_fence_after();
+      convert(false, dbg_row_of(tile_of(0), false));
     }
-    if (q == 0) flush_t(4);
+    uint32_t it = 0;
+    for (; have; ++it) {
+      wait_t(bar_acc1, it & 1, 1);          // layer 2 of this tile is waiting for A2: first
+      tc_fence_after();
+      convert(true, dbg_row_of(tile_of(it), true));
+      if (it > 0) finish_tile(it - 1);      // (its partials were drained before; hidden under layer 2)
+      const bool have_next = take_tile(it + 1) >= 0;
+      if (have_next) {
+        wait_t(bar_acc0, (it + 1) & 1, 1);
+        tc_fence_after();
+        convert(false, dbg_row_of(tile_of(it + 1), false));
+      }
+      wait_t(bar_acc2, it & 1, 6);
+      tc_fence_after();
+      pool_drain();                         // frees Z for the next tile's layer 2
+      have = have_next;
+    }
+    if (it > 0) finish_tile(it - 1);
+    if ((warp & 3) == 0) flush_t(2 + ((warp - 2) >> 2));
   }
 
   tc_fence_before();

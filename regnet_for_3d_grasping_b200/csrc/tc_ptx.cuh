@@ -65,6 +65,26 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// explicit shared-space accesses (a pointer derived from the manually aligned dynamic-smem base is generic to nvcc,
+// which then emits LD.E / ST.E with 64-bit addressing instead of LDS / STS)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -195,6 +215,43 @@ __device__ __forceinline__ float colmax_lanes8(const float (&m)[8], int lane) {
 }
 // value index kept by lane t: 4 b4 + 2 b3 + b2 = 2i + e  ->  column 8i + 2(t%4) + e = 16 b4 + 8 b3 + 2 (t & 3) + b2
 __device__ __forceinline__ int colmax_column(int lane) { return (lane & 24) + 2 * (lane & 3) + ((lane >> 2) & 1); }
+
+// The same for 16 columns at a time (.x2: 8 registers per load instead of 16 -- for kernels short of registers):
+// v[4i+0..1] = row t/4, columns 8i + 2(t%4) + {0,1}, v[4i+2..3] = row t/4 + 8, i = 0, 1.
+__device__ __forceinline__ void tmem_ld_16x256b_x2_async(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// a = rows t/4, t/4+8, b = rows t/4+16, t/4+24 of 16 columns: in-thread part, m[2i+e] = max over the four rows
+__device__ __forceinline__ void colmax16_rows4(const uint32_t (&a)[8], const uint32_t (&b)[8], float (&m)[4]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      m[2 * i + e] = fmaxf(fmaxf(__uint_as_float(a[4 * i + e]), __uint_as_float(a[4 * i + 2 + e])),
+                           fmaxf(__uint_as_float(b[4 * i + e]), __uint_as_float(b[4 * i + 2 + e])));
+}
+// cross-lane part: lane t returns the 32-row maximum of column colmax16_column(t); lanes t and t^4 hold the same
+// column (only 4 values per thread enter the 8-lane butterfly)
+__device__ __forceinline__ float colmax16_lanes8(const float (&m)[4], int lane) {
+  float w2[2];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float keep = up ? m[2 + j] : m[j], send = up ? m[j] : m[2 + j];
+      w2[j] = fmaxf(keep, __shfl_xor_sync(FULL, send, 16));
+    }
+  }
+  const bool up = lane & 8;
+  const float keep = up ? w2[1] : w2[0], send = up ? w2[0] : w2[1];
+  float r = fmaxf(keep, __shfl_xor_sync(FULL, send, 8));
+  return fmaxf(r, __shfl_xor_sync(FULL, r, 4));
+}
+// index kept by lane t: i = b4, e = b3  ->  column 8 b4 + 2 (t & 3) + b3
+__device__ __forceinline__ int colmax16_column(int lane) { return ((lane & 16) >> 1) + 2 * (lane & 3) + ((lane >> 3) & 1); }
 
 __device__ __forceinline__ uint32_t order_bits(float v) {  // unsigned order == float order
   const uint32_t u = __float_as_uint(v);

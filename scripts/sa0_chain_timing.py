@@ -36,10 +36,10 @@ t = timing.double().cpu()
 tiles = B * M * 64 / 128 / 148
 names = {0: ["-", "sempty", "a0empty", "-", "-", "-", "-", "total"],
          1: ["sfull", "a0full", "w", "a1.c0", "a1.c1-3", "a2", "z_empty", "total"],
-         2: ["sfull", "acc0", "convert", "-", "-", "-", "-", "total"],
-         3: ["sfull", "acc1", "convert", "-", "-", "-", "-", "total"],
-         4: ["sfull", "acc2", "chunks", "bar", "combine", "-", "-", "total"]}
-roles = ["producer", "mma", "conv0", "conv1", "pool"]
+         2: ["sfull", "acc0/1", "convert", "pool.chunks", "pool.bar", "pool.combine", "acc2", "total"],
+         3: ["sfull", "acc0/1", "convert", "pool.chunks", "pool.bar", "pool.combine", "acc2", "total"],
+         4: ["sfull", "acc0/1", "convert", "pool.chunks", "pool.bar", "pool.combine", "acc2", "total"]}
+roles = ["producer", "mma", "worker0", "worker1", "worker2"]
 print(f"tiles per CTA ~{tiles:.0f}; mean over CTAs, cycles per tile:")
 for r in range(5):
     m = t[:, r, :].mean(0) / tiles
