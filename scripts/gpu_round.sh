@@ -25,10 +25,8 @@ for s in $STAGES; do
     region)   timeout 600 python -m pytest tests/test_gpu_region.py -q -m gpu > gpurun_out/test_region.log 2>&1 ;;
     ncu)      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
                  --log-file gpurun_out/launches.csv python scripts/one_forward.py tc serial > gpurun_out/ncu_list.log 2>&1 ;;
-    ncufull)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 18 -c 18 \
-                 -o gpurun_out/prof_gemm python scripts/one_forward.py tc serial > gpurun_out/ncu_full.log 2>&1
-              timeout 600 ncu --set full --clock-control none --import-source on -k regex:sa0_front -s 1 -c 1 \
-                 -o gpurun_out/prof_sa0front python scripts/one_forward.py tc serial > gpurun_out/ncu_full_sa0.log 2>&1
+    ncufull)  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc|sa0_chain" -s 18 -c 18 \
+                 -o gpurun_out/prof_tensor python scripts/one_forward.py tc serial > gpurun_out/ncu_full.log 2>&1
               timeout 600 ncu --set full --clock-control none --import-source on -k regex:fps_kernel -s 3 -c 1 \
                  -o gpurun_out/prof_fps python scripts/one_forward.py tc serial > gpurun_out/ncu_full_fps.log 2>&1 ;;
     sa0chk)   timeout 600 python scripts/sa0_chain_check.py > gpurun_out/sa0_chain_check.log 2>&1 ;;

@@ -65,5 +65,30 @@ def launches(path):
         print(f"{name:66s} {c:4d} launches {v:10.1f} us {100 * v / s:5.1f}%")
 
 
+def traffic(path):
+    """JSON for bench.py's roofline.traffic: DRAM bytes (read + write) of every profiled launch, and their sum."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def to_bytes(v, unit):
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return float(v.replace(",", "")) * mult
+
+    launches_ = []
+    for r in data:
+        name = r[col["Kernel Name"]].split("(")[0].replace("regnet::<unnamed>::", "").replace("void ", "")
+        rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
+        wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
+        t = r[col["gpu__time_duration.sum"]]
+        launches_.append({"kernel": name, "dram_read_bytes": rd, "dram_write_bytes": wr,
+                          "time": t + units[col["gpu__time_duration.sum"]]})
+    print(json.dumps({"source": path, "how": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch",
+                      "launches": launches_,
+                      "dram_bytes_per_step": sum(x["dram_read_bytes"] + x["dram_write_bytes"] for x in launches_)}, indent=1))
+
+
 if __name__ == "__main__":
-    {"full": full, "list": launches}[sys.argv[1]](sys.argv[2])
+    {"full": full, "list": launches, "traffic": traffic}[sys.argv[1]](sys.argv[2])
