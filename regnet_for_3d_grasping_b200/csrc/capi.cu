@@ -244,7 +244,7 @@ int regnet_sa0_chain(const float* pc, const float* new_xyz, const int32_t* nbr, 
   if (!rc) rc = abs_copy_launch(scale2, abs2, 256, stream);
   if (!rc)
     rc = sa0_chain_launch(pc, Strides3{(int64_t)N * 6, 1, 6}, new_xyz, pc + 3, (int64_t)N * 6, 6, nbr, W0, 6, scale0,
-                          shift0, w1h, w1l, 128, scale1, shift1, w2h, w2l, 128, abs2, shift2, B, M, out, 256, dbg,
+                          shift0, w1h, w1l, 128, scale1, shift1, w2h, w2l, 128, abs2, shift2, B, M, out, 256, nullptr, nullptr, dbg,
                           nullptr, variant, stream);
   cudaError_t e = cudaStreamSynchronize(stream);
   if (!rc && e != cudaSuccess) rc = cuda_fail(e, "sa0_chain kernel");

@@ -23,6 +23,9 @@ struct Epilogue {
   __nv_bfloat16* out_lo = nullptr;
   int ld_split = 0;
   unsigned int* tile_counter = nullptr;  // tcgen05 engine: zeroed device counter => dynamic tile scheduling
+  __nv_bfloat16* pool_hi = nullptr;      // tcgen05 engine, pool != 0: the pooled values also as bf16 hi/lo planes
+  __nv_bfloat16* pool_lo = nullptr;      //   (P / pool, ld_pool) -- the gather table of the next level's first layer
+  int ld_pool = 0;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -40,6 +43,14 @@ int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, 
                    const __nv_bfloat16* Wlo, int ldw, int64_t P, int K, int cout, const Epilogue& ep,
                    cudaStream_t stream);
 int gemm_tc_supported(void);
+// Same contraction with a GATHERED A operand (grouping fused into the TMA producer, gemm_tc.cu GatherA): row p =
+// [table[nbr[p] + (p / rows_per_cloud) * n_prev, 0..C) | Z[p, 0..3)], K = C + 3; table = bf16 hi/lo planes (table_rows, ldt)
+// with C %% 64 == 0, Z = (P, 16) bf16 hi/lo planes whose first three columns are xyz - centroid; W (cout, ldw) with the
+// columns in that [feature | xyz_rel] order.  act = relu, no pooling.
+int gemm_tc_gather_launch(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int64_t table_rows, int C, int ldt,
+                          const int32_t* nbr, int rows_per_cloud, int n_prev, const __nv_bfloat16* Zhi,
+                          const __nv_bfloat16* Zlo, const __nv_bfloat16* Whi, const __nv_bfloat16* Wlo, int ldw, int64_t P,
+                          int cout, const Epilogue& ep, cudaStream_t stream);
 
 // 2-D bf16 tensor map over a (rows, cols) row-major matrix with leading dimension ld (elements); box = box_cols x
 // box_rows, swizzle_bytes in {64, 128}.  CUtensorMap is passed opaquely so that this header needs no <cuda.h>.

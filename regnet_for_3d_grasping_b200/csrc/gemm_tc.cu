@@ -57,12 +57,27 @@ __device__ __forceinline__ float act_fn(float v) {
 
 // POOL / ACT are compile-time so that each instance carries only its own epilogue (a runtime switch inlined the
 // sigmoid's division subroutine 256 times and the unrolled epilogue overflowed the instruction cache).
-template <int BN, bool POOL, int ACT>
+// GATHER: the A operand is not a materialised (P, K) matrix.  Row p of the operand is
+//   [ table[g(p), 0..C) | xyz_rel[p, 0..3) | 0 ... ],   g(p) = nbr[p] + (p / rows_per_cloud) * n_prev,
+// i.e. the grouped [feature | xyz - centroid] row of pn2_utils/modules.py:44-52 -- ball-query grouping fused into the
+// GEMM's TMA producer: the C feature columns are fetched straight from the point-major feature table (bf16 hi/lo planes,
+// L2-resident) with cp.async.bulk.tensor tile::gather4, four neighbour rows per instruction, one instruction per lane and
+// plane; the last k-block (the three xyz_rel columns, K = 16) comes from a small (P, 16) side matrix.
+// map_xhi / map_xlo then describe the feature table (box 64 x 1), map_x2hi / map_x2lo the xyz_rel planes (SWIZZLE_32B).
+struct GatherA {
+  const int32_t* nbr = nullptr;   // (P) neighbour index inside the cloud
+  uint32_t rows_per_cloud = 1;    // M * 64 operand rows per cloud (multiple of 4)
+  uint32_t n_prev = 0;            // table rows per cloud
+  int n_feat_kb = 0;              // C / 64 gathered k-blocks
+};
+
+template <int BN, bool POOL, int ACT, bool GATHER>
 __global__ void __maxnreg__(88)   // one CTA per SM by shared memory; 88 registers leave room for a co-resident FPS CTA
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
                const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
-               const __grid_constant__ CUtensorMap map_ohi, const __grid_constant__ CUtensorMap map_olo, int64_t P,
-               int K, int cout, Epilogue ep) {
+               const __grid_constant__ CUtensorMap map_ohi, const __grid_constant__ CUtensorMap map_olo,
+               const __grid_constant__ CUtensorMap map_x2hi, const __grid_constant__ CUtensorMap map_x2lo, int64_t P,
+               int K, int cout, Epilogue ep, GatherA ga) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ unsigned char smem_dyn[];
@@ -89,6 +104,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
   const int n_kblk = (K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
+    if (GATHER) {
+      tma_prefetch_desc(&map_x2hi);
+      tma_prefetch_desc(&map_x2lo);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -146,7 +165,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (GATHER) {
+      // every lane owns four consecutive rows of the tile = one gather4 per plane and k-block
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t pit = 0;; ++pit) {
+        int tile = 0;
+        if (lane == 0) tile = draw_tile(pit);
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile < 0) break;
+        const int row0 = (tile / n_ctile) * BM;
+        const int col0 = (tile % n_ctile) * BN;
+        const int64_t r4 = (int64_t)row0 + 4 * lane;
+        int g[4] = {0, 0, 0, 0};
+        if (r4 + 3 < P) {
+          const int4 j = *reinterpret_cast<const int4*>(ga.nbr + r4);
+          const int base = (int)((uint32_t)r4 / ga.rows_per_cloud) * (int)ga.n_prev;
+          g[0] = j.x + base; g[1] = j.y + base; g[2] = j.z + base; g[3] = j.w + base;
+        }
+        for (int kb = 0; kb < n_kblk; ++kb) {
+          const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t full = bar_full + 8 * stage;
+          if (lane == 0) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            if (kb < ga.n_feat_kb) {
+              mbar_arrive_expect_tx(full, C::STAGE_BYTES);
+            } else {
+              mbar_arrive_expect_tx(full, 2 * BM * 32 + 2 * C::B_BYTES);
+              tma_load_2d(sA, &map_x2hi, full, 0, row0);
+              tma_load_2d(sA + C::A_BYTES, &map_x2lo, full, 0, row0);
+            }
+            tma_load_2d(sA + 2 * C::A_BYTES, &map_whi, full, kb * BK, col0);
+            tma_load_2d(sA + 2 * C::A_BYTES + C::B_BYTES, &map_wlo, full, kb * BK, col0);
+          }
+          __syncwarp();   // the stage is free and its barrier armed before any lane's gather can complete on it
+          if (kb < ga.n_feat_kb) {
+            tma_gather4_2d(sA + lane * 512, &map_xhi, full, kb * BK, g[0], g[1], g[2], g[3]);
+            tma_gather4_2d(sA + C::A_BYTES + lane * 512, &map_xlo, full, kb * BK, g[0], g[1], g[2], g[3]);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (uint32_t pit = 0;; ++pit) {
         const int tile = draw_tile(pit);
@@ -182,10 +241,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
-          const uint64_t a_hi = make_sdesc(sA), a_lo = make_sdesc(sA + C::A_BYTES);
+          const bool xyz_kb = GATHER && kb >= ga.n_feat_kb;   // [128 x 16] SWIZZLE_32B operand of the xyz_rel columns
+          const uint64_t a_hi = xyz_kb ? make_sdesc_k16(sA) : make_sdesc(sA);
+          const uint64_t a_lo = xyz_kb ? make_sdesc_k16(sA + C::A_BYTES) : make_sdesc(sA + C::A_BYTES);
           const uint64_t b_hi = make_sdesc(sA + 2 * C::A_BYTES), b_lo = make_sdesc(sA + 2 * C::A_BYTES + C::B_BYTES);
           const int rem = K - kb * BK;
-          const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
+          const int ksteps = xyz_kb ? 1 : rem >= BK ? BK / 16 : (rem + 15) / 16;
           for (int k = 0; k < ksteps; ++k) {  // +2 per k-step: 32 bytes >> 4 inside the 128B swizzle span
             umma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
           }
@@ -325,7 +386,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
           const int64_t grow = row0 / 64 + g;
           if (grow * 64 < P && col0 + c < cout) {
             const float m = fmaxf(__uint_as_float(s_part[(2 * g) * BN + c]), __uint_as_float(s_part[(2 * g + 1) * BN + c]));
-            ep.out_f32[grow * ep.ld_f32 + col0 + c] = act_fn<ACT>(fmaf(m, s_scale[c], s_shift[c]));
+            const float y = act_fn<ACT>(fmaf(m, s_scale[c], s_shift[c]));
+            ep.out_f32[grow * ep.ld_f32 + col0 + c] = y;
+            if (ep.pool_hi) {   // the same values as bf16 hi/lo planes: the gather table of the next level's first layer
+              __nv_bfloat16 h, l;
+              split_bf16(y, h, l);
+              ep.pool_hi[grow * ep.ld_pool + col0 + c] = h;
+              ep.pool_lo[grow * ep.ld_pool + col0 + c] = l;
+            }
           }
         }
       }
@@ -372,7 +440,9 @@ EncodeTiledFn encode_fn() {
 
 int tc_make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int ld, int box_rows, int box_cols,
                 int swizzle_bytes) {
-  const CUtensorMapSwizzle swizzle = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUtensorMapSwizzle swizzle = swizzle_bytes == 32   ? CU_TENSOR_MAP_SWIZZLE_32B
+                                     : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                           : CU_TENSOR_MAP_SWIZZLE_128B;
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("gemm_tc: cuTensorMapEncodeTiled is not available from this driver");
@@ -398,66 +468,109 @@ int tc_driver_ok(void) { return encode_fn() != nullptr; }
 namespace {
 
 
-template <int BN, bool POOL, int ACT>
-int launch(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl,
-           const CUtensorMap& moh, const CUtensorMap& mol, int64_t P, int K, int cout, const Epilogue& ep,
-           cudaStream_t stream) {
+struct Maps {
+  CUtensorMap xh, xl, wh, wl, oh, ol, x2h, x2l;
+};
+
+template <int BN, bool POOL, int ACT, bool GATHER>
+int launch(const Maps& m, int64_t P, int K, int cout, const Epilogue& ep, const GatherA& ga, cudaStream_t stream) {
   int dev = 0, sms = 0;
   RN_CUDA(cudaGetDevice(&dev));
   RN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  RN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, POOL, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  RN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, POOL, ACT, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                Cfg<BN>::SMEM_BYTES));
   const int64_t n_tiles = ((P + BM - 1) / BM) * ((cout + BN - 1) / BN);
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);
-  gemm_tc_kernel<BN, POOL, ACT><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(mxh, mxl, mwh, mwl, moh, mol, P, K,
-                                                                                  cout, ep);
+  gemm_tc_kernel<BN, POOL, ACT, GATHER><<<grid, NTHREADS, Cfg<BN>::SMEM_BYTES, stream>>>(
+      m.xh, m.xl, m.wh, m.wl, m.oh, m.ol, m.x2h, m.x2l, P, K, cout, ep, ga);
   RN_LAUNCH_CHECK("gemm_tc_kernel");
   return REGNET_OK;
 }
 
-template <int BN>
-int launch_bn(const CUtensorMap& mxh, const CUtensorMap& mxl, const CUtensorMap& mwh, const CUtensorMap& mwl,
-              const CUtensorMap& moh, const CUtensorMap& mol, int64_t P, int K, int cout, const Epilogue& ep,
-              cudaStream_t stream) {
-  if (ep.pool) {
-    if (ep.act == 1) return launch<BN, true, 1>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
-    if (ep.act == 0) return launch<BN, true, 0>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
-    return launch<BN, true, 2>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+template <int BN, bool GATHER>
+int launch_bn(const Maps& m, int64_t P, int K, int cout, const Epilogue& ep, const GatherA& ga, cudaStream_t stream) {
+  if (GATHER) {   // only the instances the SA first layers use: ReLU, no pooling
+    if (!ep.pool && ep.act == 1) return launch<BN, false, 1, GATHER>(m, P, K, cout, ep, ga, stream);
+    set_error("gemm_tc: the gathered-operand variant supports act = relu without pooling only");
+    return REGNET_EINVAL;
   }
-  if (ep.act == 1) return launch<BN, false, 1>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
-  if (ep.act == 0) return launch<BN, false, 0>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
-  return launch<BN, false, 2>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+  if (ep.pool) {
+    if (ep.act == 1) return launch<BN, true, 1, false>(m, P, K, cout, ep, ga, stream);
+    if (ep.act == 0) return launch<BN, true, 0, false>(m, P, K, cout, ep, ga, stream);
+    return launch<BN, true, 2, false>(m, P, K, cout, ep, ga, stream);
+  }
+  if (ep.act == 1) return launch<BN, false, 1, false>(m, P, K, cout, ep, ga, stream);
+  if (ep.act == 0) return launch<BN, false, 0, false>(m, P, K, cout, ep, ga, stream);
+  return launch<BN, false, 2, false>(m, P, K, cout, ep, ga, stream);
 }
 
 }  // namespace
 
 int gemm_tc_supported(void) { return tc_driver_ok(); }
 
-int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, const __nv_bfloat16* Whi,
-                   const __nv_bfloat16* Wlo, int ldw, int64_t P, int K, int cout, const Epilogue& ep,
-                   cudaStream_t stream) {
-  RN_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= K && ldw >= K,
-               "gemm_tc: leading dimensions must be multiples of 8 and >= K (K=%d ldx=%d ldw=%d)", K, ldx, ldw);
+static int check_epilogue(const Epilogue& ep, int64_t P) {
   RN_CHECK_ARG(ep.pool == 0 || (ep.pool == 64 && P % 64 == 0 && ep.out_f32 && !ep.out_hi),
                "gemm_tc: pooled epilogue needs pool == 64, P %% 64 == 0 and an fp32 output");
   RN_CHECK_ARG(!ep.out_f32 || ep.pool || ep.ld_f32 % 4 == 0, "gemm_tc: fp32 output leading dimension must be a multiple of 4");
   RN_CHECK_ARG(!ep.out_hi || ep.ld_split % 8 == 0, "gemm_tc: split output leading dimension must be a multiple of 8");
   RN_CHECK_ARG(P < (1LL << 31), "gemm_tc: too many rows");
   RN_CHECK_ARG(ep.act >= 0 && ep.act <= 2, "gemm_tc: unknown activation %d", ep.act);
+  return REGNET_OK;
+}
+
+int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, const __nv_bfloat16* Whi,
+                   const __nv_bfloat16* Wlo, int ldw, int64_t P, int K, int cout, const Epilogue& ep,
+                   cudaStream_t stream) {
+  RN_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= K && ldw >= K,
+               "gemm_tc: leading dimensions must be multiples of 8 and >= K (K=%d ldx=%d ldw=%d)", K, ldx, ldw);
+  RN_TRY(check_epilogue(ep, P));
   if (P == 0) return REGNET_OK;
   const int bn = cout > 128 ? 256 : 128;
-  CUtensorMap mxh, mxl, mwh, mwl;
-  RN_TRY(tc_make_map(&mxh, Xhi, P, K, ldx, BM, BK, 128));
-  RN_TRY(tc_make_map(&mxl, Xlo, P, K, ldx, BM, BK, 128));
-  RN_TRY(tc_make_map(&mwh, Whi, cout, K, ldw, bn, BK, 128));
-  RN_TRY(tc_make_map(&mwl, Wlo, cout, K, ldw, bn, BK, 128));
-  CUtensorMap moh = mxh, mol = mxl;  // placeholders when there is no split output
+  Maps m;
+  RN_TRY(tc_make_map(&m.xh, Xhi, P, K, ldx, BM, BK, 128));
+  RN_TRY(tc_make_map(&m.xl, Xlo, P, K, ldx, BM, BK, 128));
+  RN_TRY(tc_make_map(&m.wh, Whi, cout, K, ldw, bn, BK, 128));
+  RN_TRY(tc_make_map(&m.wl, Wlo, cout, K, ldw, bn, BK, 128));
+  m.oh = m.xh; m.ol = m.xl;  // placeholders when there is no split output
   if (ep.out_hi) {
-    RN_TRY(tc_make_map(&moh, ep.out_hi, P, cout, ep.ld_split, 32, 32, 64));
-    RN_TRY(tc_make_map(&mol, ep.out_lo, P, cout, ep.ld_split, 32, 32, 64));
+    RN_TRY(tc_make_map(&m.oh, ep.out_hi, P, cout, ep.ld_split, 32, 32, 64));
+    RN_TRY(tc_make_map(&m.ol, ep.out_lo, P, cout, ep.ld_split, 32, 32, 64));
   }
-  if (bn == 256) return launch_bn<256>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
-  return launch_bn<128>(mxh, mxl, mwh, mwl, moh, mol, P, K, cout, ep, stream);
+  m.x2h = m.xh; m.x2l = m.xl;
+  const GatherA ga;
+  if (bn == 256) return launch_bn<256, false>(m, P, K, cout, ep, ga, stream);
+  return launch_bn<128, false>(m, P, K, cout, ep, ga, stream);
+}
+
+int gemm_tc_gather_launch(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, int64_t table_rows, int C, int ldt,
+                          const int32_t* nbr, int rows_per_cloud, int n_prev, const __nv_bfloat16* Zhi,
+                          const __nv_bfloat16* Zlo, const __nv_bfloat16* Whi, const __nv_bfloat16* Wlo, int ldw, int64_t P,
+                          int cout, const Epilogue& ep, cudaStream_t stream) {
+  const int K = C + 3;
+  RN_CHECK_ARG(C > 0 && C % BK == 0 && ldt % 8 == 0 && ldt >= C, "gemm_tc gather: the table needs C %% 64 == 0 columns (C=%d ldt=%d)", C, ldt);
+  RN_CHECK_ARG(ldw % 8 == 0 && ldw >= K, "gemm_tc gather: weight leading dimension (%d) must be a multiple of 8 and >= C + 3", ldw);
+  RN_CHECK_ARG(rows_per_cloud > 0 && rows_per_cloud % 4 == 0 && n_prev > 0 && table_rows < (1LL << 31),
+               "gemm_tc gather: bad grouping geometry");
+  RN_CHECK_ARG((reinterpret_cast<uintptr_t>(nbr) & 15) == 0, "gemm_tc gather: the neighbour index must be 16-byte aligned");
+  RN_TRY(check_epilogue(ep, P));
+  if (P == 0) return REGNET_OK;
+  const int bn = cout > 128 ? 256 : 128;
+  Maps m;
+  RN_TRY(tc_make_map(&m.xh, Thi, table_rows, C, ldt, 1, BK, 128));     // gather4: box = 64 columns x ONE row
+  RN_TRY(tc_make_map(&m.xl, Tlo, table_rows, C, ldt, 1, BK, 128));
+  RN_TRY(tc_make_map(&m.x2h, Zhi, P, 16, 16, BM, 16, 32));            // xyz_rel planes (P, 16), SWIZZLE_32B
+  RN_TRY(tc_make_map(&m.x2l, Zlo, P, 16, 16, BM, 16, 32));
+  RN_TRY(tc_make_map(&m.wh, Whi, cout, K, ldw, bn, BK, 128));
+  RN_TRY(tc_make_map(&m.wl, Wlo, cout, K, ldw, bn, BK, 128));
+  m.oh = m.wh; m.ol = m.wl;
+  if (ep.out_hi) {
+    RN_TRY(tc_make_map(&m.oh, ep.out_hi, P, cout, ep.ld_split, 32, 32, 64));
+    RN_TRY(tc_make_map(&m.ol, ep.out_lo, P, cout, ep.ld_split, 32, 32, 64));
+  }
+  GatherA ga;
+  ga.nbr = nbr; ga.rows_per_cloud = (uint32_t)rows_per_cloud; ga.n_prev = (uint32_t)n_prev; ga.n_feat_kb = C / BK;
+  if (bn == 256) return launch_bn<256, true>(m, P, K, cout, ep, ga, stream);
+  return launch_bn<128, true>(m, P, K, cout, ep, ga, stream);
 }
 
 }  // namespace regnet

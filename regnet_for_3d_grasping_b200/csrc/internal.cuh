@@ -41,7 +41,8 @@ int sa0_chain_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
                      const float* shift0, const __nv_bfloat16* W1hi, const __nv_bfloat16* W1lo, int ldw1,
                      const float* scale1, const float* shift1, const __nv_bfloat16* W2hi, const __nv_bfloat16* W2lo,
                      int ldw2, const float* scale2, const float* shift2, int B, int M, float* out, int ld_out,
-                     float* dbg, unsigned int* tile_counter, int variant, cudaStream_t stream);
+                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, float* dbg, unsigned int* tile_counter, int variant,
+                     cudaStream_t stream);
 int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld, int C2, const float* dense,
                       int64_t dense_bstride, int dense_ld, int C1, const int32_t* idx, const float* w, int B, int Nd,
                       int kpad, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);

@@ -57,22 +57,6 @@ constexpr int NTHREADS = 448;
 constexpr uint32_t TM_X = 0, TM_Y = 128, TM_Z = 256;
 static_assert(SMEM_BYTES <= 232448, "sa0_chain: shared memory budget");
 
-// K-major operand with 32-byte rows (K = 16 bf16): the canonical SWIZZLE_32B layout ((8,n),2):((2,SBO),1) in 16-byte
-// units -- row r at r * 32 bytes, 16-byte chunk index XOR bit 2 of the row, 8-row groups SBO = 256 bytes apart.
-// (The un-swizzled "interleave" layout with LBO = 128 B was verified to work as well during bring-up.)
-__device__ __forceinline__ uint32_t k16_offset(uint32_t row, uint32_t chunk) {
-  return row * 32u + ((chunk ^ ((row >> 2) & 1u)) << 4);
-}
-__device__ __forceinline__ uint64_t make_sdesc_k16(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-  d |= (uint64_t)1 << 16;             // LBO (unused: one swizzle span per row)
-  d |= (uint64_t)(256 >> 4) << 32;    // SBO
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)6 << 61;             // SWIZZLE_32B
-  return d;
-}
-
 // tcgen05.mma with the A operand in tensor memory (cute SM100_MMA_F16BF16_TS): A is [128 lanes x 16 bf16], two
 // consecutive k per 32-bit column, i.e. 8 columns per instruction.
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
@@ -136,6 +120,7 @@ struct Sa0ChainArgs {
   const float* scale1; const float* shift1;
   const float* scale2; const float* shift2;        // scale2 must be >= 0 (see the pool epilogue)
   float* out; int ld_out;                          // (rows / 64, 256)
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;    // optional: the same values as bf16 hi/lo planes (rows / 64, 256)
   float* dbg;                                      // MODE 1: (rows, 256): raw acc0 | raw acc1
   uint32_t M, rows;
   unsigned int* tile_counter;
@@ -499,9 +484,16 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
           const uint32_t grow = (uint32_t)tile * 2 + g;
           const float m = fmaxf(__uint_as_float(lds_u32(s_part_addr + 4 * ((2 * g) * C2 + c))),
                                 __uint_as_float(lds_u32(s_part_addr + 4 * ((2 * g + 1) * C2 + c))));
-          if (grow * 64u < a.rows)
-            a.out[(size_t)grow * a.ld_out + c] =
-                fmaxf(fmaf(m, lds_f32(s_sc2_addr + 4 * c), lds_f32(s_sc2_addr + 4 * (256 + c))), 0.f);
+          if (grow * 64u < a.rows) {
+            const float y = fmaxf(fmaf(m, lds_f32(s_sc2_addr + 4 * c), lds_f32(s_sc2_addr + 4 * (256 + c))), 0.f);
+            a.out[(size_t)grow * a.ld_out + c] = y;
+            if (a.out_hi) {   // gather table of the next level's first layer (gemm_tc.cu GatherA)
+              __nv_bfloat16 h, l;
+              split_bf16(y, h, l);
+              a.out_hi[(size_t)grow * C2 + c] = h;
+              a.out_lo[(size_t)grow * C2 + c] = l;
+            }
+          }
         }
       }
       if (TIMING) {
@@ -567,7 +559,8 @@ int sa0_chain_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
                      const float* shift0, const __nv_bfloat16* W1hi, const __nv_bfloat16* W1lo, int ldw1,
                      const float* scale1, const float* shift1, const __nv_bfloat16* W2hi, const __nv_bfloat16* W2lo,
                      int ldw2, const float* scale2, const float* shift2, int B, int M, float* out, int ld_out,
-                     float* dbg, unsigned int* tile_counter, int variant, cudaStream_t stream) {
+                     __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, float* dbg, unsigned int* tile_counter, int variant,
+                     cudaStream_t stream) {
   const int64_t rows64 = (int64_t)B * M * 64;
   RN_CHECK_ARG(rows64 > 0 && rows64 < (1LL << 31), "sa0_chain: bad row count");
   RN_CHECK_ARG(ldw1 % 8 == 0 && ldw1 >= C1 && ldw2 % 8 == 0 && ldw2 >= C1 && ldw0 >= 6, "sa0_chain: bad leading dimensions");
@@ -582,7 +575,8 @@ int sa0_chain_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
   Sa0ChainArgs a;
   a.xyz = xyz; a.xst = xst; a.new_xyz = new_xyz; a.feat = feat; a.feat_bstride = feat_bstride; a.feat_ld = feat_ld;
   a.nbr = nbr; a.W0 = W0; a.ldw0 = ldw0; a.scale0 = scale0; a.shift0 = shift0; a.scale1 = scale1; a.shift1 = shift1;
-  a.scale2 = scale2; a.shift2 = shift2; a.out = out; a.ld_out = ld_out; a.dbg = dbg; a.M = (uint32_t)M;
+  a.scale2 = scale2; a.shift2 = shift2; a.out = out; a.ld_out = ld_out; a.out_hi = out_hi; a.out_lo = out_lo;
+  a.dbg = dbg; a.M = (uint32_t)M;
   a.rows = (uint32_t)rows64; a.tile_counter = tile_counter; a.variant = variant;
   const int64_t n_tiles = (rows64 + BM - 1) / BM;
   const int grid = (int)(n_tiles < sms ? n_tiles : sms);

@@ -59,10 +59,11 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
+  int pool_planes_level = -1;              // >= 0 while the pooled layer of that SA level is being launched
   int B = 0, N = 0;
   int M[3] = {0, 0, 0};
   Layer layers[8][REGNET_MAX_LAYERS];
@@ -83,6 +84,12 @@ struct regnet_scorenet {
   int last_slot = 0;   // slot the last forward consumed (regnet_scorenet_intermediate)
   // features (fp32, point-major)
   float* sa_out[3] = {nullptr, nullptr, nullptr};    // (B,M_i,C_i)
+  // tcgen05 engine: sa_out[0], sa_out[1] also as bf16 hi/lo planes = gather tables of the next level's first layer, and
+  // the (P,16) xyz - centroid planes of the level being computed (gemm_tc.cu GatherA)
+  __nv_bfloat16* sa_hi[2] = {nullptr, nullptr};
+  __nv_bfloat16* sa_lo[2] = {nullptr, nullptr};
+  __nv_bfloat16* xyzrel_hi = nullptr;
+  __nv_bfloat16* xyzrel_lo = nullptr;
   float* fp_out[2] = {nullptr, nullptr};             // fp0 (B,M1,1024), fp1 (B,M0,512); fp2 is the caller's buffer
   float* last_allfeat = nullptr;
   // ping-pong activation arenas
@@ -175,6 +182,11 @@ int run_layer_impl(regnet_scorenet* p, const Layer& L, const Act& in, int64_t P,
     return gemm_simt_launch(in.f32, in.ld, L.w_f32, L.kpad, P, L.kpad, L.cout, ep, s);
   }
   if (out_act) { ep.out_hi = out_act->hi; ep.out_lo = out_act->lo; ep.ld_split = out_act->ld; }
+  if (pool && p->pool_planes_level >= 0 && p->sa_hi[p->pool_planes_level]) {
+    ep.pool_hi = p->sa_hi[p->pool_planes_level];
+    ep.pool_lo = p->sa_lo[p->pool_planes_level];
+    ep.ld_pool = L.cout;
+  }
   if (p->cfg.dynamic_tiles && p->gemm_idx < 64) ep.tile_counter = p->tile_counters + (p->gemm_idx++);
   return gemm_tc_launch(in.hi, in.lo, in.ld, L.w_hi, L.w_lo, L.kpad, P, L.cin, L.cout, ep, s);
 }
@@ -204,6 +216,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   static_cast<regnet_scorenet_config&>(p->cfg) = *cfg;
   if (const char* e = getenv("REGNET_FUSE_SA0")) p->cfg.fuse_sa0 = atoi(e);
   if (const char* e = getenv("REGNET_SA0_VARIANT")) p->cfg.sa0_variant = atoi(e);
+  if (const char* e = getenv("REGNET_GATHER_A")) p->cfg.gather_a = atoi(e);
   if (const char* e = getenv("REGNET_DYNAMIC_TILES")) p->cfg.dynamic_tiles = atoi(e);
   if (const char* e = getenv("REGNET_USE_GRID")) p->cfg.use_grid = atoi(e);
   if (const char* e = getenv("REGNET_FPS_CORUN")) sscanf(e, "%d,%d", &p->cfg.corun_cs, &p->cfg.corun_threads);
@@ -226,6 +239,15 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
     }
   }
   for (int i = 0; i < 3; ++i) A((void**)&p->sa_out[i], sizeof(float) * (size_t)B * M[i] * SA_CH[i][2]);
+  if (p->cfg.engine == REGNET_ENGINE_TC) {
+    for (int i = 0; i < 2; ++i) {
+      A((void**)&p->sa_hi[i], sizeof(__nv_bfloat16) * (size_t)B * M[i] * SA_CH[i][2]);
+      A((void**)&p->sa_lo[i], sizeof(__nv_bfloat16) * (size_t)B * M[i] * SA_CH[i][2]);
+    }
+    const size_t pmax = (size_t)B * std::max(M[1], M[2]) * 64;
+    A((void**)&p->xyzrel_hi, sizeof(__nv_bfloat16) * pmax * 16);
+    A((void**)&p->xyzrel_lo, sizeof(__nv_bfloat16) * pmax * 16);
+  }
   A((void**)&p->tile_counters, sizeof(unsigned int) * 64);
   A(&p->grid_ws[0], (size_t)grid_workspace_bytes(B, N));
   A(&p->grid_ws[1], (size_t)grid_workspace_bytes(B, M[0]));
@@ -509,8 +531,8 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
       prof_begin(p, "sa0_chain", ms);
       RN_TRY(sa0_chain_launch(lvl_xyz[0], lvl_st[0], G.new_xyz[0], feat, feat_bs, feat_ld, G.nbr[0], L0.w_f32, L0.kpad,
                               L0.scale, L0.shift, L1.w_hi, L1.w_lo, L1.kpad, L1.scale, L1.shift, L2.w_hi, L2.w_lo, L2.kpad,
-                              L2.scale, L2.shift, B, M[0], p->sa_out[0], SA_CH[0][2], nullptr, counter,
-                              p->cfg.sa0_variant, ms));
+                              L2.scale, L2.shift, B, M[0], p->sa_out[0], SA_CH[0][2], p->sa_hi[0], p->sa_lo[0], nullptr,
+                              counter, p->cfg.sa0_variant, ms));
       prof_end(p, ms);
       ++p->launches;
       feat = p->sa_out[i];
@@ -546,6 +568,33 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
                               L0.scale, L0.shift, L0.cout, B, M[0], 64, a1.f32, a1.hi, a1.lo, a1.ld, ms));
       prof_end(p, ms);
       ++p->launches;
+    } else if (i > 0 && (p->cfg.gather_a >> (i - 1) & 1) && p->cfg.engine == REGNET_ENGINE_TC && feat_c % 64 == 0 &&
+               p->sa_hi[i - 1]) {
+      // the grouping is fused into the first layer's TMA producer (tile::gather4 from the previous level's pooled
+      // features, kept as bf16 hi/lo planes); only the (P,16) xyz - centroid columns are materialised.  cfg.gather_a is a
+      // bit mask over levels 1, 2; default = level 1 only: gather4 moves one 128-byte row per ~24 cycles per SM, which
+      // beats the operand round trip of level 1 (1.04 -> 0.71 ms) but not of level 2, whose two 256-channel column tiles
+      // gather every row twice (0.54 -> 0.64 ms).
+      const Layer& L0 = p->layers[i][0];
+      if (!L0.set) {
+        set_error("scorenet: sa_modules.%d.mlp.0 was never given weights", i);
+        return REGNET_EINVAL;
+      }
+      prof_begin(p, i == 1 ? "sa_xyzrel.1" : "sa_xyzrel.2", ms);
+      RN_TRY(sa_operand_launch(lvl_xyz[i], lvl_st[i], G.new_xyz[i], nullptr, 0, 0, 0, G.nbr[i], B, lvl_n[i], M[i], 64, 16,
+                               nullptr, p->xyzrel_hi, p->xyzrel_lo, ms));
+      prof_end(p, ms);
+      ++p->launches;
+      Epilogue ep;
+      ep.scale = L0.scale; ep.shift = L0.shift; ep.act = 1; ep.pool = 0;
+      ep.out_hi = a1.hi; ep.out_lo = a1.lo; ep.ld_split = a1.ld;
+      if (p->cfg.dynamic_tiles && p->gemm_idx < 64) ep.tile_counter = p->tile_counters + (p->gemm_idx++);
+      prof_begin(p, GEMM_LABEL[i][0], ms);
+      RN_TRY(gemm_tc_gather_launch(p->sa_hi[i - 1], p->sa_lo[i - 1], (int64_t)B * lvl_n[i], feat_c, feat_c, G.nbr[i],
+                                   M[i] * 64, lvl_n[i], p->xyzrel_hi, p->xyzrel_lo, L0.w_hi, L0.w_lo, L0.kpad, P, L0.cout,
+                                   ep, ms));
+      prof_end(p, ms);
+      ++p->launches;
     } else {
       Act a0 = make_act(p, 0, P, kpad);
       prof_begin(p, SAOP_LABEL[i], ms);
@@ -556,7 +605,9 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
       RN_TRY(run_layer(p, GEMM_LABEL[i][0], p->layers[i][0], a0, P, 1, 0, &a1, nullptr, 0, ms));
     }
     if (need_l1) RN_TRY(run_layer(p, GEMM_LABEL[i][1], p->layers[i][1], a1, P, 1, 0, &a2, nullptr, 0, ms));
+    p->pool_planes_level = (i < 2 && p->cfg.engine == REGNET_ENGINE_TC) ? i : -1;   // picked up by run_layer_impl
     RN_TRY(run_layer(p, GEMM_LABEL[i][2], p->layers[i][2], a2, P, 1, 64, nullptr, p->sa_out[i], SA_CH[i][2], ms));
+    p->pool_planes_level = -1;
     feat = p->sa_out[i];
     feat_c = feat_ld = SA_CH[i][2];
     feat_bs = (int64_t)M[i] * feat_c;

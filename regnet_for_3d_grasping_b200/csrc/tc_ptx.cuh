@@ -54,6 +54,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// tile::gather4: four arbitrary rows (r0..r3) of a 2-D tensor, columns [c0, c0 + box_cols), land as four consecutive rows
+// of the shared-memory tile at dst (swizzled like any other row of that tile).  The tensor map's box must be
+// {box_cols, 1 row}; a {box_cols, 4} box raises "illegal instruction" (scripts/ubench/tma_gather4.cu).
+__device__ __forceinline__ void tma_gather4_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int r0, int r1,
+                                               int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
@@ -153,6 +164,21 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
+  return d;
+}
+// K-major operand with 32-byte rows (K = 16 bf16): the canonical SWIZZLE_32B layout ((8,n),2):((2,SBO),1) in 16-byte
+// units -- row r at r * 32 bytes, 16-byte chunk index XOR bit 2 of the row, 8-row groups SBO = 256 bytes apart.
+// (The un-swizzled "interleave" layout with LBO = 128 B was verified to work as well during bring-up.)
+__device__ __forceinline__ uint32_t k16_offset(uint32_t row, uint32_t chunk) {
+  return row * 32u + ((chunk ^ ((row >> 2) & 1u)) << 4);
+}
+__device__ __forceinline__ uint64_t make_sdesc_k16(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;             // LBO (unused: one swizzle span per row)
+  d |= (uint64_t)(256 >> 4) << 32;    // SBO
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;             // SWIZZLE_32B
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
