@@ -154,12 +154,85 @@ def gen_heads():
     print("heads golden ok", cls.shape, reg.shape, rcls.shape)
 
 
+def deterministic_choice(n, k, replace=True):
+    """Stand-in for np.random.choice inside the reference while the region-net fixture is generated: the reference's
+    picks come from a wall-clock-seeded global RNG and cannot be reproduced, a fixed rule can.  Without replacement:
+    the first k; with replacement: (7 i + 3) mod n.  tests/helpers.py applies the same rule to the product's mask."""
+    return np.arange(k) if not replace else (np.arange(k) * 7 + 3) % n
+
+
+def region_net_inputs(seed=5, B=2, N=900, N_C=6, N_G=16, N_GM=96):
+    """Seeded inputs of GripperRegionNetwork.forward with real geometry: centres on the cloud, groups = nearest points."""
+    g = torch.Generator().manual_seed(seed)
+    pc = torch.from_numpy(synth.batch("table", [31, 32][:B], N))
+    # shrink the scene around its centroid: ~15 points per cm^2, so that the 3 x 8 x 1 cm closing boxes of randomly
+    # oriented grasps hold anything from 0 to a few dozen points (accept / reject / both sampling branches all occur)
+    mean = pc[:, :, :3].mean(dim=1, keepdim=True)
+    pc[:, :, :3] = (pc[:, :, :3] - mean) * 0.25 + mean
+    all_feature = torch.randn(B, N, 256, generator=g)
+    center_idx = torch.stack([torch.randperm(N, generator=g)[:N_C] for _ in range(B)])
+    center_pc = torch.stack([pc[b, center_idx[b]] for b in range(B)])
+    d = torch.cdist(center_pc[:, :, :3], pc[:, :, :3])                      # (B, N_C, N)
+    more_idx = d.topk(N_GM, dim=2, largest=False)[1]
+    grp_idx = more_idx[:, :, :N_G].contiguous()
+    gather = lambda idx: torch.stack([pc[b][idx[b]] for b in range(B)])
+    return dict(pc=pc, all_feature=all_feature, center_pc=center_pc, center_pc_index=center_idx, pc_group_index=grp_idx,
+                pc_group=gather(grp_idx), pc_group_more_index=more_idx, pc_group_more=gather(more_idx))
+
+
+def gen_region_net(weight_seed=46, save=True):
+    """multi_model/gripper_region_network.py, inference call (ground_grasp=None), run UNMODIFIED on CPU: its
+    unconditional `.cuda()` calls are made no-ops and np.random.choice is replaced by deterministic_choice."""
+    import multi_model.gripper_region_network as ref
+    from regnet_for_3d_grasping_b200.weights import seeded_state_like
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    ref.np.random.choice = deterministic_choice
+    net = ref.GripperRegionNetwork(training=True, group_num=16, gripper_num=8, grasp_score_threshold=0.4, radius=0.06,
+                                   reg_channel=10).eval()
+    net.load_state_dict(seeded_state_like(net.state_dict(), seed=weight_seed), strict=True)
+    inp = region_net_inputs()
+    params = [0.08, 0.010, 0.06]
+    import contextlib
+    import io
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        out = net(inp["pc_group"], inp["pc_group_more"], inp["pc_group_index"], inp["pc_group_more_index"], inp["center_pc"],
+                  inp["center_pc_index"], inp["pc"], inp["all_feature"], params)
+        M, NGM = 12, inp["pc_group_more"].shape[2]
+        gp, gi, ginall, gmask = ref.get_gripper_region_transform(inp["pc_group_more"].view(M, NGM, 6),
+                                                                 inp["pc_group_more_index"].view(M, NGM), out[0], 8, params)
+    (next_grasp, keep2, true_mask, loss_tuple, correct_tuple, next_gt, sel_class, sel_score, sel_stage2, keep3, keep3s,
+     final_mask, final_mask_sthre, loss_refine, correct_refine, gt) = out
+    assert loss_tuple == (None, None) and next_gt is None and gt is None
+    pcs_t_mask = [int((gi[m] >= 0).any()) for m in range(M)]
+    print("accepted:", pcs_t_mask, "gripper_mask", gmask.tolist())
+    if not save:
+        return len(gmask), (0 if final_mask is None else len(final_mask)), (0 if final_mask_sthre is None else len(final_mask_sthre))
+    assert final_mask is not None and len(final_mask) > 0, "fixture should exercise the refine stage"
+    save = {k: v.numpy() for k, v in inp.items()}
+    save.update(next_grasp=next_grasp.numpy(), keep2=np.array([int(k) for k in keep2]), true_mask=true_mask.numpy(),
+                sel_class=sel_class.numpy(), sel_score=sel_score.numpy(), sel_stage2=sel_stage2.numpy(),
+                keep3=np.array([int(k) for k in keep3]), keep3s=np.array([int(k) for k in keep3s]),
+                final_mask=final_mask.numpy(), final_mask_sthre=final_mask_sthre.numpy(),
+                gripper_pc=gp.numpy(), gripper_pc_index=gi.numpy(), gripper_pc_index_inall=ginall.numpy(),
+                gripper_mask=gmask.numpy(), params=np.array(params),
+                meta=np.array("GripperRegionNetwork(True,16,8,0.4,0.06,10).eval(), weights seeded_state_like(seed=weight_seed); "
+                              "inputs gen_golden_cpu.region_net_inputs(); np.random.choice -> deterministic_choice"),
+                weight_seed=np.array(weight_seed))
+    np.savez_compressed(os.path.join(OUT, "ref_py_region_net.npz"), **save)
+    print("region-net golden ok: accepted grasps", len(gmask), "of", M, "; positives", len(final_mask), "; above threshold",
+          len(final_mask_sthre))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ScoreNetwork, ref_mods = import_reference()
     if "heads" in sys.argv:
         gen_heads()
         sys.exit(0)
+    if "region_net" in sys.argv:
+        gen_region_net()
+        sys.exit(0)
     gen_modules(ref_mods)
     gen_scorenet(ScoreNetwork)
     gen_heads()
+    gen_region_net()

@@ -13,6 +13,12 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+def _conv1x1(conv, x2d):
+    """A Conv1d(kernel 1) applied to (M, C_in) rows as an fp32 GEMM.  cuDNN convolutions default to TF32 on this
+    hardware (torch.backends.cudnn.allow_tf32), which costs ~1e-3 of relative accuracy; torch.matmul stays fp32."""
+    return torch.addmm(conv.bias, x2d, conv.weight.view(conv.out_channels, conv.in_channels).t())
+
+
 class PointNet2TwoStage(nn.Module):
     def __init__(self, num_points, input_chann, k_cls, k_reg, k_reg_theta, add_channel_flag=False):
         super().__init__()
@@ -41,14 +47,14 @@ class PointNet2TwoStage(nn.Module):
         self.sigmod = nn.Sigmoid()
 
     def _heads(self, mp_x):
-        x = F.relu(self.bn(self.conv(mp_x)))
-        c = F.relu(self.bn_cls2(self.conv_cls2(x)))
-        c = F.relu(self.bn_cls3(self.conv_cls3(c)))
-        c = self.bn_cls4(self.conv_cls4(c))
-        x_cls = c.view(c.size(0), c.size(1))
-        r = F.relu(self.bn_reg2(self.conv_reg2(x)))
-        r = F.relu(self.bn_reg3(self.conv_reg3(r)))
-        r = self.bn_reg4(self.conv_reg4(r))
+        m = mp_x.reshape(mp_x.shape[0], -1)                        # (M, C, 1) -> (M, C): every layer is a 1x1 convolution
+        x = F.relu(self.bn(_conv1x1(self.conv, m)))
+        c = F.relu(self.bn_cls2(_conv1x1(self.conv_cls2, x)))
+        c = F.relu(self.bn_cls3(_conv1x1(self.conv_cls3, c)))
+        x_cls = self.bn_cls4(_conv1x1(self.conv_cls4, c))
+        r = F.relu(self.bn_reg2(_conv1x1(self.conv_reg2, x)))
+        r = F.relu(self.bn_reg3(_conv1x1(self.conv_reg3, r)))
+        r = self.bn_reg4(_conv1x1(self.conv_reg4, r))
         x_reg = r.view(r.size(0), -1, self.k_reg_no_anchor)
         x_reg[:, :, 7:] = self.sigmod(x_reg[:, :, 7:])      # scores in (0,1); in place like the reference (:189)
         return x_cls, x_reg
@@ -90,12 +96,12 @@ class PointNet2Refine(nn.Module):
         self.sigmoid = nn.Sigmoid()
 
     def _heads(self, x):
-        x = F.relu(self.bn_formal(self.conv_formal(x)))
-        c = F.relu(self.bn_formal_cls2(self.conv_formal_cls2(x)))
-        c = self.bn_formal_cls3(self.conv_formal_cls3(c))
-        r = F.relu(self.bn_formal_reg2(self.conv_formal_reg2(x)))
-        r = self.bn_formal_reg3(self.conv_formal_reg3(r))
-        return c.view(c.shape[0], c.shape[1]), r.view(r.shape[0], r.shape[1])
+        x = F.relu(self.bn_formal(_conv1x1(self.conv_formal, x.reshape(x.shape[0], -1))))
+        c = F.relu(self.bn_formal_cls2(_conv1x1(self.conv_formal_cls2, x)))
+        c = self.bn_formal_cls3(_conv1x1(self.conv_formal_cls3, c))
+        r = F.relu(self.bn_formal_reg2(_conv1x1(self.conv_formal_reg2, x)))
+        r = self.bn_formal_reg3(_conv1x1(self.conv_formal_reg3, r))
+        return c, r
 
     def forward(self, gripper_feature, group_feature):
         """gripper_feature (M', 256, 64) [, group_feature (M', 128)] -> x_cls (M',k_cls), x_reg (M',k_reg)."""

@@ -27,3 +27,17 @@ def rel_err(got, want):
 def bq_rowhash(bq, K):
     w = (np.arange(K, dtype=np.int64) * 2654435761 % 1000003 + 1)
     return (np.asarray(bq, dtype=np.int64) * w).sum(-1)
+
+
+def region_net_fixture():
+    import torch
+    from regnet_for_3d_grasping_b200.gripper_region_network import GripperRegionNetwork
+    from regnet_for_3d_grasping_b200.weights import seeded_state_like
+    from conftest import golden
+    ref = golden("ref_py_region_net.npz")
+    net = GripperRegionNetwork(training=True, group_num=16, gripper_num=8, grasp_score_threshold=0.4, radius=0.06,
+                               reg_channel=10).eval()
+    sd = seeded_state_like(net.state_dict(), seed=int(ref["weight_seed"]))
+    inp = {k: torch.from_numpy(ref[k]) for k in ("pc", "all_feature", "center_pc", "center_pc_index", "pc_group_index",
+                                                 "pc_group", "pc_group_more_index", "pc_group_more")}
+    return ref, net, sd, inp

@@ -168,3 +168,77 @@ def test_get_grasp_allobj_shapes_test_config(lib_path):
     assert torch.equal(out2[2], gi) and torch.equal(out2[4], gmi)         # torch.manual_seed makes the draws reproducible
     with pytest.raises(NotImplementedError):
         region.get_grasp_allobj(pc.cuda(), score.cuda(), params, ["scene.p"])
+
+
+def _region_net_on_gpu():
+    import numpy as np
+    from helpers import region_net_fixture
+    ref, net, sd, inp = region_net_fixture()
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    inp = {k: v.cuda() for k, v in inp.items()}
+    params = [float(x) for x in ref["params"]]
+    args = (inp["pc_group"], inp["pc_group_more"], inp["pc_group_index"], inp["pc_group_more_index"], inp["center_pc"],
+            inp["center_pc_index"], inp["pc"], inp["all_feature"], params)
+    return ref, net, inp, params, args, np
+
+
+def test_region_network_vs_reference_python_golden(lib_path, oracle):
+    """GripperRegionNetwork mirror (rows R3-R7) against the fixture produced by the REAL reference module: the whole
+    16-tuple of the inference call, with the reference's random picks replaced by the fixture's fixed rule on both sides."""
+    from oracle import region_oracle
+    from regnet_for_3d_grasping_b200.gripper_region_network import get_gripper_region_transform
+    ref, net, inp, params, args, np = _region_net_on_gpu()
+    net._sampler = lambda mask: region_oracle.sample_rows_fixed_rule(mask.cpu(), 8).to(mask.device)
+    with torch.no_grad():
+        out = net(*args)
+    (next_grasp, keep2, true_mask, loss_tuple, correct_tuple, next_gt, sel_class, sel_score, sel_stage2, keep3, keep3s,
+     final_mask, final_mask_sthre, loss_refine, correct_refine, gt) = out
+    assert len(out) == 16 and loss_tuple == (None, None) and next_gt is None and gt is None
+    np.testing.assert_allclose(next_grasp.cpu().numpy(), ref["next_grasp"], rtol=1e-4, atol=1e-5)
+    assert [int(k) for k in keep2] == ref["keep2"].tolist() and torch.equal(true_mask.cpu(), torch.arange(12))
+    assert np.array_equal(final_mask.cpu().numpy(), ref["final_mask"])
+    assert np.array_equal(final_mask_sthre.cpu().numpy(), ref["final_mask_sthre"])
+    assert [int(k) for k in keep3] == ref["keep3"].tolist() and [int(k) for k in keep3s] == ref["keep3s"].tolist()
+    for got, key in ((sel_class, "sel_class"), (sel_score, "sel_score"), (sel_stage2, "sel_stage2")):
+        np.testing.assert_allclose(got.cpu().numpy(), ref[key], rtol=1e-4, atol=1e-5)
+    # the stand-alone closing-box function: same outputs as the reference's, dtype quirk included
+    M, NGM = 12, inp["pc_group_more"].shape[2]
+    gp, gi, ginall, gmask = get_gripper_region_transform(inp["pc_group_more"].view(M, NGM, 6),
+                                                         inp["pc_group_more_index"].view(M, NGM), next_grasp, 8, params,
+                                                         sampler=net._sampler)
+    assert gp.dtype == torch.int64 and np.array_equal(gp.cpu().numpy(), ref["gripper_pc"])
+    assert np.array_equal(gi.cpu().numpy(), ref["gripper_pc_index"])
+    assert np.array_equal(ginall.cpu().numpy(), ref["gripper_pc_index_inall"])
+    assert np.array_equal(gmask.cpu().numpy(), ref["gripper_mask"])
+
+
+def test_region_network_device_sampler_properties(lib_path, oracle):
+    """Same call with the device sampler: the accepted grasps and the closing-box membership are deterministic (equal to
+    the fixture), every sampled index is a member of its box, and a fixed seed reproduces the draw."""
+    from oracle import region_oracle
+    from regnet_for_3d_grasping_b200.gripper_region_network import closing_box_points, get_gripper_region_transform
+    ref, net, inp, params, args, np = _region_net_on_gpu()
+    net.sample_seed = 1234
+    with torch.no_grad():
+        a = net(*args)
+        b = net(*args)
+    assert torch.equal(a[11], b[11]) and torch.equal(a[6], b[6])                        # reproducible with a seed
+    M, NGM = 12, inp["pc_group_more"].shape[2]
+    pts = inp["pc_group_more"].view(M, NGM, 6)
+    _, mask = closing_box_points(pts, a[0], params)
+    _, want_mask = region_oracle.closing_box(pts.cpu(), a[0].cpu(), params)
+    assert torch.equal(mask.cpu(), want_mask)
+    _, gi, ginall, gmask = get_gripper_region_transform(pts, inp["pc_group_more_index"].view(M, NGM), a[0], 8, params, seed=7)
+    assert np.array_equal(gmask.cpu().numpy(), ref["gripper_mask"])                     # accept / reject is not random
+    for m in gmask.tolist():
+        assert mask[m][gi[m]].all()
+        assert torch.equal(ginall[m], inp["pc_group_more_index"].view(M, NGM)[m][gi[m]])
+    rejected = [m for m in range(M) if m not in gmask.tolist()]
+    assert all((gi[m] == -1).all() and mask[m].sum() <= 5 for m in rejected)
+
+
+def test_region_network_rejects_training_call(lib_path):
+    ref, net, inp, params, args, np = _region_net_on_gpu()
+    with pytest.raises(NotImplementedError):
+        net(*args, ground_grasp=torch.zeros(2, 6, 10, device="cuda"))

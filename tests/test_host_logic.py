@@ -143,3 +143,28 @@ def test_region_heads_match_reference_outputs():
     assert torch.equal(cls, cls2) and torch.equal(reg, reg2) and torch.equal(mp, mp2)
     assert torch.equal(rcls, rcls2) and torch.equal(rreg, rreg2)
     assert tuple(reg.shape) == (12, 4, 10) and (reg[:, :, 7:] > 0).all() and (reg[:, :, 7:] < 1).all()
+
+
+def test_region_network_state_dict_schema():
+    """GripperRegionNetwork mirror: Appendix B keys and parameter count (1 524 396), templates rounded through fp16, and
+    the drop-in import path resolves to it."""
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from regnet_for_3d_grasping_b200.gripper_region_network import GripperRegionNetwork, _enumerate_templates
+    net = GripperRegionNetwork(training=True, group_num=256, gripper_num=64, grasp_score_threshold=0.5, radius=0.06, reg_channel=10)
+    assert sum(p.numel() for p in net.parameters()) == 1524396
+    keys = set(net.state_dict().keys())
+    for k in ("extrat_feature_region.conv.weight", "extrat_feature_region.linear_cls.weight",
+              "extrat_feature_region.conv_reg4.bias", "extrat_feature_region.bn_cls4.running_var",
+              "extrat_feature_refine.conv_formal.weight", "extrat_feature_refine.bn_formal_reg3.num_batches_tracked"):
+        assert k in keys
+    assert tuple(net.state_dict()["extrat_feature_refine.conv_formal.weight"].shape) == (1024, 384, 1)
+    t = _enumerate_templates()
+    assert t.dtype == torch.float16 and tuple(t.shape) == (1, 4, 1, 4) and net.anchor_number == 4
+    assert abs(float(t[0, 0, 0, 0]) - 0.57735) < 1e-3 and float(t[0, 0, 0, 0]) != 3 ** 0.5 / 3      # fp16-rounded
+    code = ("import sys; sys.path.insert(0, %r); import multi_model.gripper_region_network as m; "
+            "print(m.GripperRegionNetwork.__module__)" % os.path.join(ROOT, "regnet_for_3d_grasping_b200", "dropin"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and "regnet_for_3d_grasping_b200.gripper_region_network" in out.stdout, out.stderr

@@ -133,3 +133,25 @@ def test_oracle_edge_cases(oracle):
     assert idx.abs().sum() == 0 and cnt.sum() == 0
     idx, cnt = oracle.ball_query(xyz, xyz, 1e-3, 4)         # only itself -> replicated
     assert torch.equal(idx, torch.arange(10).view(1, 10, 1).expand(1, 10, 4)) and (cnt == 1).all()
+
+
+from helpers import region_net_fixture as _region_net_fixture  # noqa: E402
+
+
+def test_region_net_oracle_vs_reference_python():
+    """oracle/region_oracle.region_net_forward against the fixture the REAL GripperRegionNetwork produced on CPU
+    (rows R3-R7 of SURVEY.md section 8a, inference call): decode, closing-box membership + index mapping, refine
+    selection.  Index outputs bit-exact, grasp parameters to fp32 round-off."""
+    import torch
+    from oracle import region_oracle
+    ref, _, sd, inp = _region_net_fixture()
+    out = region_oracle.region_net_forward(sd, inp, [float(x) for x in ref["params"]])
+    np.testing.assert_allclose(out["next_grasp"].numpy(), ref["next_grasp"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(out["gripper_mask"].numpy(), ref["gripper_mask"])
+    assert np.array_equal(out["gripper_pc_index"].numpy(), ref["gripper_pc_index"])
+    assert np.array_equal(out["gripper_pc_index_inall"].numpy(), ref["gripper_pc_index_inall"])
+    assert np.array_equal(out["final_mask"].numpy(), ref["final_mask"])
+    assert np.array_equal(out["final_mask_sthre"].numpy(), ref["final_mask_sthre"])
+    for k in ("sel_class", "sel_score", "sel_stage2"):
+        np.testing.assert_allclose(out[k].numpy(), ref[k], rtol=1e-4, atol=1e-5)
+    assert 0 < len(ref["final_mask_sthre"]) < len(ref["final_mask"]) < len(ref["gripper_mask"]) < 12   # every branch is hit
