@@ -23,6 +23,13 @@ struct Epilogue {
   __nv_bfloat16* out_lo = nullptr;
   int ld_split = 0;
   unsigned int* tile_counter = nullptr;  // tcgen05 engine: zeroed device counter => dynamic tile scheduling
+  // tcgen05 engine, pool == 0, cout <= 128: a fused 1-output head on the activated row, the reference's
+  // conv_score (cout -> 1, with bias) + bn_score + sigmoid of pointnet2.py:82-84,117-119:
+  //   dot_out[p] = sigmoid(dot_scale[0] * (y[p,:] . dot_w) + dot_shift[0])
+  const float* dot_w = nullptr;
+  const float* dot_scale = nullptr;
+  const float* dot_shift = nullptr;
+  float* dot_out = nullptr;
   __nv_bfloat16* pool_hi = nullptr;      // tcgen05 engine, pool != 0: the pooled values also as bf16 hi/lo planes
   __nv_bfloat16* pool_lo = nullptr;      //   (P / pool, ld_pool) -- the gather table of the next level's first layer
   int ld_pool = 0;

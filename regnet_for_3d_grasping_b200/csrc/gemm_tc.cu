@@ -272,11 +272,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
       const int64_t row0 = (int64_t)(tile / n_ctile) * BM;
       const int col0 = (tile % n_ctile) * BN;
       // stage this channel tile's scale / shift (previous tile's readers are past the trailing barrier)
+      const bool do_dot = !POOL && ep.dot_w != nullptr;   // fused 1-output head (Epilogue::dot_*), weights in s_part
+      float* s_dotw = reinterpret_cast<float*>(s_part);
       for (int c = et; c < BN; c += EPI_THREADS) {
         const int gc = col0 + c;
         s_scale[c] = (ep.scale && gc < cout) ? ep.scale[gc] : 1.f;
         s_shift[c] = (ep.shift && gc < cout) ? ep.shift[gc] : 0.f;
+        if (do_dot) s_dotw[c] = gc < cout ? ep.dot_w[gc] : 0.f;
       }
+      float dacc = 0.f;
       epi_bar_sync();
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
@@ -325,6 +329,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
             y[4 * j4 + 1] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, sh.y));
             y[4 * j4 + 2] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, sh.z));
             y[4 * j4 + 3] = act_fn<ACT>(fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, sh.w));
+          }
+          if (do_dot) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dacc = fmaf(y[j], s_dotw[ch * 32 + half * 16 + j], dacc);
           }
           {
             if (stage_out) {
@@ -375,6 +383,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_xhi, const __grid_constan
             }
           }
         }
+      }
+      if (do_dot && row_ok) {
+        const float v = fmaf(dacc, ep.dot_scale ? ep.dot_scale[0] : 1.f, ep.dot_shift ? ep.dot_shift[0] : 0.f);
+        ep.dot_out[row] = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-v)));
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
@@ -515,6 +527,7 @@ static int check_epilogue(const Epilogue& ep, int64_t P) {
   RN_CHECK_ARG(!ep.out_hi || ep.ld_split % 8 == 0, "gemm_tc: split output leading dimension must be a multiple of 8");
   RN_CHECK_ARG(P < (1LL << 31), "gemm_tc: too many rows");
   RN_CHECK_ARG(ep.act >= 0 && ep.act <= 2, "gemm_tc: unknown activation %d", ep.act);
+  RN_CHECK_ARG(!ep.dot_w || (ep.dot_out && !ep.pool), "gemm_tc: the fused 1-output head needs dot_out and no pooling");
   return REGNET_OK;
 }
 
@@ -524,6 +537,7 @@ int gemm_tc_launch(const __nv_bfloat16* Xhi, const __nv_bfloat16* Xlo, int ldx, 
   RN_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= K && ldw >= K,
                "gemm_tc: leading dimensions must be multiples of 8 and >= K (K=%d ldx=%d ldw=%d)", K, ldx, ldw);
   RN_TRY(check_epilogue(ep, P));
+  RN_CHECK_ARG(!ep.dot_w || cout <= 128, "gemm_tc: the fused 1-output head needs cout <= 128 (one column tile)");
   if (P == 0) return REGNET_OK;
   const int bn = cout > 128 ? 256 : 128;
   Maps m;

@@ -64,6 +64,8 @@ struct regnet_scorenet {
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
   int pool_planes_level = -1;              // >= 0 while the pooled layer of that SA level is being launched
+  const void* score_head = nullptr;        // Layer* of the score head while the last seg layer is being launched
+  float* score_out = nullptr;
   int B = 0, N = 0;
   int M[3] = {0, 0, 0};
   Layer layers[8][REGNET_MAX_LAYERS];
@@ -182,6 +184,10 @@ int run_layer_impl(regnet_scorenet* p, const Layer& L, const Act& in, int64_t P,
     return gemm_simt_launch(in.f32, in.ld, L.w_f32, L.kpad, P, L.kpad, L.cout, ep, s);
   }
   if (out_act) { ep.out_hi = out_act->hi; ep.out_lo = out_act->lo; ep.ld_split = out_act->ld; }
+  if (p->score_head) {
+    const Layer* H = static_cast<const Layer*>(p->score_head);
+    ep.dot_w = H->w_f32; ep.dot_scale = H->scale; ep.dot_shift = H->shift; ep.dot_out = p->score_out;
+  }
   if (pool && p->pool_planes_level >= 0 && p->sa_hi[p->pool_planes_level]) {
     ep.pool_hi = p->sa_hi[p->pool_planes_level];
     ep.pool_lo = p->sa_lo[p->pool_planes_level];
@@ -673,22 +679,27 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
       cur = nxt;
       which ^= 1;
     }
-    float* last = reinterpret_cast<float*>(p->arena[which]);  // (P,128) fp32
-    if (p->cfg.engine == REGNET_ENGINE_SIMT) {
-      Act o; o.f32 = last; o.ld = 128;
-      RN_TRY(run_layer(p, GEMM_LABEL[6][3], p->layers[6][3], cur, P, 1, 0, &o, nullptr, 0, ms));
-    } else {
-      RN_TRY(run_layer(p, GEMM_LABEL[6][3], p->layers[6][3], cur, P, 1, 0, nullptr, last, 128, ms));
-    }
     const Layer& H = p->layers[7][0];
     if (!H.set) {
       set_error("scorenet: score head weights were never set");
       return REGNET_EINVAL;
     }
-    prof_begin(p, "score_head", ms);
-    RN_TRY(score_head_launch(last, 128, H.w_f32, H.scale, H.shift, P, 128, score, ms));
-    prof_end(p, ms);
-    ++p->launches;
+    if (p->cfg.engine == REGNET_ENGINE_SIMT) {
+      float* last = reinterpret_cast<float*>(p->arena[which]);  // (P,128) fp32
+      Act o; o.f32 = last; o.ld = 128;
+      RN_TRY(run_layer(p, GEMM_LABEL[6][3], p->layers[6][3], cur, P, 1, 0, &o, nullptr, 0, ms));
+      prof_begin(p, "score_head", ms);
+      RN_TRY(score_head_launch(last, 128, H.w_f32, H.scale, H.shift, P, 128, score, ms));
+      prof_end(p, ms);
+      ++p->launches;
+    } else {
+      // last seg layer (256 -> 128) with the score head (128 -> 1, BN, sigmoid) fused into its epilogue: the (P,128)
+      // activation is consumed in registers and never written
+      p->score_head = &H;
+      p->score_out = score;
+      RN_TRY(run_layer(p, GEMM_LABEL[6][3], p->layers[6][3], cur, P, 1, 0, nullptr, nullptr, 0, ms));
+      p->score_head = nullptr;
+    }
   }
   return REGNET_OK;
 }
