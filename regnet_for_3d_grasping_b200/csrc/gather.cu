@@ -276,6 +276,64 @@ fp_operand_kernel(const float* __restrict__ sparse, int64_t sparse_bstride, int 
   }
 }
 
+
+// FP module with the first 1x1 convolution applied BEFORE the interpolation (both are linear, so they commute):
+//   reference (modules.py:117-127 + conv.py:24-36):  y = act(scale * W [ sum_k w_k f[idx_k] | dense ] + shift)
+//   here:   Y = f W_s^T at the Ns sparse points (tensor cores, Ns << Nd rows),  D = dense W_d^T (or a 3-channel matvec),
+//           y[n] = act(scale * (sum_k w_k Y[idx_k] + D[n]) + shift)
+// The GEMM shrinks from Nd x (C2 + C1) x cout to Ns x C2 x cout (+ Nd x C1 x cout), the (Nd, C2 + C1) operand is never
+// built, and this kernel reads 3 rows of cout floats per point from an L2-resident table.  One thread = (row, 4 channels).
+__global__ void __launch_bounds__(THREADS)
+fp_interp_affine_kernel(const float* __restrict__ Y, int64_t y_bstride, int ldy, const float* __restrict__ D, int ldd,
+                        const float* __restrict__ dense3, int64_t dense3_bstride, int dense3_ld,
+                        const float* __restrict__ Wd3, int ldw3, const int32_t* __restrict__ idx,
+                        const float* __restrict__ w, const float* __restrict__ scale, const float* __restrict__ shift,
+                        uint32_t Nd, int cout, uint32_t rows, OperandOut out) {
+  constexpr uint32_t TQ = 32, RPB = THREADS / TQ;
+  const uint32_t q = blockIdx.y * TQ + (threadIdx.x % TQ);
+  if ((int)(q * 4) >= cout) return;
+  const int c0 = (int)q * 4;
+  const float4 sc = *reinterpret_cast<const float4*>(scale + c0), sh = *reinterpret_cast<const float4*>(shift + c0);
+  float wd[4][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  if (Wd3) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) wd[u][c] = Wd3[(c0 + u) * ldw3 + c];
+  }
+  for (uint32_t row = blockIdx.x * RPB + threadIdx.x / TQ; row < rows; row += gridDim.x * RPB) {
+    const uint32_t b = row / Nd, n = row - b * Nd;
+    const int i0 = idx[row * 3], i1 = idx[row * 3 + 1], i2 = idx[row * 3 + 2];
+    const float w0 = w[row * 3], w1 = w[row * 3 + 1], w2 = w[row * 3 + 2];
+    const float* __restrict__ yp = Y + (int64_t)b * y_bstride + c0;
+    const float4 a0 = *reinterpret_cast<const float4*>(yp + (int64_t)i0 * ldy);
+    const float4 a1 = *reinterpret_cast<const float4*>(yp + (int64_t)i1 * ldy);
+    const float4 a2 = *reinterpret_cast<const float4*>(yp + (int64_t)i2 * ldy);
+    float4 v;
+    v.x = __fmaf_rn(a2.x, w2, __fmaf_rn(a1.x, w1, __fmul_rn(a0.x, w0)));
+    v.y = __fmaf_rn(a2.y, w2, __fmaf_rn(a1.y, w1, __fmul_rn(a0.y, w0)));
+    v.z = __fmaf_rn(a2.z, w2, __fmaf_rn(a1.z, w1, __fmul_rn(a0.z, w0)));
+    v.w = __fmaf_rn(a2.w, w2, __fmaf_rn(a1.w, w1, __fmul_rn(a0.w, w0)));
+    if (D) {
+      const float4 d = *reinterpret_cast<const float4*>(D + (int64_t)row * ldd + c0);
+      v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+    }
+    if (Wd3) {
+      const float* __restrict__ dp = dense3 + (int64_t)b * dense3_bstride + (int64_t)n * dense3_ld;
+      const float r0 = dp[0], r1 = dp[1], r2 = dp[2];
+      v.x = fmaf(wd[0][2], r2, fmaf(wd[0][1], r1, fmaf(wd[0][0], r0, v.x)));
+      v.y = fmaf(wd[1][2], r2, fmaf(wd[1][1], r1, fmaf(wd[1][0], r0, v.y)));
+      v.z = fmaf(wd[2][2], r2, fmaf(wd[2][1], r1, fmaf(wd[2][0], r0, v.z)));
+      v.w = fmaf(wd[3][2], r2, fmaf(wd[3][1], r1, fmaf(wd[3][0], r0, v.w)));
+    }
+    v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+    v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+    v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+    v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+    store_quad(out, (int64_t)row * cout + c0, v);
+  }
+}
+
 // fp32 rows -> bf16 hi/lo planes (used for weights and by regnet_mlp_layer)
 __global__ void __launch_bounds__(THREADS)
 split_rows_kernel(const float* __restrict__ src, int64_t rows, int cols, int ld_src, int kpad, int rot,
@@ -402,6 +460,26 @@ int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld
   fp_operand_kernel<<<grid, THREADS, 0, stream>>>(sparse, sparse_bstride, sparse_ld, C2, dense, dense_bstride, dense_ld,
                                                   C1, sparse_vec, dense_vec, idx, w, (uint32_t)Nd, kpad, (uint32_t)rows64, o);
   RN_LAUNCH_CHECK("fp_operand_kernel");
+  return REGNET_OK;
+}
+
+
+// y = relu(scale * (3-NN interpolation of Y + D [+ Wd3 . dense3]) + shift) as bf16 hi/lo planes (rows, cout); see the kernel
+int fp_interp_affine_launch(const float* Y, int64_t y_bstride, int ldy, const float* D, int ldd, const float* dense3,
+                            int64_t dense3_bstride, int dense3_ld, const float* Wd3, int ldw3, const int32_t* idx,
+                            const float* w, const float* scale, const float* shift, int B, int Nd, int cout,
+                            float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream) {
+  const int64_t rows64 = (int64_t)B * Nd;
+  RN_CHECK_ARG(cout % 4 == 0 && ldy % 4 == 0 && (!D || ldd % 4 == 0) && y_bstride % 4 == 0, "fp_interp_affine: unaligned rows");
+  RN_CHECK_ARG(rows64 < (1LL << 31), "fp_interp_affine: too many points");
+  if (rows64 == 0) return REGNET_OK;
+  const uint32_t rows = (uint32_t)rows64;
+  OperandOut o{out_f32, out_hi, out_lo};
+  const unsigned yt = (unsigned)ceil_div(cout / 4, 32);
+  dim3 grid(row_grid(rows, THREADS / 32, yt), yt);
+  fp_interp_affine_kernel<<<grid, THREADS, 0, stream>>>(Y, y_bstride, ldy, D, ldd, dense3, dense3_bstride, dense3_ld, Wd3,
+                                                        ldw3, idx, w, scale, shift, (uint32_t)Nd, cout, rows, o);
+  RN_LAUNCH_CHECK("fp_interp_affine_kernel");
   return REGNET_OK;
 }
 

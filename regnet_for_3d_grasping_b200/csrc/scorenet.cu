@@ -59,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
@@ -88,8 +88,14 @@ struct regnet_scorenet {
   float* sa_out[3] = {nullptr, nullptr, nullptr};    // (B,M_i,C_i)
   // tcgen05 engine: sa_out[0], sa_out[1] also as bf16 hi/lo planes = gather tables of the next level's first layer, and
   // the (P,16) xyz - centroid planes of the level being computed (gemm_tc.cu GatherA)
-  __nv_bfloat16* sa_hi[2] = {nullptr, nullptr};
-  __nv_bfloat16* sa_lo[2] = {nullptr, nullptr};
+  __nv_bfloat16* sa_hi[3] = {nullptr, nullptr, nullptr};
+  __nv_bfloat16* sa_lo[3] = {nullptr, nullptr, nullptr};
+  // FP modules with the first convolution applied before the interpolation (gather.cu fp_interp_affine_kernel):
+  // fp_out[0], fp_out[1] as planes (the next module's sparse operand), Y = sparse W_s^T and D = dense W_d^T in fp32
+  __nv_bfloat16* fp_hi[2] = {nullptr, nullptr};
+  __nv_bfloat16* fp_lo[2] = {nullptr, nullptr};
+  float* fp_y = nullptr;
+  float* fp_d = nullptr;
   __nv_bfloat16* xyzrel_hi = nullptr;
   __nv_bfloat16* xyzrel_lo = nullptr;
   float* fp_out[2] = {nullptr, nullptr};             // fp0 (B,M1,1024), fp1 (B,M0,512); fp2 is the caller's buffer
@@ -223,6 +229,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   if (const char* e = getenv("REGNET_FUSE_SA0")) p->cfg.fuse_sa0 = atoi(e);
   if (const char* e = getenv("REGNET_SA0_VARIANT")) p->cfg.sa0_variant = atoi(e);
   if (const char* e = getenv("REGNET_GATHER_A")) p->cfg.gather_a = atoi(e);
+  if (const char* e = getenv("REGNET_FP_LINEAR_FIRST")) p->cfg.fp_linear_first = atoi(e);
   if (const char* e = getenv("REGNET_DYNAMIC_TILES")) p->cfg.dynamic_tiles = atoi(e);
   if (const char* e = getenv("REGNET_USE_GRID")) p->cfg.use_grid = atoi(e);
   if (const char* e = getenv("REGNET_FPS_CORUN")) sscanf(e, "%d,%d", &p->cfg.corun_cs, &p->cfg.corun_threads);
@@ -246,10 +253,19 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   }
   for (int i = 0; i < 3; ++i) A((void**)&p->sa_out[i], sizeof(float) * (size_t)B * M[i] * SA_CH[i][2]);
   if (p->cfg.engine == REGNET_ENGINE_TC) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       A((void**)&p->sa_hi[i], sizeof(__nv_bfloat16) * (size_t)B * M[i] * SA_CH[i][2]);
       A((void**)&p->sa_lo[i], sizeof(__nv_bfloat16) * (size_t)B * M[i] * SA_CH[i][2]);
     }
+    A((void**)&p->fp_hi[0], sizeof(__nv_bfloat16) * (size_t)B * M[1] * 1024);
+    A((void**)&p->fp_lo[0], sizeof(__nv_bfloat16) * (size_t)B * M[1] * 1024);
+    A((void**)&p->fp_hi[1], sizeof(__nv_bfloat16) * (size_t)B * M[0] * 512);
+    A((void**)&p->fp_lo[1], sizeof(__nv_bfloat16) * (size_t)B * M[0] * 512);
+    // Y: (B*M2,1024) | (B*M1,512) | (B*M0,256);  D: (B*M1,1024) | (B*M0,512)
+    const size_t ymax = std::max({(size_t)B * M[2] * 1024, (size_t)B * M[1] * 512, (size_t)B * M[0] * 256});
+    const size_t dmax = std::max((size_t)B * M[1] * 1024, (size_t)B * M[0] * 512);
+    A((void**)&p->fp_y, sizeof(float) * ymax);
+    A((void**)&p->fp_d, sizeof(float) * dmax);
     const size_t pmax = (size_t)B * std::max(M[1], M[2]) * 64;
     A((void**)&p->xyzrel_hi, sizeof(__nv_bfloat16) * pmax * 16);
     A((void**)&p->xyzrel_lo, sizeof(__nv_bfloat16) * pmax * 16);
@@ -611,7 +627,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
       RN_TRY(run_layer(p, GEMM_LABEL[i][0], p->layers[i][0], a0, P, 1, 0, &a1, nullptr, 0, ms));
     }
     if (need_l1) RN_TRY(run_layer(p, GEMM_LABEL[i][1], p->layers[i][1], a1, P, 1, 0, &a2, nullptr, 0, ms));
-    p->pool_planes_level = (i < 2 && p->cfg.engine == REGNET_ENGINE_TC) ? i : -1;   // picked up by run_layer_impl
+    p->pool_planes_level = p->cfg.engine == REGNET_ENGINE_TC ? i : -1;   // picked up by run_layer_impl
     RN_TRY(run_layer(p, GEMM_LABEL[i][2], p->layers[i][2], a2, P, 1, 64, nullptr, p->sa_out[i], SA_CH[i][2], ms));
     p->pool_planes_level = -1;
     feat = p->sa_out[i];
@@ -635,13 +651,56 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     const int64_t P = (int64_t)B * nd;
     const int kpad = round_up(sparse_c + dense_c, 16);
     Act cur = make_act(p, 0, P, kpad);
-    prof_begin(p, FPOP_LABEL[f], ms);
-    RN_TRY(fp_operand_launch(sparse, (int64_t)sparse_n * sparse_c, sparse_c, sparse_c, dense, dense_bs, dense_ld, dense_c,
-                             G.nn_idx[f], G.nn_w[f], B, nd, kpad, cur.f32, cur.hi, cur.lo, ms));
-    prof_end(p, ms);
-    ++p->launches;
-    int which = 1;
-    for (int l = 0; l < FP_NL[f]; ++l) {
+    int which = 1, first_layer = 0;
+    const bool linear_first = p->cfg.fp_linear_first && p->cfg.engine == REGNET_ENGINE_TC;
+    if (linear_first) {
+      // The first convolution commutes with the (linear) 3-NN interpolation and with the concat: apply it at the Ns
+      // sparse points (Y) and to the dense features (D), then interpolate Y, add D, BN + ReLU.  5x fewer GEMM rows for
+      // fp2 (76.8 K instead of 384 K), and the (Nd, C2 + C1) operand is never built.
+      const Layer& L0 = p->layers[3 + f][0];
+      if (!L0.set) {
+        set_error("scorenet: fp_modules.%d.mlp.0 was never given weights", f);
+        return REGNET_EINVAL;
+      }
+      const int cout0 = L0.cout;
+      const __nv_bfloat16* sp_hi = f == 0 ? p->sa_hi[2] : p->fp_hi[f - 1];
+      const __nv_bfloat16* sp_lo = f == 0 ? p->sa_lo[2] : p->fp_lo[f - 1];
+      Epilogue ey;
+      ey.act = 0; ey.out_f32 = p->fp_y; ey.ld_f32 = cout0;
+      if (p->cfg.dynamic_tiles && p->gemm_idx < 64) ey.tile_counter = p->tile_counters + (p->gemm_idx++);
+      prof_begin(p, GEMM_LABEL[3 + f][0], ms);
+      RN_TRY(gemm_tc_launch(sp_hi, sp_lo, sparse_c, L0.w_hi, L0.w_lo, L0.kpad, (int64_t)B * sparse_n, sparse_c, cout0, ey, ms));
+      prof_end(p, ms);
+      ++p->launches;
+      if (dl > 0) {
+        Epilogue ed;
+        ed.act = 0; ed.out_f32 = p->fp_d; ed.ld_f32 = cout0;
+        if (p->cfg.dynamic_tiles && p->gemm_idx < 64) ed.tile_counter = p->tile_counters + (p->gemm_idx++);
+        prof_begin(p, f == 0 ? "gemm.fp0.l0d" : "gemm.fp1.l0d", ms);
+        RN_TRY(gemm_tc_launch(p->sa_hi[dl - 1], p->sa_lo[dl - 1], dense_c, L0.w_hi + sparse_c, L0.w_lo + sparse_c, L0.kpad, P,
+                              dense_c, cout0, ed, ms));
+        prof_end(p, ms);
+        ++p->launches;
+      }
+      Act nxt = make_act(p, which, P, cout0);
+      prof_begin(p, FPOP_LABEL[f], ms);
+      RN_TRY(fp_interp_affine_launch(p->fp_y, (int64_t)sparse_n * cout0, cout0, dl > 0 ? p->fp_d : nullptr, cout0,
+                                     dl == 0 ? pc + 3 : nullptr, (int64_t)N * 6, 6, dl == 0 ? L0.w_f32 + sparse_c : nullptr,
+                                     L0.kpad, G.nn_idx[f], G.nn_w[f], L0.scale, L0.shift, B, nd, cout0, nullptr, nxt.hi,
+                                     nxt.lo, ms));
+      prof_end(p, ms);
+      ++p->launches;
+      cur = nxt;
+      which ^= 1;
+      first_layer = 1;
+    } else {
+      prof_begin(p, FPOP_LABEL[f], ms);
+      RN_TRY(fp_operand_launch(sparse, (int64_t)sparse_n * sparse_c, sparse_c, sparse_c, dense, dense_bs, dense_ld, dense_c,
+                               G.nn_idx[f], G.nn_w[f], B, nd, kpad, cur.f32, cur.hi, cur.lo, ms));
+      prof_end(p, ms);
+      ++p->launches;
+    }
+    for (int l = first_layer; l < FP_NL[f]; ++l) {
       const bool last = l == FP_NL[f] - 1;
       const int cout = FP_CH[f][l];
       if (!last) {
@@ -650,7 +709,10 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
         cur = nxt;
         which ^= 1;
       } else if (f < 2) {
-        RN_TRY(run_layer(p, GEMM_LABEL[3 + f][l], p->layers[3 + f][l], cur, P, 1, 0, nullptr, p->fp_out[f], cout, ms));
+        Act planes;   // tcgen05 engine: also as planes, the sparse operand of the next module's Y GEMM
+        planes.hi = p->fp_hi[f]; planes.lo = p->fp_lo[f]; planes.ld = cout;
+        RN_TRY(run_layer(p, GEMM_LABEL[3 + f][l], p->layers[3 + f][l], cur, P, 1, 0, linear_first ? &planes : nullptr,
+                         p->fp_out[f], cout, ms));
         sparse = p->fp_out[f];
       } else {
         // fp2's last layer: all_feature for the caller, and the seg head's operand
