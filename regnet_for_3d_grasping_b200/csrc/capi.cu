@@ -60,6 +60,7 @@ int score_head_launch(const float* X, int ldx, const float* w, const float* scal
   if (P == 0) return REGNET_OK;
   int64_t blocks = (P + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  RN_PREFER_MAX_SMEM(score_head_kernel);
   score_head_kernel<<<(int)blocks, 256, 0, stream>>>(X, ldx, w, scale, shift, P, cin, score);
   RN_LAUNCH_CHECK("score_head_kernel");
   return REGNET_OK;

@@ -63,6 +63,21 @@ __host__ __device__ __forceinline__ int64_t round_up64(int64_t a, int64_t b) { r
 __host__ __device__ __forceinline__ int round_up(int a, int b) { return (a + b - 1) / b * b; }
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Every kernel of the forward asks for the MAXIMUM shared-memory carve-out, whatever it uses itself: the L1 / shared
+// split of an SM can only change while the SM is empty, the register-resident FPS kernel of the NEXT step becomes
+// resident at an arbitrary moment of this step and then stays for milliseconds -- if it lands on SMs that a
+// no-shared-memory kernel has just configured for a big L1, the tcgen05 kernels (217-225 KB of shared memory) cannot
+// join those SMs until it leaves, and run on the ~28 SMs without an FPS CTA (timeline: gemm.sa1.l1 0.40 -> 1.51 ms).
+#define RN_PREFER_MAX_SMEM(kernel)                                                                              \
+  do {                                                                                                          \
+    static bool done__ = false;                                                                                 \
+    if (!done__) {                                                                                              \
+      (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,                        \
+                                 (int)cudaSharedmemCarveoutMaxShared);                                          \
+      done__ = true;                                                                                            \
+    }                                                                                                           \
+  } while (0)
+
 struct Strides3 {
   int64_t b, c, n;
 };

@@ -277,6 +277,49 @@ fp_operand_kernel(const float* __restrict__ sparse, int64_t sparse_bstride, int 
 }
 
 
+// SA level >= 1 with the FEATURE part of its first 1x1 convolution applied per point, before the grouping
+// (W [f_j | x_j - c_m] = W_f f_j + W_x (x_j - c_m): the feature term does not depend on the centroid):
+//   Z = f W_f^T for the N_prev points of the previous level (tensor cores, 12.8x fewer rows than M*64 grouped positions),
+//   y[b,m,k] = relu(scale * (Z[j] + W_x (x_j - c_m)) + shift),  j = nbr[b,m,k]
+// The xyz term stays in fp32 on the difference, exactly like the reference's (x_j - c_m) operand -- folding W_x x_j into
+// Z and subtracting W_x c_m would lose ~|x| / |x - c| of relative accuracy to cancellation.  One thread = (row, 4 ch).
+__global__ void __launch_bounds__(THREADS)
+sa_gather_affine_kernel(const float* __restrict__ Z, int ldz, uint32_t n_prev, const float* __restrict__ xyz, Strides3 xst,
+                        const float* __restrict__ new_xyz, const float* __restrict__ Wx, int ldw,
+                        const int32_t* __restrict__ nbr, const float* __restrict__ scale, const float* __restrict__ shift,
+                        uint32_t M, int cout, uint32_t rows, OperandOut out) {
+  constexpr uint32_t TQ = 32, RPB = THREADS / TQ;
+  const uint32_t q = blockIdx.y * TQ + (threadIdx.x % TQ);
+  if ((int)(q * 4) >= cout) return;
+  const int c0 = (int)q * 4;
+  const float4 sc = *reinterpret_cast<const float4*>(scale + c0), sh = *reinterpret_cast<const float4*>(shift + c0);
+  float wx[4][3];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) wx[u][a] = Wx[(c0 + u) * ldw + a];
+  for (uint32_t row = blockIdx.x * RPB + threadIdx.x / TQ; row < rows; row += gridDim.x * RPB) {
+    const uint32_t bm = row >> 6;             // 64 neighbours per centroid
+    const uint32_t b = bm / M, m = bm - b * M;
+    const int j = nbr[row];
+    const float4 z = *reinterpret_cast<const float4*>(Z + ((int64_t)b * n_prev + j) * ldz + c0);
+    float rel[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      rel[a] = __fsub_rn(xyz[(int64_t)b * xst.b + a * xst.c + (int64_t)j * xst.n], new_xyz[((int64_t)b * 3 + a) * M + m]);
+    float4 v;
+    v.x = fmaf(wx[0][2], rel[2], fmaf(wx[0][1], rel[1], fmaf(wx[0][0], rel[0], z.x)));
+    v.y = fmaf(wx[1][2], rel[2], fmaf(wx[1][1], rel[1], fmaf(wx[1][0], rel[0], z.y)));
+    v.z = fmaf(wx[2][2], rel[2], fmaf(wx[2][1], rel[1], fmaf(wx[2][0], rel[0], z.z)));
+    v.w = fmaf(wx[3][2], rel[2], fmaf(wx[3][1], rel[1], fmaf(wx[3][0], rel[0], z.w)));
+    v.x = fmaxf(fmaf(v.x, sc.x, sh.x), 0.f);
+    v.y = fmaxf(fmaf(v.y, sc.y, sh.y), 0.f);
+    v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
+    v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
+    store_quad(out, (int64_t)row * cout + c0, v);
+  }
+}
+
 // FP module with the first 1x1 convolution applied BEFORE the interpolation (both are linear, so they commute):
 //   reference (modules.py:117-127 + conv.py:24-36):  y = act(scale * W [ sum_k w_k f[idx_k] | dense ] + shift)
 //   here:   Y = f W_s^T at the Ns sparse points (tensor cores, Ns << Nd rows),  D = dense W_d^T (or a 3-channel matvec),
@@ -417,11 +460,13 @@ int sa_operand_launch(const float* xyz, Strides3 xst, const float* new_xyz, cons
   const int quads = kpad / 4;
   if (quads <= 4) {
     dim3 grid(row_grid(rows, THREADS / 4, 1), 1);
+    RN_PREFER_MAX_SMEM(sa_operand_kernel<4>);
     sa_operand_kernel<4><<<grid, THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, C, vec_ok, nbr,
                                                        (uint32_t)M, kpad, rows, o);
   } else {
     const unsigned yt = (unsigned)ceil_div(quads, 32);
     dim3 grid(row_grid(rows, THREADS / 32, yt), yt);
+    RN_PREFER_MAX_SMEM(sa_operand_kernel<32>);
     sa_operand_kernel<32><<<grid, THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, C, vec_ok, nbr,
                                                         (uint32_t)M, kpad, rows, o);
   }
@@ -439,6 +484,7 @@ int sa0_fused_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
   RN_CHECK_ARG(rows64 < (1LL << 31), "sa0_fused: too many positions");
   OperandOut o{out_f32, out_hi, out_lo};
   const unsigned grid = row_grid((uint32_t)rows64, (THREADS / 32) * 4, 1);
+  RN_PREFER_MAX_SMEM(sa0_fused_kernel<128>);
   sa0_fused_kernel<128><<<grid, THREADS, 0, stream>>>(xyz, xst, new_xyz, feat, feat_bstride, feat_ld, nbr, W, ldw, scale,
                                                      shift, (uint32_t)M, (uint32_t)rows64, o, ld_out);
   RN_LAUNCH_CHECK("sa0_fused_kernel");
@@ -457,12 +503,33 @@ int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld
                         ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
   const unsigned yt = (unsigned)ceil_div(kpad / 4, 32);
   dim3 grid(row_grid((uint32_t)rows64, THREADS / 32, yt), yt);
+  RN_PREFER_MAX_SMEM(fp_operand_kernel);
   fp_operand_kernel<<<grid, THREADS, 0, stream>>>(sparse, sparse_bstride, sparse_ld, C2, dense, dense_bstride, dense_ld,
                                                   C1, sparse_vec, dense_vec, idx, w, (uint32_t)Nd, kpad, (uint32_t)rows64, o);
   RN_LAUNCH_CHECK("fp_operand_kernel");
   return REGNET_OK;
 }
 
+
+// y = relu(scale * (Z[nbr] + Wx (xyz[nbr] - centroid)) + shift) as bf16 hi/lo planes (B*M*64, cout); see the kernel
+int sa_gather_affine_launch(const float* Z, int ldz, int n_prev, const float* xyz, Strides3 xst, const float* new_xyz,
+                            const float* Wx, int ldw, const int32_t* nbr, const float* scale, const float* shift, int B,
+                            int M, int cout, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                            cudaStream_t stream) {
+  const int64_t rows64 = (int64_t)B * M * 64;
+  RN_CHECK_ARG(cout % 4 == 0 && ldz % 4 == 0, "sa_gather_affine: unaligned rows");
+  RN_CHECK_ARG(rows64 < (1LL << 31), "sa_gather_affine: too many positions");
+  if (rows64 == 0) return REGNET_OK;
+  const uint32_t rows = (uint32_t)rows64;
+  OperandOut o{out_f32, out_hi, out_lo};
+  const unsigned yt = (unsigned)ceil_div(cout / 4, 32);
+  dim3 grid(row_grid(rows, THREADS / 32, yt), yt);
+  RN_PREFER_MAX_SMEM(sa_gather_affine_kernel);
+  sa_gather_affine_kernel<<<grid, THREADS, 0, stream>>>(Z, ldz, (uint32_t)n_prev, xyz, xst, new_xyz, Wx, ldw, nbr, scale,
+                                                        shift, (uint32_t)M, cout, rows, o);
+  RN_LAUNCH_CHECK("sa_gather_affine_kernel");
+  return REGNET_OK;
+}
 
 // y = relu(scale * (3-NN interpolation of Y + D [+ Wd3 . dense3]) + shift) as bf16 hi/lo planes (rows, cout); see the kernel
 int fp_interp_affine_launch(const float* Y, int64_t y_bstride, int ldy, const float* D, int ldd, const float* dense3,
@@ -477,6 +544,7 @@ int fp_interp_affine_launch(const float* Y, int64_t y_bstride, int ldy, const fl
   OperandOut o{out_f32, out_hi, out_lo};
   const unsigned yt = (unsigned)ceil_div(cout / 4, 32);
   dim3 grid(row_grid(rows, THREADS / 32, yt), yt);
+  RN_PREFER_MAX_SMEM(fp_interp_affine_kernel);
   fp_interp_affine_kernel<<<grid, THREADS, 0, stream>>>(Y, y_bstride, ldy, D, ldd, dense3, dense3_bstride, dense3_ld, Wd3,
                                                         ldw3, idx, w, scale, shift, (uint32_t)Nd, cout, rows, o);
   RN_LAUNCH_CHECK("fp_interp_affine_kernel");

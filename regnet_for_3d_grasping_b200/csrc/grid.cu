@@ -351,6 +351,7 @@ static GridPtrs carve(void* ws, int B, int N) {
 
 int grid_build_launch(const float* pts, Strides3 st, int B, int N, float min_cell, void* ws, cudaStream_t stream) {
   const GridPtrs g = carve(ws, B, N);
+  RN_PREFER_MAX_SMEM(grid_build_kernel);
   grid_build_kernel<<<B, 1024, 0, stream>>>(pts, st, N, min_cell, g.hdr, g.cell_start, g.sorted);
   RN_LAUNCH_CHECK("grid_build_kernel");
   return REGNET_OK;
@@ -361,6 +362,7 @@ int ball_query_grid_launch(const float* pts, Strides3 pst, const float* ctr, Str
   RN_CHECK_ARG(N <= 65536, "ball_query_grid: more than 65536 points per cloud");
   const GridPtrs g = carve(const_cast<void*>(ws), B, N);
   dim3 grid(ceil_div(M, BQG_WARPS), B);
+  RN_PREFER_MAX_SMEM(ball_query_grid_kernel);
   ball_query_grid_kernel<<<grid, BQG_WARPS * 32, 0, stream>>>(pts, pst, ctr, cst, N, M, radius, g.hdr, g.cell_start,
                                                              g.sorted, index32);
   RN_LAUNCH_CHECK("ball_query_grid_kernel");
@@ -371,6 +373,7 @@ int three_nn_grid_launch(const float* qry, Strides3 qst, const float* key, Strid
                          const void* ws, int32_t* index32, float* weight, cudaStream_t stream) {
   const GridPtrs g = carve(const_cast<void*>(ws), B, Nk);
   dim3 grid(ceil_div(Nq, 128), B);
+  RN_PREFER_MAX_SMEM(three_nn_grid_kernel);
   three_nn_grid_kernel<<<grid, 128, 0, stream>>>(qry, qst, key, kst, Nq, Nk, g.hdr, g.cell_start, g.sorted, index32, weight);
   RN_LAUNCH_CHECK("three_nn_grid_kernel");
   return REGNET_OK;

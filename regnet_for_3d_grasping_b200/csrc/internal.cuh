@@ -46,6 +46,10 @@ int sa0_chain_launch(const float* xyz, Strides3 xst, const float* new_xyz, const
 int fp_operand_launch(const float* sparse, int64_t sparse_bstride, int sparse_ld, int C2, const float* dense,
                       int64_t dense_bstride, int dense_ld, int C1, const int32_t* idx, const float* w, int B, int Nd,
                       int kpad, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);
+int sa_gather_affine_launch(const float* Z, int ldz, int n_prev, const float* xyz, Strides3 xst, const float* new_xyz,
+                            const float* Wx, int ldw, const int32_t* nbr, const float* scale, const float* shift, int B,
+                            int M, int cout, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
+                            cudaStream_t stream);
 int fp_interp_affine_launch(const float* Y, int64_t y_bstride, int ldy, const float* D, int ldd, const float* dense3,
                             int64_t dense3_bstride, int dense3_ld, const float* Wd3, int ldw3, const int32_t* idx,
                             const float* w, const float* scale, const float* shift, int B, int Nd, int cout,

@@ -200,11 +200,13 @@ int ball_query_launch(const float* pts, Strides3 pst, const float* ctr, Strides3
     const size_t smem = sizeof(float4) * TILE_PTS + sizeof(uint16_t) * (size_t)K * (BQ_THREADS + 1);
     RN_CUDA(cudaFuncSetAttribute(ball_query_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(sizeof(float4) * TILE_PTS + sizeof(uint16_t) * 128 * (BQ_THREADS + 1))));
+    RN_PREFER_MAX_SMEM(ball_query_kernel<uint16_t>);
     ball_query_kernel<uint16_t><<<grid, BQ_THREADS, smem, stream>>>(pts, pst, ctr, cst, N, M, radius, K, index, count, index32);
   } else {
     const size_t smem = sizeof(float4) * TILE_PTS + sizeof(int) * (size_t)K * (BQ_THREADS + 1);
     RN_CUDA(cudaFuncSetAttribute(ball_query_kernel<int>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(sizeof(float4) * TILE_PTS + sizeof(int) * 128 * (BQ_THREADS + 1))));
+    RN_PREFER_MAX_SMEM(ball_query_kernel<int>);
     ball_query_kernel<int><<<grid, BQ_THREADS, smem, stream>>>(pts, pst, ctr, cst, N, M, radius, K, index, count, index32);
   }
   RN_LAUNCH_CHECK("ball_query_kernel");
@@ -216,6 +218,7 @@ int three_nn_launch(const float* qry, Strides3 qst, const float* key, Strides3 k
   RN_CHECK_ARG(B > 0 && Nq > 0, "point_search: empty input (B=%d, Nq=%d)", B, Nq);
   RN_CHECK_ARG(Nk >= 3, "point_search: needs at least 3 key points (got %d)", Nk);
   dim3 grid(ceil_div(Nq, BQ_THREADS), B);
+  RN_PREFER_MAX_SMEM(three_nn_kernel);
   three_nn_kernel<<<grid, BQ_THREADS, 0, stream>>>(qry, qst, key, kst, Nq, Nk, index, dist, index32, weight);
   RN_LAUNCH_CHECK("three_nn_kernel");
   return REGNET_OK;

@@ -59,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int sa_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; int corun_small = 1; int corun1_cs = 8; int corun1_threads = 256; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
@@ -96,6 +96,7 @@ struct regnet_scorenet {
   __nv_bfloat16* fp_lo[2] = {nullptr, nullptr};
   float* fp_y = nullptr;
   float* fp_d = nullptr;
+  float* sa_z = nullptr;   // SA levels 1, 2: Z = previous level's features x W_f^T, per point (gather.cu sa_gather_affine_kernel)
   __nv_bfloat16* xyzrel_hi = nullptr;
   __nv_bfloat16* xyzrel_lo = nullptr;
   float* fp_out[2] = {nullptr, nullptr};             // fp0 (B,M1,1024), fp1 (B,M0,512); fp2 is the caller's buffer
@@ -230,9 +231,12 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   if (const char* e = getenv("REGNET_SA0_VARIANT")) p->cfg.sa0_variant = atoi(e);
   if (const char* e = getenv("REGNET_GATHER_A")) p->cfg.gather_a = atoi(e);
   if (const char* e = getenv("REGNET_FP_LINEAR_FIRST")) p->cfg.fp_linear_first = atoi(e);
+  if (const char* e = getenv("REGNET_SA_LINEAR_FIRST")) p->cfg.sa_linear_first = atoi(e);
   if (const char* e = getenv("REGNET_DYNAMIC_TILES")) p->cfg.dynamic_tiles = atoi(e);
   if (const char* e = getenv("REGNET_USE_GRID")) p->cfg.use_grid = atoi(e);
   if (const char* e = getenv("REGNET_FPS_CORUN")) sscanf(e, "%d,%d", &p->cfg.corun_cs, &p->cfg.corun_threads);
+  if (const char* e = getenv("REGNET_FPS_CORUN_SMALL")) p->cfg.corun_small = atoi(e);
+  if (const char* e = getenv("REGNET_FPS_CORUN1")) sscanf(e, "%d,%d", &p->cfg.corun1_cs, &p->cfg.corun1_threads);
   p->B = cfg->batch;
   p->N = cfg->num_points;
   for (int i = 0; i < 3; ++i) p->M[i] = cfg->num_centroids[i];
@@ -266,6 +270,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
     const size_t dmax = std::max((size_t)B * M[1] * 1024, (size_t)B * M[0] * 512);
     A((void**)&p->fp_y, sizeof(float) * ymax);
     A((void**)&p->fp_d, sizeof(float) * dmax);
+    A((void**)&p->sa_z, sizeof(float) * std::max((size_t)B * M[0] * SA_CH[1][0], (size_t)B * M[1] * SA_CH[2][0]));
     const size_t pmax = (size_t)B * std::max(M[1], M[2]) * 64;
     A((void**)&p->xyzrel_hi, sizeof(__nv_bfloat16) * pmax * 16);
     A((void**)&p->xyzrel_lo, sizeof(__nv_bfloat16) * pmax * 16);
@@ -461,9 +466,16 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
     prof_begin(p, FPS_LABEL[i], gs);
     // a prefetched FPS shares its SMs with the previous step's GEMM CTAs: 4 warps (one per scheduler partition,
     // 227 registers) is the shape whose register-file footprint leaves room for them (profiles/README.md)
-    const bool corun = overlapped && fork && L.n[i] > 12288;
-    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i],
-                      corun ? p->cfg.corun_cs : 0, corun ? p->cfg.corun_threads : 0, gs));
+    // The smaller levels get 4-warp CTAs as well when prefetched: a 256- or 512-thread CTA cannot become resident next
+    // to a tensor kernel's CTA and waits for a whole GEMM launch to drain (timeline: fps.2 0.10 ms alone, 1.15 ms
+    // co-running) -- and the FPS chain is what bounds the pipelined step.
+    const bool corun = overlapped && fork && (L.n[i] > 12288 || p->cfg.corun_small);
+    int cs = 0, th = 0;
+    if (corun) {
+      cs = L.n[i] > 12288 ? p->cfg.corun_cs : L.n[i] > 2048 ? p->cfg.corun1_cs : 4;
+      th = L.n[i] > 12288 ? p->cfg.corun_threads : L.n[i] > 2048 ? p->cfg.corun1_threads : 128;
+    }
+    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], cs, th, gs));
     prof_end(p, gs);
     ++p->launches;
     if (!fps_only) RN_TRY(ball_query_level(p, G, L, i, gs));
@@ -588,6 +600,27 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
       prof_begin(p, "sa0_fused", ms);
       RN_TRY(sa0_fused_launch(lvl_xyz[0], lvl_st[0], G.new_xyz[0], feat, feat_bs, feat_ld, G.nbr[0], L0.w_f32, L0.kpad,
                               L0.scale, L0.shift, L0.cout, B, M[0], 64, a1.f32, a1.hi, a1.lo, a1.ld, ms));
+      prof_end(p, ms);
+      ++p->launches;
+    } else if (i > 0 && p->cfg.sa_linear_first && p->cfg.engine == REGNET_ENGINE_TC && feat_c % 64 == 0 && p->sa_hi[i - 1]) {
+      // levels 1, 2: the feature part of the first convolution is applied per POINT of the previous level (Z, a GEMM over
+      // N_prev rows instead of M*64 grouped rows), the grouping then gathers rows of Z and adds the fp32 xyz term
+      const Layer& L0 = p->layers[i][0];
+      if (!L0.set) {
+        set_error("scorenet: sa_modules.%d.mlp.0 was never given weights", i);
+        return REGNET_EINVAL;
+      }
+      Epilogue ez;
+      ez.act = 0; ez.out_f32 = p->sa_z; ez.ld_f32 = L0.cout;
+      if (p->cfg.dynamic_tiles && p->gemm_idx < 64) ez.tile_counter = p->tile_counters + (p->gemm_idx++);
+      prof_begin(p, GEMM_LABEL[i][0], ms);
+      RN_TRY(gemm_tc_launch(p->sa_hi[i - 1], p->sa_lo[i - 1], feat_c, L0.w_hi, L0.w_lo, L0.kpad, (int64_t)B * lvl_n[i], feat_c,
+                            L0.cout, ez, ms));
+      prof_end(p, ms);
+      ++p->launches;
+      prof_begin(p, SAOP_LABEL[i], ms);
+      RN_TRY(sa_gather_affine_launch(p->sa_z, L0.cout, lvl_n[i], lvl_xyz[i], lvl_st[i], G.new_xyz[i], L0.w_f32 + feat_c,
+                                     L0.kpad, G.nbr[i], L0.scale, L0.shift, B, M[i], L0.cout, nullptr, a1.hi, a1.lo, ms));
       prof_end(p, ms);
       ++p->launches;
     } else if (i > 0 && (p->cfg.gather_a >> (i - 1) & 1) && p->cfg.engine == REGNET_ENGINE_TC && feat_c % 64 == 0 &&
