@@ -106,10 +106,18 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
     nbits = N <= 1 ? 0 : 32 - __clz(N - 1);
     nbits = min(9, max(4, nbits));
   }
-  __shared__ uint32_t warp_d[2][W];
-  __shared__ __align__(16) uint4 warp_r[2][W];  // {tie, x, y, z}
-  __shared__ uint32_t cta_d[2][8];               // slot r is written by cluster rank r (DSMEM)
-  __shared__ __align__(16) uint4 cta_r[2][8];
+  // WARP_PUSH (cluster of at most 32 warps): every warp pushes its own record straight into every CTA of the cluster,
+  // slot = rank * W + warp, and one 32-lane argmax replaces the CTA-level stage (no __syncthreads, one pick less).
+  // The two exchange schemes never coexist in one instance, so their record arrays are sized to zero-ish when unused:
+  // the co-running instance must fit the ~2.5 KB a tensor kernel's CTA leaves of the SM's shared memory.
+  constexpr bool WARP_PUSH = MBAR && CS > 1 && CS * W <= 32;
+  constexpr int NW = WARP_PUSH ? 1 : W, NC = WARP_PUSH ? 1 : 8, NA = WARP_PUSH ? 32 : 1;
+  __shared__ uint32_t warp_d[2][NW];
+  __shared__ __align__(16) uint4 warp_r[2][NW];  // {tie, x, y, z}
+  __shared__ uint32_t cta_d[2][NC];               // slot r is written by cluster rank r (DSMEM)
+  __shared__ __align__(16) uint4 cta_r[2][NC];
+  __shared__ uint32_t all_d[2][NA];
+  __shared__ __align__(16) uint4 all_r[2][NA];
   __shared__ __align__(8) uint64_t bars[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -145,7 +153,7 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
       o[0] = cx; o[M] = cy; o[2 * (int64_t)M] = cz;
     }
   }
-  constexpr uint32_t TX_BYTES = CS * 20;  // per iteration each peer sends 16 + 4 bytes
+  constexpr uint32_t TX_BYTES = (WARP_PUSH ? CS * W : CS) * 20;  // per iteration each sender's record is 16 + 4 bytes
   if (CS > 1) {
     if (MBAR && tid == 0) {
       mbar_init(smem_u32(&bars[0]), 1);
@@ -172,6 +180,29 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
     uint32_t dmax;
     // -- warp level
     const int src1 = pick_lane(__float_as_uint(best), tie, dmax);
+    uint4 win;
+    if (WARP_PUSH) {
+      // the winning lane's record goes round the warp, lanes 0..CS-1 push it to the CS CTAs of the cluster
+      uint4 rec;
+      rec.x = __shfl_sync(FULL, tie, src1);
+      rec.y = __shfl_sync(FULL, __float_as_uint(bx), src1);
+      rec.z = __shfl_sync(FULL, __float_as_uint(by), src1);
+      rec.w = __shfl_sync(FULL, __float_as_uint(bz), src1);
+      if (lane < CS) {
+        const uint32_t slot = rank * W + warp;
+        const uint32_t dst_bar = mapa_u32(smem_u32(&bars[par]), (uint32_t)lane);
+        st_async_v4(mapa_u32(smem_u32(&all_r[par][slot]), (uint32_t)lane), rec, dst_bar);
+        st_async_u32(mapa_u32(smem_u32(&all_d[par][slot]), (uint32_t)lane), dmax, dst_bar);
+      }
+      mbar_wait_cluster(smem_u32(&bars[par]), (uint32_t)((i - 1) >> 1) & 1u);  // k-th use of this parity's barrier
+      // Re-arm for iteration i+2.  Every thread has passed the wait of iteration i before any warp of this CTA can send
+      // its record of iteration i+1 (sends follow that wait in program order), and a peer's record of iteration i+2
+      // needs this CTA's records of iteration i+1 first -- but the arming thread must not be overtaken by its OWN
+      // warp-mates' i+1 records, hence warp 0 arms before it goes on (same warp, program order).
+      if (tid == 0 && i + 2 < M) mbar_arm(smem_u32(&bars[par]), TX_BYTES);
+      const int src3 = pick_lane(lane < CS * W ? all_d[par][lane] : 0u, lane < CS * W ? all_r[par][lane].x : NO_TIE, dmax);
+      win = all_r[par][src3];
+    } else {
     if (lane == src1) {
       warp_d[par][warp] = dmax;
       warp_r[par][warp] = make_uint4(tie, __float_as_uint(bx), __float_as_uint(by), __float_as_uint(bz));
@@ -179,7 +210,7 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
     __syncthreads();
     // -- CTA level (every warp, redundantly)
     const int src2 = pick_lane(lane < W ? warp_d[par][lane] : 0u, lane < W ? warp_r[par][lane].x : NO_TIE, dmax);
-    uint4 win = warp_r[par][src2];
+    win = warp_r[par][src2];
     // -- cluster level
     if (CS > 1) {
       if (warp == 0 && lane < CS) {
@@ -204,6 +235,7 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
       }
       const int src3 = pick_lane(lane < CS ? cta_d[par][lane] : 0u, lane < CS ? cta_r[par][lane].x : NO_TIE, dmax);
       win = cta_r[par][src3];
+    }
     }
     if (dmax != 0u) {  // otherwise every remaining distance is 0: the reference repeats the previous pick
       const uint32_t t = __brev(win.x) & mask;
@@ -263,6 +295,10 @@ int dispatch_ppt(int ppt, const float* pts, Strides3 st, int B, int N, int M, in
     if (ppt <= 16) return launch_fps<CS, T, 16>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
   }
   if constexpr (T <= 128) {
+    // 25 = the BASELINE cloud (25 600 points over 8 CTAs x 128 threads): rounding it up to 32 slots per thread would
+    // add 7 dead points = 22 % more instructions to every one of the 5 119 dependent iterations
+    if (ppt <= 20) return launch_fps<CS, T, 20>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
+    if (ppt <= 25) return launch_fps<CS, T, 25>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
     if (ppt <= 32) return launch_fps<CS, T, 32>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
   }
   set_error("farthest_point_sample: %d points per thread exceeds the register-resident limit", ppt);

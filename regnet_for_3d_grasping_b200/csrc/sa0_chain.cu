@@ -52,7 +52,10 @@ constexpr int OFF_W0 = OFF_A0 + 4 * A0_PLANE;  // [hi|lo]
 constexpr int OFF_SC = OFF_W0 + 2 * A0_PLANE;  // scale0, shift0, scale1, shift1 [128]; scale2, shift2 [256]
 constexpr int OFF_PART = OFF_SC + 4096;        // pooled partials [4][256] u32
 constexpr int OFF_BAR = OFF_PART + 4096;
-constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+// No alignment slack and a 256-byte barrier block: the kernel must leave ~2.5 KB of the SM's 228 KB for a co-resident
+// FPS CTA of the next step (1.3 KB of records + its 1 KB system reservation), whichever of the two arrives first --
+// with 1.5 KB left an FPS launch that met a running sa0_chain waited for the whole kernel (timeline: fps.2 0.2 -> 1.2 ms).
+constexpr int SMEM_BYTES = OFF_BAR + 256;
 constexpr int NTHREADS = 448;
 constexpr uint32_t TM_X = 0, TM_Y = 128, TM_Z = 256;
 static_assert(SMEM_BYTES <= 232448, "sa0_chain: shared memory budget");
@@ -136,9 +139,12 @@ sa0_chain_kernel(const __grid_constant__ CUtensorMap map_w1hi, const __grid_cons
                  const __grid_constant__ CUtensorMap map_w2hi, const __grid_constant__ CUtensorMap map_w2lo,
                  const Sa0ChainArgs a) {
   constexpr bool TIMING = MODE == 2;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // the dynamic region starts right behind the 1 KB the system reserves per CTA (this kernel has no static shared
+  // memory), i.e. 1024-byte aligned as the SWIZZLE_128B operands need; checked, not assumed
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn;
   const uint32_t sb = smem_u32(smem);
+  if (sb & 1023u) __trap();
   const uint32_t bar_w = sb + OFF_BAR;            // W1 / W2 landed
   const uint32_t bar_a0full = bar_w + 8;          // [2] producers -> MMA
   const uint32_t bar_a0empty = bar_a0full + 16;   // [2] MMA -> producers

@@ -59,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int sa_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; int corun_small = 1; int corun1_cs = 8; int corun1_threads = 256; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int sa_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; int corun_small = 1; int corun1_cs = 8; int corun1_threads = 128; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
