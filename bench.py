@@ -349,6 +349,16 @@ def main():
                 "ms_by_kernel": {k: round(v, 4) for k, v in per_label.items()}, "serial_step_ms": total_ms}
         if args.engine == "simt":
             roof["kernel"] = "gemm_simt_kernel"
+        # second half of BASELINE.json's metric: "FPS+ball_query Gpts/s" on the level-0 shapes of this workload
+        # (FPS = B*N*(M-1) distance updates / t; ball query = B*M*N point tests of the reference's
+        # brute-force scan / t -- the grid kernel answers the same question while visiting ~9 cells per centroid)
+        m0 = 5120
+        t_fps, t_bq = per_label.get("fps.0"), per_label.get("ball_query.0")
+        roof["search_ops"] = {
+            "fps_gpts_per_s": B_PER_GPU * N_POINTS * (m0 - 1) / (t_fps * 1e-3) / 1e9 if t_fps else None,
+            "ball_query_gpts_per_s": B_PER_GPU * m0 * N_POINTS / (t_bq * 1e-3) / 1e9 if t_bq else None,
+            "shape": "B=15, N=25600, M=5120, r=0.02, K=64 (SA level 0), serial per-kernel CUDA-event times",
+            "fps_us_per_iteration": 1e3 * t_fps / (m0 - 1) if t_fps else None}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

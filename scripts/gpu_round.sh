@@ -18,14 +18,14 @@ for s in $STAGES; do
     benchref) timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1 ;;
     sweep)    timeout 300 python scripts/fps_sweep.py > gpurun_out/fps_sweep.log 2>&1 ;;
     timeline) timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2.log 2>&1
-              REGNET_FPS_FORCE=8,128 timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2_t128.log 2>&1
-              REGNET_FPS_FORCE=8,256 timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2_t256.log 2>&1 ;;
+              
+              ;;
     corun)    for v in 8,128 8,256 8,512; do REGNET_FPS_CORUN=$v timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_corun_${v/,/_}.log 2>&1; done ;;
     ab)       timeout 300 python scripts/pipeline_ab.py > gpurun_out/pipeline_ab.log 2>&1 ;;
     region)   timeout 600 python -m pytest tests/test_gpu_region.py -q -m gpu > gpurun_out/test_region.log 2>&1 ;;
     ncu)      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
                  --log-file gpurun_out/launches.csv python scripts/one_forward.py tc serial > gpurun_out/ncu_list.log 2>&1 ;;
-    ncufull)  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc|sa0_chain" -s 18 -c 18 \
+    ncufull)  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc|sa0_chain" -s 20 -c 20 \
                  -o gpurun_out/prof_tensor python scripts/one_forward.py tc serial > gpurun_out/ncu_full.log 2>&1
               timeout 600 ncu --set full --clock-control none --import-source on -k regex:fps_kernel -s 3 -c 1 \
                  -o gpurun_out/prof_fps python scripts/one_forward.py tc serial > gpurun_out/ncu_full_fps.log 2>&1 ;;
