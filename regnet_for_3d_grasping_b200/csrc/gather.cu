@@ -10,6 +10,9 @@
 //       feature_interpolate ; torch.cat([interp, dense])                      (modules.py:104-131)
 //     by one pass that reads point-major features (rows are contiguous => coalesced row gathers) and writes the
 //     MLP operand once, directly in the layout the GEMM engine wants (fp32 rows, or bf16 hi/lo planes).
+#include <algorithm>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace regnet {
@@ -320,6 +323,81 @@ sa_gather_affine_kernel(const float* __restrict__ Z, int ldz, uint32_t n_prev, c
   }
 }
 
+// Warp-cooperative form of the kernel above (used when cout % 8 == 0): one warp = 32 consecutive rows = half a
+// centroid's neighbour list, so the centroid is loaded once per warp and every lane fetches ONE neighbour index and its
+// coordinates (coalesced) instead of every thread re-loading all seven scalars of its row; the rows are then walked with
+// shuffles, each lane producing 8 consecutive channels: 32-byte loads of Z (1 KB per warp request), 16-byte stores to each
+// bf16 plane, four rows in flight.  Same fma chain per element => identical results.
+__device__ __forceinline__ void store_oct(const OperandOut& o, int64_t off, float4 a, float4 b) {
+  if (o.f32) {
+    *reinterpret_cast<float4*>(o.f32 + off) = a;
+    *reinterpret_cast<float4*>(o.f32 + off + 4) = b;
+  }
+  if (o.hi) {
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * u], h0, l0);
+      split_bf16(v[2 * u + 1], h1, l1);
+      __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
+      ph[u] = *reinterpret_cast<uint32_t*>(&hh);
+      pl[u] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(o.hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(o.lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS)
+sa_gather_affine_warp_kernel(const float* __restrict__ Z, int ldz, uint32_t n_prev, const float* __restrict__ xyz,
+                             Strides3 xst, const float* __restrict__ new_xyz, const float* __restrict__ Wx, int ldw,
+                             const int32_t* __restrict__ nbr, const float* __restrict__ scale,
+                             const float* __restrict__ shift, uint32_t M, int cout, uint32_t rows, OperandOut out) {
+  const uint32_t lane = threadIdx.x & 31;
+  // lanes beyond the last channel keep running (the row walk uses full-mask shuffles); they recompute the last octet
+  // and skip the store
+  const bool live = (int)(blockIdx.y * 256 + lane * 8) < cout;
+  const int c0 = live ? (int)(blockIdx.y * 256 + lane * 8) : cout - 8;
+  float sc[8], sh[8], wx[8][3];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    sc[u] = scale[c0 + u];
+    sh[u] = shift[c0 + u];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) wx[u][a] = Wx[(c0 + u) * ldw + a];
+  }
+  const uint32_t nwarps = gridDim.x * (THREADS / 32);
+  for (uint32_t base = (blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * 32; base < rows; base += nwarps * 32) {
+    const uint32_t bm = base >> 6;             // 64 neighbours per centroid: the 32 rows of a warp share (b, m)
+    const uint32_t b = bm / M, m = bm - b * M;
+    const int j = nbr[base + lane];
+    float rel[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      rel[a] = __fsub_rn(xyz[(int64_t)b * xst.b + a * xst.c + (int64_t)j * xst.n], new_xyz[((int64_t)b * 3 + a) * M + m]);
+    const float* __restrict__ zb = Z + (int64_t)b * n_prev * ldz + c0;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const int jr = __shfl_sync(0xffffffffu, j, r);
+      const float r0 = __shfl_sync(0xffffffffu, rel[0], r), r1 = __shfl_sync(0xffffffffu, rel[1], r),
+                  r2 = __shfl_sync(0xffffffffu, rel[2], r);
+      const float4 za = *reinterpret_cast<const float4*>(zb + (int64_t)jr * ldz);
+      const float4 zc = *reinterpret_cast<const float4*>(zb + (int64_t)jr * ldz + 4);
+      float v[8] = {za.x, za.y, za.z, za.w, zc.x, zc.y, zc.z, zc.w};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        v[u] = fmaf(wx[u][2], r2, fmaf(wx[u][1], r1, fmaf(wx[u][0], r0, v[u])));
+        v[u] = fmaxf(fmaf(v[u], sc[u], sh[u]), 0.f);
+      }
+      if (live)
+        store_oct(out, (int64_t)(base + r) * cout + c0, make_float4(v[0], v[1], v[2], v[3]),
+                  make_float4(v[4], v[5], v[6], v[7]));
+    }
+  }
+}
+
 // FP module with the first 1x1 convolution applied BEFORE the interpolation (both are linear, so they commute):
 //   reference (modules.py:117-127 + conv.py:24-36):  y = act(scale * W [ sum_k w_k f[idx_k] | dense ] + shift)
 //   here:   Y = f W_s^T at the Ns sparse points (tensor cores, Ns << Nd rows),  D = dense W_d^T (or a 3-channel matvec),
@@ -374,6 +452,74 @@ fp_interp_affine_kernel(const float* __restrict__ Y, int64_t y_bstride, int ldy,
     v.z = fmaxf(fmaf(v.z, sc.z, sh.z), 0.f);
     v.w = fmaxf(fmaf(v.w, sc.w, sh.w), 0.f);
     store_quad(out, (int64_t)row * cout + c0, v);
+  }
+}
+
+// Warp-cooperative form of fp_interp_affine_kernel (cout % 8 == 0): one warp = 32 consecutive points; lane l loads the
+// three neighbour indices / weights (and the 3 dense channels) of point base + l, the points are walked with shuffles,
+// each lane producing 8 consecutive channels (32-byte loads, 16-byte plane stores).  Same arithmetic per element.
+__global__ void __launch_bounds__(THREADS)
+fp_interp_affine_warp_kernel(const float* __restrict__ Y, int64_t y_bstride, int ldy, const float* __restrict__ D, int ldd,
+                             const float* __restrict__ dense3, int64_t dense3_bstride, int dense3_ld,
+                             const float* __restrict__ Wd3, int ldw3, const int32_t* __restrict__ idx,
+                             const float* __restrict__ w, const float* __restrict__ scale,
+                             const float* __restrict__ shift, uint32_t Nd, int cout, uint32_t rows, OperandOut out) {
+  const uint32_t lane = threadIdx.x & 31;
+  // lanes beyond the last channel keep running (the row walk uses full-mask shuffles); they recompute the last octet
+  // and skip the store
+  const bool live = (int)(blockIdx.y * 256 + lane * 8) < cout;
+  const int c0 = live ? (int)(blockIdx.y * 256 + lane * 8) : cout - 8;
+  float sc[8], sh[8], wd[8][3];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    sc[u] = scale[c0 + u];
+    sh[u] = shift[c0 + u];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) wd[u][c] = Wd3 ? Wd3[(c0 + u) * ldw3 + c] : 0.f;
+  }
+  const uint32_t nwarps = gridDim.x * (THREADS / 32);
+  for (uint32_t base = (blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * 32; base < rows; base += nwarps * 32) {
+    const uint32_t row = min(base + lane, rows - 1);
+    const uint32_t b = row / Nd, n = row - b * Nd;
+    const int i0 = idx[(int64_t)row * 3], i1 = idx[(int64_t)row * 3 + 1], i2 = idx[(int64_t)row * 3 + 2];
+    const float w0 = w[(int64_t)row * 3], w1 = w[(int64_t)row * 3 + 1], w2 = w[(int64_t)row * 3 + 2];
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    if (Wd3) {
+      const float* __restrict__ dp = dense3 + (int64_t)b * dense3_bstride + (int64_t)n * dense3_ld;
+      d0 = dp[0]; d1 = dp[1]; d2 = dp[2];
+    }
+    const int cnt = (int)min(32u, rows - base);
+#pragma unroll 2
+    for (int r = 0; r < cnt; ++r) {
+      const uint32_t br = __shfl_sync(0xffffffffu, b, r);
+      const int j0 = __shfl_sync(0xffffffffu, i0, r), j1 = __shfl_sync(0xffffffffu, i1, r), j2 = __shfl_sync(0xffffffffu, i2, r);
+      const float u0 = __shfl_sync(0xffffffffu, w0, r), u1 = __shfl_sync(0xffffffffu, w1, r), u2 = __shfl_sync(0xffffffffu, w2, r);
+      const float* __restrict__ yp = Y + (int64_t)br * y_bstride + c0;
+      const float4 a0 = *reinterpret_cast<const float4*>(yp + (int64_t)j0 * ldy), a0b = *reinterpret_cast<const float4*>(yp + (int64_t)j0 * ldy + 4);
+      const float4 a1 = *reinterpret_cast<const float4*>(yp + (int64_t)j1 * ldy), a1b = *reinterpret_cast<const float4*>(yp + (int64_t)j1 * ldy + 4);
+      const float4 a2 = *reinterpret_cast<const float4*>(yp + (int64_t)j2 * ldy), a2b = *reinterpret_cast<const float4*>(yp + (int64_t)j2 * ldy + 4);
+      const float x0[8] = {a0.x, a0.y, a0.z, a0.w, a0b.x, a0b.y, a0b.z, a0b.w};
+      const float x1[8] = {a1.x, a1.y, a1.z, a1.w, a1b.x, a1b.y, a1b.z, a1b.w};
+      const float x2[8] = {a2.x, a2.y, a2.z, a2.w, a2b.x, a2b.y, a2b.z, a2b.w};
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __fmaf_rn(x2[u], u2, __fmaf_rn(x1[u], u1, __fmul_rn(x0[u], u0)));
+      if (D) {
+        const float4 da = *reinterpret_cast<const float4*>(D + (int64_t)(base + r) * ldd + c0);
+        const float4 db = *reinterpret_cast<const float4*>(D + (int64_t)(base + r) * ldd + c0 + 4);
+        v[0] += da.x; v[1] += da.y; v[2] += da.z; v[3] += da.w; v[4] += db.x; v[5] += db.y; v[6] += db.z; v[7] += db.w;
+      }
+      if (Wd3) {
+        const float e0 = __shfl_sync(0xffffffffu, d0, r), e1 = __shfl_sync(0xffffffffu, d1, r), e2 = __shfl_sync(0xffffffffu, d2, r);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = fmaf(wd[u][2], e2, fmaf(wd[u][1], e1, fmaf(wd[u][0], e0, v[u])));
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = fmaxf(fmaf(v[u], sc[u], sh[u]), 0.f);
+      if (live)
+        store_oct(out, (int64_t)(base + r) * cout + c0, make_float4(v[0], v[1], v[2], v[3]),
+                  make_float4(v[4], v[5], v[6], v[7]));
+    }
   }
 }
 
@@ -522,6 +668,15 @@ int sa_gather_affine_launch(const float* Z, int ldz, int n_prev, const float* xy
   if (rows64 == 0) return REGNET_OK;
   const uint32_t rows = (uint32_t)rows64;
   OperandOut o{out_f32, out_hi, out_lo};
+  if (cout % 8 == 0 && !getenv("REGNET_AFFINE_V1")) {
+    const unsigned yw = (unsigned)ceil_div(cout, 256);
+    const unsigned gx = (unsigned)std::min<int64_t>(ceil_div((int)(rows / 32), THREADS / 32), std::max(1, 148 * 8 / (int)yw));
+    RN_PREFER_MAX_SMEM(sa_gather_affine_warp_kernel);
+    sa_gather_affine_warp_kernel<<<dim3(gx, yw), THREADS, 0, stream>>>(Z, ldz, (uint32_t)n_prev, xyz, xst, new_xyz, Wx, ldw,
+                                                                      nbr, scale, shift, (uint32_t)M, cout, rows, o);
+    RN_LAUNCH_CHECK("sa_gather_affine_warp_kernel");
+    return REGNET_OK;
+  }
   const unsigned yt = (unsigned)ceil_div(cout / 4, 32);
   dim3 grid(row_grid(rows, THREADS / 32, yt), yt);
   RN_PREFER_MAX_SMEM(sa_gather_affine_kernel);
@@ -542,6 +697,16 @@ int fp_interp_affine_launch(const float* Y, int64_t y_bstride, int ldy, const fl
   if (rows64 == 0) return REGNET_OK;
   const uint32_t rows = (uint32_t)rows64;
   OperandOut o{out_f32, out_hi, out_lo};
+  if (cout % 8 == 0 && !getenv("REGNET_AFFINE_V1")) {
+    const unsigned yw = (unsigned)ceil_div(cout, 256);
+    const unsigned gx = (unsigned)std::min<int64_t>(ceil_div((int)ceil_div((int)rows, 32), THREADS / 32), std::max(1, 148 * 8 / (int)yw));
+    RN_PREFER_MAX_SMEM(fp_interp_affine_warp_kernel);
+    fp_interp_affine_warp_kernel<<<dim3(gx, yw), THREADS, 0, stream>>>(Y, y_bstride, ldy, D, ldd, dense3, dense3_bstride,
+                                                                      dense3_ld, Wd3, ldw3, idx, w, scale, shift,
+                                                                      (uint32_t)Nd, cout, rows, o);
+    RN_LAUNCH_CHECK("fp_interp_affine_warp_kernel");
+    return REGNET_OK;
+  }
   const unsigned yt = (unsigned)ceil_div(cout / 4, 32);
   dim3 grid(row_grid(rows, THREADS / 32, yt), yt);
   RN_PREFER_MAX_SMEM(fp_interp_affine_kernel);

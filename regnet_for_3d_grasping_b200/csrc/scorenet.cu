@@ -107,6 +107,7 @@ struct regnet_scorenet {
   std::vector<void*> allocs;
   size_t total_bytes = 0;
   cudaStream_t side = nullptr;
+  cudaStream_t side2 = nullptr;            // FPS of levels 1, 2 in FPS-only mode: off the level-0 chain (see geometry_enqueue)
   cudaEvent_t ev_start = nullptr;
   int launches = 0;
   int prefetch_launches = 0;
@@ -298,6 +299,8 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   A((void**)&p->arena[1], need);
   if (!rc && cfg->use_side_stream) {
     cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess && cfg->use_side_stream == 2 && !getenv("REGNET_NO_SIDE2"))
+      e = cudaStreamCreateWithFlags(&p->side2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming);
     for (int g = 0; g < 2; ++g) {
       for (int i = 0; i < 3 && e == cudaSuccess; ++i)
@@ -323,6 +326,7 @@ int regnet_scorenet_destroy(regnet_scorenet* p) {
     if (p->geom[g].ev_nn) cudaEventDestroy(p->geom[g].ev_nn);
   }
   if (p->side) cudaStreamDestroy(p->side);
+  if (p->side2) cudaStreamDestroy(p->side2);
   for (auto& r : p->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   delete p;
   return REGNET_OK;
@@ -463,7 +467,12 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
   }
   const Levels L = make_levels(p, G, pc);
   for (int i = 0; i < 3; ++i) {
-    prof_begin(p, FPS_LABEL[i], gs);
+    // FPS-only mode: levels 1 and 2 go to a second side stream behind level 0's event.  The side stream then carries
+    // nothing but the level-0 launches of consecutive forwards, so the pipelined period is max(fps.0, MLP chain)
+    // instead of fps.0 + fps.1 + fps.2 (timeline: 6.0 + 1.0 + 0.2 ms co-running against a 7.0 ms MLP chain).
+    cudaStream_t gs_i = (fps_only && i > 0 && p->side2) ? p->side2 : gs;
+    if (gs_i != gs && i == 1) RN_CUDA(cudaStreamWaitEvent(gs_i, G.ev_bq[0], 0));
+    prof_begin(p, FPS_LABEL[i], gs_i);
     // a prefetched FPS shares its SMs with the previous step's GEMM CTAs: 4 warps (one per scheduler partition,
     // 227 registers) is the shape whose register-file footprint leaves room for them (profiles/README.md)
     // The smaller levels get 4-warp CTAs as well when prefetched: a 256- or 512-thread CTA cannot become resident next
@@ -475,11 +484,11 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
       cs = L.n[i] > 12288 ? p->cfg.corun_cs : L.n[i] > 2048 ? p->cfg.corun1_cs : 4;
       th = L.n[i] > 12288 ? p->cfg.corun_threads : L.n[i] > 2048 ? p->cfg.corun1_threads : 128;
     }
-    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], cs, th, gs));
-    prof_end(p, gs);
+    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], cs, th, gs_i));
+    prof_end(p, gs_i);
     ++p->launches;
     if (!fps_only) RN_TRY(ball_query_level(p, G, L, i, gs));
-    if (fork) RN_CUDA(cudaEventRecord(G.ev_bq[i], gs));  // level i ready (FPS only, or FPS + ball query)
+    if (fork) RN_CUDA(cudaEventRecord(G.ev_bq[i], gs_i));  // level i ready (FPS only, or FPS + ball query)
   }
   if (!fps_only) RN_TRY(three_nn_all(p, G, L, gs));
   if (fork) RN_CUDA(cudaEventRecord(G.ev_nn, gs));

@@ -31,6 +31,10 @@ for s in $STAGES; do
                  -o gpurun_out/prof_fps python scripts/one_forward.py tc serial > gpurun_out/ncu_full_fps.log 2>&1 ;;
     sa0chk)   timeout 600 python scripts/sa0_chain_check.py > gpurun_out/sa0_chain_check.log 2>&1 ;;
     bench3)   REGNET_FUSE_SA0=3 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_chain.log 2>&1 ;;
+    side2)    timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_side2.log 2>&1
+              timeout 300 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_side2.log 2>&1
+              REGNET_NO_SIDE2=1 timeout 300 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_noside2.log 2>&1
+              for v in 1,256 2,256 4,128 4,256; do REGNET_FPS_CORUN1=$v timeout 300 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_side2_c1_${v/,/_}.log 2>&1; done ;;
     alltests) timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/test_all.log 2>&1 ;;
   esac
   echo "    exit $?"
