@@ -83,7 +83,10 @@ def config_block(extra=None):
            "batch_per_gpu": B_PER_GPU, "points": N_POINTS, "centroids": [5120, 1024, 256], "neighbours": 64,
            "weights": "seeded random init, randomised BN statistics, eval mode",
            "l2": "no explicit flush: each step streams ~5 GB of activations, far above the 126 MB L2",
-           "pipelining": "geometry chain of step i+1 prefetched on a side stream while the MLPs of step i run"}
+           "pipelining": "steady state: geometry chain (FPS, ball query, 3-NN) of step i+1 prefetched on side streams "
+                         "while the MLPs of step i run; the timed region starts with the first batch's geometry in flight "
+                         "(issued by the last warm-up step) and includes the prefetch of the batch after its last step: "
+                         "K geometry chains + K MLP chains are executed inside it"}
     if extra:
         cfg.update(extra)
     return cfg
@@ -191,7 +194,7 @@ def run_reference_arm(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="tc", choices=["tc", "simt"])
@@ -237,18 +240,33 @@ def main():
     plan.bind_state(sd)
     feat = torch.empty(B_PER_GPU, N_POINTS, 256, device=dev)
     score = torch.empty(B_PER_GPU, N_POINTS, device=dev)
-    # Throughput loop, software-pipelined across steps: the geometry chain of step i+1 (side stream) is enqueued
+    # Throughput loop, software-pipelined across steps: the geometry chain of step i+1 (side streams) is enqueued
     # before the MLPs of step i, so FPS's sequential latency hides behind tensor work.  Every step still computes
     # its full forward; `pcs` alternates two device copies of the batch so consecutive steps use distinct buffers.
+    # STEADY STATE: the loop keeps exactly one prefetch outstanding across calls -- the warm-up leaves the geometry of
+    # the first timed batch in flight (the synchronize before the timed region waits for it), and every timed step,
+    # the last one included, prefetches the batch after it; the region ends with a join on that prefetch.  The timed
+    # region therefore executes exactly K geometry chains and K MLP chains.  The cold-start variant (pipeline filled
+    # inside the region: K+0 chains, first FPS exposed) is reported next to it as ms_per_step_cold_pipeline.
     pcs = [pc, pc.clone()]
+    step_no = [0]
 
     def run_steps(n):
+        for _ in range(n):
+            i = step_no[0]
+            plan.prefetch(pcs[(i + 1) & 1])
+            plan.forward(pcs[i & 1], feat, score)
+            step_no[0] = i + 1
+        plan.join_prefetch()
+
+    def run_steps_cold(n):
         plan.prefetch(pcs[0])
         for i in range(n):
             if i + 1 < n:
                 plan.prefetch(pcs[(i + 1) & 1])
             plan.forward(pcs[i & 1], feat, score)
 
+    plan.prefetch(pcs[0])
     run_steps(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -261,7 +279,14 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = plan.launch_count * args.steps
+    plan.forward(pcs[step_no[0] & 1], feat, score)   # consumes the outstanding prefetch (untimed)
     torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    run_steps_cold(args.steps)
+    c1.record()
+    torch.cuda.synchronize()
+    ms_cold = c0.elapsed_time(c1)
     latency_ms = None
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
@@ -277,19 +302,26 @@ def main():
     host_score = torch.empty(B_PER_GPU, N_POINTS).pin_memory()
     dev_in = [torch.empty_like(pc), torch.empty_like(pc)]
 
+    e2e_no = [0]
+
+    def e2e_upload(i):
+        dev_in[i & 1].copy_(host_pc, non_blocking=True)
+        net.prefetch(dev_in[i & 1])
+
     def e2e_steps(n):
-        # per step: H2D of the batch from pinned memory, ScoreNetwork.forward, D2H of the scores.  The upload +
-        # prefetch of step i+1 are issued before forward(i) so they overlap it (public API: ScoreNetwork.prefetch).
-        dev_in[0].copy_(host_pc, non_blocking=True)
-        net.prefetch(dev_in[0])
-        for i in range(n):
-            if i + 1 < n:
-                dev_in[(i + 1) & 1].copy_(host_pc, non_blocking=True)
-                net.prefetch(dev_in[(i + 1) & 1])
+        # per step: H2D of the NEXT batch from pinned memory + its prefetch (public API: ScoreNetwork.prefetch),
+        # ScoreNetwork.forward of the current batch, D2H of its scores.  Steady state as above: K uploads, K geometry
+        # chains, K forwards and K read-backs inside the timed region.
+        for _ in range(n):
+            i = e2e_no[0]
+            e2e_upload(i + 1)
             with torch.no_grad():
                 _, s, _ = net(dev_in[i & 1])
             host_score.copy_(s, non_blocking=True)
+            e2e_no[0] = i + 1
+        net.join_prefetch()
 
+    e2e_upload(0)
     e2e_steps(args.warmup)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -298,6 +330,9 @@ def main():
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+    with torch.no_grad():
+        net(dev_in[e2e_no[0] & 1])   # consumes the outstanding prefetch (untimed)
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
@@ -368,7 +403,8 @@ def main():
     if rank == 0:
         clouds = world * B_PER_GPU * args.steps
         line = {"metric": METRIC, "value": clouds / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "latency_ms_unpipelined": latency_ms, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_cold_pipeline": ms_cold / args.steps,
+                "latency_ms_unpipelined": latency_ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16x3-split (fp32 parity, fp32 accumulate)" if args.engine == "tc" else "f32",
                 "data": "synthetic",
                 "config": config_block({"engine": args.engine, "parallelism": f"{world} independent shard(s) of {B_PER_GPU} clouds"}),

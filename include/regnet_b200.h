@@ -114,7 +114,9 @@ typedef struct regnet_scorenet_config {
   int32_t num_neighbours[3];   /* utils/pointnet2.py:42  (64,64,64); must be 64 for the pooled epilogue */
   int32_t engine;              /* REGNET_ENGINE_* */
   int32_t use_side_stream;     /* 0: one stream; 1: geometry chain (FPS/ball query/3-NN) on an internal second stream;
-                                  2: only FPS there (co-resides with the GEMM CTAs), the rest on the caller's stream */
+                                  2: only FPS there (co-resides with the GEMM CTAs), the rest on the caller's stream;
+                                  3: as 2, plus ball query of levels 1-2 and the 3-NN searches behind their FPS on a
+                                     further internal stream (level 0's ball query stays on the caller's stream) */
 } regnet_scorenet_config;
 
 typedef struct regnet_scorenet regnet_scorenet;   /* opaque plan */
@@ -142,6 +144,8 @@ int regnet_scorenet_forward(regnet_scorenet* plan, const float* pc, float* all_f
  * following forward(pc_next) finds its geometry ready.  `pc` must stay valid and unchanged until that forward has
  * completed.  At most two prefetches may be outstanding.  Without a prefetch, forward computes the geometry itself. */
 int regnet_scorenet_prefetch(regnet_scorenet* plan, const float* pc, void* stream);
+/* Make `stream` wait for every outstanding prefetch (their side-stream work), e.g. before timing or reusing `pc`. */
+int regnet_scorenet_join_prefetch(regnet_scorenet* plan, void* stream);
 
 /* Read back intermediates of the last forward for parity tests (device pointers into the plan's workspace,
  * valid until the next forward).  what: "fps0".."fps2" int32 (B,M_i); "bq0".."bq2" int32 (B,M_i,64);

@@ -697,7 +697,9 @@ int fp_interp_affine_launch(const float* Y, int64_t y_bstride, int ldy, const fl
   if (rows64 == 0) return REGNET_OK;
   const uint32_t rows = (uint32_t)rows64;
   OperandOut o{out_f32, out_hi, out_lo};
-  if (cout % 8 == 0 && !getenv("REGNET_AFFINE_V1")) {
+  // the warp-per-32-points form needs enough warps to fill the GPU (FP level 2: 12 000); the small levels keep one
+  // thread per (point, 4 channels)
+  if (cout % 8 == 0 && (int64_t)(rows / 32) * ceil_div(cout, 256) >= 8192 && !getenv("REGNET_AFFINE_V1")) {
     const unsigned yw = (unsigned)ceil_div(cout, 256);
     const unsigned gx = (unsigned)std::min<int64_t>(ceil_div((int)ceil_div((int)rows, 32), THREADS / 32), std::max(1, 148 * 8 / (int)yw));
     RN_PREFER_MAX_SMEM(fp_interp_affine_warp_kernel);

@@ -238,6 +238,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   if (const char* e = getenv("REGNET_FPS_CORUN")) sscanf(e, "%d,%d", &p->cfg.corun_cs, &p->cfg.corun_threads);
   if (const char* e = getenv("REGNET_FPS_CORUN_SMALL")) p->cfg.corun_small = atoi(e);
   if (const char* e = getenv("REGNET_FPS_CORUN1")) sscanf(e, "%d,%d", &p->cfg.corun1_cs, &p->cfg.corun1_threads);
+  if (const char* e = getenv("REGNET_SIDE_MODE")) { if (p->cfg.use_side_stream >= 2) p->cfg.use_side_stream = atoi(e); }
   p->B = cfg->batch;
   p->N = cfg->num_points;
   for (int i = 0; i < 3; ++i) p->M[i] = cfg->num_centroids[i];
@@ -297,9 +298,9 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   p->arena_bytes = need;
   A((void**)&p->arena[0], need);
   A((void**)&p->arena[1], need);
-  if (!rc && cfg->use_side_stream) {
+  if (!rc && p->cfg.use_side_stream) {
     cudaError_t e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
-    if (e == cudaSuccess && cfg->use_side_stream == 2 && !getenv("REGNET_NO_SIDE2"))
+    if (e == cudaSuccess && p->cfg.use_side_stream >= 2 && !getenv("REGNET_NO_SIDE2"))
       e = cudaStreamCreateWithFlags(&p->side2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming);
     for (int g = 0; g < 2; ++g) {
@@ -459,7 +460,12 @@ static int three_nn_all(regnet_scorenet* p, regnet_scorenet::Geom& G, const Leve
 static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaStream_t ms, bool overlapped) {
   regnet_scorenet::Geom& G = p->geom[slot];
   const bool fork = p->side != nullptr && p->profiling != 1;  // serial profiling puts everything on `ms`
-  const bool fps_only = fork && p->cfg.use_side_stream == 2;
+  // mode 2: only FPS leaves the caller's stream.  mode 3 (needs side2): ball query of levels 1-2 and the 3-NN searches
+  // follow their FPS on the second side stream (they have > 1 ms of slack before the MLP chain needs them and are
+  // latency-bound kernels that fill the tails of the persistent GEMM launches); level 0's ball query stays on the
+  // caller's stream, it is the first thing the MLP chain needs.
+  const bool mode3 = fork && p->cfg.use_side_stream == 3 && p->side2 != nullptr;
+  const bool fps_only = fork && (p->cfg.use_side_stream == 2 || (p->cfg.use_side_stream == 3 && !mode3));
   cudaStream_t gs = fork ? p->side : ms;
   if (fork) {
     RN_CUDA(cudaEventRecord(p->ev_start, ms));
@@ -467,10 +473,10 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
   }
   const Levels L = make_levels(p, G, pc);
   for (int i = 0; i < 3; ++i) {
-    // FPS-only mode: levels 1 and 2 go to a second side stream behind level 0's event.  The side stream then carries
+    // FPS-only modes: levels 1 and 2 go to a second side stream behind level 0's event.  The side stream then carries
     // nothing but the level-0 launches of consecutive forwards, so the pipelined period is max(fps.0, MLP chain)
     // instead of fps.0 + fps.1 + fps.2 (timeline: 6.0 + 1.0 + 0.2 ms co-running against a 7.0 ms MLP chain).
-    cudaStream_t gs_i = (fps_only && i > 0 && p->side2) ? p->side2 : gs;
+    cudaStream_t gs_i = ((fps_only || mode3) && i > 0 && p->side2) ? p->side2 : gs;
     if (gs_i != gs && i == 1) RN_CUDA(cudaStreamWaitEvent(gs_i, G.ev_bq[0], 0));
     prof_begin(p, FPS_LABEL[i], gs_i);
     // a prefetched FPS shares its SMs with the previous step's GEMM CTAs: 4 warps (one per scheduler partition,
@@ -487,11 +493,12 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
     RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], cs, th, gs_i));
     prof_end(p, gs_i);
     ++p->launches;
-    if (!fps_only) RN_TRY(ball_query_level(p, G, L, i, gs));
+    if (!fps_only && !(mode3 && i == 0)) RN_TRY(ball_query_level(p, G, L, i, gs_i));
     if (fork) RN_CUDA(cudaEventRecord(G.ev_bq[i], gs_i));  // level i ready (FPS only, or FPS + ball query)
   }
-  if (!fps_only) RN_TRY(three_nn_all(p, G, L, gs));
-  if (fork) RN_CUDA(cudaEventRecord(G.ev_nn, gs));
+  cudaStream_t ns = mode3 ? p->side2 : gs;
+  if (!fps_only) RN_TRY(three_nn_all(p, G, L, ns));
+  if (fork) RN_CUDA(cudaEventRecord(G.ev_nn, ns));
   return REGNET_OK;
 }
 
@@ -510,6 +517,17 @@ int regnet_scorenet_prefetch(regnet_scorenet* p, const float* pc, void* stream_)
   p->geom[slot].pc = pc;
   p->geom[slot].pending = true;
   p->next_slot ^= 1;
+  return REGNET_OK;
+}
+
+int regnet_scorenet_join_prefetch(regnet_scorenet* p, void* stream_) {
+  RN_CHECK_ARG(p, "scorenet_join_prefetch: null plan");
+  if (!p->side) return REGNET_OK;   // single-stream plans: prefetches are already in `stream` order
+  for (int g = 0; g < 2; ++g) {
+    if (!p->geom[g].pending) continue;
+    for (int i = 0; i < 3; ++i) RN_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, p->geom[g].ev_bq[i], 0));
+    RN_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, p->geom[g].ev_nn, 0));
+  }
   return REGNET_OK;
 }
 
@@ -543,7 +561,8 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   p->gemm_idx = 0;
   if (p->cfg.engine == REGNET_ENGINE_TC && p->cfg.dynamic_tiles)
     RN_CUDA(cudaMemsetAsync(p->tile_counters, 0, sizeof(unsigned int) * 64, ms));
-  const bool fps_only = fork && p->cfg.use_side_stream == 2;
+  const bool mode3 = fork && p->cfg.use_side_stream == 3 && p->side2 != nullptr;
+  const bool fps_only = fork && (p->cfg.use_side_stream == 2 || (p->cfg.use_side_stream == 3 && !mode3));
   const Levels L = make_levels(p, G, pc);
   const float* const* lvl_xyz = L.xyz;
   const Strides3* lvl_st = L.st;
@@ -555,7 +574,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   int feat_ld = 6, feat_c = 3;
   for (int i = 0; i < 3; ++i) {
     if (fork) RN_CUDA(cudaStreamWaitEvent(ms, G.ev_bq[i], 0));
-    if (fps_only) RN_TRY(ball_query_level(p, G, L, i, ms));
+    if (fps_only || (mode3 && i == 0)) RN_TRY(ball_query_level(p, G, L, i, ms));
     const int64_t P = (int64_t)B * M[i] * 64;
     const int kpad = round_up(feat_c + 3, 16);
     Act a1 = make_act(p, 1, P, SA_CH[i][0]);

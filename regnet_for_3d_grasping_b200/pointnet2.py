@@ -101,6 +101,11 @@ class PointNet2Seg(nn.Module):
         plan = self._plan_for(pc.size(0), pc.size(1), pc.device)
         plan.prefetch(pc)
 
+    def join_prefetch(self):
+        """Make the current stream wait for the side-stream work of every outstanding prefetch()."""
+        for plan in self._plans.values():
+            plan.join_prefetch()
+
     def forward(self, points, add_channel1=None, add_channel2=None):
         fused = (not self.training and self._fusable and add_channel1 is None and points.is_cuda
                  and points.size(2) >= NUM_CENTROIDS[0])

@@ -24,6 +24,10 @@ class ScoreNetwork(nn.Module):
         the same tensor must be passed to forward() afterwards."""
         self.extrat_featurePN2.prefetch(pc)
 
+    def join_prefetch(self):
+        """Optional: make the current stream wait for every outstanding prefetch()."""
+        self.extrat_featurePN2.join_prefetch()
+
     def forward(self, pc, pc_score=None, pc_label=None):
         """pc (B,N,>=6) [, pc_score (B,N)] -> (all_feature (B,N,256), output_score (B,N), loss | None).
         all_feature is the 256-channel output of the last feature-propagation layer (pointnet2.py:121), not the

@@ -38,7 +38,7 @@ def fold_bn(sd, prefix, eps=BN_EPS):
 
 class ScoreNetPlan:
     def __init__(self, batch, num_points, device, engine=None, num_centroids=NUM_CENTROIDS, radius=RADIUS,
-                 side_stream=2):
+                 side_stream=3):
         lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -57,7 +57,8 @@ class ScoreNetPlan:
             cfg.radius[i] = float(radius[i])
             cfg.num_neighbours[i] = NUM_NEIGHBOURS[i]
         cfg.engine = engine
-        # 0: single stream; 1: whole geometry chain on the side stream; 2: only FPS on the side stream (default)
+        # 0: single stream; 1: whole geometry chain on the side stream; 2: only FPS on side streams;
+        # 3 (default): FPS on side streams + ball query of levels 1-2 and 3-NN behind their FPS (regnet_b200.h)
         cfg.use_side_stream = int(side_stream)
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
@@ -136,6 +137,11 @@ class ScoreNetPlan:
             raise RuntimeError("prefetch needs the contiguous (B, N, 6) float32 tensor that forward() will receive")
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().regnet_scorenet_prefetch(self._h, _p(pc), _lib.current_stream_ptr()))
+
+    def join_prefetch(self):
+        """Make the current stream wait for every outstanding prefetch()."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().regnet_scorenet_join_prefetch(self._h, _lib.current_stream_ptr()))
 
     def profile_forward(self, pc):
         """One forward with every launch bracketed by CUDA events (serial, caller's stream).

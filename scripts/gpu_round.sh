@@ -13,8 +13,9 @@ for s in $STAGES; do
     mlp)      timeout 600 python -m pytest tests/test_gpu_mlp.py -q -m gpu -s > gpurun_out/test_mlp.log 2>&1 ;;
     scorenet) timeout 900 python -m pytest tests/test_gpu_scorenet.py -q -m gpu > gpurun_out/test_scorenet.log 2>&1 ;;
     smoke)    timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 ;;
-    bench)    timeout 600 python bench.py --steps 5 --warmup 3 --engine simt --no-cpu-baseline > gpurun_out/bench_simt.log 2>&1
-              timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_tc.log 2>&1 ;;
+    bench)    timeout 900 python bench.py > gpurun_out/bench_tc.log 2>&1 ;;
+    benchsimt) timeout 600 python bench.py --steps 5 --warmup 3 --engine simt --no-cpu-baseline > gpurun_out/bench_simt.log 2>&1 ;;
+    refcuda)  timeout 900 python oracle/bench_ref_cuda.py > gpurun_out/ref_cuda_baseline.json 2> gpurun_out/ref_cuda_baseline.log ;;
     benchref) timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1 ;;
     sweep)    timeout 300 python scripts/fps_sweep.py > gpurun_out/fps_sweep.log 2>&1 ;;
     timeline) timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_mode2.log 2>&1
@@ -28,7 +29,9 @@ for s in $STAGES; do
     ncufull)  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:gemm_tc|sa0_chain" -s 20 -c 20 \
                  -o gpurun_out/prof_tensor python scripts/one_forward.py tc serial > gpurun_out/ncu_full.log 2>&1
               timeout 600 ncu --set full --clock-control none --import-source on -k regex:fps_kernel -s 3 -c 1 \
-                 -o gpurun_out/prof_fps python scripts/one_forward.py tc serial > gpurun_out/ncu_full_fps.log 2>&1 ;;
+                 -o gpurun_out/prof_fps python scripts/one_forward.py tc serial > gpurun_out/ncu_full_fps.log 2>&1
+              timeout 600 ncu --set full --clock-control none --import-source on -k regex:affine_warp -c 3 \
+                 -o gpurun_out/prof_affine python scripts/one_forward.py tc serial > gpurun_out/ncu_full_affine.log 2>&1 ;;
     sa0chk)   timeout 600 python scripts/sa0_chain_check.py > gpurun_out/sa0_chain_check.log 2>&1 ;;
     bench3)   REGNET_FUSE_SA0=3 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_chain.log 2>&1 ;;
     side2)    timeout 300 python scripts/timeline.py 2 > gpurun_out/timeline_side2.log 2>&1

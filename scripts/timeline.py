@@ -10,6 +10,7 @@ from regnet_for_3d_grasping_b200.scorenet import ScoreNetPlan  # noqa: E402
 
 B, N = 15, 25600
 mode = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 pc = torch.from_numpy(synth.batch("table", range(B), N)).cuda()
 pcs = [pc, pc.clone()]
 plan = ScoreNetPlan(B, N, "cuda", side_stream=mode)
@@ -28,7 +29,7 @@ def run(n):
 
 run(3)
 torch.cuda.synchronize()
-recs = plan.timeline(lambda: run(4))
+recs = plan.timeline(lambda: run(steps))
 print(f"# side_mode={mode} FPS_FORCE={os.environ.get('REGNET_FPS_FORCE')}  label start_ms dur_ms end_ms")
 for label, ms, t0 in recs:
     print(f"{label:18s} {t0:9.3f} {ms:8.3f} {t0 + ms:9.3f}")
