@@ -66,6 +66,19 @@ int regnet_ball_query(const float* points, int64_t psb, int64_t psc, int64_t psn
                       int64_t csb, int64_t csc, int64_t csn, int B, int N, int M, float radius, int K,
                       int64_t* index, int64_t* count, int32_t* index32, void* stream);
 
+/* Grid-accelerated forms of ball_query / point_search: identical results (indices, counts, squared distances), the
+ * caller lends regnet_search_workspace_bytes(B, N) bytes of device scratch (N = points per cloud for ball_query, keys
+ * per cloud for point_search).  Used when K == 64 (ball query), 4096 <= N <= 65536 and the workspace is big enough;
+ * otherwise they fall through to regnet_ball_query / regnet_point_search.  Replace the same reference entry points
+ * (csrc/ball_query_kernel.cu:87-131, csrc/interpolate_kernel.cu:88-128). */
+int64_t regnet_search_workspace_bytes(int B, int N);
+int regnet_ball_query_ws(const float* points, int64_t psb, int64_t psc, int64_t psn, const float* centroids,
+                         int64_t csb, int64_t csc, int64_t csn, int B, int N, int M, float radius, int K,
+                         int64_t* index, int64_t* count, void* workspace, int64_t workspace_bytes, void* stream);
+int regnet_point_search_ws(const float* query, int64_t qsb, int64_t qsc, int64_t qsn, const float* key, int64_t ksb,
+                           int64_t ksc, int64_t ksn, int B, int Nq, int Nk, int k, int64_t* index, float* distance,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 /* csrc/grouping.h:7-14 GroupPointsForward / GroupPointsBackward (csrc/grouping_kernel.cu:29-51, 54-149).
  * input (B,C,N) strided; index (B,M,K) int64 contiguous; out (B,C,M,K) contiguous.
  * backward: grad_out (B,C,M,K) contiguous -> grad_in (B,C,N) contiguous, zero-filled then scatter-added. */

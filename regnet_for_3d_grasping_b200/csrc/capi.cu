@@ -1,5 +1,6 @@
 // extern "C" surface of libregnet_b200.so, section 1 + 3 of include/regnet_b200.h (pn2_ext operator ABI and the
 // stand-alone MLP layer).  Section 2 (the fused ScoreNet plan) lives in scorenet.cu.
+#include <stdlib.h>
 #include <mutex>
 #include <string>
 
@@ -119,6 +120,43 @@ int regnet_ball_query(const float* points, int64_t psb, int64_t psc, int64_t psn
   RN_CHECK_ARG(points && centroids, "ball_query: null input");
   return ball_query_launch(points, Strides3{psb, psc, psn}, centroids, Strides3{csb, csc, csn}, B, N, M, radius, K,
                            index, count, index32, (cudaStream_t)stream);
+}
+
+// Grid-accelerated forms of the two search operators (same results, see grid.cu): the caller lends
+// regnet_search_workspace_bytes(B, N) bytes of device scratch.  They apply when the uniform grid pays off and its
+// limits hold; otherwise (or with a null workspace) the call falls through to the brute-force scan.
+int64_t regnet_search_workspace_bytes(int B, int N) { return grid_workspace_bytes(B, N); }
+
+static bool grid_applies(int n_indexed, int K, const void* ws, int64_t ws_bytes, int B) {
+  return ws != nullptr && K == 64 && n_indexed >= 4096 && n_indexed <= 65536 &&
+         ws_bytes >= grid_workspace_bytes(B, n_indexed) && !getenv("REGNET_API_BRUTE");
+}
+
+int regnet_ball_query_ws(const float* points, int64_t psb, int64_t psc, int64_t psn, const float* centroids,
+                         int64_t csb, int64_t csc, int64_t csn, int B, int N, int M, float radius, int K,
+                         int64_t* index, int64_t* count, void* workspace, int64_t workspace_bytes, void* stream) {
+  RN_CHECK_ARG(points && centroids && index && count, "ball_query: null argument");
+  if (!grid_applies(N, K, workspace, workspace_bytes, B) || !(radius > 0.f))
+    return regnet_ball_query(points, psb, psc, psn, centroids, csb, csc, csn, B, N, M, radius, K, index, count, nullptr,
+                             stream);
+  RN_CHECK_ARG(B > 0 && N > 0 && M > 0, "ball_query: empty input");
+  const Strides3 pst{psb, psc, psn}, cst{csb, csc, csn};
+  RN_TRY(grid_build_launch(points, pst, B, N, radius * 1.001f + 1e-7f, workspace, (cudaStream_t)stream));
+  return ball_query_grid_launch(points, pst, centroids, cst, B, N, M, radius, workspace, nullptr, (cudaStream_t)stream,
+                                index, count);
+}
+
+int regnet_point_search_ws(const float* query, int64_t qsb, int64_t qsc, int64_t qsn, const float* key, int64_t ksb,
+                           int64_t ksc, int64_t ksn, int B, int Nq, int Nk, int k, int64_t* index, float* distance,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+  RN_CHECK_ARG(query && key && index && distance, "point_search: null argument");
+  if (k != 3 || !grid_applies(Nk, 64, workspace, workspace_bytes, B))
+    return regnet_point_search(query, qsb, qsc, qsn, key, ksb, ksc, ksn, B, Nq, Nk, k, index, distance, stream);
+  RN_CHECK_ARG(B > 0 && Nq > 0, "point_search: empty input");
+  const Strides3 qst{qsb, qsc, qsn}, kst{ksb, ksc, ksn};
+  RN_TRY(grid_build_launch(key, kst, B, Nk, 0.f, workspace, (cudaStream_t)stream));
+  return three_nn_grid_launch(query, qst, key, kst, B, Nq, Nk, workspace, nullptr, nullptr, (cudaStream_t)stream, index,
+                              distance);
 }
 
 int regnet_group_points_forward(const float* input, int64_t sb, int64_t sc, int64_t sn, const int64_t* index,

@@ -149,7 +149,9 @@ __device__ __forceinline__ void bitonic64(uint32_t& a, uint32_t& b, int lane) {
 __global__ void __launch_bounds__(BQG_WARPS * 32)
 ball_query_grid_kernel(const float* __restrict__ pts, Strides3 pst, const float* __restrict__ ctr, Strides3 cst, int N,
                        int M, float radius, const GridHeader* __restrict__ hdr, const int* __restrict__ cell_start,
-                       const float4* __restrict__ sorted, int32_t* __restrict__ index32) {
+                       const float4* __restrict__ sorted, int32_t* __restrict__ index32, int64_t* __restrict__ index64,
+                       int64_t* __restrict__ count64) {
+  // outputs: index32 (the fused plan) and / or index64 + count64 (the pn2_ext operator surface), whichever is non-null
   constexpr int K = 64;
   __shared__ uint16_t lists[BQG_WARPS][BQG_LIST];
   const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -187,7 +189,11 @@ ball_query_grid_kernel(const float* __restrict__ pts, Strides3 pst, const float*
     }
   }
   __syncwarp();
-  int32_t* __restrict__ out = index32 + ((int64_t)b * M + m) * K;
+  const int64_t obase = ((int64_t)b * M + m) * K;
+  auto put = [&](int k, int v) {
+    if (index32) index32[obase + k] = v;
+    if (index64) index64[obase + k] = v;
+  };
   if (overflow) {
     // more hits than the list holds (very dense ball): exact scan of the original order, first K hits
     const float* __restrict__ p = pts + (int64_t)b * pst.b;
@@ -199,11 +205,12 @@ ball_query_grid_kernel(const float* __restrict__ pts, Strides3 pst, const float*
       const unsigned bits = __ballot_sync(FULL, hit);
       if (got == 0 && bits) first = t0 + __ffs(bits) - 1;
       const int slot = got + __popc(bits & ((1u << lane) - 1u));
-      if (hit && slot < K) out[slot] = j;
+      if (hit && slot < K) put(slot, j);
       got += __popc(bits);
     }
     got = min(got, K);
-    for (int k = got + lane; k < K; k += 32) out[k] = first;
+    for (int k = got + lane; k < K; k += 32) put(k, first);
+    if (count64 && lane == 0) count64[(int64_t)b * M + m] = got;
     return;
   }
   // keep the K smallest original indices: find the K-th smallest by bisection on the index value
@@ -242,8 +249,9 @@ ball_query_grid_kernel(const float* __restrict__ pts, Strides3 pst, const float*
   bb = lane + 32 < n ? (uint32_t)list[lane + 32] : 0xffffffffu;
   bitonic64(a, bb, lane);
   const uint32_t first = n > 0 ? __shfl_sync(FULL, a, 0) : 0u;
-  out[lane] = (int32_t)(lane < n ? a : first);
-  out[lane + 32] = (int32_t)(lane + 32 < n ? bb : first);
+  put(lane, (int)(lane < n ? a : first));
+  put(lane + 32, (int)(lane + 32 < n ? bb : first));
+  if (count64 && lane == 0) count64[(int64_t)b * M + m] = n;
 }
 
 // ---- 3-NN over the grid of KEYS: one thread per query --------------------------------------------------------------
@@ -264,7 +272,9 @@ __device__ __forceinline__ void top3_insert(float d, int j, float& d0, float& d1
 __global__ void __launch_bounds__(128)
 three_nn_grid_kernel(const float* __restrict__ qry, Strides3 qst, const float* __restrict__ key, Strides3 kst, int Nq,
                      int Nk, const GridHeader* __restrict__ hdr, const int* __restrict__ cell_start,
-                     const float4* __restrict__ sorted, int32_t* __restrict__ index32, float* __restrict__ weight) {
+                     const float4* __restrict__ sorted, int32_t* __restrict__ index32, float* __restrict__ weight,
+                     int64_t* __restrict__ index64, float* __restrict__ dist) {
+  // outputs: index32 + normalised weights (the fused plan) and / or index64 + squared distances (operator surface)
   const int b = blockIdx.y;
   const int i = blockIdx.x * 128 + threadIdx.x;
   if (i >= Nq) return;
@@ -319,6 +329,9 @@ three_nn_grid_kernel(const float* __restrict__ qry, Strides3 qst, const float* _
                              kp[(int64_t)j * kst.n + 2 * kst.c]), j, d0, d1, d2, i0, i1, i2);
   }
   const int64_t o = ((int64_t)b * Nq + i) * 3;
+  if (index64) { index64[o] = i0; index64[o + 1] = i1; index64[o + 2] = i2; }
+  if (dist) { dist[o] = d0; dist[o + 1] = d1; dist[o + 2] = d2; }
+  if (!index32) return;
   index32[o] = i0; index32[o + 1] = i1; index32[o + 2] = i2;
   const float v0 = __fdiv_rn(1.0f, fmaxf(d0, 1e-10f));
   const float v1 = __fdiv_rn(1.0f, fmaxf(d1, 1e-10f));
@@ -358,23 +371,26 @@ int grid_build_launch(const float* pts, Strides3 st, int B, int N, float min_cel
 }
 
 int ball_query_grid_launch(const float* pts, Strides3 pst, const float* ctr, Strides3 cst, int B, int N, int M,
-                           float radius, const void* ws, int32_t* index32, cudaStream_t stream) {
+                           float radius, const void* ws, int32_t* index32, cudaStream_t stream, int64_t* index64,
+                           int64_t* count64) {
   RN_CHECK_ARG(N <= 65536, "ball_query_grid: more than 65536 points per cloud");
   const GridPtrs g = carve(const_cast<void*>(ws), B, N);
   dim3 grid(ceil_div(M, BQG_WARPS), B);
   RN_PREFER_MAX_SMEM(ball_query_grid_kernel);
   ball_query_grid_kernel<<<grid, BQG_WARPS * 32, 0, stream>>>(pts, pst, ctr, cst, N, M, radius, g.hdr, g.cell_start,
-                                                             g.sorted, index32);
+                                                             g.sorted, index32, index64, count64);
   RN_LAUNCH_CHECK("ball_query_grid_kernel");
   return REGNET_OK;
 }
 
 int three_nn_grid_launch(const float* qry, Strides3 qst, const float* key, Strides3 kst, int B, int Nq, int Nk,
-                         const void* ws, int32_t* index32, float* weight, cudaStream_t stream) {
+                         const void* ws, int32_t* index32, float* weight, cudaStream_t stream, int64_t* index64,
+                         float* dist) {
   const GridPtrs g = carve(const_cast<void*>(ws), B, Nk);
   dim3 grid(ceil_div(Nq, 128), B);
   RN_PREFER_MAX_SMEM(three_nn_grid_kernel);
-  three_nn_grid_kernel<<<grid, 128, 0, stream>>>(qry, qst, key, kst, Nq, Nk, g.hdr, g.cell_start, g.sorted, index32, weight);
+  three_nn_grid_kernel<<<grid, 128, 0, stream>>>(qry, qst, key, kst, Nq, Nk, g.hdr, g.cell_start, g.sorted, index32, weight,
+                                                 index64, dist);
   RN_LAUNCH_CHECK("three_nn_grid_kernel");
   return REGNET_OK;
 }

@@ -67,9 +67,11 @@ int score_head_launch(const float* X, int ldx, const float* w, const float* scal
 int64_t grid_workspace_bytes(int B, int N);
 int grid_build_launch(const float* pts, Strides3 st, int B, int N, float min_cell, void* ws, cudaStream_t stream);
 int ball_query_grid_launch(const float* pts, Strides3 pst, const float* ctr, Strides3 cst, int B, int N, int M,
-                           float radius, const void* ws, int32_t* index32, cudaStream_t stream);
+                           float radius, const void* ws, int32_t* index32, cudaStream_t stream,
+                           int64_t* index64 = nullptr, int64_t* count64 = nullptr);
 int three_nn_grid_launch(const float* qry, Strides3 qst, const float* key, Strides3 kst, int B, int Nq, int Nk,
-                         const void* ws, int32_t* index32, float* weight, cudaStream_t stream);
+                         const void* ws, int32_t* index32, float* weight, cudaStream_t stream,
+                         int64_t* index64 = nullptr, float* dist = nullptr);
 
 int* oob_flag();  // per-device lazily allocated device int, set by kernels that meet an out-of-range index
 

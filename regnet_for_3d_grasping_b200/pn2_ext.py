@@ -76,8 +76,16 @@ def ball_query(points, centroids, radius, num_neighbours):
     if B == 0 or M == 0:
         return [index, count]
     with torch.cuda.device(points.device):
-        _lib.check(_lib.load().regnet_ball_query(*_strided3(points), *_strided3(centroids), B, N, M, float(radius), K,
-                                                 _p(index), _p(count), None, _stream()))
+        lib = _lib.load()
+        if K == 64 and 4096 <= N <= 65536:
+            # big clouds: the uniform-grid kernels (same results); scratch comes from torch's caching allocator
+            nbytes = int(lib.regnet_search_workspace_bytes(B, N))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
+            _lib.check(lib.regnet_ball_query_ws(*_strided3(points), *_strided3(centroids), B, N, M, float(radius), K,
+                                                _p(index), _p(count), _p(ws), nbytes, _stream()))
+        else:
+            _lib.check(lib.regnet_ball_query(*_strided3(points), *_strided3(centroids), B, N, M, float(radius), K,
+                                             _p(index), _p(count), None, _stream()))
     return [index, count]
 
 
@@ -132,8 +140,15 @@ def point_search(query_xyz, key_xyz, num_neighbours):
     if B == 0 or Nq == 0:
         return [index, dist]
     with torch.cuda.device(query_xyz.device):
-        _lib.check(_lib.load().regnet_point_search(*_strided3(query_xyz), *_strided3(key_xyz), B, Nq, Nk, 3, _p(index),
-                                                   _p(dist), _stream()))
+        lib = _lib.load()
+        if 4096 <= Nk <= 65536:
+            nbytes = int(lib.regnet_search_workspace_bytes(B, Nk))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=query_xyz.device)
+            _lib.check(lib.regnet_point_search_ws(*_strided3(query_xyz), *_strided3(key_xyz), B, Nq, Nk, 3, _p(index),
+                                                  _p(dist), _p(ws), nbytes, _stream()))
+        else:
+            _lib.check(lib.regnet_point_search(*_strided3(query_xyz), *_strided3(key_xyz), B, Nq, Nk, 3, _p(index),
+                                               _p(dist), _stream()))
     return [index, dist]
 
 

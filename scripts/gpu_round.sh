@@ -38,6 +38,7 @@ for s in $STAGES; do
               timeout 300 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_side2.log 2>&1
               REGNET_NO_SIDE2=1 timeout 300 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_noside2.log 2>&1
               for v in 1,256 2,256 4,128 4,256; do REGNET_FPS_CORUN1=$v timeout 300 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_side2_c1_${v/,/_}.log 2>&1; done ;;
+    opsgrid)  timeout 600 python -m pytest tests/test_gpu_ops.py -q -m gpu -x > gpurun_out/test_ops.log 2>&1 ;;
     alltests) timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/test_all.log 2>&1 ;;
   esac
   echo "    exit $?"

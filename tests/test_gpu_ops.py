@@ -183,3 +183,21 @@ def test_dgcnn_alias(ext):
     g = dgcnn_ext.gather_knn_backward(torch.ones(2, 4, 5, 3, device="cuda"), knn)
     ref = torch.zeros(2, 4, 5, device="cuda").scatter_add_(2, knn.view(2, 1, 15).expand(2, 4, 15), torch.ones(2, 4, 15, device="cuda"))
     assert torch.allclose(g, ref)
+
+
+@pytest.mark.parametrize("kind,N,M,radius", [("table", 25600, 5120, 0.02), ("table", 8192, 2048, 0.4),
+                                            ("lattice", 5120, 1024, 0.08), ("cube", 4096, 1024, 0.1)])
+def test_grid_and_brute_force_operator_paths_agree(ext, monkeypatch, kind, N, M, radius):
+    """pn2_ext.ball_query / point_search route big clouds through the uniform-grid kernels (regnet_ball_query_ws /
+    regnet_point_search_ws); REGNET_API_BRUTE forces the brute-force scan.  Both must give the same bits, including
+    the dense-ball overflow path (radius 0.4 on a table cloud: thousands of hits per ball) and keys == queries."""
+    from regnet_for_3d_grasping_b200 import synth
+    xyz = torch.from_numpy(synth.batch(kind, [21, 22], N)).cuda()[:, :, :3].permute(0, 2, 1)
+    idx = ext.farthest_point_sample(xyz, M)
+    new_xyz = xyz.gather(2, idx.unsqueeze(1).expand(2, 3, M))
+    got = ext.ball_query(xyz, new_xyz, radius, 64) + ext.point_search(new_xyz, xyz, 3) + ext.point_search(xyz, xyz, 3)
+    monkeypatch.setenv("REGNET_API_BRUTE", "1")
+    want = ext.ball_query(xyz, new_xyz, radius, 64) + ext.point_search(new_xyz, xyz, 3) + ext.point_search(xyz, xyz, 3)
+    for g, w, what in zip(got, want, ["bq index", "bq count", "nn index", "nn dist", "self nn index", "self nn dist"]):
+        assert torch.equal(g, w), f"{kind} N={N}: {what} differs between the grid and the brute-force path"
+    assert int(got[1].min()) >= 1   # every centroid is one of the points
