@@ -188,3 +188,30 @@ def test_prefetch_pipeline_equals_plain_forward(lib_path):
     f2, s2 = plan.forward(batches[1])
     torch.cuda.synchronize()
     assert torch.equal(s, want[0][1]) and torch.equal(s2, want[1][1])
+
+
+@pytest.mark.parametrize("B,N", [(15, 25600), (11, 25000)])
+def test_warp_producers_and_stream_modes_give_identical_bits(lib_path, monkeypatch, B, N):
+    """The warp-cooperative gather-affine / interpolate-affine producers compute the same fma chains as the
+    thread-per-(row, 4 channels) kernels they replace (REGNET_AFFINE_V1=1 selects those), and the three-stream
+    orchestration (side mode 3) only reorders launches: all variants must agree bit for bit -- at the BASELINE batch and
+    at a ragged one (11 x 25 000: B*N is not a multiple of 32, so the interpolate producer's tail path runs)."""
+    from regnet_for_3d_grasping_b200 import synth, weights
+    from regnet_for_3d_grasping_b200.scorenet import ScoreNetPlan
+    sd = weights.random_scorenet_state(seed=6)
+    pc = torch.from_numpy(synth.batch("table", range(300, 300 + B), N)).cuda()
+
+    def run(side_stream):
+        plan = ScoreNetPlan(B, N, "cuda", side_stream=side_stream)
+        plan.bind_state(sd)
+        f, s = plan.forward(pc)
+        torch.cuda.synchronize()
+        plan.close()
+        return f, s
+
+    f3, s3 = run(3)
+    f0, s0 = run(0)
+    assert torch.equal(f3, f0) and torch.equal(s3, s0), "side-stream mode 3 differs from the single-stream forward"
+    monkeypatch.setenv("REGNET_AFFINE_V1", "1")
+    f1, s1 = run(3)
+    assert torch.equal(f3, f1) and torch.equal(s3, s1), "warp-cooperative producers differ from the per-thread producers"
