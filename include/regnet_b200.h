@@ -209,6 +209,30 @@ int regnet_mask_sample(const uint8_t* mask, int rows, int G, int K, int min_coun
 int regnet_gather_max(const float* feat, const int64_t* index, int B, int N, int NC, int G, int C, float* out,
                       void* stream);
 
+/* ---- 3b. training-mode pieces of the shared MLP ----------------------------------------------------------------------
+ * BatchNorm with BATCH statistics + ReLU, forward and backward, over (B, C, L) fp32 contiguous tensors (torch's NCHW /
+ * NCL layout; L = M*K for the 2-D blocks).  Replaces nn.BatchNorm{1,2}d(training) + nn.ReLU(inplace) of
+ * nn/modules/conv.py:24-36,64-76 (cuDNN bn_fw_tr / bn_bw kernels + two elementwise passes in torch).
+ *   forward : y = [relu](gamma * (x - mean_c) * invstd_c + beta), mean / biased variance over (B, L) per channel;
+ *             running_mean / running_var (nullable) are updated in place like torch: (1-momentum)*old + momentum*new,
+ *             unbiased variance; save_mean, save_invstd, scale = gamma*invstd, shift = beta - mean*scale (C floats each)
+ *             are outputs the backward needs.  L must be a multiple of 4, B*C <= 65535; B*L == 1 -> EINVAL (torch:
+ *             "Expected more than 1 value per channel when training").
+ *   backward: dx, dgamma, dbeta from dy (gradient w.r.t. y) and the saved tensors; the ReLU mask is recomputed.
+ * workspace: regnet_bn_workspace_bytes(B, C, L) bytes of device scratch, contents undefined afterwards. */
+int64_t regnet_bn_workspace_bytes(int B, int C, int64_t L);
+int regnet_bn_relu_train_forward(const float* x, int B, int C, int64_t L, const float* gamma, const float* beta, float eps,
+                                 float momentum, int relu, float* running_mean, float* running_var, float* y,
+                                 float* save_mean, float* save_invstd, float* scale, float* shift, void* workspace,
+                                 int64_t workspace_bytes, void* stream);
+int regnet_bn_relu_train_backward(const float* dy, const float* x, int B, int C, int64_t L, const float* save_mean,
+                                  const float* save_invstd, const float* scale, const float* shift, int relu, float* dx,
+                                  float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, void* stream);
+/* Max over the innermost 64 elements of (rows, 64) fp32 (torch.max(x, 3)[0] of modules.py:245 for K = 64) with the
+ * arg-max kept as one byte per row, and its backward (dx = dout at the arg-max, 0 elsewhere; every element written). */
+int regnet_maxpool64_forward(const float* x, int64_t rows, float* out, uint8_t* argmax, void* stream);
+int regnet_maxpool64_backward(const float* dout, const uint8_t* argmax, int64_t rows, float* dx, void* stream);
+
 /* ---- 4. building blocks exposed for tests / micro-benchmarks ------------------------------------------- */
 
 /* Y = act(scale * (X W^T) + shift), X (P,cin) fp32 row-major, W (cout,cin) fp32 row-major.

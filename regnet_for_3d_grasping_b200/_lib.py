@@ -55,6 +55,13 @@ _SIGNATURES = {
     "regnet_scorenet_launch_count": (c_int, [c_ptr]),
     "regnet_scorenet_set_profiling": (c_int, [c_ptr, c_int]),
     "regnet_scorenet_profile": (c_int, [c_ptr, ctypes.c_char_p, c_i64]),
+    "regnet_bn_workspace_bytes": (c_i64, [c_int, c_int, c_i64]),
+    "regnet_bn_relu_train_forward": (c_int, [c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_f32, c_f32, c_int, c_ptr, c_ptr,
+                                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "regnet_bn_relu_train_backward": (c_int, [c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr,
+                                              c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "regnet_maxpool64_forward": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "regnet_maxpool64_backward": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "regnet_select_score_center_workspace": (c_i64, [c_int, c_int, c_int]),
     "regnet_select_score_center": (c_int, [c_ptr, c_ptr, c_int, c_int, c_int, c_f32, ctypes.c_uint64, c_ptr, c_ptr, c_ptr,
                                            c_ptr, c_i64, c_ptr]),

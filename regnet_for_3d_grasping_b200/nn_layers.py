@@ -8,6 +8,8 @@ scorenet.py consumes the same parameters folded to (W, scale, shift)."""
 import torch.nn.functional as F
 from torch import nn
 
+from . import train_ops
+
 
 def init_bn(module):
     if module.weight is not None:
@@ -32,6 +34,10 @@ class _ConvBnRelu(nn.Module):
     def forward(self, x):
         x = self.conv(x)
         if self.bn is not None:
+            if self.training and train_ops.bn_supported(x, self.bn):
+                # batch-statistics BN + ReLU in two streaming passes of this repo's kernels (csrc/train_ops.cu) instead
+                # of cuDNN's bn_fw_tr / bn_bw + separate ReLU passes; same values within fp32 rounding
+                return train_ops.bn_relu_train(x, self.bn, self.relu is not None)
             x = self.bn(x)
         return x if self.relu is None else self.relu(x)
 

@@ -1,0 +1,138 @@
+"""GPU parity, training-mode kernels (csrc/train_ops.cu) through the C ABI: batch-statistics BatchNorm + ReLU forward /
+backward and the 64-neighbour max-pool, against torch in float64 (the floating-point oracle for these kernels:
+nn/modules/conv.py:24-36,64-76 and modules.py:245 are plain torch calls in the reference).
+Tolerances: 2e-5 relative to the tensor's largest magnitude for values and input gradients, 1e-4 for the parameter
+gradients (sums over up to 10^6 fp32 terms)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(got, want, tol, what):
+    err = (got.double().cpu() - want.cpu()).abs().max().item()
+    ref = max(want.abs().max().item(), 1e-30)
+    assert err <= tol * ref, f"{what}: max abs err {err:.3e} vs magnitude {ref:.3e}"
+
+
+@pytest.mark.parametrize("shape,relu,offset", [((3, 16, 4096), True, 0.0), ((2, 130, 20, 64), True, 3.0),
+                                               ((15, 64, 1024, 64), True, -1.0), ((4, 33, 25600), False, 50.0),
+                                               ((1, 8, 8), True, 0.5)])
+def test_bn_relu_train_matches_float64_torch(lib_path, shape, relu, offset):
+    from regnet_for_3d_grasping_b200 import train_ops
+    g = torch.Generator().manual_seed(sum(shape))
+    C = shape[1]
+    x = (torch.randn(shape, generator=g) * (torch.rand(1, C, *([1] * (len(shape) - 2)), generator=g) * 2 + 0.5) + offset
+         + torch.randn(1, C, *([1] * (len(shape) - 2)), generator=g))
+    bn_cls = torch.nn.BatchNorm2d if len(shape) == 4 else torch.nn.BatchNorm1d
+    ref = bn_cls(C).double()
+    with torch.no_grad():
+        ref.weight.copy_(torch.randn(C, generator=g))          # both signs
+        ref.bias.copy_(torch.randn(C, generator=g) * 0.3)
+        ref.running_mean.copy_(torch.randn(C, generator=g))
+        ref.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    ours = bn_cls(C).cuda()
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    ref.train(); ours.train()
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    yr = torch.relu(yr) if relu else yr
+    dy = torch.randn(shape, generator=g)
+    yr.backward(dy.double())
+    xo = x.cuda().requires_grad_(True)
+    assert train_ops.bn_supported(xo, ours)
+    yo = train_ops.bn_relu_train(xo, ours, relu)
+    yo.backward(dy.cuda())
+    torch.cuda.synchronize()
+    _close(yo, yr.detach(), 2e-5, "y")
+    _close(ours.running_mean, ref.running_mean, 1e-5, "running_mean")
+    _close(ours.running_var, ref.running_var, 1e-5, "running_var")
+    assert int(ours.num_batches_tracked) == 1
+    _close(xo.grad, xr.grad, 2e-5, "dx")
+    _close(ours.weight.grad, ref.weight.grad, 1e-4, "dgamma")
+    _close(ours.bias.grad, ref.bias.grad, 1e-4, "dbeta")
+
+
+def test_bn_one_value_per_channel_is_rejected_like_torch(lib_path):
+    from regnet_for_3d_grasping_b200 import train_ops
+    bn = torch.nn.BatchNorm1d(4).cuda().train()
+    x = torch.randn(1, 4, 1, device="cuda")
+    assert not train_ops.bn_supported(x, bn)       # the module then takes torch's path, which raises ValueError
+    with pytest.raises(ValueError, match="more than 1 value per channel"):
+        bn(x)
+
+
+def test_maxpool64_forward_backward(lib_path):
+    from regnet_for_3d_grasping_b200 import train_ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 37, 129, 64, generator=g)
+    x[0, 0, 0] = 0.0                         # all-equal row: first index wins
+    x[1, 2, 3, 10:20] = x[1, 2, 3].max() + 1  # tie among duplicates
+    xo = x.cuda().requires_grad_(True)
+    out = train_ops.max_over_neighbours(xo)
+    want = x.max(dim=3)[0]
+    assert torch.equal(out.cpu(), want)
+    dout = torch.randn(3, 37, 129, generator=g)
+    out.backward(dout.cuda())
+    dx = xo.grad.cpu()
+    assert torch.equal(dx.sum(dim=3), dout)                       # one position per row carries the whole gradient
+    assert torch.equal((dx != 0).sum(dim=3), (dout != 0).long())
+    picked = (dx != 0) | ((dout == 0).unsqueeze(-1) & False)
+    assert torch.equal(x[picked], want.unsqueeze(-1).expand_as(x)[picked])   # ... and it is a maximum of its row
+    assert dx[1, 2, 3, 10] == dout[1, 2, 3] and dx[0, 0, 0, 0] == dout[0, 0, 0]
+
+
+def test_training_gradients_fused_and_torch_paths_against_float64(lib_path, oracle, monkeypatch):
+    """Back-propagation through the whole SA / FP stack in train mode (batch-statistics BN everywhere), three ways on the
+    same weights and input: this repo's BN / max-pool kernels, torch's (cuDNN) kernels, and a float64 restatement
+    (oracle/ref_modules.py, fp32 search operators, float64 MLPs) as the truth.  BN backward is ill-conditioned
+    (g - mean(g) - xhat * mean(g * xhat) cancels), so two fp32 implementations differ by ~1e-2 of a first-layer gradient;
+    the requirement is that the fused path is as close to the float64 truth as torch's own path is (within a factor 3,
+    or 1e-4 relative)."""
+    from oracle import ref_modules
+    from regnet_for_3d_grasping_b200 import pn2_ext, synth, weights
+    from regnet_for_3d_grasping_b200.score_network import ScoreNetwork
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sd = weights.random_scorenet_state(seed=3)
+        pc = torch.from_numpy(synth.batch("table", [1, 2], 6144)).cuda()
+        probe = torch.randn(2, 6144, 256, generator=torch.Generator().manual_seed(9)).cuda()
+        # float64 truth
+        sd64 = {k: (v.cuda().double().requires_grad_(k.endswith(("weight", "bias"))) if v.is_floating_point() else v.cuda())
+                for k, v in sd.items()}
+        f64, _, _ = ref_modules.scorenet_forward(sd64, pc, pn2_ext, dtype=torch.float64, training=True)
+        (f64 * probe.double()).mean().backward()
+        truth = {k: v.grad for k, v in sd64.items() if v.is_floating_point() and v.grad is not None}
+        res = []
+        for torch_path in (False, True):
+            monkeypatch.setenv("REGNET_TRAIN_TORCH", "1" if torch_path else "0")
+            net = ScoreNetwork(training=True).cuda()
+            net.load_state_dict(sd)
+            net.train()
+            torch.manual_seed(11)                       # same dropout masks in the seg head
+            feat, _, _ = net(pc)
+            (feat * probe).mean().backward()
+            torch.cuda.synchronize()
+            res.append((feat.detach().clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None},
+                        {k: b.clone() for k, b in net.named_buffers()}))
+        (f0, g0, b0), (f1, g1, b1) = res
+        scale = f64.abs().max().item()
+        e0, e1 = (f0.double() - f64).abs().max().item() / scale, (f1.double() - f64).abs().max().item() / scale
+        assert e0 <= max(3 * e1, 1e-4), f"all_feature: fused err {e0:.3e}, torch err {e1:.3e}"
+        checked = 0
+        for k in g0:
+            if k not in truth:
+                continue
+            ref = truth[k].abs().max().item()
+            if ref == 0:
+                continue
+            d0 = (g0[k].double() - truth[k]).abs().max().item() / ref
+            d1 = (g1[k].double() - truth[k]).abs().max().item() / ref
+            assert d0 <= max(3 * d1, 1e-4), f"{k}: fused grad err {d0:.3e}, torch grad err {d1:.3e} (relative to max |grad|)"
+            checked += 1
+        assert checked >= 40
+        for k in b0:      # running statistics / counters updated the same way
+            assert torch.allclose(b0[k].float(), b1[k].float(), rtol=1e-4, atol=1e-6), k
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
