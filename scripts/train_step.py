@@ -73,7 +73,7 @@ def main():
                           "points": args.points, "loss": float(loss), "parameters": nparam,
                           "grad_allreduce_bytes_per_step": 4 * nparam if world > 1 else 0,
                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
-                          "path": "modules.py op-by-op: pn2_ext operators (this repo's kernels) + torch conv / BN / autograd"}))
+                          "path": "modules.py op-by-op: this repo's point operators, BN+ReLU and max-pool training kernels + torch GEMMs / autograd"}))
     if world > 1:
         dist.destroy_process_group()
 
