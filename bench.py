@@ -304,9 +304,17 @@ def main():
 
     e2e_no = [0]
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def e2e_upload(i):
-        dev_in[i & 1].copy_(host_pc, non_blocking=True)
-        net.prefetch(dev_in[i & 1])
+        # H2D of batch i and its prefetch are issued on a copy stream, ordered behind the last reader of that buffer
+        # (forward(i-2), the newest work on the compute stream when this is called).  The geometry side streams start
+        # behind the copy; the compute stream itself never waits for the copy, only -- through the per-level events of
+        # forward(i) -- for the geometry that followed it.
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
+            dev_in[i & 1].copy_(host_pc, non_blocking=True)
+            net.prefetch(dev_in[i & 1])
 
     def e2e_steps(n):
         # per step: H2D of the NEXT batch from pinned memory + its prefetch (public API: ScoreNetwork.prefetch),
@@ -317,9 +325,14 @@ def main():
             e2e_upload(i + 1)
             with torch.no_grad():
                 _, s, _ = net(dev_in[i & 1])
-            host_score.copy_(s, non_blocking=True)
+            # D2H of the scores on the copy stream too, behind this forward (the compute stream goes straight on)
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                host_score.copy_(s, non_blocking=True)
+            s.record_stream(copy_stream)
             e2e_no[0] = i + 1
         net.join_prefetch()
+        torch.cuda.current_stream().wait_stream(copy_stream)   # the region ends after the last read-back
 
     e2e_upload(0)
     e2e_steps(args.warmup)
