@@ -300,39 +300,44 @@ def main():
     net.load_state_dict(sd)
     net.extrat_featurePN2.engine = engine
     host_score = torch.empty(B_PER_GPU, N_POINTS).pin_memory()
-    dev_in = [torch.empty_like(pc), torch.empty_like(pc)]
-
+    dev_in = [torch.empty_like(pc) for _ in range(3)]   # triple-buffered inputs: upload(i+2) overlaps forward(i)
     e2e_no = [0]
-
-    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_stream, d2h_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    done = {}
 
     def e2e_upload(i):
-        # H2D of batch i and its prefetch are issued on a copy stream, ordered behind the last reader of that buffer
-        # (forward(i-2), the newest work on the compute stream when this is called).  The geometry side streams start
-        # behind the copy; the compute stream itself never waits for the copy, only -- through the per-level events of
-        # forward(i) -- for the geometry that followed it.
-        copy_stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(copy_stream):
-            dev_in[i & 1].copy_(host_pc, non_blocking=True)
-            net.prefetch(dev_in[i & 1])
+        # Called before forward(i-1) is enqueued, i.e. while forward(i-2) is the newest work on the compute stream.
+        # H2D of batch i on a copy stream as soon as the last reader of its buffer (forward(i-3)) is done; its prefetch
+        # on the same stream, additionally behind forward(i-2) (the last reader of the geometry slot it reuses).  The
+        # compute stream itself never waits for a copy, only -- through the per-level events of forward(i) -- for the
+        # geometry that followed it.
+        if i - 3 in done:
+            h2d_stream.wait_event(done.pop(i - 3))
+        with torch.cuda.stream(h2d_stream):
+            dev_in[i % 3].copy_(host_pc, non_blocking=True)
+        h2d_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(h2d_stream):
+            net.prefetch(dev_in[i % 3])
 
     def e2e_steps(n):
         # per step: H2D of the NEXT batch from pinned memory + its prefetch (public API: ScoreNetwork.prefetch),
         # ScoreNetwork.forward of the current batch, D2H of its scores.  Steady state as above: K uploads, K geometry
         # chains, K forwards and K read-backs inside the timed region.
+        main = torch.cuda.current_stream()
         for _ in range(n):
             i = e2e_no[0]
             e2e_upload(i + 1)
             with torch.no_grad():
-                _, s, _ = net(dev_in[i & 1])
-            # D2H of the scores on the copy stream too, behind this forward (the compute stream goes straight on)
-            copy_stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(copy_stream):
+                _, s, _ = net(dev_in[i % 3])
+            done[i] = main.record_event()
+            d2h_stream.wait_event(done[i])                 # read-back on its own stream, behind this forward
+            with torch.cuda.stream(d2h_stream):
                 host_score.copy_(s, non_blocking=True)
-            s.record_stream(copy_stream)
+            s.record_stream(d2h_stream)
             e2e_no[0] = i + 1
         net.join_prefetch()
-        torch.cuda.current_stream().wait_stream(copy_stream)   # the region ends after the last read-back
+        main.wait_stream(d2h_stream)                       # the region ends after the last read-back
+        main.wait_stream(h2d_stream)                       # ... and the last upload
 
     e2e_upload(0)
     e2e_steps(args.warmup)
@@ -344,7 +349,7 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     with torch.no_grad():
-        net(dev_in[e2e_no[0] & 1])   # consumes the outstanding prefetch (untimed)
+        net(dev_in[e2e_no[0] % 3])   # consumes the outstanding prefetch (untimed)
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
