@@ -228,6 +228,18 @@ int regnet_bn_relu_train_forward(const float* x, int B, int C, int64_t L, const 
 int regnet_bn_relu_train_backward(const float* dy, const float* x, int B, int C, int64_t L, const float* save_mean,
                                   const float* save_invstd, const float* scale, const float* shift, int relu, float* dx,
                                   float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, void* stream);
+/* The pooled (last) block of a set-abstraction MLP: batch-statistics BN + ReLU + max over the 64 neighbours in one go
+ * (conv.py:64-76 followed by modules.py:245).  x (B, C, M, 64) fp32 contiguous -> out (B, C, M), argmax (B, C, M) bytes;
+ * the (B, C, M, 64) activation is never written, and backward reads its gradient from (dout, argmax) instead of a dense
+ * tensor.  Other arguments as regnet_bn_relu_train_*; workspace regnet_bn_workspace_bytes(B, C, 64 * M). */
+int regnet_bn_relu_max64_train_forward(const float* x, int B, int C, int64_t M, const float* gamma, const float* beta,
+                                       float eps, float momentum, int relu, float* running_mean, float* running_var,
+                                       float* out, uint8_t* argmax, float* save_mean, float* save_invstd, float* scale,
+                                       float* shift, void* workspace, int64_t workspace_bytes, void* stream);
+int regnet_bn_relu_max64_train_backward(const float* dout, const uint8_t* argmax, const float* x, int B, int C, int64_t M,
+                                        const float* save_mean, const float* save_invstd, const float* scale,
+                                        const float* shift, int relu, float* dx, float* dgamma, float* dbeta,
+                                        void* workspace, int64_t workspace_bytes, void* stream);
 /* Max over the innermost 64 elements of (rows, 64) fp32 (torch.max(x, 3)[0] of modules.py:245 for K = 64) with the
  * arg-max kept as one byte per row, and its backward (dx = dout at the arg-max, 0 elsewhere; every element written). */
 int regnet_maxpool64_forward(const float* x, int64_t rows, float* out, uint8_t* argmax, void* stream);

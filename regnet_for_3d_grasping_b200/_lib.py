@@ -60,6 +60,10 @@ _SIGNATURES = {
                                              c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "regnet_bn_relu_train_backward": (c_int, [c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr,
                                               c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "regnet_bn_relu_max64_train_forward": (c_int, [c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_f32, c_f32, c_int, c_ptr, c_ptr,
+                                                   c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "regnet_bn_relu_max64_train_backward": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
+                                                    c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "regnet_maxpool64_forward": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "regnet_maxpool64_backward": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "regnet_select_score_center_workspace": (c_i64, [c_int, c_int, c_int]),

@@ -284,6 +284,100 @@ maxpool64_bwd_kernel(const float* __restrict__ dout, const uint8_t* __restrict__
   }
 }
 
+// ---- pooled layer (last block of an SA module): BN + ReLU + max over the 64 neighbours without materialising y ----------
+// forward pass 2: out[b,c,m] = max_k relu(fma(x[b,c,m,k], scale, shift)), arg-max kept as a byte
+template <bool RELU>
+__global__ void __launch_bounds__(TB)
+bn_apply_max64_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, int C,
+                      int64_t M, float* __restrict__ out, uint8_t* __restrict__ arg) {
+  const int bc = blockIdx.y, c = bc % C;
+  const float sc = scale[c], sh = shift[c];
+  const int lane16 = threadIdx.x & 15, half = (threadIdx.x >> 4) & 1;
+  const int64_t warp = ((int64_t)blockIdx.x * TB + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * TB) >> 5;
+  const float* __restrict__ xr = x + (int64_t)bc * M * 64;
+  for (int64_t m2 = warp * 2; m2 < M; m2 += nwarps * 2) {
+    const int64_t m = m2 + half;
+    const bool live = m < M;
+    float4 v = live ? *reinterpret_cast<const float4*>(xr + m * 64 + lane16 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh); v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+    if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    float best = v.x; int k = lane16 * 4;
+    if (v.y > best) { best = v.y; k = lane16 * 4 + 1; }
+    if (v.z > best) { best = v.z; k = lane16 * 4 + 2; }
+    if (v.w > best) { best = v.w; k = lane16 * 4 + 3; }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(FULL, best, o);
+      const int ok = __shfl_xor_sync(FULL, k, o);
+      if (ob > best || (ob == best && ok < k)) { best = ob; k = ok; }
+    }
+    if (live && lane16 == 0) { out[(int64_t)bc * M + m] = best; arg[(int64_t)bc * M + m] = (uint8_t)k; }
+  }
+}
+
+// backward pass 1: the gradient w.r.t. y is dout at the arg-max (if it passed the ReLU) and 0 elsewhere
+template <bool RELU>
+__global__ void __launch_bounds__(TB)
+bn_max64_bwd_reduce_kernel(const float* __restrict__ dout, const uint8_t* __restrict__ arg, const float* __restrict__ x,
+                           const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                           const float* __restrict__ scale, const float* __restrict__ shift, int C, int64_t M,
+                           float* __restrict__ partial) {
+  const int c = blockIdx.x, b = blockIdx.y;
+  const int64_t bc = (int64_t)b * C + c;
+  const float mu = save_mean[c], is = save_invstd[c], sc = scale[c], sh = shift[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t m = threadIdx.x; m < M; m += TB) {
+    const float xv = x[(bc * M + m) * 64 + arg[bc * M + m]];
+    const float g = (!RELU || fmaf(xv, sc, sh) > 0.f) ? dout[bc * M + m] : 0.f;
+    s1 += g;
+    s2 = fmaf(g, (xv - mu) * is, s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(FULL, s1, o);
+    s2 += __shfl_xor_sync(FULL, s2, o);
+  }
+  __shared__ float sh1[TB / 32], sh2[TB / 32];
+  if ((threadIdx.x & 31) == 0) { sh1[threadIdx.x >> 5] = s1; sh2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, bsum = 0.f;
+    for (int i = 0; i < TB / 32; ++i) { a += sh1[i]; bsum += sh2[i]; }
+    float* o = partial + ((int64_t)c * gridDim.y + blockIdx.y) * 2;
+    o[0] = a; o[1] = bsum;
+  }
+}
+
+// backward pass 2: dx = scale * (g - mean(g) - xhat * mean(g * xhat)) for every position
+template <bool RELU>
+__global__ void __launch_bounds__(TB)
+bn_max64_bwd_apply_kernel(const float* __restrict__ dout, const uint8_t* __restrict__ arg, const float* __restrict__ x,
+                          const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                          const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ k1,
+                          const float* __restrict__ k2, int C, int64_t M, float* __restrict__ dx) {
+  const int bc = blockIdx.y, c = bc % C;
+  const float mu = save_mean[c], is = save_invstd[c], sc = scale[c], sh = shift[c], m1 = k1[c], m2 = k2[c];
+  const int lane16 = threadIdx.x & 15;
+  const int64_t hw = ((int64_t)blockIdx.x * TB + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * TB) >> 4;
+  for (int64_t m = hw; m < M; m += nhw) {
+    const int64_t r = (int64_t)bc * M + m;
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * 64 + lane16 * 4);
+    const float dp = dout[r];
+    const int k = (int)arg[r] - lane16 * 4;
+    float4 g;
+    g.x = (k == 0 && (!RELU || fmaf(xv.x, sc, sh) > 0.f)) ? dp : 0.f;
+    g.y = (k == 1 && (!RELU || fmaf(xv.y, sc, sh) > 0.f)) ? dp : 0.f;
+    g.z = (k == 2 && (!RELU || fmaf(xv.z, sc, sh) > 0.f)) ? dp : 0.f;
+    g.w = (k == 3 && (!RELU || fmaf(xv.w, sc, sh) > 0.f)) ? dp : 0.f;
+    float4 o;
+    o.x = sc * (g.x - m1 - (xv.x - mu) * is * m2);
+    o.y = sc * (g.y - m1 - (xv.y - mu) * is * m2);
+    o.z = sc * (g.z - m1 - (xv.z - mu) * is * m2);
+    o.w = sc * (g.w - m1 - (xv.w - mu) * is * m2);
+    *reinterpret_cast<float4*>(dx + r * 64 + lane16 * 4) = o;
+  }
+}
+
 inline unsigned apply_grid_x(int64_t L, int rows_bc) {
   int64_t gx = (L / 4 + TB - 1) / TB;
   const int64_t cap = std::max<int64_t>(1, (148LL * 16 + rows_bc - 1) / rows_bc);   // ~16 resident blocks per SM overall
@@ -360,6 +454,56 @@ int regnet_bn_relu_train_backward(const float* dy, const float* x, int B, int C,
   if (relu) bn_bwd_apply_kernel<true><<<grid, TB, 0, s>>>(dy, x, save_mean, save_invstd, scale, shift, k1, k2, C, L, dx);
   else bn_bwd_apply_kernel<false><<<grid, TB, 0, s>>>(dy, x, save_mean, save_invstd, scale, shift, k1, k2, C, L, dx);
   RN_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return REGNET_OK;
+}
+
+int regnet_bn_relu_max64_train_forward(const float* x, int B, int C, int64_t M, const float* gamma, const float* beta,
+                                       float eps, float momentum, int relu, float* running_mean, float* running_var,
+                                       float* out, uint8_t* argmax, float* save_mean, float* save_invstd, float* scale,
+                                       float* shift, void* workspace, int64_t workspace_bytes, void* stream_) {
+  RN_CHECK_ARG(x && out && argmax && save_mean && save_invstd && scale && shift && workspace,
+               "bn_relu_max64_train_forward: null argument");
+  const int64_t L = M * 64;
+  RN_TRY(check_shape(B, C, L));
+  RN_CHECK_ARG(workspace_bytes >= regnet_bn_workspace_bytes(B, C, L), "bn_relu_max64_train_forward: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const ChunkPlan cp = plan_chunks(L);
+  const int P = B * cp.sl;
+  float* partial = reinterpret_cast<float*>(workspace);
+  bn_stats_kernel<<<dim3(C, P), TB, 0, s>>>(x, C, L, cp.chunk, cp.sl, partial);
+  RN_LAUNCH_CHECK("bn_stats_kernel");
+  bn_finalize_kernel<<<(C + 3) / 4, 128, 0, s>>>(x, L, partial, P, C, gamma, beta, eps, momentum, running_mean, running_var,
+                                                 save_mean, save_invstd, scale, shift);
+  RN_LAUNCH_CHECK("bn_finalize_kernel");
+  const dim3 grid(apply_grid_x(L, B * C), B * C);
+  if (relu) bn_apply_max64_kernel<true><<<grid, TB, 0, s>>>(x, scale, shift, C, M, out, argmax);
+  else bn_apply_max64_kernel<false><<<grid, TB, 0, s>>>(x, scale, shift, C, M, out, argmax);
+  RN_LAUNCH_CHECK("bn_apply_max64_kernel");
+  return REGNET_OK;
+}
+
+int regnet_bn_relu_max64_train_backward(const float* dout, const uint8_t* argmax, const float* x, int B, int C, int64_t M,
+                                        const float* save_mean, const float* save_invstd, const float* scale,
+                                        const float* shift, int relu, float* dx, float* dgamma, float* dbeta,
+                                        void* workspace, int64_t workspace_bytes, void* stream_) {
+  RN_CHECK_ARG(dout && argmax && x && save_mean && save_invstd && scale && shift && dx && dgamma && dbeta && workspace,
+               "bn_relu_max64_train_backward: null argument");
+  const int64_t L = M * 64;
+  RN_TRY(check_shape(B, C, L));
+  RN_CHECK_ARG(workspace_bytes >= regnet_bn_workspace_bytes(B, C, L), "bn_relu_max64_train_backward: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream_;
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* k1 = partial + (int64_t)C * B * plan_chunks(L).sl * 3;
+  float* k2 = k1 + C;
+  if (relu) bn_max64_bwd_reduce_kernel<true><<<dim3(C, B), TB, 0, s>>>(dout, argmax, x, save_mean, save_invstd, scale, shift, C, M, partial);
+  else bn_max64_bwd_reduce_kernel<false><<<dim3(C, B), TB, 0, s>>>(dout, argmax, x, save_mean, save_invstd, scale, shift, C, M, partial);
+  RN_LAUNCH_CHECK("bn_max64_bwd_reduce_kernel");
+  bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, s>>>(partial, B, C, (double)B * (double)L, dgamma, dbeta, k1, k2);
+  RN_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  const dim3 grid(apply_grid_x(L, B * C), B * C);
+  if (relu) bn_max64_bwd_apply_kernel<true><<<grid, TB, 0, s>>>(dout, argmax, x, save_mean, save_invstd, scale, shift, k1, k2, C, M, dx);
+  else bn_max64_bwd_apply_kernel<false><<<grid, TB, 0, s>>>(dout, argmax, x, save_mean, save_invstd, scale, shift, k1, k2, C, M, dx);
+  RN_LAUNCH_CHECK("bn_max64_bwd_apply_kernel");
   return REGNET_OK;
 }
 

@@ -9,7 +9,6 @@ import torch
 from torch import nn
 
 from . import function as _F
-from . import train_ops
 from .nn_layers import SharedMLP
 
 
@@ -96,7 +95,7 @@ class PointNetSAModule(nn.Module):
         else:
             new_xyz = xyz if self.num_centroids == -1 else _F.gather_points(xyz, self.sampler(xyz))
             group_feature, _ = self.grouper(new_xyz, xyz, feature, use_xyz=self.use_xyz)
-        new_feature = train_ops.max_over_neighbours(self.mlp(group_feature))   # torch.max(x, 3)[0], modules.py:245
+        new_feature = self.mlp.forward_max_over_neighbours(group_feature)   # torch.max(self.mlp(x), 3)[0], modules.py:245
         return new_xyz, new_feature
 
     def init_weights(self, init_fn=None):

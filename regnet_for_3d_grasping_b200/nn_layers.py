@@ -5,6 +5,8 @@ ReLU), nn/modules/mlp.py:55-114 (SharedMLP) and nn/init.py:4-8 (init_bn), so tha
 (`<layer>.conv.weight`, `<layer>.bn.{weight,bias,running_mean,running_var,num_batches_tracked}`).
 The forward here is the *training* path (torch conv + BN, autograd); in eval mode the fused plan in
 scorenet.py consumes the same parameters folded to (W, scale, shift)."""
+import os
+
 import torch.nn.functional as F
 from torch import nn
 
@@ -84,6 +86,22 @@ class SharedMLP(nn.ModuleList):
             if self.training and self.dropout_prob > 0.0:
                 x = drop(x, p=self.dropout_prob, training=True)
         return x
+
+    def forward_max_over_neighbours(self, x):
+        """torch.max(self(x), 3)[0] (modules.py:245).  In train mode on CUDA the last block's BatchNorm + ReLU and the
+        max over the 64 neighbours are one pair of kernels: its (B, C, M, 64) activation is never written."""
+        last = self[len(self) - 1]
+        if (self.training and self.ndim == 2 and self.dropout_prob == 0.0 and last.bn is not None and x.is_cuda
+                and os.environ.get("REGNET_TRAIN_UNFUSED_MAX", "0") != "1"):
+            for i in range(len(self) - 1):
+                x = self[i](x)
+            x = last.conv(x)
+            if train_ops.bn_relu_max64_supported(x, last.bn):
+                return train_ops.bn_relu_max64_train(x, last.bn, last.relu is not None)
+            x = last.bn(x)
+            x = x if last.relu is None else last.relu(x)
+            return train_ops.max_over_neighbours(x)
+        return train_ops.max_over_neighbours(self.forward(x))
 
     def init_weights(self, init_fn=None):
         for block in self:

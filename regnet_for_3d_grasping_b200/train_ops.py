@@ -83,6 +83,57 @@ def bn_relu_train(x, bn, relu):
     return y
 
 
+class _BnReluMax64Train(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, relu):
+        x = x.contiguous()
+        B, C, M = x.size(0), x.size(1), x.size(2)
+        lib = _lib.load()
+        out = torch.empty(B, C, M, dtype=torch.float32, device=x.device)
+        arg = torch.empty(B, C, M, dtype=torch.uint8, device=x.device)
+        stats = torch.empty(4, C, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            nbytes = int(lib.regnet_bn_workspace_bytes(B, C, M * 64))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _lib.check(lib.regnet_bn_relu_max64_train_forward(
+                _p(x), B, C, M, _p(weight), _p(bias), float(eps), float(momentum), int(relu), _p(running_mean),
+                _p(running_var), _p(out), _p(arg), _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]), _p(ws), nbytes,
+                _stream()))
+        ctx.save_for_backward(x, stats, arg)
+        ctx.relu = bool(relu)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, stats, arg = ctx.saved_tensors
+        dout = dout.contiguous()
+        B, C, M = x.size(0), x.size(1), x.size(2)
+        lib = _lib.load()
+        dx = torch.empty_like(x)
+        dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            nbytes = int(lib.regnet_bn_workspace_bytes(B, C, M * 64))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _lib.check(lib.regnet_bn_relu_max64_train_backward(
+                _p(dout), _p(arg), _p(x), B, C, M, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]), int(ctx.relu),
+                _p(dx), _p(dgamma), _p(dbeta), _p(ws), nbytes, _stream()))
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+def bn_relu_max64_supported(x, bn):
+    return x.dim() == 4 and x.size(3) == 64 and bn_supported(x, bn)
+
+
+def bn_relu_max64_train(x, bn, relu):
+    """max_k [relu](bn(x))[..., k] for x (B, C, M, 64) with batch statistics: the pooled block of a set-abstraction MLP
+    (conv.py:64-76 + modules.py:245) without the (B, C, M, 64) activation."""
+    y = _BnReluMax64Train.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu)
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return y
+
+
 class _MaxPool64(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):

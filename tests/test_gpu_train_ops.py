@@ -136,3 +136,39 @@ def test_training_gradients_fused_and_torch_paths_against_float64(lib_path, orac
             assert torch.allclose(b0[k].float(), b1[k].float(), rtol=1e-4, atol=1e-6), k
     finally:
         torch.backends.cudnn.allow_tf32 = True
+
+
+@pytest.mark.parametrize("shape,relu", [((2, 24, 40, 64), True), ((15, 64, 1024, 64), True), ((3, 10, 7, 64), False)])
+def test_bn_relu_max64_train_matches_float64_torch(lib_path, shape, relu):
+    """The pooled block (BN + ReLU + max over 64 neighbours, no materialised activation) against torch in float64."""
+    from regnet_for_3d_grasping_b200 import train_ops
+    g = torch.Generator().manual_seed(shape[2])
+    C = shape[1]
+    x = torch.randn(shape, generator=g) * (torch.rand(1, C, 1, 1, generator=g) + 0.5) + torch.randn(1, C, 1, 1, generator=g)
+    x[:, :, :, 32:48] = x[:, :, :, 16:32]                       # duplicated neighbours (under-full balls): tied maxima
+    ref = torch.nn.BatchNorm2d(C).double()
+    with torch.no_grad():
+        ref.weight.copy_(torch.randn(C, generator=g))
+        ref.bias.copy_(torch.randn(C, generator=g) * 0.3)
+    ours = torch.nn.BatchNorm2d(C).cuda()
+    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    ref.train(); ours.train()
+    xr = x.double().requires_grad_(True)
+    yr = ref(xr)
+    yr = (torch.relu(yr) if relu else yr).max(dim=3)[0]
+    dout = torch.randn(shape[:3], generator=g)
+    yr.backward(dout.double())
+    xo = x.cuda().requires_grad_(True)
+    assert train_ops.bn_relu_max64_supported(xo, ours)
+    yo = train_ops.bn_relu_max64_train(xo, ours, relu)
+    yo.backward(dout.cuda())
+    torch.cuda.synchronize()
+    _close(yo, yr.detach(), 2e-5, "pooled")
+    _close(ours.running_var, ref.running_var, 1e-5, "running_var")
+    _close(ours.weight.grad, ref.weight.grad, 1e-4, "dgamma")
+    _close(ours.bias.grad, ref.bias.grad, 1e-4, "dbeta")
+    # dx: ties may route the pooled gradient to a different duplicate than torch; sums over the duplicated columns
+    # (what reaches the source point) must agree, and so must every untied column
+    dxo, dxr = xo.grad.double().cpu(), xr.grad
+    fold = lambda t: torch.cat([t[..., :16], t[..., 16:32] + t[..., 32:48], t[..., 48:]], dim=-1)
+    _close(fold(dxo), fold(dxr), 5e-5, "dx (duplicates folded)")
