@@ -99,6 +99,54 @@ interp_backward_kernel(const float* __restrict__ gout, const int64_t* __restrict
   }
 }
 
+// Row-accumulating forms of the two scatter-add backward kernels: one CTA owns one (b, c) row of the gradient w.r.t. the
+// source points (N floats, <= 48 KB), accumulates it in SHARED memory (RED.ADD on smem instead of one L2 atomic per
+// contribution: FP level 2 issues 590 M of them) and writes it once; the index / weight rows are shared by the C rows
+// of a cloud and stay in L2.  No memset needed.  Summation order still varies between runs, like the reference's.
+constexpr int ROW_SMEM_MAX = 12288;   // floats per row
+
+__global__ void __launch_bounds__(THREADS)
+interp_backward_rows_kernel(const float* __restrict__ gout, const int64_t* __restrict__ index,
+                            const float* __restrict__ weight, int C, int Ns, int Nd, float* __restrict__ gin,
+                            int* __restrict__ oob) {
+  extern __shared__ float acc[];
+  const int64_t bc = blockIdx.x, b = bc / C;
+  for (int j = threadIdx.x; j < Ns; j += THREADS) acc[j] = 0.f;
+  __syncthreads();
+  const float* __restrict__ g = gout + bc * Nd;
+  const int64_t* __restrict__ idx = index + b * Nd * 3;
+  const float* __restrict__ w = weight + b * Nd * 3;
+  for (int n = threadIdx.x; n < Nd; n += THREADS) {
+    const float gv = g[n];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int64_t j = idx[(int64_t)n * 3 + k];
+      if (j < 0 || j >= Ns) { *oob = 1; continue; }
+      atomicAdd(acc + j, __fmul_rn(gv, w[(int64_t)n * 3 + k]));
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Ns; j += THREADS) gin[bc * Ns + j] = acc[j];
+}
+
+__global__ void __launch_bounds__(THREADS)
+group_backward_rows_kernel(const float* __restrict__ gout, const int64_t* __restrict__ index, int C, int N, int MK,
+                           float* __restrict__ gin, int* __restrict__ oob) {
+  extern __shared__ float acc[];
+  const int64_t bc = blockIdx.x, b = bc / C;
+  for (int j = threadIdx.x; j < N; j += THREADS) acc[j] = 0.f;
+  __syncthreads();
+  const float* __restrict__ g = gout + bc * MK;
+  const int64_t* __restrict__ idx = index + b * MK;
+  for (int e = threadIdx.x; e < MK; e += THREADS) {
+    const int64_t j = idx[e];
+    if (j < 0 || j >= N) { *oob = 1; continue; }
+    atomicAdd(acc + j, g[e]);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += THREADS) gin[bc * N + j] = acc[j];
+}
+
 // ---- fused operand producers ----------------------------------------------------------------------------------
 // Output row r (one grouped position / one dense point) has `kpad` columns; FOUR adjacent columns per thread so that
 // feature rows move as 16-byte vectors and enough bytes are in flight per thread to cover the gather latency.
@@ -559,6 +607,13 @@ int group_forward_launch(const float* in, Strides3 st, const int64_t* index, int
 
 int group_backward_launch(const float* gout, const int64_t* index, int B, int C, int N, int M, int K, float* gin,
                           int* d_oob, cudaStream_t stream) {
+  if (N <= ROW_SMEM_MAX && (int64_t)M * K >= 4 * (int64_t)N && (int64_t)M * K < (1LL << 31) && (int64_t)B * C > 0 &&
+      !getenv("REGNET_SCATTER_GLOBAL")) {
+    group_backward_rows_kernel<<<(unsigned)((int64_t)B * C), THREADS, sizeof(float) * (size_t)N, stream>>>(
+        gout, index, C, N, M * K, gin, d_oob);
+    RN_LAUNCH_CHECK("group_backward_rows_kernel");
+    return REGNET_OK;
+  }
   RN_CUDA(cudaMemsetAsync(gin, 0, sizeof(float) * (size_t)B * C * N, stream));
   const int64_t total = (int64_t)B * C * M * K;
   if (total == 0) return REGNET_OK;
@@ -578,6 +633,12 @@ int interp_forward_launch(const float* in, Strides3 st, const int64_t* index, co
 
 int interp_backward_launch(const float* gout, const int64_t* index, const float* weight, int B, int C, int Ns,
                            int Nd, float* gin, int* d_oob, cudaStream_t stream) {
+  if (Ns <= ROW_SMEM_MAX && Nd >= Ns && (int64_t)B * C > 0 && !getenv("REGNET_SCATTER_GLOBAL")) {
+    interp_backward_rows_kernel<<<(unsigned)((int64_t)B * C), THREADS, sizeof(float) * (size_t)Ns, stream>>>(
+        gout, index, weight, C, Ns, Nd, gin, d_oob);
+    RN_LAUNCH_CHECK("interp_backward_rows_kernel");
+    return REGNET_OK;
+  }
   RN_CUDA(cudaMemsetAsync(gin, 0, sizeof(float) * (size_t)B * C * Ns, stream));
   const int64_t total = (int64_t)B * C * Nd;
   if (total == 0) return REGNET_OK;

@@ -201,3 +201,32 @@ def test_grid_and_brute_force_operator_paths_agree(ext, monkeypatch, kind, N, M,
     for g, w, what in zip(got, want, ["bq index", "bq count", "nn index", "nn dist", "self nn index", "self nn dist"]):
         assert torch.equal(g, w), f"{kind} N={N}: {what} differs between the grid and the brute-force path"
     assert int(got[1].min()) >= 1   # every centroid is one of the points
+
+
+@pytest.mark.parametrize("force_global", [False, True])
+def test_scatter_add_backward_both_paths(ext, oracle, monkeypatch, force_global):
+    """group_points_backward / interpolate_backward: the shared-memory row-accumulating kernels (default when the row
+    fits) and the global-atomics kernels (REGNET_SCATTER_GLOBAL, or big rows) against the oracle, at an SA-level-1-like
+    shape with under-full balls (duplicated neighbours => many contributions per source point)."""
+    if force_global:
+        monkeypatch.setenv("REGNET_SCATTER_GLOBAL", "1")
+    from regnet_for_3d_grasping_b200 import synth
+    g = torch.Generator().manual_seed(15)
+    B, C, N, M, K = 2, 24, 5120, 1024, 64
+    pts = synth.batch("table", [31, 32], N)
+    xyz_c = torch.from_numpy(pts[:, :, :3]).permute(0, 2, 1)
+    idx = oracle.farthest_point_sample(xyz_c, M)
+    new_xyz = xyz_c.gather(2, idx.unsqueeze(1).expand(B, 3, M))
+    bq, _ = oracle.ball_query(xyz_c, new_xyz, 0.03, K)
+    gout = torch.randn(B, C, M, K, generator=g)
+    got = ext.group_points_backward(gout.cuda(), bq.cuda(), N).cpu()
+    want = oracle.group_points_backward(gout, bq, N)
+    assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+    nn, nnd = oracle.point_search(xyz_c, new_xyz, 3)
+    inv = 1.0 / torch.clamp(nnd, min=1e-10)
+    w = inv / inv.sum(2, keepdim=True)
+    iout = torch.randn(B, C, N, generator=g)
+    got = ext.interpolate_backward(iout.cuda(), nn.cuda(), w.cuda(), M).cpu()
+    want = oracle.interpolate_backward(iout, nn, w, M)
+    assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+    ext.check_index_errors()
