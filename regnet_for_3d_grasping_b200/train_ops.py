@@ -36,7 +36,7 @@ def bn_supported(x, bn):
     if not (bn.training and bn.affine and bn.track_running_stats and bn.momentum is not None):
         return False
     B, C, L = _bn_shape(x)
-    return L % 4 == 0 and B * C <= 65535 and B * L > 1
+    return L % 4 == 0 and B * C <= 65535 and B <= 1023 and B * L > 1
 
 
 class _BnReluTrain(torch.autograd.Function):

@@ -39,6 +39,7 @@ for s in $STAGES; do
               REGNET_NO_SIDE2=1 timeout 300 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_noside2.log 2>&1
               for v in 1,256 2,256 4,128 4,256; do REGNET_FPS_CORUN1=$v timeout 300 python bench.py --steps 20 --no-cpu-baseline > gpurun_out/bench_side2_c1_${v/,/_}.log 2>&1; done ;;
     opsgrid)  timeout 600 python -m pytest tests/test_gpu_ops.py -q -m gpu -x > gpurun_out/test_ops.log 2>&1 ;;
+    e2e)      timeout 300 python scripts/e2e_inference.py > gpurun_out/e2e_c3.json 2> gpurun_out/e2e_c3.err ;;
     alltests) timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/test_all.log 2>&1 ;;
   esac
   echo "    exit $?"
