@@ -197,6 +197,14 @@ int regnet_select_score_center(const float* pc, const float* score, int B, int N
 int regnet_ball_crop_sample(const float* pc, const float* center_pc, int B, int N, int NC, float radius, int group_num,
                             uint64_t seed, int64_t* index, float* group, int32_t* count, void* stream);
 
+/* Grid form of regnet_ball_crop_sample: same membership test, counts and sampling distribution, candidates taken from a
+ * uniform (x, y) grid of the cloud instead of all N points (the no-replacement picks are not in ascending index order).
+ * workspace: regnet_ball_crop_workspace_bytes(B, N) bytes of device scratch; falls through to the scan for small clouds. */
+int64_t regnet_ball_crop_workspace_bytes(int B, int N);
+int regnet_ball_crop_sample_ws(const float* pc, const float* center_pc, int B, int N, int NC, float radius, int group_num,
+                               uint64_t seed, int64_t* index, float* group, int32_t* count, void* workspace,
+                               int64_t workspace_bytes, void* stream);
+
 /* multi_model/gripper_region_network.py:532-544: per-row sampler over a (rows,G) byte mask: more than K set -> K
  * without replacement (ascending), more than min_count -> K with replacement, else the row is rejected (-1).
  * index (rows,K) int64; count (rows) int32 optional. */

@@ -17,23 +17,9 @@ namespace regnet {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int GMAX = 64;                 // at most GMAX x GMAX cells
-constexpr int MAX_CELLS = GMAX * GMAX;
-
-struct GridHeader {                      // one per cloud
-  float x0, y0, inv_h;
-  int gx, gy;
-  float h;
-  int pad[2];
-};
-
-__device__ __forceinline__ int cell_coord(float v, float v0, float inv_h, int g) {
-  int c = (int)floorf((v - v0) * inv_h);
-  return min(g - 1, max(0, c));
-}
-
 // ---- build: bin the points of each cloud --------------------------------------------------------------------------
 // sorted[b][pos] = {x, y, z, bits(original index)}; cell_start[b][c] .. cell_start[b][c+1] is cell c's run.
+template <bool STABLE>
 __global__ void __launch_bounds__(1024)
 grid_build_kernel(const float* __restrict__ pts, Strides3 st, int N, float min_cell, GridHeader* __restrict__ hdr,
                   int* __restrict__ cell_start, float4* __restrict__ sorted) {
@@ -109,8 +95,34 @@ grid_build_kernel(const float* __restrict__ pts, Strides3 st, int N, float min_c
   int* __restrict__ cs = cell_start + (int64_t)b * (MAX_CELLS + 1);
   for (int c = tid; c <= cells; c += 1024) cs[c] = c < cells ? hist[c] : N;
   __syncthreads();
-  // scatter (order inside a cell is arbitrary; the queries re-establish index order themselves)
   float4* __restrict__ out = sorted + (int64_t)b * N;
+  if (STABLE) {
+    // Stable scatter: inside a cell the points keep ascending original index, so whatever enumerates a cell run sees a
+    // reproducible order (the ball crop's random draws depend on it).  Chunks of 1024 consecutive points; within a
+    // warp the same-cell lanes are ranked with match.any, and the 32 warps of a chunk reserve their slots in turn.
+    for (int base = 0; base < N; base += 1024) {
+      const int j = base + tid;
+      int c = -1;
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (j < N) {
+        x = p[(int64_t)j * st.n]; y = p[(int64_t)j * st.n + st.c]; z = p[(int64_t)j * st.n + 2 * st.c];
+        c = cell_coord(y, ymin, inv_h, gy) * gx + cell_coord(x, xmin, inv_h, gx);
+      }
+      const unsigned same = __match_any_sync(FULL, c);
+      const int rank = __popc(same & ((1u << lane) - 1u)), leader = __ffs(same) - 1, group = __popc(same);
+      for (int w = 0; w < 32; ++w) {
+        if (warp == w) {
+          int pos0 = 0;
+          if (lane == leader && c >= 0) { pos0 = hist[c]; hist[c] = pos0 + group; }
+          pos0 = __shfl_sync(FULL, pos0, leader);
+          if (c >= 0) out[pos0 + rank] = make_float4(x, y, z, __int_as_float(j));
+        }
+        __syncthreads();
+      }
+    }
+    return;
+  }
+  // scatter (order inside a cell is arbitrary; the queries re-establish index order themselves)
   for (int j = tid; j < N; j += 1024) {
     const float x = p[(int64_t)j * st.n], y = p[(int64_t)j * st.n + st.c], z = p[(int64_t)j * st.n + 2 * st.c];
     const int c = cell_coord(y, ymin, inv_h, gy) * gx + cell_coord(x, xmin, inv_h, gx);
@@ -348,13 +360,7 @@ int64_t grid_workspace_bytes(int B, int N) {
   return (int64_t)B * (sizeof(GridHeader) + sizeof(int) * (MAX_CELLS + 1) + sizeof(float4) * (int64_t)N) + 256;
 }
 
-struct GridPtrs {
-  GridHeader* hdr;
-  int* cell_start;
-  float4* sorted;
-};
-
-static GridPtrs carve(void* ws, int B, int N) {
+GridPtrs grid_carve(void* ws, int B, int N) {
   GridPtrs g;
   g.sorted = reinterpret_cast<float4*>(ws);
   g.hdr = reinterpret_cast<GridHeader*>(g.sorted + (int64_t)B * N);
@@ -362,10 +368,17 @@ static GridPtrs carve(void* ws, int B, int N) {
   return g;
 }
 
-int grid_build_launch(const float* pts, Strides3 st, int B, int N, float min_cell, void* ws, cudaStream_t stream) {
-  const GridPtrs g = carve(ws, B, N);
-  RN_PREFER_MAX_SMEM(grid_build_kernel);
-  grid_build_kernel<<<B, 1024, 0, stream>>>(pts, st, N, min_cell, g.hdr, g.cell_start, g.sorted);
+int grid_build_launch(const float* pts, Strides3 st, int B, int N, float min_cell, void* ws, cudaStream_t stream,
+                      bool stable) {
+  const GridPtrs g = grid_carve(ws, B, N);
+  if (stable) {
+    RN_PREFER_MAX_SMEM(grid_build_kernel<true>);
+    grid_build_kernel<true><<<B, 1024, 0, stream>>>(pts, st, N, min_cell, g.hdr, g.cell_start, g.sorted);
+    RN_LAUNCH_CHECK("grid_build_kernel");
+    return REGNET_OK;
+  }
+  RN_PREFER_MAX_SMEM(grid_build_kernel<false>);
+  grid_build_kernel<false><<<B, 1024, 0, stream>>>(pts, st, N, min_cell, g.hdr, g.cell_start, g.sorted);
   RN_LAUNCH_CHECK("grid_build_kernel");
   return REGNET_OK;
 }
@@ -374,7 +387,7 @@ int ball_query_grid_launch(const float* pts, Strides3 pst, const float* ctr, Str
                            float radius, const void* ws, int32_t* index32, cudaStream_t stream, int64_t* index64,
                            int64_t* count64) {
   RN_CHECK_ARG(N <= 65536, "ball_query_grid: more than 65536 points per cloud");
-  const GridPtrs g = carve(const_cast<void*>(ws), B, N);
+  const GridPtrs g = grid_carve(const_cast<void*>(ws), B, N);
   dim3 grid(ceil_div(M, BQG_WARPS), B);
   RN_PREFER_MAX_SMEM(ball_query_grid_kernel);
   ball_query_grid_kernel<<<grid, BQG_WARPS * 32, 0, stream>>>(pts, pst, ctr, cst, N, M, radius, g.hdr, g.cell_start,
@@ -386,7 +399,7 @@ int ball_query_grid_launch(const float* pts, Strides3 pst, const float* ctr, Str
 int three_nn_grid_launch(const float* qry, Strides3 qst, const float* key, Strides3 kst, int B, int Nq, int Nk,
                          const void* ws, int32_t* index32, float* weight, cudaStream_t stream, int64_t* index64,
                          float* dist) {
-  const GridPtrs g = carve(const_cast<void*>(ws), B, Nk);
+  const GridPtrs g = grid_carve(const_cast<void*>(ws), B, Nk);
   dim3 grid(ceil_div(Nq, 128), B);
   RN_PREFER_MAX_SMEM(three_nn_grid_kernel);
   three_nn_grid_kernel<<<grid, 128, 0, stream>>>(qry, qst, key, kst, Nq, Nk, g.hdr, g.cell_start, g.sorted, index32, weight,

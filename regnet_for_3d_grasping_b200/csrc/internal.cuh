@@ -64,8 +64,31 @@ int score_head_launch(const float* X, int ldx, const float* w, const float* scal
                       int cin, float* score, cudaStream_t stream);
 
 // uniform-grid neighbour search (grid.cu); ws = grid_workspace_bytes(B, N) bytes of device scratch per grid
+constexpr int GMAX = 64;                 // at most GMAX x GMAX cells
+constexpr int MAX_CELLS = GMAX * GMAX;
+
+struct GridHeader {                      // one per cloud
+  float x0, y0, inv_h;
+  int gx, gy;
+  float h;
+  int pad[2];
+};
+
+struct GridPtrs {                        // views into a grid workspace
+  GridHeader* hdr;                       // [B]
+  int* cell_start;                       // [B][MAX_CELLS + 1]: cell c's run is sorted[cell_start[c] .. cell_start[c + 1])
+  float4* sorted;                        // [B][N] = {x, y, z, bits(original index)}
+};
+
+__device__ __forceinline__ int cell_coord(float v, float v0, float inv_h, int g) {
+  int c = (int)floorf((v - v0) * inv_h);
+  return min(g - 1, max(0, c));
+}
+
+GridPtrs grid_carve(void* ws, int B, int N);
 int64_t grid_workspace_bytes(int B, int N);
-int grid_build_launch(const float* pts, Strides3 st, int B, int N, float min_cell, void* ws, cudaStream_t stream);
+int grid_build_launch(const float* pts, Strides3 st, int B, int N, float min_cell, void* ws, cudaStream_t stream,
+                      bool stable = false);   // stable: ascending original index inside every cell
 int ball_query_grid_launch(const float* pts, Strides3 pst, const float* ctr, Strides3 cst, int B, int N, int M,
                            float radius, const void* ws, int32_t* index32, cudaStream_t stream,
                            int64_t* index64 = nullptr, int64_t* count64 = nullptr);

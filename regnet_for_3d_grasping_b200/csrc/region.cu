@@ -12,6 +12,8 @@
 // generator instead of numpy's Mersenne twister: same distributions (uniform subsets without replacement via
 // selection sampling, i.i.d. uniform draws with replacement), different streams -- the reference itself seeds from
 // the wall clock (train.py:59, test.py:56), so its draws are not reproducible either.
+#include <stdlib.h>
+
 #include "internal.cuh"
 
 namespace regnet {
@@ -221,6 +223,96 @@ ball_crop_sample_kernel(const float* __restrict__ pc, const float* __restrict__ 
   if (lane == 0 && count_out) count_out[cid] = cnt;
 }
 
+// Grid form of the ball crop: the candidates of a centre are the three cell-row runs of its 3x3 cell block in the
+// uniform (x, y) grid of the cloud (cell edge >= radius, grid.cu) instead of all N points -- ~70 candidates for the
+// 8 mm crop and ~1 400 for the 64 mm crop of a 25 600-point table-top cloud.  Same membership test, same counts, same
+// uniform sampling (Algorithm S does not care in which order the members are visited); the grid is built with the
+// STABLE scatter, so the visiting order -- and with it every draw -- is reproducible for a given seed; the picks of
+// the no-replacement case come out in cell order instead of ascending index order.
+__global__ void __launch_bounds__(CROP_WARPS * 32)
+ball_crop_grid_kernel(const float* __restrict__ pc, const float* __restrict__ center_pc, int N, int NC, float radius,
+                      int G, uint64_t seed, const GridHeader* __restrict__ hdr, const int* __restrict__ cell_start,
+                      const float4* __restrict__ sorted, int64_t* __restrict__ index, float* __restrict__ group,
+                      int32_t* __restrict__ count_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* lists = reinterpret_cast<int*>(smem_raw);  // [CROP_WARPS][G]
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * CROP_WARPS + warp;
+  if (c >= NC) return;
+  const float* __restrict__ P = pc + (int64_t)b * N * 6;
+  const float* q = center_pc + ((int64_t)b * NC + c) * 6;
+  const float cx = q[0], cy = q[1], cz = q[2];
+  const GridHeader g = hdr[b];
+  const int* __restrict__ cs = cell_start + (int64_t)b * (MAX_CELLS + 1);
+  const float4* __restrict__ sp = sorted + (int64_t)b * N;
+  const int gx0 = cell_coord(cx, g.x0, g.inv_h, g.gx), gy0 = cell_coord(cy, g.y0, g.inv_h, g.gy);
+  int beg[3], end[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int ry = gy0 + d - 1;
+    if (ry < 0 || ry >= g.gy) { beg[d] = end[d] = 0; continue; }
+    beg[d] = cs[ry * g.gx + max(0, gx0 - 1)];
+    end[d] = cs[ry * g.gx + min(g.gx - 1, gx0 + 1) + 1];
+  }
+  // pass 1: count
+  int cnt = 0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    for (int t = beg[d] + lane; t < end[d]; t += 32) cnt += in_ball(sp[t], cx, cy, cz, radius);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+  const uint64_t cid = (uint64_t)b * NC + c;
+  int64_t* out_i = index + cid * G;
+  float* out_g = group + cid * (int64_t)G * 6;
+  int* list = lists + warp * G;
+  int seen = 0, chosen = 0;
+  if (cnt > 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      for (int t0 = beg[d]; t0 < end[d]; t0 += 32) {
+        const int t = t0 + lane;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool hit = false;
+        if (t < end[d]) { v = sp[t]; hit = in_ball(v, cx, cy, cz, radius); }
+        const int j = __float_as_int(v.w);
+        unsigned m = __ballot_sync(FULL, hit);
+        if (cnt >= G) {                                   // np.random.choice(len, G, replace=False): Algorithm S
+          while (m && chosen < G) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int jb = __shfl_sync(FULL, j, bit);
+            const float u = rand_u01(seed, cid, (uint64_t)seen);
+            if (u * (float)(cnt - seen) < (float)(G - chosen)) {
+              if (lane == 0) out_i[chosen] = jb;
+              if (lane < 6) out_g[(int64_t)chosen * 6 + lane] = P[(int64_t)jb * 6 + lane];
+              ++chosen;
+            }
+            ++seen;
+          }
+        } else {
+          if (hit) list[seen + __popc(m & ((1u << lane) - 1u))] = j;
+          seen += __popc(m);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  if (cnt == 0) {                                       // row keeps the reference's -1 fill (:324-325)
+    for (int k = lane; k < G; k += 32) out_i[k] = -1;
+    for (int k = lane; k < G * 6; k += 32) out_g[k] = -1.0f;
+  } else if (cnt < G) {                                 // :336-337  np.random.choice(len, G, replace=True)
+    for (int k = lane; k < G; k += 32) {
+      int h = (int)(rand_u01(seed, cid, (uint64_t)k) * (float)cnt);
+      h = min(h, cnt - 1);
+      const int j = list[h];
+      out_i[k] = j;
+#pragma unroll
+      for (int qq = 0; qq < 6; ++qq) out_g[(int64_t)k * 6 + qq] = P[(int64_t)j * 6 + qq];
+    }
+  }
+  if (lane == 0 && count_out) count_out[cid] = cnt;
+}
+
 // ---- R6: per-row masked sampler ------------------------------------------------------------------------------------
 // rows x G mask -> K indices per row: more than K set -> K without replacement; more than `min_count` -> K with
 // replacement; otherwise the row is rejected and keeps -1 (gripper_region_network.py:532-544: "> region_num",
@@ -363,6 +455,31 @@ int regnet_ball_crop_sample(const float* pc, const float* center_pc, int B, int 
   ball_crop_sample_kernel<<<grid, CROP_WARPS * 32, smem, s>>>(pc, center_pc, N, NC, radius, group_num, seed, index, group,
                                                               count);
   RN_LAUNCH_CHECK("ball_crop_sample_kernel");
+  return REGNET_OK;
+}
+
+int64_t regnet_ball_crop_workspace_bytes(int B, int N) { return grid_workspace_bytes(B, N); }
+
+int regnet_ball_crop_sample_ws(const float* pc, const float* center_pc, int B, int N, int NC, float radius, int group_num,
+                               uint64_t seed, int64_t* index, float* group, int32_t* count, void* workspace,
+                               int64_t workspace_bytes, void* stream_) {
+  if (!workspace || workspace_bytes < grid_workspace_bytes(B, N) || N < 2048 || !(radius > 0.f) || getenv("REGNET_API_BRUTE"))
+    return regnet_ball_crop_sample(pc, center_pc, B, N, NC, radius, group_num, seed, index, group, count, stream_);
+  cudaStream_t s = (cudaStream_t)stream_;
+  RN_CHECK_ARG(pc && center_pc && index && group, "ball_crop_sample: null argument");
+  RN_CHECK_ARG(B > 0 && N > 0 && NC > 0 && group_num > 0, "ball_crop_sample: empty problem");
+  if (group_num > 4096) {
+    set_error("ball_crop_sample: group_num=%d exceeds the supported maximum of 4096", group_num);
+    return REGNET_ELIMIT;
+  }
+  RN_TRY(grid_build_launch(pc, Strides3{(int64_t)N * 6, 1, 6}, B, N, radius * 1.001f + 1e-7f, workspace, s, true));
+  const GridPtrs g = grid_carve(workspace, B, N);
+  RN_CUDA(cudaFuncSetAttribute(ball_crop_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(sizeof(int) * CROP_WARPS * 4096)));
+  dim3 grid(ceil_div(NC, CROP_WARPS), B);
+  ball_crop_grid_kernel<<<grid, CROP_WARPS * 32, sizeof(int) * (size_t)CROP_WARPS * group_num, s>>>(
+      pc, center_pc, N, NC, radius, group_num, seed, g.hdr, g.cell_start, g.sorted, index, group, count);
+  RN_LAUNCH_CHECK("ball_crop_grid_kernel");
   return REGNET_OK;
 }
 

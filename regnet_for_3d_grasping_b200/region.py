@@ -73,9 +73,12 @@ def get_group_pc(pc, center_pc, center_pc_index, group_num, width, height, depth
     group = torch.empty(B, NC, group_num, 6, dtype=torch.float32, device=pc.device)
     count = torch.empty(B, NC, dtype=torch.int32, device=pc.device)
     with torch.cuda.device(pc.device):
-        _lib.check(_lib.load().regnet_ball_crop_sample(_p(pc), _p(center_pc), B, N, NC, float(radius), int(group_num),
-                                                       _seed(seed), _p(index), _p(group), _p(count),
-                                                       _lib.current_stream_ptr()))
+        lib = _lib.load()
+        nbytes = int(lib.regnet_ball_crop_workspace_bytes(B, N))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=pc.device)      # scratch of the uniform grid
+        _lib.check(lib.regnet_ball_crop_sample_ws(_p(pc), _p(center_pc), B, N, NC, float(radius), int(group_num),
+                                                  _seed(seed), _p(index), _p(group), _p(count), _p(ws), nbytes,
+                                                  _lib.current_stream_ptr()))
     if return_count:
         return index, group, count
     return index, group

@@ -48,8 +48,14 @@ def test_select_score_center_random_branches(lib_path):
     assert not torch.equal(cidx2[0].cpu(), cidx[0]) and torch.equal(cidx2[2].cpu(), cidx[2])
 
 
+@pytest.mark.parametrize("scan", [False, True], ids=["grid", "scan"])
 @pytest.mark.parametrize("r_time,G", [(0.1, 256), (0.8, 1024), (0.8, 2048)])
-def test_ball_crop_membership_and_counts(lib_path, r_time, G):
+def test_ball_crop_membership_and_counts(lib_path, monkeypatch, r_time, G, scan):
+    """Both forms of the crop (uniform-grid candidates = default for big clouds; REGNET_API_BRUTE = scan of all points)
+    against the reference's membership test.  The reference draws with np.random.choice, i.e. in random order: only the
+    scan form happens to return the no-replacement picks in ascending index order."""
+    if scan:
+        monkeypatch.setenv("REGNET_API_BRUTE", "1")
     from oracle import region_oracle
     from regnet_for_3d_grasping_b200 import region
     B, N, NC = 2, 25600, 96
@@ -74,9 +80,9 @@ def test_ball_crop_membership_and_counts(lib_path, r_time, G):
             assert torch.equal(grp[b, c], pc[b, row])
             if n >= G:
                 saw_wo = True
-                assert row.unique().numel() == G and (row[1:] > row[:-1]).all()
+                assert row.unique().numel() == G and (not scan or (row[1:] > row[:-1]).all())
                 if n == G:
-                    assert torch.equal(row, torch.nonzero(mask[c]).view(-1))
+                    assert torch.equal(row.sort()[0], torch.nonzero(mask[c]).view(-1))
             else:
                 saw_w = True
     assert cnt.view(-1)[5].item() == 0
