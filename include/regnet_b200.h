@@ -205,6 +205,14 @@ int regnet_ball_crop_sample_ws(const float* pc, const float* center_pc, int B, i
                                uint64_t seed, int64_t* index, float* group, int32_t* count, void* workspace,
                                int64_t workspace_bytes, void* stream);
 
+/* Closing-box membership of every point of every grasp's crop (gripper_region_network.py:505-528): points (M, G, C)
+ * fp32 with xyz first, centre (M, 3), rot (M, 3, 3) = rows approach / axis_y / minor normal; a point is inside iff
+ * 0 < x' < xlim, |y'| < ylim, |z'| < zlim for p' = rot (p - centre); xlim / ylim per grasp (M floats) when the row
+ * pointers are non-null, else the scalars.  mask (M, G) bytes.  M <= 65535 per call. */
+int regnet_closing_box_mask(const float* points, int M, int G, int C, const float* centre, const float* rot,
+                            const float* xlim_row, const float* ylim_row, float xlim, float ylim, float zlim,
+                            uint8_t* mask, void* stream);
+
 /* multi_model/gripper_region_network.py:532-544: per-row sampler over a (rows,G) byte mask: more than K set -> K
  * without replacement (ascending), more than min_count -> K with replacement, else the row is rejected (-1).
  * index (rows,K) int64; count (rows) int32 optional. */

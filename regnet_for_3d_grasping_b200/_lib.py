@@ -74,6 +74,8 @@ _SIGNATURES = {
     "regnet_ball_crop_workspace_bytes": (c_i64, [c_int, c_int]),
     "regnet_ball_crop_sample_ws": (c_int, [c_ptr, c_ptr, c_int, c_int, c_int, c_f32, c_int, ctypes.c_uint64, c_ptr, c_ptr,
                                            c_ptr, c_ptr, c_i64, c_ptr]),
+    "regnet_closing_box_mask": (c_int, [c_ptr, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_f32, c_ptr,
+                                        c_ptr]),
     "regnet_mask_sample": (c_int, [c_ptr, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_ptr, c_ptr, c_ptr]),
     "regnet_gather_max": (c_int, [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "regnet_mlp_layer": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),

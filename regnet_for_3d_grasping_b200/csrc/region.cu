@@ -12,6 +12,7 @@
 // generator instead of numpy's Mersenne twister: same distributions (uniform subsets without replacement via
 // selection sampling, i.i.d. uniform draws with replacement), different streams -- the reference itself seeds from
 // the wall clock (train.py:59, test.py:56), so its draws are not reproducible either.
+#include <algorithm>
 #include <stdlib.h>
 
 #include "internal.cuh"
@@ -313,6 +314,32 @@ ball_crop_grid_kernel(const float* __restrict__ pc, const float* __restrict__ ce
   if (lane == 0 && count_out) count_out[cid] = cnt;
 }
 
+// ---- R6: closing-box membership -------------------------------------------------------------------------------------------
+// mask[m, g] = point g of grasp m's crop lies in the gripper's closing box: p' = R_m (p - c_m), then the six strict
+// half-space tests 0 < x' < depth/2, |y'| < width/2, |z'| < height/2 (gripper_region_network.py:505-528: a bmm over the
+// whole (M, G, 3) crop followed by six comparison passes; here one pass, nothing but the mask is written).
+__global__ void __launch_bounds__(256)
+closing_box_mask_kernel(const float* __restrict__ pts, int C, int G, const float* __restrict__ centre,
+                        const float* __restrict__ rot, const float* __restrict__ xlim_row,
+                        const float* __restrict__ ylim_row, float xlim, float ylim, float zlim,
+                        uint8_t* __restrict__ mask) {
+  const int m = blockIdx.y;
+  const float cx = centre[m * 3], cy = centre[m * 3 + 1], cz = centre[m * 3 + 2];
+  float r[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r[i] = rot[m * 9 + i];
+  const float xl = xlim_row ? xlim_row[m] : xlim, yl = ylim_row ? ylim_row[m] : ylim;
+  const float* __restrict__ row = pts + (int64_t)m * G * C;
+  for (int g = blockIdx.x * 256 + threadIdx.x; g < G; g += gridDim.x * 256) {
+    const float dx = __fsub_rn(row[(int64_t)g * C], cx), dy = __fsub_rn(row[(int64_t)g * C + 1], cy),
+                dz = __fsub_rn(row[(int64_t)g * C + 2], cz);
+    const float x = fmaf(r[2], dz, fmaf(r[1], dy, __fmul_rn(r[0], dx)));
+    const float y = fmaf(r[5], dz, fmaf(r[4], dy, __fmul_rn(r[3], dx)));
+    const float z = fmaf(r[8], dz, fmaf(r[7], dy, __fmul_rn(r[6], dx)));
+    mask[(int64_t)m * G + g] = (x > 0.f) & (x < xl) & (y > -yl) & (y < yl) & (z > -zlim) & (z < zlim);
+  }
+}
+
 // ---- R6: per-row masked sampler ------------------------------------------------------------------------------------
 // rows x G mask -> K indices per row: more than K set -> K without replacement; more than `min_count` -> K with
 // replacement; otherwise the row is rejected and keeps -1 (gripper_region_network.py:532-544: "> region_num",
@@ -480,6 +507,19 @@ int regnet_ball_crop_sample_ws(const float* pc, const float* center_pc, int B, i
   ball_crop_grid_kernel<<<grid, CROP_WARPS * 32, sizeof(int) * (size_t)CROP_WARPS * group_num, s>>>(
       pc, center_pc, N, NC, radius, group_num, seed, g.hdr, g.cell_start, g.sorted, index, group, count);
   RN_LAUNCH_CHECK("ball_crop_grid_kernel");
+  return REGNET_OK;
+}
+
+int regnet_closing_box_mask(const float* points, int M, int G, int C, const float* centre, const float* rot,
+                            const float* xlim_row, const float* ylim_row, float xlim, float ylim, float zlim,
+                            uint8_t* mask, void* stream_) {
+  RN_CHECK_ARG(points && centre && rot && mask, "closing_box_mask: null argument");
+  RN_CHECK_ARG(M >= 0 && G > 0 && C >= 3 && M <= 65535 * 64, "closing_box_mask: bad sizes");
+  if (M == 0) return REGNET_OK;
+  RN_CHECK_ARG(M <= 65535, "closing_box_mask: more than 65535 grasps per call");
+  closing_box_mask_kernel<<<dim3((unsigned)std::min(8, ceil_div(G, 256)), (unsigned)M), 256, 0, (cudaStream_t)stream_>>>(
+      points, C, G, centre, rot, xlim_row, ylim_row, xlim, ylim, zlim, mask);
+  RN_LAUNCH_CHECK("closing_box_mask_kernel");
   return REGNET_OK;
 }
 

@@ -96,17 +96,28 @@ def get_gripper_region_transform(group_points, group_index, grasp, region_num, g
     true_mask_index (M',) = grasps with more than 5 points in the box.  Rejected rows hold -1.
     `sampler(mask) -> (M, region_num) int64` replaces the device sampler (tests use a deterministic rule)."""
     M, G, C = group_points.shape
-    pcs_t, mask = closing_box_points(group_points, grasp, gripper_params)
+    widths, height, depths = gripper_params
+    rot = closing_box_frame(grasp)
+    centre = grasp[:, 0:3].float()
+    if group_points.is_cuda and group_points.dtype == torch.float32 and M > 0:
+        # one pass over the crops: nothing but the membership mask is written (the reference's bmm materialises the
+        # transformed (M,G,3) crop, 98 MB at the test configuration, and makes six comparison passes over it)
+        half = lambda v: (v.float().reshape(-1) / 2) if isinstance(v, torch.Tensor) else v / 2
+        mask = region.closing_box_mask(group_points, centre, rot, half(depths), half(widths), height / 2)
+    else:
+        _, mask = closing_box_points(group_points, grasp, gripper_params)
     if sampler is not None:
-        index = sampler(mask)
+        index = sampler(mask.bool())
     else:
         index = region.sample_mask_rows(mask, region_num, min_count=5, seed=seed)
     ok = index[:, 0] >= 0
     safe = index.clamp(min=0)
     # the reference allocates these with torch.full(..., -1), i.e. as int64, so the float crop it writes into gripper_pc
-    # is truncated (SURVEY.md A.7; nothing consumes gripper_pc) -- same dtype and values here
-    picked = torch.cat([pcs_t.gather(1, safe[:, :, None].expand(M, region_num, 3)),
-                        group_points[:, :, 3:].float().gather(1, safe[:, :, None].expand(M, region_num, C - 3))], dim=-1)
+    # is truncated (SURVEY.md A.7; nothing consumes gripper_pc) -- same dtype and values here.  Only the picked points
+    # are transformed into the gripper frame.
+    chosen = group_points.float().gather(1, safe[:, :, None].expand(M, region_num, C))
+    chosen_t = torch.bmm(rot, (chosen[:, :, :3] - centre[:, None, :]).permute(0, 2, 1)).permute(0, 2, 1)
+    picked = torch.cat([chosen_t, chosen[:, :, 3:]], dim=-1)
     gripper_pc = torch.where(ok[:, None, None], picked.long(), torch.full_like(picked, -1).long())
     gripper_pc_index = torch.where(ok[:, None], index, torch.full_like(index, -1))
     inall = group_index.long().gather(1, safe)

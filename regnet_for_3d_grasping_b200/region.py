@@ -120,6 +120,29 @@ def sample_mask_rows(mask, num, min_count=5, seed=None, return_count=False):
     return index
 
 
+def closing_box_mask(group_points, centre, rot, x_limit, y_limit, z_limit):
+    """(M,G) uint8 membership of the gripper's closing box (gripper_region_network.py:505-528) in one pass:
+    group_points (M,G,C>=3) fp32, centre (M,3), rot (M,3,3); x_limit / y_limit: python floats or (M,) / (M,1) tensors."""
+    _need(group_points, "group_points")
+    pts = group_points.contiguous()
+    M, G, C = pts.shape
+    centre = centre.float().contiguous()
+    rot = rot.float().contiguous()
+    xr = x_limit.float().reshape(-1).contiguous() if isinstance(x_limit, torch.Tensor) else None
+    yr = y_limit.float().reshape(-1).contiguous() if isinstance(y_limit, torch.Tensor) else None
+    if (xr is not None and xr.numel() != M) or (yr is not None and yr.numel() != M):
+        raise RuntimeError("closing_box_mask: per-grasp limits must have one value per grasp")
+    mask = torch.empty(M, G, dtype=torch.uint8, device=pts.device)
+    with torch.cuda.device(pts.device):
+        for lo in range(0, M, 65535):
+            hi = min(M, lo + 65535)
+            _lib.check(_lib.load().regnet_closing_box_mask(
+                _p(pts[lo:hi]), hi - lo, G, C, _p(centre[lo:hi]), _p(rot[lo:hi]), _p(xr[lo:hi]) if xr is not None else None,
+                _p(yr[lo:hi]) if yr is not None else None, 0.0 if xr is not None else float(x_limit),
+                0.0 if yr is not None else float(y_limit), float(z_limit), _p(mask[lo:hi]), _lib.current_stream_ptr()))
+    return mask
+
+
 def gather_max(all_feature, index):
     """max over each group's feature rows: all_feature (B,N,C) point-major contiguous, index (B,N_C,G) int64
     -> (B,N_C,C).  Equals MaxPool1d(G)(all_feature.view(-1,C)[index + b*N].permute(0,2,1)) of

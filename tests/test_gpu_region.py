@@ -244,6 +244,37 @@ def test_region_network_device_sampler_properties(lib_path, oracle):
     assert all((gi[m] == -1).all() and mask[m].sum() <= 5 for m in rejected)
 
 
+def test_closing_box_mask_kernel_equals_batched_reference_expression(lib_path):
+    """The one-pass membership kernel against the reference's expression (bmm of the frame with the centred crop + six
+    strict comparisons, gripper_region_network.py:505-528) on random grasps, scalar and per-grasp limits.  The two
+    evaluate the same 3-term dot products in different orders, so a point may flip only if it sits within rounding
+    distance of a face of the box."""
+    from regnet_for_3d_grasping_b200 import region
+    from regnet_for_3d_grasping_b200.gripper_region_network import closing_box_frame, closing_box_points
+    g = torch.Generator().manual_seed(3)
+    M, G = 700, 2048
+    pts = (torch.rand(M, G, 6, generator=g) - 0.5) * 0.12
+    grasp = torch.cat([(torch.rand(M, 3, generator=g) - 0.5) * 0.02, torch.randn(M, 3, generator=g),
+                       (torch.rand(M, 1, generator=g) - 0.5) * 6.0, torch.rand(M, 3, generator=g)], dim=1)
+    grasp[0, 3:6] = 0.0                                     # degenerate axis: the reference's fix-up rows
+    pts, grasp = pts.cuda(), grasp.cuda()
+    for params in ([0.08, 0.010, 0.06], [torch.rand(M, 1, generator=g).cuda() * 0.1 + 0.02, 0.012,
+                                         torch.rand(M, 1, generator=g).cuda() * 0.1 + 0.02]):
+        pcs_t, want = closing_box_points(pts, grasp, params)
+        widths, height, depths = params
+        half = lambda v: (v.reshape(-1) / 2) if isinstance(v, torch.Tensor) else v / 2
+        got = region.closing_box_mask(pts, grasp[:, :3], closing_box_frame(grasp), half(depths), half(widths), height / 2)
+        assert got.dtype == torch.uint8 and tuple(got.shape) == (M, G)
+        diff = got.bool() != want
+        assert 0.01 < want.float().mean().item() < 0.9      # the box is neither empty nor everything
+        if diff.any():
+            xl = half(depths).view(-1, 1) if isinstance(depths, torch.Tensor) else depths / 2
+            yl = half(widths).view(-1, 1) if isinstance(widths, torch.Tensor) else widths / 2
+            x, y, z = pcs_t[..., 0], pcs_t[..., 1], pcs_t[..., 2]
+            face = torch.stack([x.abs(), (x - xl).abs(), (y.abs() - yl).abs(), (z.abs() - height / 2).abs()]).min(0)[0]
+            assert diff.float().mean().item() < 1e-5 and (face[diff] < 1e-6).all()
+
+
 def test_region_network_rejects_training_call(lib_path):
     ref, net, inp, params, args, np = _region_net_on_gpu()
     with pytest.raises(NotImplementedError):
