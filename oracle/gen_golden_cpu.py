@@ -223,6 +223,124 @@ def gen_region_net(weight_seed=46, save=True):
           len(final_mask_sthre))
 
 
+def region_loss_inputs(seed=3, B=2, NC=40, A=4):
+    """Seeded inputs of GripperRegionNetwork.compute_loss / compute_loss_refine (training call): regressions, anchor
+    scores, and a ground truth (B, NC, 10) = (centre, axis, theta, 3 scores) with two centres that have no grasp (-1)."""
+    g = torch.Generator().manual_seed(seed)
+    M = B * NC
+    first_grasp = torch.randn(M, A, 10, generator=g) * 0.3
+    first_grasp[:, :, 7:] = torch.rand(M, A, 3, generator=g)
+    centers = torch.rand(M, 3, generator=g)
+    first_cls = torch.randn(M, A, generator=g)
+    ground = torch.cat([centers.view(B, NC, 3) + torch.randn(B, NC, 3, generator=g) * 0.01,
+                        torch.nn.functional.normalize(torch.randn(B, NC, 3, generator=g), dim=-1),
+                        (torch.rand(B, NC, 1, generator=g) - 0.5) * 3, torch.rand(B, NC, 3, generator=g)], dim=-1)
+    ground[0, 3, -1] = -1
+    ground[1, 7, -1] = -1
+    m = 50
+    next_grasp = torch.cat([torch.rand(m, 3, generator=g), torch.nn.functional.normalize(torch.randn(m, 3, generator=g), dim=-1),
+                            (torch.rand(m, 1, generator=g) - 0.5) * 3, torch.rand(m, 3, generator=g)], dim=-1)
+    next_gt = next_grasp.clone()
+    next_gt[:, :3] += torch.randn(m, 3, generator=g) * 0.02          # some within 2.5 cm, some not
+    next_gt[:, 3:6] = torch.nn.functional.normalize(next_gt[:, 3:6] + torch.randn(m, 3, generator=g) * 0.5, dim=-1)
+    next_gt[:, 6] += torch.randn(m, generator=g) * 0.8
+    next_x_cls = torch.randn(m, 2, generator=g)
+    next_x_reg = torch.randn(m, 10, generator=g) * 0.1
+    return dict(first_grasp=first_grasp, centers=centers, first_cls=first_cls, ground=ground, next_grasp=next_grasp,
+                next_gt=next_gt, next_x_cls=next_x_cls, next_x_reg=next_x_reg)
+
+
+def gen_region_losses():
+    """The TRAINING branches of multi_model/gripper_region_network.py (compute_loss with a ground truth, :92-199, and
+    compute_loss_refine with next_gt, :217-309) run on CPU from the reference's own file.  Two shims, both stated here:
+    `.cuda()` is a no-op and np.random.choice is deterministic_choice (as for the inference fixture); and
+    nn.CosineEmbeddingLoss receives a 1-D all-ones target of the inputs' length -- torch >= 1.10 rejects the (n, 1)
+    target the reference passes (once even with a mismatched n, :283), torch 1.8 (the reference's pin) broadcast it,
+    which for an all-ones target gives mean(1 - cos) whatever its length."""
+    import contextlib
+    import io
+    import multi_model.gripper_region_network as ref
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    ref.np.random.choice = deterministic_choice
+    net = ref.GripperRegionNetwork(training=True, group_num=16, gripper_num=8, grasp_score_threshold=0.4, radius=0.06,
+                                   reg_channel=10).eval()
+    class _Cos(torch.nn.CosineEmbeddingLoss):
+        def forward(self, a, b, y):
+            return super().forward(a, b, a.new_ones(a.shape[0]))   # what the (n, 1) ones target meant under torch 1.8
+    net.criterion_cos = _Cos(reduction="mean")
+    inp = region_loss_inputs()
+    anchors = net._enumerate_anchors(inp["centers"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        next_grasp, loss_tuple, correct_tuple, next_gt, tt_gt, gmask = net.compute_loss(
+            inp["first_grasp"].clone(), anchors, inp["first_cls"].clone(), inp["ground"].clone())
+        (sel_class, sel_score, sel_stage2, class_select, score_select, loss_refine, correct_refine) = net.compute_loss_refine(
+            inp["next_grasp"].clone(), inp["next_x_cls"].clone(), inp["next_x_reg"].clone(), inp["next_gt"].clone())
+    out = {k: v.numpy() for k, v in inp.items()}
+    out.update(l_next_grasp=next_grasp.numpy(), l_loss=np.array([float(x) for x in loss_tuple]),
+               l_correct=np.array([float(x) for x in correct_tuple]), l_next_gt=next_gt.numpy(), l_tt_gt=tt_gt.numpy(),
+               l_gmask=gmask.numpy(), r_sel_class=sel_class.numpy(), r_sel_score=sel_score.numpy(),
+               r_sel_stage2=sel_stage2.numpy(), r_class_select=class_select.numpy(), r_score_select=score_select.numpy(),
+               r_loss=np.array([float(x) for x in loss_refine]), r_correct=np.array([float(x) for x in correct_refine]),
+               meta=np.array("GripperRegionNetwork(True,16,8,0.4,0.06,10): compute_loss / compute_loss_refine with ground "
+                             "truth; inputs gen_golden_cpu.region_loss_inputs(); np.random.choice -> deterministic_choice"))
+    np.savez_compressed(os.path.join(OUT, "ref_py_region_losses.npz"), **out)
+    print("region-loss golden ok: stage-1 loss", out["l_loss"][0], "acc", out["l_correct"], "; refine loss", out["r_loss"][0],
+          "TP/TN/FP/FN", out["r_correct"])
+
+
+def region_net_ground(inp, seed=23):
+    """A ground truth for region_net_inputs(): (B, N_C, 10) = grasp near each centre (centre, axis, theta, 3 scores); one
+    centre without a grasp."""
+    g = torch.Generator().manual_seed(seed)
+    c = inp["center_pc"][:, :, :3]
+    B, NC = c.shape[:2]
+    ground = torch.cat([c + torch.randn(B, NC, 3, generator=g) * 0.004,
+                        torch.nn.functional.normalize(torch.randn(B, NC, 3, generator=g), dim=-1),
+                        (torch.rand(B, NC, 1, generator=g) - 0.5) * 3, torch.rand(B, NC, 3, generator=g)], dim=-1)
+    ground[1, 2, -1] = -1
+    return ground
+
+
+def gen_region_net_train(weight_seed=46):
+    """The TRAINING call of the reference's GripperRegionNetwork.forward (ground_grasp given), eval-mode BatchNorm so that
+    the fixture does not depend on batch statistics; shims as in gen_region_losses()."""
+    import contextlib
+    import io
+    import multi_model.gripper_region_network as ref
+    from regnet_for_3d_grasping_b200.weights import seeded_state_like
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    ref.np.random.choice = deterministic_choice
+    net = ref.GripperRegionNetwork(training=True, group_num=16, gripper_num=8, grasp_score_threshold=0.4, radius=0.06,
+                                   reg_channel=10).eval()
+    net.load_state_dict(seeded_state_like(net.state_dict(), seed=weight_seed), strict=True)
+
+    class _Cos(torch.nn.CosineEmbeddingLoss):
+        def forward(self, a, b, y):
+            return super().forward(a, b, a.new_ones(a.shape[0]))
+    net.criterion_cos = _Cos(reduction="mean")
+    inp = region_net_inputs()
+    ground = region_net_ground(inp)
+    params = [0.08, 0.010, 0.06]
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        out = net(inp["pc_group"], inp["pc_group_more"], inp["pc_group_index"], inp["pc_group_more_index"], inp["center_pc"],
+                  inp["center_pc_index"], inp["pc"], inp["all_feature"], params, ground)
+    (next_grasp, keep2, true_mask, loss_tuple, correct_tuple, next_gt, sel_class, sel_score, sel_stage2, keep3, keep3s,
+     final_mask, final_mask_sthre, loss_refine, correct_refine, gt) = out
+    assert final_mask is not None and loss_refine[0] is not None, "fixture should exercise the refine losses"
+    f = lambda tup: np.array([float(x) for x in tup])
+    np.savez_compressed(os.path.join(OUT, "ref_py_region_net_train.npz"), ground=ground.numpy(), next_grasp=next_grasp.numpy(),
+                        keep2=np.array([int(k) for k in keep2]), true_mask=true_mask.numpy(), loss=f(loss_tuple),
+                        correct=f(correct_tuple), next_gt=next_gt.numpy(), sel_class=sel_class.numpy(),
+                        sel_score=sel_score.numpy(), sel_stage2=sel_stage2.numpy(), keep3=np.array([int(k) for k in keep3]),
+                        keep3s=np.array([int(k) for k in keep3s]), final_mask=final_mask.numpy(),
+                        final_mask_sthre=final_mask_sthre.numpy(), loss_refine=f(loss_refine), correct_refine=f(correct_refine),
+                        gt=gt.numpy(), weight_seed=np.array(weight_seed),
+                        meta=np.array("training call of GripperRegionNetwork(True,16,8,0.4,0.06,10).eval() on "
+                                      "region_net_inputs() + region_net_ground(); np.random.choice -> deterministic_choice"))
+    print("region-net training golden ok: loss", f(loss_tuple)[0], "refine loss", f(loss_refine)[0], "kept", len(true_mask),
+          "final", len(final_mask), "gt", tuple(gt.shape))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ScoreNetwork, ref_mods = import_reference()
@@ -232,7 +350,15 @@ if __name__ == "__main__":
     if "region_net" in sys.argv:
         gen_region_net()
         sys.exit(0)
+    if "region_net_train" in sys.argv:
+        gen_region_net_train()
+        sys.exit(0)
+    if "region_losses" in sys.argv:
+        gen_region_losses()
+        sys.exit(0)
     gen_modules(ref_mods)
     gen_scorenet(ScoreNetwork)
     gen_heads()
     gen_region_net()
+    gen_region_losses()
+    gen_region_net_train()

@@ -1,6 +1,6 @@
 """GraspRegionNet + RefineNet of REGNet on device: mirror of
 multi_model/gripper_region_network.py with the same constructor, `forward` signature, 16-tuple result and state-dict keys
-(Appendix B), for the inference call of test.py:137-140 (`ground_grasp=None`).
+(Appendix B), for the inference call of test.py:137-140 (`ground_grasp=None`) and the training call (train.py:240-243).
 
 What changes underneath (nothing a caller can see except speed):
   * R3  the (B*N_C, N_G, 256) feature gather + MaxPool1d (:385-395, pointnet2.py:161) is one `gather_max` kernel; the
@@ -14,13 +14,16 @@ What changes underneath (nothing a caller can see except speed):
 Random draws (which 64 of the points inside the closing box) come from the device generator of region.py; the reference
 uses numpy's wall-clock-seeded global RNG, so only the distribution can match (tests/test_gpu_region.py).
 
-The training branches (`ground_grasp` given: anchor classification / regression losses, :92-199, :217-309) are the
-"loss bookkeeping" row of SURVEY.md section 8(f) and are not provided: they raise NotImplementedError.
+The training branches (`ground_grasp` given: anchor classification / regression losses, :92-199, :217-309; the "loss
+bookkeeping" row of SURVEY.md section 8(f)) are vectorised restatements pinned against the reference's own methods
+(tests/golden/ref_py_region_losses.npz); the class-balanced subsets keep the reference's host draws (np.random.choice).
 """
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import region
 from .region_heads import PointNet2Refine, PointNet2TwoStage
@@ -126,6 +129,18 @@ def get_gripper_region_transform(group_points, group_index, grasp, region_num, g
     return gripper_pc, gripper_pc_index, gripper_pc_index_inall, true_mask_index
 
 
+def _gather_max(all_feature, index):
+    """max over each group's feature rows, (B,N,C) x (B,N_C,G) -> (B,N_C,C): the one-pass kernel, or -- when a gradient
+    has to flow back into all_feature (joint training of ScoreNet and the region heads) -- the reference's own
+    gather + max expression (:385-395), which autograd understands."""
+    if torch.is_grad_enabled() and all_feature.requires_grad:
+        B, N, C = all_feature.shape
+        add = torch.arange(B, device=index.device).view(B, 1, 1) * N
+        rows = all_feature.reshape(-1, C)[(index.long() + add).reshape(-1)]
+        return rows.view(B, index.shape[1], index.shape[2], C).max(dim=2)[0]
+    return region.gather_max(all_feature, index.long())
+
+
 class GripperRegionNetwork(nn.Module):
     def __init__(self, training, group_num, gripper_num, grasp_score_threshold, radius, reg_channel):
         super().__init__()
@@ -168,29 +183,113 @@ class GripperRegionNetwork(nn.Module):
                                 g[:, 7:]], dim=-1)
         return next_grasp, predict, t
 
+    def _cos_loss(self, a, b):
+        """criterion_cos(a, b, ones): mean(1 - cos) -- the reference passes an (n, 1) ones target, which torch 1.8
+        broadcast and current torch rejects; the value it meant is this."""
+        return self.criterion_cos(a, b, a.new_ones(a.shape[0]))
+
     def compute_loss(self, first_grasp, anchors, first_cls, ground):
-        """Inference part of the reference method (:46-90): next_grasp, (None, None), (None,)*4, None, None, all rows."""
-        if ground is not None:
-            raise NotImplementedError("anchor losses (gripper_region_network.py:92-199) are SURVEY.md section 8(f) row 3; "
-                                      "this mirror covers the inference call (ground_grasp=None)")
-        next_grasp, _, _ = self.decode_first_stage(first_grasp, anchors, first_cls)
-        gmask = torch.arange(first_grasp.shape[0], device=first_grasp.device)
-        return next_grasp, (None, None), (None, None, None, None), None, None, gmask
+        """Reference method (:46-199).  first_grasp (M,A,10), anchors (M,A,7), first_cls (M,A), ground (B,N_C,10) | None ->
+        next_grasp (m,10), loss_tuple, correct_tuple, next_gt (m,10) | None, tt_gt (m,7) | None, gmask (m,) with m = the
+        centres that have a ground-truth grasp (all of them without ground).
+
+        Vectorised: the reference addresses the (anchor, centre) pair through a transposed flat index built by Python
+        loops of per-element device writes (:79-80, :108-109), loops over anchors with `.sum()` synchronisations and
+        prints some forty tensors per call; here the pairs are addressed as [centre, anchor] directly.  The balanced
+        anchor sampling keeps the reference's host draws (np.random.choice, same order, same arguments :121-127)."""
+        if ground is None:
+            next_grasp, _, _ = self.decode_first_stage(first_grasp, anchors, first_cls)
+            gmask = torch.arange(first_grasp.shape[0], device=first_grasp.device)
+            return next_grasp, (None, None), (None, None, None, None), None, None, gmask
+        D = ground.shape[2]
+        flat = ground.reshape(-1, D)
+        gmask = torch.nonzero(flat[:, -1] != -1).view(-1)
+        anchors, first_grasp, first_cls = anchors[gmask], first_grasp[gmask], first_cls[gmask]
+        next_grasp, predict, _ = self.decode_first_stage(first_grasp, anchors, first_cls)
+        m, A = first_cls.shape
+        rows = torch.arange(m, device=first_grasp.device)
+        ground_gt, ground_score_gt = flat[gmask, :7], flat[gmask, 7:]
+        # closest anchor orientation per centre (:99-105): argmin over anchors of 1 - cos(anchor axis, ground axis)
+        sim = compute_cos_sim(anchors[:, :, 3:6].reshape(-1, 3),
+                              ground_gt[:, None, 3:6].expand(m, A, 3).reshape(-1, 3)).view(m, A)
+        ground_8 = torch.sort(sim, dim=1, descending=False)[1][:, 0]
+        # class-balanced subset for the anchor classification loss (:111-133)
+        counts = torch.bincount(ground_8, minlength=A).cpu().numpy()
+        per_anchor = int(counts.min()) if counts.min() > 0 else 1
+        picked = []
+        for a in range(A):
+            members = torch.nonzero(ground_8 == a).view(-1)
+            if len(members) == 0:
+                continue
+            picked.append(members[torch.as_tensor(np.random.choice(len(members), per_anchor, replace=False),
+                                                  device=members.device, dtype=torch.long)])
+        balanced = torch.cat(picked)
+        loss_class = self.criterion_cls(first_cls[balanced], ground_8[balanced].long())
+        correct_tuple = ((ground_8 == predict).sum().float(), (ground_8 != predict).sum().float())
+        # regression of the ground-truth anchor (:143-162)
+        g, tt_gt = first_grasp[rows, ground_8], anchors[rows, ground_8]
+        axis = g[:, 3:6] + tt_gt[:, 3:6]
+        norm = torch.sqrt((axis * axis).sum(dim=1) + 1e-12).view(-1, 1)
+        loss1 = F.smooth_l1_loss(g[:, :3], (ground_gt[:, :3] - tt_gt[:, :3]) / self.radius, reduction='mean')
+        loss2 = F.smooth_l1_loss(g[:, 3:6] * norm, ground_gt[:, 3:6] - tt_gt[:, 3:6], reduction='mean')
+        loss3 = F.smooth_l1_loss(g[:, 6:7], (ground_gt[:, 6:7] - tt_gt[:, 6:7]) / math.pi, reduction='mean')
+        loss4 = F.smooth_l1_loss(g[:, 7:], ground_score_gt, reduction='mean')
+        # diagnostics of the predicted anchor against the ground truth (:176-181)
+        with torch.no_grad():
+            d_center = F.smooth_l1_loss(next_grasp[:, :3], ground_gt[:, :3], reduction='mean')
+            d_cos = self._cos_loss(next_grasp[:, 3:6], ground_gt[:, 3:6])
+            d_theta = F.smooth_l1_loss(next_grasp[:, 6:7], ground_gt[:, 6:7], reduction='mean')
+            d_score = F.smooth_l1_loss(next_grasp[:, 7:], ground_score_gt, reduction='mean')
+        next_gt = torch.cat((ground_gt, ground_score_gt), dim=1)
+        loss = loss1 * 10 + loss2 * 5 + loss3 + loss4 + loss_class
+        loss_tuple = (loss, loss_class.data, loss1.data, loss2.data, loss3.data, loss4.data, d_center, d_cos, d_theta, d_score)
+        return next_grasp, loss_tuple, correct_tuple, next_gt, tt_gt, gmask
 
     # ---- R7: refine decode ----------------------------------------------------------------------------------------
     def compute_loss_refine(self, next_grasp, next_x_cls, next_x_reg, next_gt):
-        """(:201-309, inference part) final = stage-1 grasp + refine offsets; keep the grasps classified positive, and
-        those that also score above the threshold."""
-        if next_gt is not None:
-            raise NotImplementedError("refine losses (gripper_region_network.py:217-309) are SURVEY.md section 8(f) row 3")
+        """(:201-309) final = stage-1 grasp + refine offsets; keep the grasps classified positive, and those that also
+        score above the threshold.  With next_gt: a stage-1 grasp counts as positive when it is within 2.5 cm, 60 degrees
+        of axis and 60 degrees of angle of its ground truth (:234-243); class-balanced cross-entropy + regression of the
+        positives towards their ground truth, and the reference's diagnostics (18-tuple) and confusion counts."""
         final = next_grasp.clone()
         final[:, :3] = final[:, :3] + next_x_reg[:, :3] * self.radius
         final[:, 3:] = final[:, 3:] + next_x_reg[:, 3:]
-        positive = torch.max(next_x_cls, dim=-1)[1] == 1
+        predicted = torch.max(next_x_cls, dim=-1)[1]
+        positive = predicted == 1
         class_select = torch.nonzero(positive).view(-1)
         score_select = torch.nonzero(positive & (final[:, 7] > self.grasp_score_thre)).view(-1)
-        return (final[class_select].data, final[score_select].data, next_grasp[class_select].data, class_select,
-                score_select, (None, None), (None, None, None, None))
+        sel_class, sel_score, sel_stage2 = final[class_select].data, final[score_select].data, next_grasp[class_select].data
+        if next_gt is None:
+            return sel_class, sel_score, sel_stage2, class_select, score_select, (None, None), (None, None, None, None)
+        close = torch.sqrt(((next_grasp[:, :3] - next_gt[:, :3]) ** 2).sum(dim=1)) < 0.025
+        aligned = compute_cos_sim(next_grasp[:, 3:6], next_gt[:, 3:6]).view(-1) < 0.5
+        turned = torch.abs(next_grasp[:, 6] - next_gt[:, 6]) < 1.047
+        gt_class = (close & aligned & turned).float()
+        gt_1, gt_0 = torch.nonzero(gt_class == 1).view(-1), torch.nonzero(gt_class == 0).view(-1)
+        num = min(len(gt_0), len(gt_1))
+        zero = next_x_cls.new_zeros(())
+        loss = loss_class = l_center = l_r = l_theta = l_score = zero
+        diag = [zero] * 12
+        if num > 0:
+            pick = lambda members: members[torch.as_tensor(np.random.choice(len(members), num, replace=False),
+                                                           device=members.device, dtype=torch.long)]
+            index = torch.cat((pick(gt_0), pick(gt_1)), dim=-1)
+            loss_class = self.criterion_cls(next_x_cls.view(-1, 2)[index], gt_class[index].long())
+            l_center = F.smooth_l1_loss(next_x_reg[gt_1, :3], (next_gt[gt_1, :3] - next_grasp[gt_1, :3]) / self.radius)
+            l_r = F.smooth_l1_loss(next_x_reg[gt_1, 3:6], next_gt[gt_1, 3:6] - next_grasp[gt_1, 3:6])
+            l_theta = F.smooth_l1_loss(next_x_reg[gt_1, 6], next_gt[gt_1, 6] - next_grasp[gt_1, 6])
+            l_score = F.smooth_l1_loss(next_x_reg[gt_1, 7:], next_gt[gt_1, 7:] - next_grasp[gt_1, 7:])
+            loss = loss_class + l_center + l_r + l_theta + l_score
+        if len(class_select) > 0:
+            with torch.no_grad():
+                def four(pred, sel):
+                    return [F.smooth_l1_loss(pred[:, :3], next_gt[sel, :3]), self._cos_loss(pred[:, 3:6], next_gt[sel, 3:6]),
+                            F.smooth_l1_loss(pred[:, 6], next_gt[sel, 6]), F.smooth_l1_loss(pred[:, 7:], next_gt[sel, 7:])]
+                diag = four(sel_stage2, class_select) + four(sel_class, class_select) + four(sel_score, score_select)
+        p1, g1 = predicted.view(-1) == 1, gt_class.view(-1) == 1
+        correct = ((g1 & p1).sum().float(), (~g1 & ~p1).sum().float(), (~g1 & p1).sum().float(), (g1 & ~p1).sum().float())
+        loss_tuple = (loss, loss_class.data, l_center.data, l_r.data, l_theta.data, l_score) + tuple(diag)
+        return sel_class, sel_score, sel_stage2, class_select, score_select, loss_tuple, correct
 
     def refine_forward(self, pc_group_more_xyz, pc_group_more_index, true_mask, all_feature, group_feature_mp, next_grasp,
                        gripper_params, next_gt=None):
@@ -205,13 +304,15 @@ class GripperRegionNetwork(nn.Module):
             return out
         cloud = (true_mask // N_C)[gripper_mask]
         flat_index = (inall[gripper_mask].long() + cloud.view(-1, 1) * N).view(1, -1, self.gripper_number)
-        pooled = region.gather_max(all_feature.contiguous().view(1, B * N, C), flat_index)[0]      # (M', 256)
+        pooled = _gather_max(all_feature.contiguous().view(1, B * N, C), flat_index)[0]      # (M', 256)
         centre_half = group_feature_mp.view(-1, 128)[gripper_mask].contiguous()     # the reference's (2M,128) re-view
         next_x_cls, next_x_reg = self.extrat_feature_refine.forward_pooled(pooled, centre_half)
         if next_gt is not None:
             next_gt = next_gt[gripper_mask]
         (select_grasp_class, select_grasp_score, select_grasp_class_stage2, class_select, score_select, loss_refine_tuple,
          correct_refine_tuple) = self.compute_loss_refine(next_grasp[gripper_mask], next_x_cls, next_x_reg, next_gt)
+        if next_gt is not None:
+            next_gt = next_gt[class_select]
         kept = true_mask[gripper_mask]
         return (select_grasp_class, select_grasp_score, select_grasp_class_stage2, kept[class_select], kept[score_select],
                 loss_refine_tuple, correct_refine_tuple, next_gt)
@@ -222,7 +323,7 @@ class GripperRegionNetwork(nn.Module):
         """Same arguments and 16-tuple as the reference (:361-434)."""
         B, N_C, N_G, _ = pc_group.shape
         anchors = self._enumerate_anchors(center_pc[:, :, :3].reshape(-1, 3).float())
-        pooled = region.gather_max(all_feature, pc_group_index.long())                     # (B, N_C, 256): R3
+        pooled = _gather_max(all_feature, pc_group_index.long())                           # (B, N_C, 256): R3
         x_cls, x_reg, mp_center_feature = self.extrat_feature_region.forward_pooled(pooled.view(B * N_C, -1))
         next_grasp, loss_tuple, correct_tuple, next_gt, _, true_mask = self.compute_loss(x_reg, anchors, x_cls, ground_grasp)
 

@@ -275,7 +275,55 @@ def test_closing_box_mask_kernel_equals_batched_reference_expression(lib_path):
             assert diff.float().mean().item() < 1e-5 and (face[diff] < 1e-6).all()
 
 
-def test_region_network_rejects_training_call(lib_path):
+def test_region_network_training_call_vs_reference_golden(lib_path, oracle, monkeypatch):
+    """The TRAINING call (ground_grasp given, train.py:240-243) against the fixture produced by the reference's own
+    forward (oracle/gen_golden_cpu.py region_net_train): both loss tuples (10 + 18 values), confusion counts, masks,
+    matched ground truths and selected grasps; random picks replaced by the fixture's fixed rule on both sides."""
+    import numpy
+    from conftest import golden
+    from oracle import region_oracle
+    from oracle.gen_golden_cpu import deterministic_choice
     ref, net, inp, params, args, np = _region_net_on_gpu()
-    with pytest.raises(NotImplementedError):
-        net(*args, ground_grasp=torch.zeros(2, 6, 10, device="cuda"))
+    tr = golden("ref_py_region_net_train.npz")
+    monkeypatch.setattr(numpy.random, "choice", deterministic_choice)
+    net._sampler = lambda mask: region_oracle.sample_rows_fixed_rule(mask.cpu(), 8).to(mask.device)
+    ground = torch.from_numpy(tr["ground"]).cuda()
+    with torch.no_grad():
+        out = net(*args, ground_grasp=ground)
+    (next_grasp, keep2, true_mask, loss_tuple, correct_tuple, next_gt, sel_class, sel_score, sel_stage2, keep3, keep3s,
+     final_mask, final_mask_sthre, loss_refine, correct_refine, gt) = out
+    assert np.array_equal(true_mask.cpu().numpy(), tr["true_mask"]) and [int(k) for k in keep2] == tr["keep2"].tolist()
+    np.testing.assert_allclose(next_grasp.cpu().numpy(), tr["next_grasp"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose([float(x) for x in loss_tuple], tr["loss"], rtol=2e-4, atol=1e-6)
+    assert [float(x) for x in correct_tuple] == tr["correct"].tolist()
+    np.testing.assert_allclose(next_gt.cpu().numpy(), tr["next_gt"], rtol=1e-6)
+    assert np.array_equal(final_mask.cpu().numpy(), tr["final_mask"])
+    assert np.array_equal(final_mask_sthre.cpu().numpy(), tr["final_mask_sthre"])
+    assert [int(k) for k in keep3] == tr["keep3"].tolist() and [int(k) for k in keep3s] == tr["keep3s"].tolist()
+    np.testing.assert_allclose([float(x) for x in loss_refine], tr["loss_refine"], rtol=2e-4, atol=1e-6)
+    assert [float(x) for x in correct_refine] == tr["correct_refine"].tolist()
+    np.testing.assert_allclose(gt.cpu().numpy(), tr["gt"], rtol=1e-6)
+    for got, key in ((sel_class, "sel_class"), (sel_score, "sel_score"), (sel_stage2, "sel_stage2")):
+        np.testing.assert_allclose(got.cpu().numpy(), tr[key], rtol=1e-4, atol=1e-5)
+
+
+def test_region_network_training_step_backpropagates(lib_path):
+    """train.py --mode train shape of the region step: train-mode heads (batch statistics), both losses summed, gradients
+    reach the head parameters AND all_feature (joint training with ScoreNet: the gather + max falls back to autograd's)."""
+    ref, net, inp, params, args, np = _region_net_on_gpu()
+    from oracle.gen_golden_cpu import region_net_ground
+    ground = region_net_ground({"center_pc": inp["center_pc"].cpu()}).cuda()
+    net.train()
+    net.sample_seed = 5
+    all_feature = inp["all_feature"].clone().requires_grad_(True)
+    args = list(args)
+    args[7] = all_feature
+    out = net(*args, ground_grasp=ground)
+    loss = out[3][0] + (out[13][0] if out[13][0] is not None else 0.0)
+    assert torch.isfinite(loss)
+    loss.backward()
+    assert all_feature.grad is not None and all_feature.grad.abs().sum() > 0
+    grads = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    assert "extrat_feature_region.conv.weight" in grads and grads["extrat_feature_region.conv_reg4.weight"].abs().sum() > 0
+    if out[13][0] is not None and out[13][0].requires_grad:
+        assert grads["extrat_feature_refine.conv_formal.weight"].abs().sum() > 0

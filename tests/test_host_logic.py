@@ -168,3 +168,40 @@ def test_region_network_state_dict_schema():
             "print(m.GripperRegionNetwork.__module__)" % os.path.join(ROOT, "regnet_for_3d_grasping_b200", "dropin"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and "regnet_for_3d_grasping_b200.gripper_region_network" in out.stdout, out.stderr
+
+
+def test_region_losses_match_reference_training_branches(monkeypatch):
+    """compute_loss (with a ground truth) and compute_loss_refine (with next_gt) of the GripperRegionNetwork mirror against
+    the fixture produced by the reference's own methods (oracle/gen_golden_cpu.py region_losses): every element of both
+    loss tuples, the confusion counts, the decoded / selected grasps and the masks; np.random.choice is replaced by the
+    fixture's fixed rule on both sides."""
+    import numpy as np
+    from conftest import golden
+    from oracle.gen_golden_cpu import deterministic_choice
+    from regnet_for_3d_grasping_b200 import gripper_region_network as grn
+    ref = golden("ref_py_region_losses.npz")
+    monkeypatch.setattr(np.random, "choice", deterministic_choice)
+    net = grn.GripperRegionNetwork(training=True, group_num=16, gripper_num=8, grasp_score_threshold=0.4, radius=0.06,
+                                   reg_channel=10).eval()
+    t = lambda k: torch.from_numpy(ref[k])
+    anchors = net._enumerate_anchors(t("centers"))
+    next_grasp, loss_tuple, correct, next_gt, tt_gt, gmask = net.compute_loss(t("first_grasp"), anchors, t("first_cls"), t("ground"))
+    assert torch.equal(gmask, t("l_gmask")) and len(gmask) == 78
+    assert torch.allclose(next_grasp, t("l_next_grasp"), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(next_gt, t("l_next_gt")) and torch.allclose(tt_gt, t("l_tt_gt"))
+    np.testing.assert_allclose([float(x) for x in loss_tuple], ref["l_loss"], rtol=2e-6)
+    assert [float(x) for x in correct] == ref["l_correct"].tolist()
+    out = net.compute_loss_refine(t("next_grasp"), t("next_x_cls"), t("next_x_reg"), t("next_gt"))
+    sel_class, sel_score, sel_stage2, class_select, score_select, loss_refine, correct_refine = out
+    assert torch.equal(class_select, t("r_class_select")) and torch.equal(score_select, t("r_score_select"))
+    assert torch.allclose(sel_class, t("r_sel_class")) and torch.allclose(sel_score, t("r_sel_score"))
+    assert torch.allclose(sel_stage2, t("r_sel_stage2"))
+    np.testing.assert_allclose([float(x) for x in loss_refine], ref["r_loss"], rtol=2e-6)
+    assert [float(x) for x in correct_refine] == ref["r_correct"].tolist()
+    # the stage-1 loss back-propagates into the regressions and the anchor scores
+    fg, fc = t("first_grasp").requires_grad_(True), t("first_cls").requires_grad_(True)
+    net.compute_loss(fg, anchors, fc, t("ground"))[1][0].backward()
+    assert fg.grad.abs().sum() > 0 and fc.grad.abs().sum() > 0
+    # inference call unchanged
+    ng, lt, ct, gt, tt, gm = net.compute_loss(t("first_grasp"), anchors, t("first_cls"), None)
+    assert lt == (None, None) and gt is None and len(gm) == 80
