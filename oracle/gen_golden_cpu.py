@@ -341,6 +341,34 @@ def gen_region_net_train(weight_seed=46):
           "final", len(final_mask), "gt", tuple(gt.shape))
 
 
+def gen_center_grasp():
+    """dataset_utils/get_regiondataset.py:_get_center_grasp (+ _transform_grasp), the reference's own functions on CPU,
+    over two synthetic scene files (synth.scene_grasps).  `open3d`, which that module imports and these functions never
+    touch, is stubbed with an empty module; `.cuda()` is a no-op."""
+    import contextlib
+    import io
+    import tempfile
+    import types
+    sys.modules.setdefault("open3d", types.ModuleType("open3d"))
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    import dataset_utils.get_regiondataset as ref
+    inp = region_net_inputs(N_C=24)
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = [synth.write_scene_file(os.path.join(tmp, f"scene{b}.p"), 70 + b, inp["pc"][b].numpy(), n_grasps=10, hit_frac=0.5) for b in range(2)]
+        with contextlib.redirect_stdout(io.StringIO()):
+            labels = ref._get_center_grasp(inp["center_pc_index"], inp["center_pc"], paths, 0.06, True)
+            frames = ref._get_center_grasp(inp["center_pc_index"], inp["center_pc"], paths, 0.06, False)
+    found = int((labels[:, :, 7] != -1).sum())
+    assert 5 < found < labels.shape[0] * labels.shape[1], "fixture should have centres with and without a grasp"
+    np.savez_compressed(os.path.join(OUT, "ref_py_center_grasp.npz"), center_pc=inp["center_pc"].numpy(),
+                        center_pc_index=inp["center_pc_index"].numpy(), pc=inp["pc"].numpy(), labels=labels.numpy(),
+                        frames=frames.numpy(),
+                        meta=np.array("_get_center_grasp(center_pc_index, center_pc, [scene0, scene1], depth=0.06) with "
+                                      "use_theta True / False; scenes = synth.write_scene_file(seed 70 + b, pc[b], n_grasps=10, hit_frac=0.5); "
+                                      "inputs region_net_inputs(N_C=24)"))
+    print("centre-grasp golden ok:", tuple(labels.shape), "labelled centres", found)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ScoreNetwork, ref_mods = import_reference()
@@ -349,6 +377,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "region_net" in sys.argv:
         gen_region_net()
+        sys.exit(0)
+    if "center_grasp" in sys.argv:
+        gen_center_grasp()
         sys.exit(0)
     if "region_net_train" in sys.argv:
         gen_region_net_train()
@@ -362,3 +393,4 @@ if __name__ == "__main__":
     gen_region_net()
     gen_region_losses()
     gen_region_net_train()
+    gen_center_grasp()

@@ -84,12 +84,93 @@ def get_group_pc(pc, center_pc, center_pc_index, group_num, width, height, depth
     return index, group
 
 
+def _load_scene_grasps(path, device):
+    """The grasp annotations of one scene file: (frames (G,4,4), score, antipodal, centre score) as fp32 tensors on
+    `device`, for both on-disk formats of the reference (get_regiondataset.py:63-87)."""
+    import numpy as np
+    data = np.load(path, allow_pickle=True)
+    t = lambda v: (torch.as_tensor(np.asarray(v), dtype=torch.float32) if not isinstance(v, torch.Tensor) else v.float()).to(device)
+    if "frame" in data.keys():
+        score = t(data["antipodal_score"])
+        return t(data["frame"]), score, score, score
+    return (t(data["select_frame"]), t(data["select_antipodal_score"]), t(data["select_antipodal_score"]),
+            t(data["select_center_score"]))
+
+
+def transform_grasp(grasp_ori, grasp_score_ori, antipodal_score_ori, center_score_ori):
+    """get_regiondataset.py:136-199: (B,N_C,3,4) frames [x | y | z | centre] -> (B,N_C,10) = (centre, closing axis with
+    non-negative x, angle in (-pi, pi], score, antipodal score, centre score); rows without a grasp stay -1 (8 columns
+    when no scene carries antipodal scores, like the reference)."""
+    import math
+    B, CN = grasp_score_ori.shape
+    cols = 8 if bool((antipodal_score_ori == -1).all()) else 10
+    out = torch.full((B, CN, cols), -1.0, device=grasp_ori.device)
+    axis_x = grasp_ori[:, :, :3, 0].reshape(B * CN, 3)
+    axis_y = grasp_ori[:, :, :3, 1].reshape(B * CN, 3).clone()
+    axis_z = grasp_ori[:, :, :3, 2].reshape(B * CN, 3)
+    no_grasp = (axis_x == -1).all(dim=1)
+    angle = torch.atan2(axis_x[:, 2], axis_z[:, 2])
+    flip = axis_y[:, 0] < 0
+    angle = torch.where(flip, math.pi - angle, angle)
+    axis_y = torch.where(flip[:, None], -axis_y, axis_y)
+    angle = torch.where(angle >= 2 * math.pi, angle - 2 * math.pi, angle)
+    angle = torch.where(angle <= -2 * math.pi, angle + 2 * math.pi, angle)
+    angle = torch.where(angle > math.pi, angle - 2 * math.pi, angle)
+    angle = torch.where(angle <= -math.pi, angle + 2 * math.pi, angle)
+    angle = torch.where(no_grasp, torch.full_like(angle, -1.0), angle)
+    out[:, :, :3] = grasp_ori[:, :, :3, 3]
+    out[:, :, 3:6] = axis_y.view(B, CN, 3)
+    out[:, :, 6] = angle.view(B, CN)
+    out[:, :, 7] = grasp_score_ori
+    if cols > 8:
+        out[:, :, 8] = antipodal_score_ori
+        out[:, :, 9] = center_score_ori
+    return out
+
+
+def get_center_grasp(center_pc_index, center_pc, data_paths, depth, use_theta=True):
+    """get_regiondataset.py:45-134 (_get_center_grasp): the annotated grasp nearest to every centre (squared distance by
+    the reference's |a|^2 + |b|^2 - 2ab expansion, kept iff it does not exceed 0.005) -> grasp_labels (B,N_C,10)
+    (or (B,N_C,13) frames + score with use_theta=False); centres without a grasp are -1.  One scene file per cloud; the
+    per-cloud work is a (N_C x G) distance matrix on the centres' device."""
+    dev = center_pc.device
+    B, NC = center_pc_index.shape
+    label = torch.full((B, NC, 3, 4), -1.0, device=dev)
+    score_l = torch.full((B, NC), -1.0, device=dev)
+    anti_l = torch.full((B, NC), -1.0, device=dev)
+    cent_l = torch.full((B, NC), -1.0, device=dev)
+    for i, path in enumerate(data_paths):
+        grasp, score, anti, cent = _load_scene_grasps(path, dev)
+        gx = grasp[:, :3, 0]
+        centre = (grasp[:, :3, 3] + gx * depth).float()
+        centre = (centre - gx * depth).float()               # the reference's round trip (:92-93)
+        p1 = center_pc[i][:, :3].float()
+        d = -2 * p1.mm(centre.transpose(1, 0))
+        d = d + (centre * centre).sum(1).view(1, -1)
+        d = d + (p1 * p1).sum(1).view(-1, 1)
+        dmin, arg = torch.min(d.double(), dim=1)
+        keep = ~(dmin > 0.005)
+        label[i] = torch.where(keep[:, None, None], grasp[arg, :3, :4], label[i])
+        score_l[i] = torch.where(keep, score[arg], score_l[i])
+        anti_l[i] = torch.where(keep, anti[arg], anti_l[i])
+        cent_l[i] = torch.where(keep, cent[arg], cent_l[i])
+    if use_theta:
+        return transform_grasp(label, score_l, anti_l, cent_l)
+    flat = label.view(-1, 3, 4)
+    inv = flat[:, 0, 1] < 0
+    flat[inv, :, 1:2] = -flat[inv, :, 1:2]
+    out = torch.full((B, NC, 13), -1.0, device=dev)
+    out[:, :, :12] = flat.transpose(2, 1).contiguous().view(B, NC, 12)
+    out[:, :, 12:13] = score_l.view(B, NC, 1)
+    return out
+
+
 def get_grasp_allobj(pc, predict_score, params, data_paths, use_theta=True, seed=None):
     """Drop-in for dataset_utils.get_regiondataset.get_grasp_allobj (get_regiondataset.py:13-42).
 
-    Returns (center_pc, center_pc_index, pc_group_index, pc_group, pc_group_more_index, pc_group_more, grasp_labels).
-    grasp_labels needs the scene files on disk (_get_center_grasp, :45-134); that lookup is a later row of the
-    scope table and is not provided: pass data_paths=[] (the inference path of test.py:135)."""
+    Returns (center_pc, center_pc_index, pc_group_index, pc_group, pc_group_more_index, pc_group_more, grasp_labels);
+    grasp_labels is None for data_paths=[] (the inference path of test.py:135), else the label lookup of
+    get_center_grasp over the scenes' annotation files (one path per cloud)."""
     (center_num, score_thre, group_num, r_time_group, group_num_more, r_time_group_more, width, height, depth) = params
     s = None if seed is None else int(seed)
     center_pc, center_pc_index = select_score_center(pc, predict_score, center_num, score_thre, seed=s)
@@ -97,10 +178,10 @@ def get_grasp_allobj(pc, predict_score, params, data_paths, use_theta=True, seed
                                             seed=None if s is None else s + 1)
     pc_group_more_index, pc_group_more = get_group_pc(pc, center_pc, center_pc_index, group_num_more, width, height, depth,
                                                       r_time_group_more, seed=None if s is None else s + 2)
+    grasp_labels = None
     if len(data_paths) > 0:
-        raise NotImplementedError("grasp label lookup (_get_center_grasp) is not part of this round's scope; "
-                                  "call with data_paths=[]")
-    return center_pc, center_pc_index, pc_group_index, pc_group, pc_group_more_index, pc_group_more, None
+        grasp_labels = get_center_grasp(center_pc_index, center_pc, data_paths, depth, use_theta)
+    return center_pc, center_pc_index, pc_group_index, pc_group, pc_group_more_index, pc_group_more, grasp_labels
 
 
 def sample_mask_rows(mask, num, min_count=5, seed=None, return_count=False):

@@ -102,3 +102,33 @@ def scores_like_dataset(seed, b, n):
     """pc_score labels ~ tanh(U[0,1]) (scoredataset.py:79-81 applies tanh to the raw antipodal score)."""
     rng = np.random.default_rng(seed)
     return np.tanh(rng.uniform(0, 1, (b, n))).astype(np.float32)
+
+
+def scene_grasps(seed, points, n_grasps=600, hit_frac=0.6):
+    """Synthetic grasp annotations of one scene in the reference's on-disk format (get_regiondataset.py:63-72):
+    `frame` (G,4,4) rigid transforms (columns approach / closing axis / minor normal / centre) and `antipodal_score` (G,).
+    A fraction of the grasps sits within a few millimetres of cloud points so that centres find a label, the rest
+    floats around the scene."""
+    rng = np.random.default_rng(seed)
+    pts = np.asarray(points)[:, :3]
+    q = rng.normal(size=(n_grasps, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    rot = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                    2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                    2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], axis=1).reshape(n_grasps, 3, 3)
+    near = rng.random(n_grasps) < hit_frac
+    centre = pts[rng.integers(0, len(pts), n_grasps)] + rng.normal(scale=0.002, size=(n_grasps, 3))
+    centre[~near] = pts.mean(0) + rng.normal(scale=0.3, size=((~near).sum(), 3))
+    frame = np.tile(np.eye(4), (n_grasps, 1, 1))
+    frame[:, :3, :3] = rot
+    frame[:, :3, 3] = centre
+    return {"frame": frame, "antipodal_score": rng.random(n_grasps)}
+
+
+def write_scene_file(path, seed, points, **kw):
+    """Pickle scene_grasps(...) the way the reference's dataset stores a scene (np.load(path, allow_pickle=True) reads it)."""
+    import pickle
+    with open(path, "wb") as f:
+        pickle.dump(scene_grasps(seed, points, **kw), f)
+    return path

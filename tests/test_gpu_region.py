@@ -157,7 +157,7 @@ def test_gather_max_equals_reference_expression(lib_path):
     assert torch.equal(got, want)
 
 
-def test_get_grasp_allobj_shapes_test_config(lib_path):
+def test_get_grasp_allobj_shapes_test_config(lib_path, tmp_path):
     """test.py:68-71 parameters (center_num 4000, group_num 256, group_num_more 2048) on one cloud."""
     from regnet_for_3d_grasping_b200 import region
     pc, score = _scene(1, 25600, 21)
@@ -172,8 +172,15 @@ def test_get_grasp_allobj_shapes_test_config(lib_path):
     torch.manual_seed(0)
     out2 = region.get_grasp_allobj(pc.cuda(), score.cuda(), params, [])
     assert torch.equal(out2[2], gi) and torch.equal(out2[4], gmi)         # torch.manual_seed makes the draws reproducible
-    with pytest.raises(NotImplementedError):
-        region.get_grasp_allobj(pc.cuda(), score.cuda(), params, ["scene.p"])
+    # with a scene annotation file: grasp labels (centre, axis, angle, 3 scores) per centre, -1 where none is near
+    from regnet_for_3d_grasping_b200 import synth
+    path = synth.write_scene_file(str(tmp_path / "scene.p"), 9, pc[0].numpy(), n_grasps=40, hit_frac=0.5)
+    labels = region.get_grasp_allobj(pc.cuda(), score.cuda(), params, [path])[6]
+    assert tuple(labels.shape) == (1, 4000, 10) and labels.is_cuda
+    has = labels[0, :, 7] != -1
+    # (rows without a grasp: -1 everywhere except the axis, which the reference's sign flip turns into (1, 1, 1))
+    assert 0 < int(has.sum()) < 4000 and (labels[0][~has][:, [0, 1, 2, 6, 7, 8, 9]] == -1).all()
+    assert (labels[0][:, 3] >= 0).all()
 
 
 def _region_net_on_gpu():

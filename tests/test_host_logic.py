@@ -205,3 +205,22 @@ def test_region_losses_match_reference_training_branches(monkeypatch):
     # inference call unchanged
     ng, lt, ct, gt, tt, gm = net.compute_loss(t("first_grasp"), anchors, t("first_cls"), None)
     assert lt == (None, None) and gt is None and len(gm) == 80
+
+
+def test_center_grasp_label_lookup_matches_reference(tmp_path):
+    """region.get_center_grasp (+ transform_grasp) against the fixture produced by the reference's own _get_center_grasp
+    on two synthetic scene files, which the test re-creates from the same seeds: labelled and unlabelled centres, the
+    (centre, axis, angle, scores) form and the raw-frame form."""
+    from conftest import golden
+    from regnet_for_3d_grasping_b200 import region, synth
+    ref = golden("ref_py_center_grasp.npz")
+    pc = ref["pc"]
+    paths = [synth.write_scene_file(str(tmp_path / f"scene{b}.p"), 70 + b, pc[b], n_grasps=10, hit_frac=0.5) for b in range(2)]
+    cidx, cpc = torch.from_numpy(ref["center_pc_index"]), torch.from_numpy(ref["center_pc"])
+    labels = region.get_center_grasp(cidx, cpc, paths, 0.06, True)
+    want = torch.from_numpy(ref["labels"])
+    assert tuple(labels.shape) == tuple(want.shape) == (2, 24, 10)
+    assert torch.equal(labels[:, :, 7] == -1, want[:, :, 7] == -1) and 0 < int((want[:, :, 7] == -1).sum()) < 48
+    assert torch.allclose(labels, want, rtol=1e-6, atol=1e-7)
+    frames = region.get_center_grasp(cidx, cpc, paths, 0.06, False)
+    assert torch.allclose(frames, torch.from_numpy(ref["frames"]), rtol=1e-6, atol=1e-7)
