@@ -87,6 +87,33 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ms = sharding.max_over_ranks([e0.elapsed_time(e1)], dev)[0]
+    # one extra, synchronised step for a wall-clock breakdown of the stages (diagnostic, not part of the timing)
+    import time
+    br = {}
+
+    def tick(name, t0):
+        torch.cuda.synchronize()
+        br[name] = round((time.perf_counter() - t0) * 1e3, 2)
+        return time.perf_counter()
+
+    opt_score.zero_grad(set_to_none=True)
+    opt_region.zero_grad(set_to_none=True)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    all_feature, output_score, loss = score_model(pc, tgt)
+    t = tick("scorenet_forward_ms", t)
+    got = region.get_grasp_allobj(pc, output_score.detach(), params, [], seed=1)
+    t = tick("centres_and_crops_ms", t)
+    labels = region.get_center_grasp(got[1], got[0], paths, depth)
+    t = tick("label_lookup_ms", t)
+    out = region_model(got[3], got[5], got[2], got[4], got[0], got[1], pc, all_feature, gripper_params, labels, paths)
+    t = tick("region_forward_and_losses_ms", t)
+    total = loss.sum() + out[3][0].sum() + (out[13][0].sum() if out[13][0] is not None else 0.0)
+    total.backward()
+    t = tick("backward_ms", t)
+    opt_score.step()
+    opt_region.step()
+    t = tick("optimisers_ms", t)
     if rank == 0:
         print(json.dumps({"metric": "clouds/s, full REGNet training step (ScoreNet + region crops + labels + GraspRegionNet + "
                                     "RefineNet losses, bwd, all-reduce, Adam)",
@@ -94,7 +121,7 @@ def main():
                           "ms_per_step": ms / args.steps, "steps": args.steps, "batch_per_gpu": args.batch,
                           "points": args.points, "centres_per_cloud": 64, "labelled_centres_last_step": stats["labelled"],
                           "refined_grasps_last_step": stats["refined"], "loss": stats["loss"],
-                          "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
+                          "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30, "breakdown_synchronised": br}))
     if world > 1:
         dist.destroy_process_group()
 
