@@ -224,3 +224,7 @@ def test_center_grasp_label_lookup_matches_reference(tmp_path):
     assert torch.allclose(labels, want, rtol=1e-6, atol=1e-7)
     frames = region.get_center_grasp(cidx, cpc, paths, 0.06, False)
     assert torch.allclose(frames, torch.from_numpy(ref["frames"]), rtol=1e-6, atol=1e-7)
+    # the annotation tensors are cached per (path, mtime, size): same answer from the cache, and a rewritten file is re-read
+    assert len(region._SCENE_CACHE) >= 2 and torch.equal(region.get_center_grasp(cidx, cpc, paths, 0.06, True), labels)
+    synth.write_scene_file(paths[0], 999, pc[0], n_grasps=11, hit_frac=0.5)
+    assert not torch.equal(region.get_center_grasp(cidx, cpc, paths, 0.06, True)[0], labels[0])
