@@ -8,13 +8,18 @@ One "step" = one ScoreNet forward over a batch of 15 synthetic 25 600-point clou
 (BASELINE.json configs[1]); clouds are independent units, so N GPUs = N independent shards of 15 clouds each
 ("weak" scaling, no data-path collective).  Prints ONE JSON line on rank 0.
 
-  value        clouds/s with the batch already resident in HBM (CUDA events, max over ranks)
-  e2e          the same through the public module API (ScoreNetwork.forward) from PINNED HOST memory:
-               H2D copy of the batch + forward + D2H of the per-point scores inside the timed region
-               (all_feature stays on the device, as in the reference, where the region stage consumes it there)
-  roofline     per-kernel CUDA-event times from a profiled pass (plan.profile_forward): the shared-MLP GEMM
-               engine against the measured bf16 tensor peak, algorithmic FLOPs = 2*MACs (one pass; the
-               split-bf16 engine issues 3 tensor passes, so frac <= 1/3 by construction)
+  value        clouds/s with the batch already resident in HBM (CUDA events, max over ranks), pipeline in steady state:
+               the timed region executes exactly K geometry chains (FPS / ball query / 3-NN, prefetched on side streams)
+               and K MLP chains; ms_per_step_cold_pipeline = the same K steps started from an empty pipeline
+  e2e          the same through the public module API (ScoreNetwork.prefetch / forward) from PINNED HOST memory:
+               per step one H2D copy of a batch (triple-buffered, copy stream), one forward and one D2H of the per-point
+               scores (second copy stream) inside the timed region; all_feature stays on the device, as in the
+               reference, where the region stage consumes it there
+  roofline     per-kernel CUDA-event times from a profiled pass (plan.profile_forward): the tensor-core launches against
+               the measured bf16 tensor peak, algorithmic FLOPs = 2*MACs of the reference's layer table (the split-bf16
+               engine issues 3 tensor passes per executed FLOP and executes fewer FLOPs than the table counts, see
+               `note`); `traffic` = DRAM bytes of those launches from the committed ncu capture; `search_ops` = FPS /
+               ball-query Gpts/s of the level-0 shapes
   cpu_baseline the oracle port of the reference path (oracle/ref_modules.py + oracle/pn2_oracle.c, torch CPU
                convolutions) on a bounded sample, host cores stated
   --impl reference   only the CPU reference arm, same metric/unit/config
