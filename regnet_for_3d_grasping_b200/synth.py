@@ -132,3 +132,35 @@ def write_scene_file(path, seed, points, **kw):
     with open(path, "wb") as f:
         pickle.dump(scene_grasps(seed, points, **kw), f)
     return path
+
+
+def training_scene(seed, n_view=30000, n_grasps=3000):
+    """One scene in the reference's training-set format (dataset_utils/scoredataset.py:63-66, get_regiondataset.py:63-72,
+    eval_utils/torch_scene_point_cloud.py:9-13): the single-view cloud with colours, per-point grasp scores and object
+    labels (0 = table), the grasp annotations, and a scene cloud with normals for the evaluation code."""
+    rng = np.random.default_rng(seed)
+    cloud = table_scene(seed, n_view, dup_frac=0.0)
+    xyz, rgb = cloud[:, :3].astype(np.float64), cloud[:, 3:6].astype(np.float64)
+    label = (xyz[:, 2] > 0.7515).astype(np.float64) * (1 + (np.abs(np.floor(xyz[:, 0] * 10)) % 5))   # 0 = table plane
+    score = np.where(label > 0, rng.random(n_view) * 2.0, rng.random(n_view) * 0.2)                    # tanh'ed by the dataset
+    d = scene_grasps(seed + 1, cloud, n_grasps=n_grasps, hit_frac=0.9)
+    normals = np.tile(np.array([0.0, 0.0, 1.0]), (n_view, 1))
+    d.update(view_cloud=xyz, view_cloud_color=rgb, view_cloud_score=score, view_cloud_label=label, scene_cloud=xyz,
+             scene_normal=normals)
+    return d
+
+
+def write_dataset(root, n_scenes=10, seed=0, **kw):
+    """<root>/training_data/scene_XXXX.p files that dataset_utils.scoredataset.ScoreDataset(all_points_num, root, tag, ...)
+    lists and np.load(..., allow_pickle=True)'s (scoredataset.py:37-62)."""
+    import os
+    import pickle
+    out = os.path.join(root, "training_data")
+    os.makedirs(out, exist_ok=True)
+    paths = []
+    for i in range(n_scenes):
+        path = os.path.join(out, f"scene_{i:04d}.p")
+        with open(path, "wb") as f:
+            pickle.dump(training_scene(seed + 10 * i, **kw), f)
+        paths.append(path)
+    return paths

@@ -228,3 +228,49 @@ def test_center_grasp_label_lookup_matches_reference(tmp_path):
     assert len(region._SCENE_CACHE) >= 2 and torch.equal(region.get_center_grasp(cidx, cpc, paths, 0.06, True), labels)
     synth.write_scene_file(paths[0], 999, pc[0], n_grasps=11, hit_frac=0.5)
     assert not torch.equal(region.get_center_grasp(cidx, cpc, paths, 0.06, True)[0], labels[0])
+
+
+def test_import_shims_and_synthetic_dataset(tmp_path):
+    """the stand-ins for `tensorboardX` / `transforms3d` that the reference's train.py / utils.py
+    import (checked against scipy), and the synthetic training set in the reference's on-disk format -- read back the way
+    dataset_utils/scoredataset.py:61-82 reads it (and through the reference's own ScoreDataset where /root/reference
+    exists)."""
+    import importlib
+    import os
+    import sys
+    import numpy as np
+    from scipy.spatial.transform import Rotation
+    from regnet_for_3d_grasping_b200 import synth
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dropin = os.path.join(ROOT, "regnet_for_3d_grasping_b200", "dropin")
+    sys.path.insert(0, dropin)
+    try:
+        t3d = importlib.import_module("transforms3d")
+        tbx = importlib.import_module("tensorboardX")
+        for a in [(-0.87 * np.pi, 0.0, 0.0), (0.3, -1.1, 2.0), (3.0, 0.2, -0.4)]:
+            m = t3d.quaternions.quat2mat(t3d.euler.euler2quat(*a))
+            assert np.abs(m - Rotation.from_euler("xyz", a).as_matrix()).max() < 1e-12
+        q = t3d.quaternions.axangle2quat([1, 0, 0], np.pi * 1.13)
+        assert np.abs(t3d.quaternions.quat2mat(q) - Rotation.from_rotvec([np.pi * 1.13, 0, 0]).as_matrix()).max() < 1e-12
+        w = tbx.SummaryWriter(str(tmp_path / "log"))
+        w.add_scalar("loss", 1.5, 0)
+        w.close()
+    finally:
+        sys.path.remove(dropin)
+    paths = synth.write_dataset(str(tmp_path / "data"), n_scenes=5, seed=3, n_view=4000, n_grasps=50)
+    assert len(paths) == 5 and sorted(os.listdir(tmp_path / "data" / "training_data")) == [os.path.basename(p) for p in paths]
+    data = np.load(paths[2], allow_pickle=True)
+    n = len(data["view_cloud"])
+    assert data["view_cloud"].shape == (n, 3) and data["view_cloud_color"].shape == (n, 3)
+    assert data["view_cloud_score"].shape == (n,) and data["view_cloud_label"].shape == (n,)
+    assert data["frame"].shape == (50, 4, 4) and data["antipodal_score"].shape == (50,) and data["scene_cloud"].shape == (n, 3)
+    assert (data["view_cloud_label"] == 0).any() and (data["view_cloud_label"] > 0).any()
+    if os.path.isdir("/root/reference/dataset_utils"):      # build container only: the reference's own dataset class
+        sys.path.insert(0, "/root/reference")
+        try:
+            from dataset_utils.scoredataset import ScoreDataset
+            ds = ScoreDataset(2048, str(tmp_path / "data"), "train", 1, [0.08])
+            view, view_score, view_label, data_path, width = ds[0]
+            assert view.shape == (2048, 6) and view_score.shape == (2048,) and len(ds) == 4 and os.path.exists(data_path)
+        finally:
+            sys.path.remove("/root/reference")
