@@ -274,3 +274,54 @@ def test_import_shims_and_synthetic_dataset(tmp_path):
             assert view.shape == (2048, 6) and view_score.shape == (2048,) and len(ds) == 4 and os.path.exists(data_path)
         finally:
             sys.path.remove("/root/reference")
+
+
+def test_open3d_standin_covers_the_reference_call_sites(tmp_path):
+    """The `open3d` stand-in (dropin/open3d): point-cloud container, normals (PCA, oriented to the camera), kd-tree
+    searches against brute force, voxel down-sampling, PCD round trips (binary and ascii) -- the calls of test.py:102-106
+    and dataset_utils/eval_score/eval_utils/{pointcloud,torch_scene_point_cloud,evaluation_data_generator}.py."""
+    import importlib
+    import os
+    import sys
+    import numpy as np
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dropin = os.path.join(ROOT, "regnet_for_3d_grasping_b200", "dropin")
+    sys.path.insert(0, dropin)
+    try:
+        o3d = importlib.import_module("open3d")
+        rng = np.random.default_rng(0)
+        pts = rng.random((600, 3))
+        pts[:, 2] = 0.002 * rng.random(600)                                   # a thin slab: normals are +-z
+        cloud = o3d.geometry.PointCloud()
+        cloud.points = o3d.utility.Vector3dVector(pts)
+        cloud.colors = o3d.utility.Vector3dVector(rng.random((600, 3)))
+        cloud.estimate_normals(search_param=o3d.geometry.KDTreeSearchParamHybrid(radius=0.2, max_nn=30),
+                               fast_normal_computation=False)
+        cloud.normalize_normals()
+        cloud.orient_normals_towards_camera_location(np.array([0.0, 0.0, 5.0]))
+        n = np.asarray(cloud.normals)
+        assert n.shape == (600, 3) and n[:, 2].min() > 0.99 and np.allclose(np.linalg.norm(n, axis=1), 1.0)
+        tree = o3d.geometry.KDTreeFlann(cloud)
+        q = pts[7]
+        d2 = ((pts - q) ** 2).sum(1)
+        k, idx, dist = tree.search_radius_vector_3d(q, 0.15)
+        assert k == int((d2 <= 0.15 ** 2).sum()) and sorted(idx) == sorted(np.nonzero(d2 <= 0.15 ** 2)[0].tolist()) and idx[0] == 7
+        k, idx, dist = tree.search_knn_vector_3d(q, 5)
+        assert k == 5 and idx == np.argsort(d2, kind="stable")[:5].tolist() and np.allclose(dist, np.sort(d2)[:5])
+        assert tree.search_hybrid_vector_3d(q, 0.15, 3)[0] == 3
+        moved = o3d.geometry.PointCloud()
+        moved.points = pts.copy()
+        T = np.eye(4)
+        T[:3, 3] = [1.0, 2.0, 3.0]
+        assert np.allclose(np.asarray(moved.transform(T).points), pts + [1.0, 2.0, 3.0])
+        assert 0 < len(cloud.voxel_down_sample(0.25).points) <= 16 + 4
+        for ascii_ in (False, True):
+            path = str(tmp_path / f"cloud_{int(ascii_)}.pcd")
+            o3d.io.write_point_cloud(path, cloud, write_ascii=ascii_)
+            back = o3d.io.read_point_cloud(path)
+            assert np.abs(np.asarray(back.points) - pts.astype(np.float32)).max() < 1e-7
+            assert np.abs(np.asarray(back.colors) - np.asarray(cloud.colors)).max() <= 0.5 / 255 + 1e-9
+    finally:
+        sys.path.remove(dropin)
+        for name in [m for m in sys.modules if m == "open3d" or m.startswith("open3d.")]:
+            del sys.modules[name]
