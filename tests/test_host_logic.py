@@ -325,3 +325,31 @@ def test_open3d_standin_covers_the_reference_call_sites(tmp_path):
         sys.path.remove(dropin)
         for name in [m for m in sys.modules if m == "open3d" or m.startswith("open3d.")]:
             del sys.modules[name]
+
+
+def test_region_loss_edge_cases():
+    """compute_loss_refine when no stage-1 grasp matches its ground truth (no class-balanced pair, :260) and when nothing
+    is classified positive (:274): zero losses / diagnostics, counts still reported -- the reference's behaviour."""
+    from regnet_for_3d_grasping_b200 import gripper_region_network as grn
+    net = grn.GripperRegionNetwork(training=True, group_num=16, gripper_num=8, grasp_score_threshold=0.4, radius=0.06,
+                                   reg_channel=10).eval()
+    g = torch.Generator().manual_seed(1)
+    m = 9
+    next_grasp = torch.rand(m, 10, generator=g)
+    next_gt = next_grasp.clone()
+    next_gt[:, :3] += 1.0                                    # every ground truth 1.7 m away: all of class 0
+    cls = torch.stack([torch.ones(m), -torch.ones(m)], dim=1)  # everything predicted negative
+    out = net.compute_loss_refine(next_grasp, cls, torch.zeros(m, 10), next_gt)
+    sel_class, sel_score, sel_stage2, class_select, score_select, loss_tuple, correct = out
+    assert len(class_select) == 0 and len(score_select) == 0 and sel_class.shape == (0, 10)
+    assert len(loss_tuple) == 18 and all(float(x) == 0.0 for x in loss_tuple)
+    assert [float(x) for x in correct] == [0.0, float(m), 0.0, 0.0]           # TP, TN, FP, FN
+    # everything predicted positive, still no positive ground truth: diagnostics are computed, the loss stays 0
+    out = net.compute_loss_refine(next_grasp, -cls, torch.zeros(m, 10), next_gt)
+    assert len(out[3]) == m and float(out[5][0]) == 0.0 and float(out[5][10]) > 0 and [float(x) for x in out[6]] == [0.0, 0.0, float(m), 0.0]
+    # stage 1: a ground truth in which only one anchor orientation occurs (the other anchors have no member)
+    centers = torch.rand(6, 3, generator=g)
+    anchors = net._enumerate_anchors(centers)
+    ground = torch.cat([centers, anchors[:, 0, 3:6], torch.zeros(6, 1), torch.rand(6, 3, generator=g)], dim=1).view(1, 6, 10)
+    ng, lt, ct, gt, tt, gm = net.compute_loss(torch.zeros(6, 4, 10), anchors, torch.randn(6, 4, generator=g), ground)
+    assert len(gm) == 6 and torch.isfinite(lt[0]) and torch.allclose(tt, anchors[:, 0]) and float(ct[0] + ct[1]) == 6.0
