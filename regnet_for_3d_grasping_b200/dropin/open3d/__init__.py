@@ -9,6 +9,9 @@ Call sites: test.py:102-106, dataset_utils/eval_score/eval_utils/pointcloud.py:8
 evaluation_data_generator.py:59-61,247-261.  numpy + scipy.spatial.cKDTree underneath; `visualization` only says that no
 display is available.  It exists so that `import open3d` -- which the reference does at module import time in files that
 training needs -- succeeds without the real package; it is not part of the accelerated path."""
-from . import geometry, io, utility, visualization  # noqa: F401
+from _bootstrap import installed_elsewhere as _installed_elsewhere   # the drop-in directory is on sys.path (that is how this package was found)
 
-__version__ = "0.0-regnet-b200-standin"
+if _installed_elsewhere("open3d") is None:      # otherwise sys.modules["open3d"] now is the real package
+    from . import geometry, io, utility, visualization  # noqa: F401
+
+    __version__ = "0.0-regnet-b200-standin"
