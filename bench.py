@@ -409,6 +409,18 @@ def main():
                 "ms_by_kernel": {k: round(v, 4) for k, v in per_label.items()}, "serial_step_ms": total_ms}
         if args.engine == "simt":
             roof["kernel"] = "gemm_simt_kernel"
+        # HBM-bound producers (gather-affine / interpolate-affine): algorithmic DRAM bytes = the bf16 hi/lo planes written
+        # once (4 B / element) + the per-source-point table and the index rows read once, against the measured copy peak
+        def hbm(label, rows, cout, table_rows, idx_per_row):
+            t = per_label.get(label)
+            if not t:
+                return None
+            nbytes = rows * cout * 4 + table_rows * cout * 4 + rows * idx_per_row * 4
+            return {"kernel": label, "bytes": nbytes, "ms": round(t, 4), "achieved": nbytes / (t * 1e-3) / 1e9,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / (t * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        roof["hbm_kernels"] = [h for h in (hbm("sa_operand.1", B_PER_GPU * 1024 * 64, 256, B_PER_GPU * 5120, 1),
+                                           hbm("sa_operand.2", B_PER_GPU * 256 * 64, 512, B_PER_GPU * 1024, 1),
+                                           hbm("fp_operand.2", B_PER_GPU * N_POINTS, 256, B_PER_GPU * 5120, 6)) if h]
         # second half of BASELINE.json's metric: "FPS+ball_query Gpts/s" on the level-0 shapes of this workload
         # (FPS = B*N*(M-1) distance updates / t; ball query = B*M*N point tests of the reference's
         # brute-force scan / t -- the grid kernel answers the same question while visiting ~9 cells per centroid)
