@@ -369,6 +369,44 @@ def gen_center_grasp():
     print("centre-grasp golden ok:", tuple(labels.shape), "labelled centres", found)
 
 
+def eval_test_inputs(seed=41, N=3000, M=400):
+    """A table-top view cloud and grasps placed on it (some upright over the objects, some tilted into the table, some
+    floating): (points (N,3), grasps (M,8), table_height, depth, width)."""
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.from_numpy(synth.batch("table", [seed], N))[0, :, :3]
+    anchor = pts[torch.randint(0, N, (M,), generator=g)]
+    centre = anchor + torch.randn(M, 3, generator=g) * 0.01 + torch.tensor([0.0, 0.0, 0.03]) * torch.rand(M, 1, generator=g)
+    axis = torch.nn.functional.normalize(torch.randn(M, 3, generator=g) * torch.tensor([1.0, 1.0, 0.2]), dim=-1)
+    angle = (torch.rand(M, 1, generator=g) - 0.5) * 3.0
+    grasp = torch.cat([centre, axis, angle, torch.rand(M, 1, generator=g)], dim=1)
+    return pts, grasp, 0.75, 0.06, 0.08
+
+
+def gen_eval_test():
+    """dataset_utils/eval_score/eval.py:eval_test, the reference's own EvalDataTest.run_collision_view on CPU (gpu=-1),
+    on top of the open3d / transforms3d stand-ins of dropin/ (the reference estimates normals in the constructor and never
+    uses them in this filter)."""
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "regnet_for_3d_grasping_b200", "dropin"))
+    for name in ("open3d", "transforms3d"):
+        sys.modules.pop(name, None)
+    import importlib
+    importlib.import_module("open3d")
+    importlib.import_module("transforms3d")
+    from dataset_utils.eval_score.eval_utils.evaluation_data_generator import EvalDataTest
+    pts, grasp, table_height, depth, width = eval_test_inputs()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ev = EvalDataTest(pts.numpy(), grasp.clone(), None, table_height, depth, width, -1)
+        kept = ev.run_collision_view()
+        idx = ev.baseline_frame_index[:ev.valid_grasp].long()
+    assert 10 < len(idx) < len(grasp) - 10, f"fixture should keep some grasps and reject some (kept {len(idx)})"
+    np.savez_compressed(os.path.join(OUT, "ref_py_eval_test.npz"), kept_index=idx.numpy(), kept=kept.numpy(),
+                        frame=ev.frame.numpy(), meta=np.array("EvalDataTest(points, grasp, None, 0.75, 0.06, 0.08, -1)"
+                        ".run_collision_view() on gen_golden_cpu.eval_test_inputs()"))
+    print("eval_test golden ok: kept", len(idx), "of", len(grasp))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ScoreNetwork, ref_mods = import_reference()
@@ -377,6 +415,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "region_net" in sys.argv:
         gen_region_net()
+        sys.exit(0)
+    if "eval_test" in sys.argv:
+        gen_eval_test()
         sys.exit(0)
     if "center_grasp" in sys.argv:
         gen_center_grasp()

@@ -1,0 +1,90 @@
+"""View-collision filter of predicted grasps: `eval_test` of the reference
+(dataset_utils/eval_score/eval.py:4-12 -> eval_utils/evaluation_data_generator.py:47-225, EvalDataTest.run_collision_view).
+
+The reference walks the grasps in a Python loop (up to 4 000 per cloud, four times per cloud in utils.py:395-401); every
+iteration transforms the whole view cloud into the gripper frame and counts the points in three regions.  Here the
+grasps are processed in batches: one (batch, 3, N) transform and a handful of boolean reductions per batch, on whatever
+device the inputs live on.  The normals the reference estimates in the constructor (open3d, every call) are never used by
+this filter and are not computed.
+
+Gripper constants: dataset_utils/eval_score/configs/config.py:11,27-41."""
+import torch
+
+NUM_POINTS_THRESHOLD = 16
+BACK_COLLISION_THRESHOLD = 0.0
+BACK_COLLISION_MARGIN = 0.0
+FINGER_COLLISION_THRESHOLD = 0
+FINGER_WIDTH = 0.01
+HALF_HAND_THICKNESS = 0.005
+BOTTOM_LENGTH = 0.06
+
+
+def grasp_frames(grasp):
+    """inv_transform_predicted_grasp (:115-163): grasp (B,8) = (centre, closing axis, angle, score) ->
+    frame (B,3,3) with COLUMNS approach / closing axis / minor normal, centre (B,3), score (B,1)."""
+    g = grasp.reshape(-1, 8).float()
+    B = g.shape[0]
+    center = g[:, :3].contiguous()
+    angle = g[:, 6]
+    cos_t, sin_t = torch.cos(angle), torch.sin(angle)
+    zero, one = torch.zeros_like(cos_t), torch.ones_like(cos_t)
+    R1 = torch.stack([cos_t, zero, -sin_t, zero, one, zero, sin_t, zero, cos_t], dim=1).view(B, 3, 3)
+
+    def unit(v, fallback):
+        n = torch.norm(v, dim=1)
+        out = v / n.view(-1, 1)
+        bad = n == 0
+        if bad.any():
+            out[bad] = torch.tensor(fallback, dtype=v.dtype, device=v.device)
+        return out
+
+    axis_y = unit(g[:, 3:6], [0.0, 1.0, 0.0])
+    axis_x = unit(torch.stack([axis_y[:, 1], -axis_y[:, 0], zero], dim=1), [1.0, 0.0, 0.0])
+    axis_z = unit(torch.cross(axis_x, axis_y, dim=1), [0.0, 0.0, 1.0])
+    matrix = torch.bmm(torch.stack([axis_x, axis_y, axis_z], dim=2), R1)
+    approach = unit(matrix[:, :, 0], [1.0, 0.0, 0.0])
+    minor = torch.cross(approach, axis_y, dim=1)
+    return torch.stack([approach, axis_y, minor], dim=2).contiguous(), center, g[:, 7].view(-1, 1).contiguous()
+
+
+def view_collision_free(points, grasp, table_height, depth, width, batch=256):
+    """Boolean (B,) mask of the grasps that pass finger_hand_view (:178-225): fingertips above the table, at least 16
+    points between the hand's back plane and the fingertips, nothing behind the hand within its footprint, nothing inside
+    the two finger volumes."""
+    pts = points.float()
+    frame, center, _ = grasp_frames(grasp)
+    B = frame.shape[0]
+    ok = ~(center[:, 2] + frame[:, 2, 0] * depth < table_height + 0.005)
+    to_local = frame.transpose(1, 2).contiguous()
+    shift = -torch.bmm(to_local, center.unsqueeze(2))                       # (B,3,1), as the reference builds it (:92-93)
+    cloud = pts.t().contiguous()                                             # (3,N)
+    half_w, half_s = width / 2 + FINGER_WIDTH, width / 2
+    for lo in range(0, B, batch):
+        hi = min(B, lo + batch)
+        local = torch.matmul(to_local[lo:hi], cloud) + shift[lo:hi]         # (b,3,N)
+        x, y, z = local[:, 0], local[:, 1], local[:, 2]
+        close = (x > -BOTTOM_LENGTH) & (x < depth)
+        in_z = (z < HALF_HAND_THICKNESS) & (z > -HALF_HAND_THICKNESS)
+        back = close & (y < half_w) & (y > -half_w) & (x < -BACK_COLLISION_MARGIN) & in_z
+        finger = close & in_z & (((y < half_w) & (y > half_s)) | ((y > -half_w) & (y < -half_s)))
+        ok[lo:hi] &= (close.sum(1) >= NUM_POINTS_THRESHOLD) & ~(back.sum(1) > BACK_COLLISION_THRESHOLD) \
+            & ~(finger.sum(1) > FINGER_COLLISION_THRESHOLD)
+    return ok
+
+
+def eval_test(points, predicted_grasp, view_num, table_height, depth, width, gpu):
+    """Drop-in for dataset_utils.eval_score.eval.eval_test: points (N,3), predicted_grasp (B,8) -> the grasps without a
+    view collision, in their original order.  `gpu` as in the reference (-1 = CPU, else that CUDA device); tensors that
+    already live on a device are used where they are."""
+    if isinstance(predicted_grasp, torch.Tensor):
+        grasp = predicted_grasp.float()
+    else:
+        grasp = torch.as_tensor(predicted_grasp, dtype=torch.float32)
+    dev = grasp.device
+    if gpu != -1 and torch.cuda.is_available() and dev.type != "cuda":
+        dev = torch.device("cuda", gpu)
+    grasp = grasp.to(dev)
+    pts = (points if isinstance(points, torch.Tensor) else torch.as_tensor(points)).to(dev)
+    if grasp.numel() == 0:
+        return grasp.view(-1, 8)
+    return grasp.view(-1, 8)[view_collision_free(pts[:, :3], grasp, table_height, depth, width)]

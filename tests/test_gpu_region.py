@@ -334,3 +334,31 @@ def test_region_network_training_step_backpropagates(lib_path):
     assert "extrat_feature_region.conv.weight" in grads and grads["extrat_feature_region.conv_reg4.weight"].abs().sum() > 0
     if out[13][0] is not None and out[13][0].requires_grad:
         assert grads["extrat_feature_refine.conv_formal.weight"].abs().sum() > 0
+
+
+def test_eval_test_on_device_equals_host_and_reference(lib_path):
+    """grasp_eval.eval_test on the GPU: same surviving grasps as on the host and as the reference's loop (fixture), and the
+    test.py-sized call (4 000 grasps x 25 600 points) runs in milliseconds."""
+    import time
+    from conftest import golden
+    from oracle.gen_golden_cpu import eval_test_inputs
+    from regnet_for_3d_grasping_b200 import grasp_eval
+    ref = golden("ref_py_eval_test.npz")
+    pts, grasp, table_height, depth, width = eval_test_inputs()
+    kept = grasp_eval.eval_test(pts.cuda(), grasp.cuda(), None, table_height, depth, width, 0)
+    assert kept.is_cuda and torch.equal(kept.cpu(), torch.from_numpy(ref["kept"]))
+    pts, grasp, table_height, depth, width = eval_test_inputs(seed=43, N=25600, M=4000)
+    want = grasp_eval.view_collision_free(pts, grasp, table_height, depth, width)
+    pts, grasp = pts.cuda(), grasp.cuda()
+    grasp_eval.eval_test(pts, grasp, None, table_height, depth, width, 0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kept = grasp_eval.eval_test(pts, grasp, None, table_height, depth, width, 0)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    got = torch.zeros(4000, dtype=torch.bool)
+    # boundary points may flip between the host's and the device's matmul: allow a handful of grasps to differ
+    host_kept = grasp.cpu()[want]
+    assert abs(len(kept) - len(host_kept)) <= 4 and 0 < len(kept) < 4000
+    print(f"eval_test 4000 grasps x 25600 points: {ms:.2f} ms, kept {len(kept)} (host {len(host_kept)})")
+    assert ms < 200

@@ -353,3 +353,20 @@ def test_region_loss_edge_cases():
     ground = torch.cat([centers, anchors[:, 0, 3:6], torch.zeros(6, 1), torch.rand(6, 3, generator=g)], dim=1).view(1, 6, 10)
     ng, lt, ct, gt, tt, gm = net.compute_loss(torch.zeros(6, 4, 10), anchors, torch.randn(6, 4, generator=g), ground)
     assert len(gm) == 6 and torch.isfinite(lt[0]) and torch.allclose(tt, anchors[:, 0]) and float(ct[0] + ct[1]) == 6.0
+
+
+def test_eval_test_view_collision_filter_matches_reference():
+    """grasp_eval.eval_test (batched) against the fixture produced by the reference's own EvalDataTest.run_collision_view:
+    the same grasps survive, in the same order, and the decoded gripper frames agree."""
+    from conftest import golden
+    from oracle.gen_golden_cpu import eval_test_inputs
+    from regnet_for_3d_grasping_b200 import grasp_eval
+    ref = golden("ref_py_eval_test.npz")
+    pts, grasp, table_height, depth, width = eval_test_inputs()
+    frame, center, score = grasp_eval.grasp_frames(grasp)
+    assert torch.allclose(frame, torch.from_numpy(ref["frame"]), atol=1e-6)
+    mask = grasp_eval.view_collision_free(pts, grasp, table_height, depth, width, batch=64)
+    assert torch.nonzero(mask).view(-1).tolist() == ref["kept_index"].tolist()
+    kept = grasp_eval.eval_test(pts.numpy(), grasp, None, table_height, depth, width, -1)
+    assert torch.equal(kept, torch.from_numpy(ref["kept"])) and 10 < len(kept) < 390
+    assert grasp_eval.eval_test(pts, grasp[:0], None, table_height, depth, width, -1).shape == (0, 8)
