@@ -407,6 +407,52 @@ def gen_eval_test():
     print("eval_test golden ok: kept", len(idx), "of", len(grasp))
 
 
+def eval_validate_inputs(seed=47, N=20000, N2=60000, M=4000):
+    """View cloud, a denser scene cloud of the same synthetic scene with random unit normals (the score only uses |n_y|
+    in the gripper frame), and top-down grasps over the objects (approach ~ -z, random yaw, small tilt): some straddle an
+    object, most hit something with a finger."""
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.from_numpy(synth.batch("table", [seed], N))[0, :, :3]
+    scene = torch.from_numpy(synth.batch("table", [seed], N2))[0, :, :3]
+    pts[:, 2], scene[:, 2] = 1.5 - pts[:, 2], 1.5 - scene[:, 2]      # synth's objects lie towards the camera (smaller z):
+    normals = torch.nn.functional.normalize(torch.randn(N2, 3, generator=g) * torch.tensor([0.6, 0.6, 1.0]), dim=-1)
+    obj = pts[pts[:, 2] > 0.775]                                     # mirrored about the table plane they stand ON it
+    anchor = obj[torch.randint(0, len(obj), (M,), generator=g)]
+    centre = anchor + torch.cat([torch.randn(M, 2, generator=g) * 0.01, torch.rand(M, 1, generator=g) * 0.04], dim=1)
+    yaw = torch.rand(M, generator=g) * 6.2832
+    axis = torch.stack([torch.cos(yaw), torch.sin(yaw), torch.randn(M, generator=g) * 0.05], dim=1)
+    angle = -1.5708 + torch.randn(M, 1, generator=g) * 0.2
+    grasp = torch.cat([centre, torch.nn.functional.normalize(axis, dim=-1), angle, torch.rand(M, 1, generator=g)], dim=1)
+    data = dict(view_cloud=pts.numpy(), scene_cloud=scene.numpy().astype(np.float64),
+                scene_normal=normals.numpy().astype(np.float64))
+    return data, grasp, 0.75, 0.06, 0.08
+
+
+def gen_eval_validate():
+    """dataset_utils/eval_score/eval.py:eval_validate, the reference's own EvalDataValidate.run_collision on CPU
+    (gpu=-1; torch.cuda.is_available() is False here, so its scene tensors stay on the CPU too), on the stand-ins."""
+    import contextlib
+    import importlib
+    import io
+    sys.path.insert(0, os.path.join(ROOT, "regnet_for_3d_grasping_b200", "dropin"))
+    for name in ("open3d", "transforms3d"):
+        sys.modules.pop(name, None)
+    importlib.import_module("open3d")
+    importlib.import_module("transforms3d")
+    from dataset_utils.eval_score.eval_utils.evaluation_data_generator import EvalDataValidate
+    data, grasp, table_height, depth, width = eval_validate_inputs()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ev = EvalDataValidate(data, grasp.clone(), 0, table_height, depth, width, -1)
+        vgr, score, n_view, g_view, g_scene = ev.run_collision()
+    assert 5 < vgr < n_view < len(grasp), f"fixture should exercise both filters (view {n_view}, scene {vgr})"
+    np.savez_compressed(os.path.join(OUT, "ref_py_eval_validate.npz"), vgr=np.array(vgr), score=np.array(score),
+                        n_view=np.array(n_view), grasp_view=g_view.numpy(), grasp_scene=g_scene.numpy(),
+                        antipodal=ev.antipodal_score.numpy(),
+                        meta=np.array("EvalDataValidate(data, grasp, 0, 0.75, 0.06, 0.08, -1).run_collision() on "
+                                      "gen_golden_cpu.eval_validate_inputs()"))
+    print("eval_validate golden ok: view", n_view, "scene", vgr, "score", score)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ScoreNetwork, ref_mods = import_reference()
@@ -415,6 +461,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "region_net" in sys.argv:
         gen_region_net()
+        sys.exit(0)
+    if "eval_validate" in sys.argv:
+        gen_eval_validate()
         sys.exit(0)
     if "eval_test" in sys.argv:
         gen_eval_test()
@@ -435,3 +484,5 @@ if __name__ == "__main__":
     gen_region_losses()
     gen_region_net_train()
     gen_center_grasp()
+    gen_eval_test()
+    gen_eval_validate()

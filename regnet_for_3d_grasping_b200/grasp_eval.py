@@ -11,6 +11,8 @@ Gripper constants: dataset_utils/eval_score/configs/config.py:11,27-41."""
 import torch
 
 NUM_POINTS_THRESHOLD = 16
+CLOSE_REGION_MIN_POINTS = 16
+NEIGHBOR_DEPTH = 0.005
 BACK_COLLISION_THRESHOLD = 0.0
 BACK_COLLISION_MARGIN = 0.0
 FINGER_COLLISION_THRESHOLD = 0
@@ -70,6 +72,80 @@ def view_collision_free(points, grasp, table_height, depth, width, batch=256):
         ok[lo:hi] &= (close.sum(1) >= NUM_POINTS_THRESHOLD) & ~(back.sum(1) > BACK_COLLISION_THRESHOLD) \
             & ~(finger.sum(1) > FINGER_COLLISION_THRESHOLD)
     return ok
+
+
+def _region_tests(cloud, to_local, shift, depth, width):
+    """The gripper-frame region tests shared by the view and the scene filters (:420-470, :480-525) for a batch of
+    grasps: (local y (b,N), close-plane count, back-collision count, finger-collision count, closing-region mask)."""
+    local = torch.matmul(to_local, cloud) + shift                            # (b,3,N)
+    x, y, z = local[:, 0], local[:, 1], local[:, 2]
+    d = depth.view(-1, 1) if isinstance(depth, torch.Tensor) else depth
+    close = (x > -BOTTOM_LENGTH) & (x < d)
+    half_w, half_s = width / 2 + FINGER_WIDTH, width / 2
+    in_z = close & (z < HALF_HAND_THICKNESS) & (z > -HALF_HAND_THICKNESS)
+    back = in_z & (y < half_w) & (y > -half_w) & (x < -BACK_COLLISION_MARGIN)
+    finger = in_z & (((y < half_w) & (y > half_s)) | ((y > -half_w) & (y < -half_s)))
+    region = in_z & (y < half_s) & (y > -half_s)
+    return y, close.sum(1), back.sum(1), finger.sum(1), region
+
+
+def eval_validate(formal_dict, predicted_grasp, view_num, table_height, depth, width, gpu, batch=128):
+    """Drop-in for dataset_utils.eval_score.eval.eval_validate (EvalDataValidate.run_collision,
+    evaluation_data_generator.py:231-538): grasps (B,8) -> (number of grasps without a SCENE collision, sum of their
+    antipodal scores, number without a VIEW collision, those grasps, and the scene-collision-free ones).
+
+    View filter = eval_test's with the validate variant's constants (fingertips may dip 5 mm below the table top, and the
+    closing region must hold 16 view points).  Scene filter = the same region tests on the 8x denser scene cloud; a
+    surviving grasp scores mean|n_y| over the outer `min(span / 3, 5 mm)` strip on the left of its closing region times
+    the same on the right, n = scene normals in the gripper frame (:395-416).  `depth` may be a float or one value per
+    grasp.  The view-cloud normals the reference estimates in its constructor are not used by anything and not computed."""
+    import numpy as np
+    as_t = lambda v: v if isinstance(v, torch.Tensor) else torch.as_tensor(np.asarray(v))
+    grasp = as_t(predicted_grasp).float()
+    dev = grasp.device
+    if gpu != -1 and torch.cuda.is_available() and dev.type != "cuda":
+        dev = torch.device("cuda", gpu)
+    grasp = grasp.to(dev).view(-1, 8)
+    view = as_t(formal_dict["view_cloud"]).float().to(dev)[:, :3].t().contiguous()
+    scene = as_t(formal_dict["scene_cloud"]).float().to(dev)[:, :3].t().contiguous()
+    if "scene_normal" not in formal_dict:
+        raise RuntimeError("eval_validate: the scene file carries no 'scene_normal' (estimate them once with open3d and store them)")
+    normal = as_t(formal_dict["scene_normal"]).float().to(dev)[:, :3].t().contiguous()
+    frame, center, _ = grasp_frames(grasp)
+    B = frame.shape[0]
+    per_grasp_depth = isinstance(depth, torch.Tensor) and depth.numel() > 1
+    dep = depth.float().to(dev).view(-1) if per_grasp_depth else float(depth)
+    to_local = frame.transpose(1, 2).contiguous()
+    shift = -torch.bmm(to_local, center.unsqueeze(2))
+    ok = ~(center[:, 2] + frame[:, 2, 0] * dep < table_height - 0.005)
+    for lo in range(0, B, batch):
+        hi = min(B, lo + batch)
+        _, n_close, n_back, n_finger, region = _region_tests(view, to_local[lo:hi], shift[lo:hi],
+                                                             dep[lo:hi] if per_grasp_depth else dep, width)
+        ok[lo:hi] &= (n_close >= NUM_POINTS_THRESHOLD) & ~(n_back > BACK_COLLISION_THRESHOLD) \
+            & ~(n_finger > FINGER_COLLISION_THRESHOLD) & (region.sum(1) >= CLOSE_REGION_MIN_POINTS)
+    keep = torch.nonzero(ok).view(-1)
+    grasp_view = grasp[keep]
+    V = len(keep)
+    free = torch.zeros(V, dtype=torch.bool, device=dev)
+    score = torch.zeros(V, dtype=torch.float32, device=dev)
+    inf = float("inf")
+    for lo in range(0, V, batch):
+        sel = keep[lo:lo + batch]
+        y, n_close, n_back, n_finger, region = _region_tests(scene, to_local[sel], shift[sel],
+                                                             dep[sel] if per_grasp_depth else dep, width)
+        good = (n_close >= NUM_POINTS_THRESHOLD) & ~(n_back > BACK_COLLISION_THRESHOLD) \
+            & ~(n_finger > FINGER_COLLISION_THRESHOLD) & (region.sum(1) >= CLOSE_REGION_MIN_POINTS)
+        left_y = torch.where(region, y, torch.full_like(y, -inf)).amax(1, keepdim=True)
+        right_y = torch.where(region, y, torch.full_like(y, inf)).amin(1, keepdim=True)
+        strip = torch.minimum((left_y - right_y) / 3, torch.full_like(left_y, NEIGHBOR_DEPTH))
+        ny = torch.matmul(to_local[sel][:, 1:2, :], normal)[:, 0].abs()      # |y component of the normals in the gripper frame|
+        left = region & (y > left_y - strip)
+        right = region & (y < right_y + strip)
+        mean = lambda m: (ny * m).sum(1) / m.sum(1).clamp(min=1)
+        free[lo:lo + len(sel)] = good
+        score[lo:lo + len(sel)] = torch.where(good, mean(left) * mean(right), torch.zeros_like(mean(left)))
+    return int(free.sum()), float(score.sum()), V, grasp_view, grasp_view[free]
 
 
 def eval_test(points, predicted_grasp, view_num, table_height, depth, width, gpu):

@@ -370,3 +370,20 @@ def test_eval_test_view_collision_filter_matches_reference():
     kept = grasp_eval.eval_test(pts.numpy(), grasp, None, table_height, depth, width, -1)
     assert torch.equal(kept, torch.from_numpy(ref["kept"])) and 10 < len(kept) < 390
     assert grasp_eval.eval_test(pts, grasp[:0], None, table_height, depth, width, -1).shape == (0, 8)
+
+
+def test_eval_validate_matches_reference():
+    """grasp_eval.eval_validate (batched view filter, scene filter and antipodal score) against the fixture produced by
+    the reference's own EvalDataValidate.run_collision: same grasp sets, same counts, same total score."""
+    from conftest import golden
+    from oracle.gen_golden_cpu import eval_validate_inputs
+    from regnet_for_3d_grasping_b200 import grasp_eval
+    ref = golden("ref_py_eval_validate.npz")
+    data, grasp, table_height, depth, width = eval_validate_inputs()
+    vgr, score, n_view, g_view, g_scene = grasp_eval.eval_validate(data, grasp, 0, table_height, depth, width, -1)
+    assert n_view == int(ref["n_view"]) == 300 and vgr == int(ref["vgr"]) == 20
+    assert torch.equal(g_view, torch.from_numpy(ref["grasp_view"])) and torch.equal(g_scene, torch.from_numpy(ref["grasp_scene"]))
+    assert abs(score - float(ref["score"])) <= 1e-5 * float(ref["score"])
+    # one depth per grasp (utils.py passes a tensor when the model predicts the depth): same answer for a constant tensor
+    out = grasp_eval.eval_validate(data, grasp, 0, table_height, torch.full((len(grasp),), depth), width, -1)
+    assert out[0] == vgr and out[2] == n_view and abs(out[1] - score) < 1e-6
