@@ -3,6 +3,8 @@
 The CUDA operators cannot run here, so the module wiring is exercised with the C oracle patched in under
 `function.pn2_ext` -- the oracle is the checker's stand-in for the kernels, the modules under test are the
 product's.  Outputs are compared with fixtures produced by the reference's own modules."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -387,3 +389,27 @@ def test_eval_validate_matches_reference():
     # one depth per grasp (utils.py passes a tensor when the model predicts the depth): same answer for a constant tensor
     out = grasp_eval.eval_validate(data, grasp, 0, table_height, torch.full((len(grasp),), depth), width, -1)
     assert out[0] == vgr and out[2] == n_view and abs(out[1] - score) < 1e-6
+
+
+def test_grasp_label_encoding_round_trips_through_the_decoder():
+    """Size-independent property tying the two ends of the region stage together: a gripper frame encoded as a label
+    (region.transform_grasp: centre, closing axis with x >= 0, angle) and decoded again (grasp_eval.grasp_frames, the same
+    algebra as closing_box_frame) gives back the approach axis, the closing axis up to the encoder's sign convention, and
+    the minor normal with that sign -- for arbitrary rotations."""
+    from scipy.spatial.transform import Rotation
+    from regnet_for_3d_grasping_b200 import grasp_eval, region
+    from regnet_for_3d_grasping_b200.gripper_region_network import closing_box_frame
+    M = 3000
+    rot = torch.from_numpy(Rotation.random(M, random_state=0).as_matrix()).float()
+    centre = torch.rand(M, 3, generator=torch.Generator().manual_seed(0))
+    score = torch.rand(1, M, generator=torch.Generator().manual_seed(1))
+    label = region.transform_grasp(torch.cat([rot, centre.view(M, 3, 1)], dim=2).view(1, M, 3, 4), score, score, score)[0]
+    assert (label[:, 3] >= 0).all() and (label[:, 6].abs() <= math.pi + 1e-6).all() and torch.equal(label[:, :3], centre)
+    frame, c2, s2 = grasp_eval.grasp_frames(label[:, :8])
+    sign = torch.where(rot[:, 0, 1] < 0, -1.0, 1.0).view(M, 1)
+    assert torch.allclose(frame[:, :, 0], rot[:, :, 0], atol=2e-6)               # approach
+    assert torch.allclose(frame[:, :, 1], sign * rot[:, :, 1], atol=2e-6)        # closing axis, flipped to x >= 0
+    assert torch.allclose(frame[:, :, 2], sign * rot[:, :, 2], atol=2e-6)        # minor normal follows
+    assert torch.equal(c2, centre) and torch.equal(s2.view(-1), score.view(-1))
+    # the closing-box crop of the refine stage uses the same frame (rows instead of columns)
+    assert torch.allclose(closing_box_frame(label[:, :8]), frame.transpose(1, 2), atol=2e-6)
