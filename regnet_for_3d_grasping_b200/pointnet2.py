@@ -82,8 +82,10 @@ class PointNet2Seg(nn.Module):
         if plan is None:
             plan = ScoreNetPlan(B, N, device, engine=self.engine)
             self._plans[key] = plan
-        sd = {"x." + k: v for k, v in self.state_dict().items()}
-        plan.bind_state(sd, root="x.", key=self._state_key())
+        state_key = self._state_key()
+        if plan._bound_key != state_key:       # parameters changed (or first use): fold BN again and upload
+            sd = {"x." + k: v for k, v in self.state_dict().items()}
+            plan.bind_state(sd, root="x.", key=state_key)
         return plan
 
     def _forward_fused(self, points):
