@@ -150,12 +150,13 @@ def training_scene(seed, n_view=30000, n_grasps=3000):
     return d
 
 
-def write_dataset(root, n_scenes=10, seed=0, **kw):
-    """<root>/training_data/scene_XXXX.p files that dataset_utils.scoredataset.ScoreDataset(all_points_num, root, tag, ...)
-    lists and np.load(..., allow_pickle=True)'s (scoredataset.py:37-62)."""
+def write_dataset(root, n_scenes=10, seed=0, split="training_data", **kw):
+    """<root>/<split>/scene_XXXX.p files that dataset_utils.scoredataset.ScoreDataset(all_points_num, root, tag, ...)
+    lists and np.load(..., allow_pickle=True)'s (scoredataset.py:37-62): split "training_data" feeds the train / validate
+    tags (80 / 20 %), "training_data_test" the test tag."""
     import os
     import pickle
-    out = os.path.join(root, "training_data")
+    out = os.path.join(root, split)
     os.makedirs(out, exist_ok=True)
     paths = []
     for i in range(n_scenes):

@@ -4,6 +4,8 @@ The CUDA operators cannot run here, so the module wiring is exercised with the C
 `function.pn2_ext` -- the oracle is the checker's stand-in for the kernels, the modules under test are the
 product's.  Outputs are compared with fixtures produced by the reference's own modules."""
 import math
+import os
+import sys
 
 import numpy as np
 import pytest
@@ -413,3 +415,18 @@ def test_grasp_label_encoding_round_trips_through_the_decoder():
     assert torch.equal(c2, centre) and torch.equal(s2.view(-1), score.view(-1))
     # the closing-box crop of the refine stage uses the same frame (rows instead of columns)
     assert torch.allclose(closing_box_frame(label[:, :8]), frame.transpose(1, 2), atol=2e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
+def test_reference_train_py_runs_unchanged_on_the_dropin():
+    """The acceptance criterion of the drop-in, as far as it can be exercised without a GPU: the reference's own
+    train.py --mode pretrain_score (file untouched, run in a subprocess by scripts/dryrun_reference_train.py) completes an
+    epoch of training + validation on a synthetic data set with every `multi_model.*` / `pn2_ext` / third-party import
+    resolving to this repository, and saves a model whose class is this repository's ScoreNetwork."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "dryrun_reference_train.py")], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "dry run ok: pretrain_score" in r.stdout and "regnet_for_3d_grasping_b200.score_network.ScoreNetwork" in r.stdout
+    assert r.stdout.count("train Epoch: 0") == 2 and "validate Epoch: 0" in r.stdout
