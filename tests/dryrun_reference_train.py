@@ -1,6 +1,6 @@
 """Build-container check that the reference's OWN train.py runs on top of this repository's drop-in surfaces:
 
-    python scripts/dryrun_reference_train.py [pretrain_score]
+    python tests/dryrun_reference_train.py [pretrain_score]
 
 runs /root/reference/train.py --mode pretrain_score (unmodified file, executed with runpy) for one epoch on a synthetic
 data set, with `dropin/` ahead of the reference on sys.path, so that `multi_model.*`, `pn2_ext`,
@@ -18,7 +18,7 @@ import time
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repository root
 REF = "/root/reference"
 
 

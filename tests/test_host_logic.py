@@ -420,12 +420,12 @@ def test_grasp_label_encoding_round_trips_through_the_decoder():
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
 def test_reference_train_py_runs_unchanged_on_the_dropin():
     """The acceptance criterion of the drop-in, as far as it can be exercised without a GPU: the reference's own
-    train.py --mode pretrain_score (file untouched, run in a subprocess by scripts/dryrun_reference_train.py) completes an
+    train.py --mode pretrain_score (file untouched, run in a subprocess by tests/dryrun_reference_train.py) completes an
     epoch of training + validation on a synthetic data set with every `multi_model.*` / `pn2_ext` / third-party import
     resolving to this repository, and saves a model whose class is this repository's ScoreNetwork."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "dryrun_reference_train.py")], capture_output=True,
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "dryrun_reference_train.py")], capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "dry run ok: pretrain_score" in r.stdout and "regnet_for_3d_grasping_b200.score_network.ScoreNetwork" in r.stdout
