@@ -261,6 +261,52 @@ int regnet_bn_relu_max64_train_backward(const float* dout, const uint8_t* argmax
 int regnet_maxpool64_forward(const float* x, int64_t rows, float* out, uint8_t* argmax, void* stream);
 int regnet_maxpool64_backward(const float* dout, const uint8_t* argmax, int64_t rows, float* dx, void* stream);
 
+/* ---- 3c. training-path 1x1 convolutions on the tcgen05 engine (csrc/conv_train.cu) -------------------------------------
+ * Replace what torch runs for nn.Conv1d / nn.Conv2d(kernel 1, bias=False) inside nn/modules/conv.py:24-36,64-76 in train
+ * mode -- the cuDNN / cutlass forward, dgrad and wgrad kernels -- in torch's own (B, C, L) layout (L = M*K for 2-D blocks).
+ * Operands are bf16 hi/lo PLANES (x ~= hi + lo, what regnet_split_planes / regnet_bn_apply_ex / regnet_bn_backward_ex
+ * write): passes = 3 issues hi*hi + lo*hi + hi*lo (fp32 parity, ~1e-5), passes = 1 issues hi*hi only (plain bf16).
+ * hi / lo arguments are device pointers to bf16 arrays of the stated shape. */
+
+/* x (n) fp32 -> hi, lo (n) bf16. */
+int regnet_split_planes(const float* x, int64_t n, void* hi, void* lo, void* stream);
+/* W (rows, cols) fp32 row-major -> planes (rows, ld_out), or with transpose != 0 the planes of W^T (cols, ld_out);
+ * zero padded, ld_out a multiple of 8.  (A conv weight (cout, cin, 1[, 1]) is W with rows = cout, cols = cin.) */
+int regnet_split_weight(const float* W, int rows, int cols, int transpose, int ld_out, void* hi, void* lo, void* stream);
+/* out[b, r, l] = sum_k A[r, k] x[b, k, l]:  x planes (B, K, L), A planes (rows, lda) with K valid columns, out (B, rows, L)
+ * fp32.  fprop: A = W (rows = cout, K = cin); dgrad: A = W^T (rows = cin, K = cout) and x = the output gradient.
+ * moments (nullable): (rows, 2) doubles receiving per-row sum and sum of squares of `out` over (b, l) -- the batch
+ * statistics BatchNorm needs, accumulated in the epilogue (zeroed by this call).  L % 8 == 0, lda % 8 == 0. */
+int regnet_conv1x1_train(const void* x_hi, const void* x_lo, int B, int K, int64_t L, const void* a_hi, const void* a_lo,
+                         int rows, int lda, float* out, double* moments, int passes, void* stream);
+/* dW[co, ci] = sum_{b,l} g[b, co, l] x[b, ci, l]: g planes (B, Co, L), x planes (B, Ci, L), dW (Co, Ci) fp32 (overwritten).
+ * Split-K over (b, l) across the SMs, partial tiles reduced in a fixed order (deterministic).
+ * workspace: regnet_conv1x1_wgrad_workspace_bytes(B, Co, Ci, L) bytes of device scratch. */
+int64_t regnet_conv1x1_wgrad_workspace_bytes(int B, int Co, int Ci, int64_t L);
+int regnet_conv1x1_train_wgrad(const void* g_hi, const void* g_lo, const void* x_hi, const void* x_lo, int B, int Co,
+                               int Ci, int64_t L, float* dW, void* workspace, int64_t workspace_bytes, int passes,
+                               void* stream);
+/* BatchNorm (batch statistics) pieces for the chained MLP: statistics from the convolution's moments; apply with the
+ * result as fp32 (y) and / or planes (y_hi, y_lo) and an optional dropout (F.dropout of nn/modules/mlp.py:101-105: a
+ * counter-based mask regenerated from drop_seed in the backward, keep probability 1 - drop_p, kept values scaled by
+ * 1 / (1 - drop_p)); backward with the gradient w.r.t. the convolution output as fp32 (dz) and / or planes. */
+int regnet_bn_finalize_moments(const double* moments, int C, double count, const float* gamma, const float* beta, float eps,
+                               float momentum, float* running_mean, float* running_var, float* save_mean,
+                               float* save_invstd, float* scale, float* shift, void* stream);
+int regnet_bn_apply_ex(const float* z, int B, int C, int64_t L, const float* scale, const float* shift, int relu,
+                       float drop_p, uint64_t drop_seed, float* y, void* y_hi, void* y_lo, void* stream);
+int regnet_bn_backward_ex(const float* dy, const float* z, int B, int C, int64_t L, const float* save_mean,
+                          const float* save_invstd, const float* scale, const float* shift, int relu, float drop_p,
+                          uint64_t drop_seed, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+/* the pooled block with given statistics: out[b,c,m] = max_k [relu](fma(z[b,c,m,k], scale, shift)), and its backward */
+int regnet_bn_apply_max64(const float* z, int B, int C, int64_t M, const float* scale, const float* shift, int relu,
+                          float* out, uint8_t* argmax, void* stream);
+int regnet_bn_max64_backward_ex(const float* dout, const uint8_t* argmax, const float* z, int B, int C, int64_t M,
+                                const float* save_mean, const float* save_invstd, const float* scale, const float* shift,
+                                int relu, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta, void* workspace,
+                                int64_t workspace_bytes, void* stream);
+
 /* ---- 4. building blocks exposed for tests / micro-benchmarks ------------------------------------------- */
 
 /* Y = act(scale * (X W^T) + shift), X (P,cin) fp32 row-major, W (cout,cin) fp32 row-major.

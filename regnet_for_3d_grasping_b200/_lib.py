@@ -64,6 +64,22 @@ _SIGNATURES = {
                                                    c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "regnet_bn_relu_max64_train_backward": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
                                                     c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "regnet_split_planes": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "regnet_split_weight": (c_int, [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "regnet_conv1x1_train": (c_int, [c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_int,
+                                     c_ptr]),
+    "regnet_conv1x1_wgrad_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_i64]),
+    "regnet_conv1x1_train_wgrad": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_i64, c_ptr, c_ptr, c_i64,
+                                           c_int, c_ptr]),
+    "regnet_bn_finalize_moments": (c_int, [c_ptr, c_int, ctypes.c_double, c_ptr, c_ptr, c_f32, c_f32, c_ptr, c_ptr, c_ptr,
+                                           c_ptr, c_ptr, c_ptr, c_ptr]),
+    "regnet_bn_apply_ex": (c_int, [c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_int, c_f32, ctypes.c_uint64, c_ptr, c_ptr,
+                                   c_ptr, c_ptr]),
+    "regnet_bn_backward_ex": (c_int, [c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32,
+                                      ctypes.c_uint64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "regnet_bn_apply_max64": (c_int, [c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
+    "regnet_bn_max64_backward_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
+                                            c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "regnet_maxpool64_forward": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "regnet_maxpool64_backward": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "regnet_select_score_center_workspace": (c_i64, [c_int, c_int, c_int]),

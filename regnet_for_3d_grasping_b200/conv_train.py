@@ -1,0 +1,286 @@
+"""Training-path shared MLP on this repo's tensor-core engine (csrc/conv_train.cu + csrc/train_ops.cu).
+
+Mirrors what torch executes for the reference's SharedMLP in train mode
+(multi_model/utils/pn2_utils/nn/modules/mlp.py:95-106 over nn/modules/conv.py:24-36,64-76: 1x1 conv without bias ->
+BatchNorm with batch statistics -> ReLU [-> dropout], and for set-abstraction modules the max over the 64 neighbours of
+modules.py:245), forward and backward, as ONE autograd function per MLP:
+
+  forward   per block: Z = W x on tcgen05 (operands as bf16 hi/lo planes, the batch moments of Z accumulated in the GEMM
+            epilogue) -> statistics -> y = dropout(relu(bn(Z))) written directly as the next block's planes
+  backward  per block: (dy, Z) -> dZ planes (+ dgamma, dbeta) -> dW = dZ x^T (split-K wgrad), dx = W^T dZ (dgrad)
+
+No cuDNN / cuBLAS kernel runs on this path.  `passes` selects the arithmetic: 3 = split-bf16 (fp32 parity, default),
+1 = plain bf16 (REGNET_TRAIN_PASSES=1)."""
+import os
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return _lib.current_stream_ptr()
+
+
+def default_passes():
+    return 1 if os.environ.get("REGNET_TRAIN_PASSES", "3") == "1" else 3
+
+
+def enabled():
+    """REGNET_TRAIN_TORCH=1 keeps torch's modules; REGNET_TRAIN_CONV_TORCH=1 keeps only the convolutions on torch."""
+    return os.environ.get("REGNET_TRAIN_TORCH", "0") != "1" and os.environ.get("REGNET_TRAIN_CONV_TORCH", "0") != "1"
+
+
+def _round8(n):
+    return (n + 7) // 8 * 8
+
+
+# ---- thin wrappers over the C ABI ------------------------------------------------------------------------------------
+def split_planes(x):
+    """fp32 tensor -> (hi, lo) bf16 tensors of the same shape with x ~= hi + lo."""
+    x = x.contiguous()
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().regnet_split_planes(_p(x), x.numel(), _p(hi), _p(lo), _stream()))
+    return hi, lo
+
+
+def split_weight(w2d, transpose=False):
+    """(rows, cols) fp32 -> planes (rows, ld) or, transposed, (cols, ld); ld = columns rounded up to 8, zero padded."""
+    w2d = w2d.contiguous()
+    rows, cols = w2d.shape
+    out_rows, out_cols = (cols, rows) if transpose else (rows, cols)
+    ld = _round8(out_cols)
+    hi = torch.empty(out_rows, ld, dtype=torch.bfloat16, device=w2d.device)
+    lo = torch.empty(out_rows, ld, dtype=torch.bfloat16, device=w2d.device)
+    with torch.cuda.device(w2d.device):
+        _lib.check(_lib.load().regnet_split_weight(_p(w2d), rows, cols, int(transpose), ld, _p(hi), _p(lo), _stream()))
+    return hi, lo
+
+
+def conv1x1(x_hi, x_lo, a_hi, a_lo, rows, K, want_moments=False, passes=3):
+    """out[b, r, l] = sum_k A[r, k] x[b, k, l] for x planes (B, K, L) -> fp32 (B, rows, L) [, moments (rows, 2) fp64]."""
+    B, Kx, L = x_hi.shape
+    assert Kx == K and a_hi.shape[0] == rows and a_hi.shape[1] >= K
+    out = torch.empty(B, rows, L, dtype=torch.float32, device=x_hi.device)
+    moments = torch.empty(rows, 2, dtype=torch.float64, device=x_hi.device) if want_moments else None
+    with torch.cuda.device(x_hi.device):
+        _lib.check(_lib.load().regnet_conv1x1_train(_p(x_hi), _p(x_lo), B, K, L, _p(a_hi), _p(a_lo), rows, a_hi.shape[1],
+                                                    _p(out), _p(moments), passes, _stream()))
+    return (out, moments) if want_moments else out
+
+
+def wgrad(g_hi, g_lo, x_hi, x_lo, passes=3):
+    """dW[co, ci] = sum_{b,l} g[b, co, l] x[b, ci, l] for planes (B, Co, L), (B, Ci, L) -> fp32 (Co, Ci)."""
+    B, Co, L = g_hi.shape
+    Ci = x_hi.shape[1]
+    lib = _lib.load()
+    dW = torch.empty(Co, Ci, dtype=torch.float32, device=g_hi.device)
+    with torch.cuda.device(g_hi.device):
+        nbytes = int(lib.regnet_conv1x1_wgrad_workspace_bytes(B, Co, Ci, L))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=g_hi.device)
+        _lib.check(lib.regnet_conv1x1_train_wgrad(_p(g_hi), _p(g_lo), _p(x_hi), _p(x_lo), B, Co, Ci, L, _p(dW), _p(ws),
+                                                  nbytes, passes, _stream()))
+    return dW
+
+
+def _bn_ws(lib, B, C, L, device):
+    nbytes = int(lib.regnet_bn_workspace_bytes(B, C, L))
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+# ---- the chained MLP ---------------------------------------------------------------------------------------------------
+class _Spec:
+    """Static description of one chain call (not a tensor: passed to the autograd function as a plain object)."""
+
+    def __init__(self, blocks, pooled, dropout_p, passes, seeds):
+        self.bns = [b.bn for b in blocks]
+        self.relu = [b.relu is not None for b in blocks]
+        self.pooled = pooled
+        self.dropout_p = float(dropout_p)
+        self.passes = passes
+        self.seeds = seeds          # one dropout seed per block (unused when dropout_p == 0)
+
+
+class _MLPChainTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, spec, *params):
+        n = len(spec.bns)
+        weights, gammas, betas = params[:n], params[n:2 * n], params[2 * n:3 * n]
+        lib = _lib.load()
+        dev = x.device
+        shape = x.shape
+        B, C0 = shape[0], shape[1]
+        L = x.numel() // max(B * C0, 1)
+        x3 = x.contiguous().view(B, C0, L)
+        saved = []
+        with torch.cuda.device(dev):
+            hi, lo = split_planes(x3)
+            out = None
+            arg = None
+            for i in range(n):
+                w = weights[i]
+                cout, cin = w.shape[0], w.shape[1]
+                a_hi, a_lo = split_weight(w.reshape(cout, cin))
+                z, moments = conv1x1(hi, lo, a_hi, a_lo, cout, cin, want_moments=True, passes=spec.passes)
+                bn = spec.bns[i]
+                stats = torch.empty(4, cout, dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
+                _lib.check(lib.regnet_bn_finalize_moments(
+                    _p(moments), cout, float(B) * float(L), _p(gammas[i]), _p(betas[i]), float(bn.eps), float(bn.momentum),
+                    _p(bn.running_mean), _p(bn.running_var), _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
+                    _stream()))
+                saved += [hi, lo, z, stats]
+                last = i == n - 1
+                if last and spec.pooled:
+                    M = L // 64
+                    out = torch.empty(B, cout, M, dtype=torch.float32, device=dev)
+                    arg = torch.empty(B, cout, M, dtype=torch.uint8, device=dev)
+                    _lib.check(lib.regnet_bn_apply_max64(_p(z), B, cout, M, _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
+                                                         _p(out), _p(arg), _stream()))
+                elif last:
+                    out = torch.empty(B, cout, L, dtype=torch.float32, device=dev)
+                    _lib.check(lib.regnet_bn_apply_ex(_p(z), B, cout, L, _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
+                                                      spec.dropout_p, spec.seeds[i], _p(out), None, None, _stream()))
+                else:
+                    hi = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
+                    lo = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
+                    _lib.check(lib.regnet_bn_apply_ex(_p(z), B, cout, L, _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
+                                                      spec.dropout_p, spec.seeds[i], None, _p(hi), _p(lo), _stream()))
+        ctx.spec = spec
+        ctx.n = n
+        ctx.in_shape = shape
+        ctx.L = L
+        ctx.save_for_backward(*(list(weights) + saved + ([arg] if arg is not None else [])))
+        if spec.pooled:
+            return out.view(B, out.shape[1], shape[2])
+        return out.view((B, out.shape[1]) + tuple(shape[2:]))
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, n, L = ctx.spec, ctx.n, ctx.L
+        tensors = ctx.saved_tensors
+        weights = tensors[:n]
+        saved = tensors[n:n + 4 * n]
+        arg = tensors[n + 4 * n] if spec.pooled else None
+        lib = _lib.load()
+        dev = dout.device
+        B = ctx.in_shape[0]
+        dws, dgs, dbs = [None] * n, [None] * n, [None] * n
+        dy = dout.contiguous()
+        with torch.cuda.device(dev):
+            for i in range(n - 1, -1, -1):
+                hi, lo, z, stats = saved[4 * i:4 * i + 4]
+                w = weights[i]
+                cout, cin = w.shape[0], w.shape[1]
+                g_hi = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
+                g_lo = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
+                dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
+                dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
+                ws, nbytes = _bn_ws(lib, B, cout, L, dev)
+                if i == n - 1 and spec.pooled:
+                    _lib.check(lib.regnet_bn_max64_backward_ex(
+                        _p(dy), _p(arg), _p(z), B, cout, L // 64, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
+                        int(spec.relu[i]), None, _p(g_hi), _p(g_lo), _p(dgamma), _p(dbeta), _p(ws), nbytes, _stream()))
+                else:
+                    _lib.check(lib.regnet_bn_backward_ex(
+                        _p(dy), _p(z), B, cout, L, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
+                        int(spec.relu[i]), spec.dropout_p, spec.seeds[i], None, _p(g_hi), _p(g_lo), _p(dgamma), _p(dbeta),
+                        _p(ws), nbytes, _stream()))
+                dgs[i], dbs[i] = dgamma, dbeta
+                if ctx.needs_input_grad[2 + i]:
+                    dws[i] = wgrad(g_hi, g_lo, hi, lo, passes=spec.passes).view(w.shape)
+                if i > 0 or ctx.needs_input_grad[0]:
+                    t_hi, t_lo = split_weight(w.reshape(cout, cin), transpose=True)
+                    dy = conv1x1(g_hi, g_lo, t_hi, t_lo, cin, cout, passes=spec.passes)
+                else:
+                    dy = None
+                del g_hi, g_lo
+        dx = dy.view(ctx.in_shape) if dy is not None else None
+        return (dx, None) + tuple(dws) + tuple(dgs) + tuple(dbs)
+
+
+def chain_supported(mlp, x):
+    """The chained path takes fp32 CUDA tensors whose per-entry position count is a multiple of 8, blocks of
+    1x1 conv (no bias) + affine BatchNorm with running statistics."""
+    if not (enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() in (3, 4) and x.numel() > 0):
+        return False
+    B, C = x.size(0), x.size(1)
+    L = x.numel() // (B * C)
+    if L % 8 != 0 or B * L <= 1 or B > 1023:
+        return False
+    if mlp.dropout_prob > 0.0 and mlp.ndim != 1:     # F.dropout2d drops whole channels: not the fused element mask
+        return False
+    for blk in mlp:
+        bn, conv = blk.bn, blk.conv
+        if bn is None or conv.bias is not None or not (bn.training and bn.affine and bn.track_running_stats):
+            return False
+        if bn.momentum is None or any(k != 1 for k in conv.kernel_size) or B * conv.out_channels > 65535:
+            return False
+    return True
+
+
+def mlp_chain_train(mlp, x, pooled):
+    """SharedMLP.forward (pooled=False) or torch.max(SharedMLP.forward(x), 3)[0] (pooled=True) in train mode."""
+    blocks = list(mlp)
+    p = float(mlp.dropout_prob) if mlp.training else 0.0
+    seeds = [int(s) for s in torch.randint(0, 2 ** 62, (len(blocks),))] if p > 0.0 else [0] * len(blocks)
+    spec = _Spec(blocks, pooled, p, default_passes(), seeds)
+    params = [b.conv.weight for b in blocks] + [b.bn.weight for b in blocks] + [b.bn.bias for b in blocks]
+    y = _MLPChainTrain.apply(x, spec, *params)
+    for b in blocks:
+        if b.bn.num_batches_tracked is not None:
+            b.bn.num_batches_tracked.add_(1)
+    return y
+
+
+class _Conv1x1Train(torch.autograd.Function):
+    """A lone 1x1 convolution (optionally with bias) on the same engine: nn.Conv1d(k=1) of pointnet2.py:82 (conv_score)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, passes):
+        B, C, L = x.shape
+        cout = weight.shape[0]
+        with torch.cuda.device(x.device):
+            hi, lo = split_planes(x)
+            a_hi, a_lo = split_weight(weight.reshape(cout, C))
+            y = conv1x1(hi, lo, a_hi, a_lo, cout, C, passes=passes)
+        if bias is not None:
+            y += bias.view(1, cout, 1)
+        ctx.save_for_backward(hi, lo, weight)
+        ctx.has_bias = bias is not None
+        ctx.passes = passes
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        hi, lo, weight = ctx.saved_tensors
+        cout, C = weight.shape[0], weight.shape[1]
+        dy = dy.contiguous()
+        dx = dw = db = None
+        with torch.cuda.device(dy.device):
+            g_hi, g_lo = split_planes(dy)
+            if ctx.needs_input_grad[1]:
+                dw = wgrad(g_hi, g_lo, hi, lo, passes=ctx.passes).view(weight.shape)
+            if ctx.needs_input_grad[0]:
+                t_hi, t_lo = split_weight(weight.reshape(cout, C), transpose=True)
+                dx = conv1x1(g_hi, g_lo, t_hi, t_lo, C, cout, passes=ctx.passes)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=(0, 2))
+        return dx, dw, db, None
+
+
+def conv1x1_supported(conv, x):
+    return (enabled() and x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.numel() > 0
+            and x.size(2) % 8 == 0 and tuple(conv.kernel_size) == (1,) and tuple(conv.stride) == (1,)
+            and conv.groups == 1)
+
+
+def conv1x1_train(conv, x):
+    """conv(x) for an nn.Conv1d with kernel size 1, through the tcgen05 engine (autograd-aware)."""
+    return _Conv1x1Train.apply(x.contiguous(), conv.weight, conv.bias, default_passes())

@@ -63,6 +63,8 @@ int gemm_tc_gather_launch(const __nv_bfloat16* Thi, const __nv_bfloat16* Tlo, in
 // box_rows, swizzle_bytes in {64, 128}.  CUtensorMap is passed opaquely so that this header needs no <cuda.h>.
 int tc_make_map(::CUtensorMap_st* map, const void* base, int64_t rows, int cols, int ld, int box_rows, int box_cols,
                 int swizzle_bytes);
+int tc_make_map3(::CUtensorMap_st* map, const void* base, int elem_bytes, int64_t d0, int64_t d1, int64_t d2,
+                 int64_t stride1, int64_t stride2, int box0, int box1);
 int tc_driver_ok(void);  // 1 when the driver entry point for tensor maps is available on this box
 
 }  // namespace regnet

@@ -477,6 +477,36 @@ int tc_make_map(CUtensorMap* map, const void* base, int64_t rows, int cols, int 
 
 int tc_driver_ok(void) { return encode_fn() != nullptr; }
 
+// 3-D map over a (d2, d1, d0) array with d0 contiguous (torch's (B, C, L) tensors: d0 = L, d1 = C, d2 = B);
+// box = box0 x box1 x 1, SWIZZLE_128B when box0 * elem_bytes == 128, otherwise no swizzle.
+int tc_make_map3(CUtensorMap* map, const void* base, int elem_bytes, int64_t d0, int64_t d1, int64_t d2, int64_t stride1,
+                 int64_t stride2, int box0, int box1) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("tc_make_map3: cuTensorMapEncodeTiled is not available from this driver");
+    return REGNET_ECUDA;
+  }
+  RN_CHECK_ARG(elem_bytes == 2 || elem_bytes == 4, "tc_make_map3: element size %d", elem_bytes);
+  RN_CHECK_ARG((stride1 * elem_bytes) % 16 == 0 && (stride2 * elem_bytes) % 16 == 0 &&
+                   (reinterpret_cast<uintptr_t>(base) & 15) == 0,
+               "tc_make_map3: rows must start on 16-byte boundaries (innermost extent %lld x %d bytes)", (long long)stride1,
+               elem_bytes);
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)stride1 * elem_bytes, (cuuint64_t)stride2 * elem_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle swz = box0 * elem_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tc_make_map3: cuTensorMapEncodeTiled failed with CUresult %d (dims %lld x %lld x %lld)", (int)r, (long long)d0,
+              (long long)d1, (long long)d2);
+    return REGNET_ECUDA;
+  }
+  return REGNET_OK;
+}
+
 namespace {
 
 

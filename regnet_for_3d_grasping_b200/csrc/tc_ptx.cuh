@@ -70,6 +70,18 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -166,6 +178,20 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major, SWIZZLE_128B operand (cute UMMA canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), T = 8 bf16): the MN
+// extent is contiguous in memory, 64 elements (128 bytes) per row; 8 consecutive k rows form one 1024-byte swizzle
+// atom (SBO = distance between 8-row k groups), 64-element MN chunks are LBO bytes apart.  That is exactly what TMA
+// writes for a {64 (MN, contiguous), kb rows} box with CU_TENSOR_MAP_SWIZZLE_128B: SBO = 1024, LBO = kb * 128.
+// One K = 16 instruction consumes two k groups, so the k-step advance of the start address is 2048 bytes.
+__device__ __forceinline__ uint64_t make_sdesc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // K-major operand with 32-byte rows (K = 16 bf16): the canonical SWIZZLE_32B layout ((8,n),2):((2,SBO),1) in 16-byte
 // units -- row r at r * 32 bytes, 16-byte chunk index XOR bit 2 of the row, 8-row groups SBO = 256 bytes apart.
 // (The un-swizzled "interleave" layout with LBO = 128 B was verified to work as well during bring-up.)
@@ -186,6 +212,8 @@ __device__ __forceinline__ uint64_t make_sdesc_k16(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+constexpr uint32_t IDESC_A_MN_MAJOR = 1u << 15;   // a_major_ / b_major_ bits: 0 = K-major, 1 = MN-major
+constexpr uint32_t IDESC_B_MN_MAJOR = 1u << 16;
 
 // ---- 64-row max-pool of an accumulator tile -------------------------------------------------------------------
 // tcgen05.ld.16x256b.x4: the warp reads 16 TMEM lanes x 32 columns; thread t receives, for each 8-column group i,

@@ -378,6 +378,200 @@ bn_max64_bwd_apply_kernel(const float* __restrict__ dout, const uint8_t* __restr
   }
 }
 
+
+// ---- fused-chain variants (conv_train.cu produces Z and its moments; the MLP chain keeps activations as bf16 planes) ------
+// Dropout (nn/modules/mlp.py:101-105: F.dropout after every block of the seg MLP) is a counter-based mask: element 4i..4i+3
+// of the tensor take 16 bits each of splitmix64(i, seed), so forward and backward regenerate the same mask from the seed
+// and no mask tensor exists.
+__device__ __forceinline__ uint64_t drop_bits(uint64_t i, uint64_t seed) {
+  uint64_t z = i + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// keep-or-zero multipliers of the four elements of vector i: keep when the 16-bit draw is >= thr = round(p * 65536)
+__device__ __forceinline__ float4 drop_mult(uint64_t i, uint64_t seed, uint32_t thr, float inv_keep) {
+  const uint64_t r = drop_bits(i, seed);
+  float4 m;
+  m.x = (uint32_t)(r & 0xffff) >= thr ? inv_keep : 0.f;
+  m.y = (uint32_t)((r >> 16) & 0xffff) >= thr ? inv_keep : 0.f;
+  m.z = (uint32_t)((r >> 32) & 0xffff) >= thr ? inv_keep : 0.f;
+  m.w = (uint32_t)(r >> 48) >= thr ? inv_keep : 0.f;
+  return m;
+}
+
+struct DropCfg {
+  uint64_t seed;
+  uint32_t thr;     // 0 = no dropout
+  float inv_keep;
+};
+
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t i, float4 v) {
+  __nv_bfloat16 h[4], l[4];
+  split_bf16(v.x, h[0], l[0]);
+  split_bf16(v.y, h[1], l[1]);
+  split_bf16(v.z, h[2], l[2]);
+  split_bf16(v.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<uint2*>(l);
+}
+
+// per-channel (sum, sum of squares) in fp64 -> mean / invstd / scale / shift + running statistics (as bn_finalize_kernel)
+__global__ void __launch_bounds__(128)
+bn_finalize_moments_kernel(const double* __restrict__ moments, int C, double count, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                           float* __restrict__ running_var, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                           float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  const double mean = moments[2 * c] / count;
+  const double var = fmax(moments[2 * c + 1] / count - mean * mean, 0.0);
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float mu = (float)mean;
+  save_mean[c] = mu;
+  save_invstd[c] = invstd;
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  const float sc = g * invstd;
+  scale[c] = sc;
+  shift[c] = fmaf(-mu, sc, bt);
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
+  if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * count / fmax(count - 1.0, 1.0));
+}
+
+// y = dropout([relu](fma(z, scale, shift))) written as fp32 and / or as bf16 hi/lo planes
+template <bool RELU, bool DROP>
+__global__ void __launch_bounds__(TB)
+bn_apply_ex_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, int C,
+                   int64_t L, DropCfg dc, float* __restrict__ y, __nv_bfloat16* __restrict__ hi,
+                   __nv_bfloat16* __restrict__ lo) {
+  const int bc = blockIdx.y, c = bc % C;
+  const float sc = scale[c], sh = shift[c];
+  const int64_t base = (int64_t)bc * L;
+  for (int64_t l = ((int64_t)blockIdx.x * TB + threadIdx.x) * 4; l < L; l += (int64_t)gridDim.x * TB * 4) {
+    float4 v = *reinterpret_cast<const float4*>(x + base + l);
+    v.x = fmaf(v.x, sc, sh); v.y = fmaf(v.y, sc, sh); v.z = fmaf(v.z, sc, sh); v.w = fmaf(v.w, sc, sh);
+    if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (DROP) {
+      const float4 m = drop_mult((uint64_t)(base + l) >> 2, dc.seed, dc.thr, dc.inv_keep);
+      v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    }
+    if (y) *reinterpret_cast<float4*>(y + base + l) = v;
+    if (hi) store_planes4(hi, lo, base + l, v);
+  }
+}
+
+template <bool RELU, bool DROP>
+__global__ void __launch_bounds__(TB)
+bn_bwd_reduce_ex_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ save_mean,
+                        const float* __restrict__ save_invstd, const float* __restrict__ scale,
+                        const float* __restrict__ shift, int C, int64_t L, int64_t chunk, int sl, DropCfg dc,
+                        float* __restrict__ partial) {
+  const int c = blockIdx.x, b = blockIdx.y / sl, s = blockIdx.y % sl;
+  const int64_t l0 = (int64_t)s * chunk, l1 = min(L, l0 + chunk);
+  const int64_t base = ((int64_t)b * C + c) * L;
+  const float mu = save_mean[c], is = save_invstd[c], sc = scale[c], sh = shift[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t l = l0 + (int64_t)threadIdx.x * 4; l < l1; l += TB * 4) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + base + l);
+    float4 g = *reinterpret_cast<const float4*>(dy + base + l);
+    if (DROP) {
+      const float4 m = drop_mult((uint64_t)(base + l) >> 2, dc.seed, dc.thr, dc.inv_keep);
+      g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+    }
+    if (RELU) {
+      g.x = fmaf(xv.x, sc, sh) > 0.f ? g.x : 0.f; g.y = fmaf(xv.y, sc, sh) > 0.f ? g.y : 0.f;
+      g.z = fmaf(xv.z, sc, sh) > 0.f ? g.z : 0.f; g.w = fmaf(xv.w, sc, sh) > 0.f ? g.w : 0.f;
+    }
+    s1 += (g.x + g.y) + (g.z + g.w);
+    s2 = fmaf(g.x, (xv.x - mu) * is, fmaf(g.y, (xv.y - mu) * is, fmaf(g.z, (xv.z - mu) * is, fmaf(g.w, (xv.w - mu) * is, s2))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(FULL, s1, o);
+    s2 += __shfl_xor_sync(FULL, s2, o);
+  }
+  __shared__ float sh1[TB / 32], sh2[TB / 32];
+  if ((threadIdx.x & 31) == 0) { sh1[threadIdx.x >> 5] = s1; sh2[threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, bsum = 0.f;
+    for (int i = 0; i < TB / 32; ++i) { a += sh1[i]; bsum += sh2[i]; }
+    float* o = partial + ((int64_t)c * gridDim.y + blockIdx.y) * 2;
+    o[0] = a; o[1] = bsum;
+  }
+}
+
+template <bool RELU, bool DROP>
+__global__ void __launch_bounds__(TB)
+bn_bwd_apply_ex_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ save_mean,
+                       const float* __restrict__ save_invstd, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const float* __restrict__ k1, const float* __restrict__ k2, int C,
+                       int64_t L, DropCfg dc, float* __restrict__ dx, __nv_bfloat16* __restrict__ dhi,
+                       __nv_bfloat16* __restrict__ dlo) {
+  const int bc = blockIdx.y, c = bc % C;
+  const float mu = save_mean[c], is = save_invstd[c], sc = scale[c], sh = shift[c], m1 = k1[c], m2 = k2[c];
+  const int64_t base = (int64_t)bc * L;
+  for (int64_t l = ((int64_t)blockIdx.x * TB + threadIdx.x) * 4; l < L; l += (int64_t)gridDim.x * TB * 4) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + base + l);
+    float4 g = *reinterpret_cast<const float4*>(dy + base + l);
+    if (DROP) {
+      const float4 m = drop_mult((uint64_t)(base + l) >> 2, dc.seed, dc.thr, dc.inv_keep);
+      g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+    }
+    if (RELU) {
+      g.x = fmaf(xv.x, sc, sh) > 0.f ? g.x : 0.f; g.y = fmaf(xv.y, sc, sh) > 0.f ? g.y : 0.f;
+      g.z = fmaf(xv.z, sc, sh) > 0.f ? g.z : 0.f; g.w = fmaf(xv.w, sc, sh) > 0.f ? g.w : 0.f;
+    }
+    float4 o;
+    o.x = sc * (g.x - m1 - (xv.x - mu) * is * m2);
+    o.y = sc * (g.y - m1 - (xv.y - mu) * is * m2);
+    o.z = sc * (g.z - m1 - (xv.z - mu) * is * m2);
+    o.w = sc * (g.w - m1 - (xv.w - mu) * is * m2);
+    if (dx) *reinterpret_cast<float4*>(dx + base + l) = o;
+    if (dhi) store_planes4(dhi, dlo, base + l, o);
+  }
+}
+
+// pooled block, backward pass 2 with the gradient written as planes (and / or fp32)
+template <bool RELU>
+__global__ void __launch_bounds__(TB)
+bn_max64_bwd_apply_ex_kernel(const float* __restrict__ dout, const uint8_t* __restrict__ arg, const float* __restrict__ x,
+                             const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                             const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ k1,
+                             const float* __restrict__ k2, int C, int64_t M, float* __restrict__ dx,
+                             __nv_bfloat16* __restrict__ dhi, __nv_bfloat16* __restrict__ dlo) {
+  const int bc = blockIdx.y, c = bc % C;
+  const float mu = save_mean[c], is = save_invstd[c], sc = scale[c], sh = shift[c], m1 = k1[c], m2 = k2[c];
+  const int lane16 = threadIdx.x & 15;
+  const int64_t hw = ((int64_t)blockIdx.x * TB + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * TB) >> 4;
+  for (int64_t m = hw; m < M; m += nhw) {
+    const int64_t r = (int64_t)bc * M + m;
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * 64 + lane16 * 4);
+    const float dp = dout[r];
+    const int k = (int)arg[r] - lane16 * 4;
+    float4 g;
+    g.x = (k == 0 && (!RELU || fmaf(xv.x, sc, sh) > 0.f)) ? dp : 0.f;
+    g.y = (k == 1 && (!RELU || fmaf(xv.y, sc, sh) > 0.f)) ? dp : 0.f;
+    g.z = (k == 2 && (!RELU || fmaf(xv.z, sc, sh) > 0.f)) ? dp : 0.f;
+    g.w = (k == 3 && (!RELU || fmaf(xv.w, sc, sh) > 0.f)) ? dp : 0.f;
+    float4 o;
+    o.x = sc * (g.x - m1 - (xv.x - mu) * is * m2);
+    o.y = sc * (g.y - m1 - (xv.y - mu) * is * m2);
+    o.z = sc * (g.z - m1 - (xv.z - mu) * is * m2);
+    o.w = sc * (g.w - m1 - (xv.w - mu) * is * m2);
+    if (dx) *reinterpret_cast<float4*>(dx + r * 64 + lane16 * 4) = o;
+    if (dhi) store_planes4(dhi, dlo, r * 64 + lane16 * 4, o);
+  }
+}
+
+DropCfg make_drop(float p, uint64_t seed) {
+  DropCfg dc;
+  dc.seed = seed;
+  dc.thr = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
+  dc.inv_keep = p > 0.f ? 65536.f / (float)(65536u - dc.thr) : 1.f;   // exact keep probability of the 16-bit draw
+  return dc;
+}
+
 inline unsigned apply_grid_x(int64_t L, int rows_bc) {
   int64_t gx = (L / 4 + TB - 1) / TB;
   const int64_t cap = std::max<int64_t>(1, (148LL * 16 + rows_bc - 1) / rows_bc);   // ~16 resident blocks per SM overall
@@ -504,6 +698,118 @@ int regnet_bn_relu_max64_train_backward(const float* dout, const uint8_t* argmax
   if (relu) bn_max64_bwd_apply_kernel<true><<<grid, TB, 0, s>>>(dout, argmax, x, save_mean, save_invstd, scale, shift, k1, k2, C, M, dx);
   else bn_max64_bwd_apply_kernel<false><<<grid, TB, 0, s>>>(dout, argmax, x, save_mean, save_invstd, scale, shift, k1, k2, C, M, dx);
   RN_LAUNCH_CHECK("bn_max64_bwd_apply_kernel");
+  return REGNET_OK;
+}
+
+int regnet_bn_finalize_moments(const double* moments, int C, double count, const float* gamma, const float* beta, float eps,
+                               float momentum, float* running_mean, float* running_var, float* save_mean,
+                               float* save_invstd, float* scale, float* shift, void* stream_) {
+  RN_CHECK_ARG(moments && save_mean && save_invstd && scale && shift && C > 0, "bn_finalize_moments: null argument");
+  if (count <= 1.0) {
+    set_error("Expected more than 1 value per channel when training");
+    return REGNET_EINVAL;
+  }
+  bn_finalize_moments_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(
+      moments, C, count, gamma, beta, eps, momentum, running_mean, running_var, save_mean, save_invstd, scale, shift);
+  RN_LAUNCH_CHECK("bn_finalize_moments_kernel");
+  return REGNET_OK;
+}
+
+int regnet_bn_apply_ex(const float* z, int B, int C, int64_t L, const float* scale, const float* shift, int relu,
+                       float drop_p, uint64_t drop_seed, float* y, void* y_hi, void* y_lo, void* stream_) {
+  RN_CHECK_ARG(z && scale && shift && (y || (y_hi && y_lo)), "bn_apply_ex: null argument");
+  RN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "bn_apply_ex: dropout probability %f", drop_p);
+  RN_TRY(check_shape(B, C, L));
+  cudaStream_t s = (cudaStream_t)stream_;
+  const DropCfg dc = make_drop(drop_p, drop_seed);
+  const dim3 grid(apply_grid_x(L, B * C), B * C);
+  __nv_bfloat16* hi = (__nv_bfloat16*)y_hi;
+  __nv_bfloat16* lo = (__nv_bfloat16*)y_lo;
+  if (dc.thr) {
+    if (relu) bn_apply_ex_kernel<true, true><<<grid, TB, 0, s>>>(z, scale, shift, C, L, dc, y, hi, lo);
+    else bn_apply_ex_kernel<false, true><<<grid, TB, 0, s>>>(z, scale, shift, C, L, dc, y, hi, lo);
+  } else {
+    if (relu) bn_apply_ex_kernel<true, false><<<grid, TB, 0, s>>>(z, scale, shift, C, L, dc, y, hi, lo);
+    else bn_apply_ex_kernel<false, false><<<grid, TB, 0, s>>>(z, scale, shift, C, L, dc, y, hi, lo);
+  }
+  RN_LAUNCH_CHECK("bn_apply_ex_kernel");
+  return REGNET_OK;
+}
+
+int regnet_bn_backward_ex(const float* dy, const float* z, int B, int C, int64_t L, const float* save_mean,
+                          const float* save_invstd, const float* scale, const float* shift, int relu, float drop_p,
+                          uint64_t drop_seed, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta,
+                          void* workspace, int64_t workspace_bytes, void* stream_) {
+  RN_CHECK_ARG(dy && z && save_mean && save_invstd && scale && shift && (dz || (dz_hi && dz_lo)) && dgamma && dbeta && workspace,
+               "bn_backward_ex: null argument");
+  RN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "bn_backward_ex: dropout probability %f", drop_p);
+  RN_TRY(check_shape(B, C, L));
+  RN_CHECK_ARG(workspace_bytes >= regnet_bn_workspace_bytes(B, C, L), "bn_backward_ex: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const DropCfg dc = make_drop(drop_p, drop_seed);
+  const ChunkPlan cp = plan_chunks(L);
+  const int P = B * cp.sl;
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* k1 = partial + (int64_t)C * P * 3;
+  float* k2 = k1 + C;
+  const dim3 rgrid(C, P);
+#define RN_BWD_REDUCE(R, D) \
+  bn_bwd_reduce_ex_kernel<R, D><<<rgrid, TB, 0, s>>>(dy, z, save_mean, save_invstd, scale, shift, C, L, cp.chunk, cp.sl, dc, partial)
+  if (dc.thr) { if (relu) RN_BWD_REDUCE(true, true); else RN_BWD_REDUCE(false, true); }
+  else { if (relu) RN_BWD_REDUCE(true, false); else RN_BWD_REDUCE(false, false); }
+#undef RN_BWD_REDUCE
+  RN_LAUNCH_CHECK("bn_bwd_reduce_ex_kernel");
+  bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, s>>>(partial, P, C, (double)B * (double)L, dgamma, dbeta, k1, k2);
+  RN_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  const dim3 grid(apply_grid_x(L, B * C), B * C);
+  __nv_bfloat16* hi = (__nv_bfloat16*)dz_hi;
+  __nv_bfloat16* lo = (__nv_bfloat16*)dz_lo;
+#define RN_BWD_APPLY(R, D) \
+  bn_bwd_apply_ex_kernel<R, D><<<grid, TB, 0, s>>>(dy, z, save_mean, save_invstd, scale, shift, k1, k2, C, L, dc, dz, hi, lo)
+  if (dc.thr) { if (relu) RN_BWD_APPLY(true, true); else RN_BWD_APPLY(false, true); }
+  else { if (relu) RN_BWD_APPLY(true, false); else RN_BWD_APPLY(false, false); }
+#undef RN_BWD_APPLY
+  RN_LAUNCH_CHECK("bn_bwd_apply_ex_kernel");
+  return REGNET_OK;
+}
+
+int regnet_bn_apply_max64(const float* z, int B, int C, int64_t M, const float* scale, const float* shift, int relu,
+                          float* out, uint8_t* argmax, void* stream_) {
+  RN_CHECK_ARG(z && scale && shift && out && argmax, "bn_apply_max64: null argument");
+  const int64_t L = M * 64;
+  RN_TRY(check_shape(B, C, L));
+  cudaStream_t s = (cudaStream_t)stream_;
+  const dim3 grid(apply_grid_x(L, B * C), B * C);
+  if (relu) bn_apply_max64_kernel<true><<<grid, TB, 0, s>>>(z, scale, shift, C, M, out, argmax);
+  else bn_apply_max64_kernel<false><<<grid, TB, 0, s>>>(z, scale, shift, C, M, out, argmax);
+  RN_LAUNCH_CHECK("bn_apply_max64_kernel");
+  return REGNET_OK;
+}
+
+int regnet_bn_max64_backward_ex(const float* dout, const uint8_t* argmax, const float* z, int B, int C, int64_t M,
+                                const float* save_mean, const float* save_invstd, const float* scale, const float* shift,
+                                int relu, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta, void* workspace,
+                                int64_t workspace_bytes, void* stream_) {
+  RN_CHECK_ARG(dout && argmax && z && save_mean && save_invstd && scale && shift && (dz || (dz_hi && dz_lo)) && dgamma &&
+                   dbeta && workspace, "bn_max64_backward_ex: null argument");
+  const int64_t L = M * 64;
+  RN_TRY(check_shape(B, C, L));
+  RN_CHECK_ARG(workspace_bytes >= regnet_bn_workspace_bytes(B, C, L), "bn_max64_backward_ex: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream_;
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* k1 = partial + (int64_t)C * B * plan_chunks(L).sl * 3;
+  float* k2 = k1 + C;
+  if (relu) bn_max64_bwd_reduce_kernel<true><<<dim3(C, B), TB, 0, s>>>(dout, argmax, z, save_mean, save_invstd, scale, shift, C, M, partial);
+  else bn_max64_bwd_reduce_kernel<false><<<dim3(C, B), TB, 0, s>>>(dout, argmax, z, save_mean, save_invstd, scale, shift, C, M, partial);
+  RN_LAUNCH_CHECK("bn_max64_bwd_reduce_kernel");
+  bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, s>>>(partial, B, C, (double)B * (double)L, dgamma, dbeta, k1, k2);
+  RN_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  const dim3 grid(apply_grid_x(L, B * C), B * C);
+  __nv_bfloat16* hi = (__nv_bfloat16*)dz_hi;
+  __nv_bfloat16* lo = (__nv_bfloat16*)dz_lo;
+  if (relu) bn_max64_bwd_apply_ex_kernel<true><<<grid, TB, 0, s>>>(dout, argmax, z, save_mean, save_invstd, scale, shift, k1, k2, C, M, dz, hi, lo);
+  else bn_max64_bwd_apply_ex_kernel<false><<<grid, TB, 0, s>>>(dout, argmax, z, save_mean, save_invstd, scale, shift, k1, k2, C, M, dz, hi, lo);
+  RN_LAUNCH_CHECK("bn_max64_bwd_apply_ex_kernel");
   return REGNET_OK;
 }
 

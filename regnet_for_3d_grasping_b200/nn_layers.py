@@ -10,7 +10,7 @@ import os
 import torch.nn.functional as F
 from torch import nn
 
-from . import train_ops
+from . import conv_train, train_ops
 
 
 def init_bn(module):
@@ -80,6 +80,9 @@ class SharedMLP(nn.ModuleList):
         self.dropout_prob = dropout_prob
 
     def forward(self, x):
+        if self.training and len(self) > 0 and conv_train.chain_supported(self, x):
+            # train mode on CUDA: the whole MLP as one autograd function on this repo's tensor-core engine (conv_train.py)
+            return conv_train.mlp_chain_train(self, x, pooled=False)
         drop = F.dropout if self.ndim == 1 else F.dropout2d
         for block in self:
             x = block(x)
@@ -91,6 +94,9 @@ class SharedMLP(nn.ModuleList):
         """torch.max(self(x), 3)[0] (modules.py:245).  In train mode on CUDA the last block's BatchNorm + ReLU and the
         max over the 64 neighbours are one pair of kernels: its (B, C, M, 64) activation is never written."""
         last = self[len(self) - 1]
+        if (self.training and self.ndim == 2 and x.dim() == 4 and x.size(3) == 64 and self.dropout_prob == 0.0
+                and conv_train.chain_supported(self, x)):
+            return conv_train.mlp_chain_train(self, x, pooled=True)
         if (self.training and self.ndim == 2 and self.dropout_prob == 0.0 and last.bn is not None and x.is_cuda
                 and os.environ.get("REGNET_TRAIN_UNFUSED_MAX", "0") != "1"):
             for i in range(len(self) - 1):

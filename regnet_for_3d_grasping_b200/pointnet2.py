@@ -13,7 +13,7 @@ caller a contiguous (B,N,256) tensor.
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, conv_train, train_ops
 from .modules import PointNetSAModule, PointnetFPModule
 from .nn_layers import SharedMLP
 from .scorenet import NUM_CENTROIDS, NUM_NEIGHBOURS, RADIUS, ScoreNetPlan
@@ -69,7 +69,13 @@ class PointNet2Seg(nn.Module):
             extra = [a.view(B, 1, N).repeat(1, c, 1).float() for a in (add_channel1, add_channel2)]
             sparse_feature = torch.cat([sparse_feature] + extra, dim=1)
         x = self.mlp(sparse_feature)
-        x_score = self.bn_score(self.conv_score(x)).transpose(2, 1).contiguous()
+        if self.training and conv_train.conv1x1_supported(self.conv_score, x):
+            s = conv_train.conv1x1_train(self.conv_score, x)      # 128 -> k_score on the tcgen05 engine (no cuDNN)
+            s = (train_ops.bn_relu_train(s, self.bn_score, False) if train_ops.bn_supported(s, self.bn_score)
+                 else self.bn_score(s))
+            x_score = s.transpose(2, 1).contiguous()
+        else:
+            x_score = self.bn_score(self.conv_score(x)).transpose(2, 1).contiguous()
         return sparse_feature, self.sigmoid(x_score).view(B, N)
 
     # -- fused path (eval) ---------------------------------------------------------------------------------------

@@ -1,0 +1,188 @@
+"""GPU parity, training-path 1x1 convolutions on the tcgen05 engine (csrc/conv_train.cu) through the C ABI, and the chained
+shared MLP built on them (conv_train.py), against torch in float64 -- the floating-point oracle for this path: the
+reference's nn/modules/conv.py:24-36,64-76 and mlp.py:95-106 are plain torch modules.
+Tolerance: 1e-4 relative (BASELINE.json north_star) for the split-bf16 arithmetic; 2e-2 for the one-pass bf16 mode."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, want):
+    return ((got.double().cpu() - want.cpu()).abs().max() / want.abs().max().clamp_min(1e-30)).item()
+
+
+FPROP_SHAPES = [(1, 64, 256, 128), (2, 6, 320, 128), (3, 259, 1280, 256), (1, 128, 1024, 1), (2, 1536, 256, 1024),
+                (2, 515, 2056, 256), (4, 128, 8192, 128)]
+
+
+@pytest.mark.parametrize("B,K,L,rows", FPROP_SHAPES)
+def test_conv1x1_forward_and_moments(lib_path, B, K, L, rows):
+    from regnet_for_3d_grasping_b200 import conv_train as ct
+    g = torch.Generator().manual_seed(B * 1000 + K + L + rows)
+    x = torch.randn(B, K, L, generator=g) + 0.3
+    w = torch.randn(rows, K, generator=g) / K ** 0.5
+    want = torch.einsum("rk,bkl->brl", w.double(), x.double())
+    hi, lo = ct.split_planes(x.cuda())
+    a_hi, a_lo = ct.split_weight(w.cuda())
+    out, mom = ct.conv1x1(hi, lo, a_hi, a_lo, rows, K, want_moments=True, passes=3)
+    assert _rel(out, want) < 1e-4
+    assert _rel(mom[:, 0], want.sum(dim=(0, 2))) < 1e-4 or want.sum(dim=(0, 2)).abs().max() < 1e-3
+    assert _rel(mom[:, 1], (want * want).sum(dim=(0, 2))) < 1e-4
+    out1 = ct.conv1x1(hi, lo, a_hi, a_lo, rows, K, passes=1)
+    assert _rel(out1, want) < 2e-2
+    # dgrad is the same kernel with the transposed weight
+    t_hi, t_lo = ct.split_weight(w.cuda(), transpose=True)
+    gz = torch.randn(B, rows, L, generator=g)
+    g_hi, g_lo = ct.split_planes(gz.cuda())
+    dx = ct.conv1x1(g_hi, g_lo, t_hi, t_lo, K, rows, passes=3)
+    assert _rel(dx, torch.einsum("rk,brl->bkl", w.double(), gz.double())) < 1e-4
+
+
+@pytest.mark.parametrize("B,Co,Ci,L", [(1, 128, 128, 256), (2, 128, 6, 320), (3, 256, 259, 1280), (2, 1024, 1536, 256),
+                                       (2, 1, 128, 1024), (5, 512, 256, 4104)])
+def test_wgrad(lib_path, B, Co, Ci, L):
+    from regnet_for_3d_grasping_b200 import conv_train as ct
+    g = torch.Generator().manual_seed(B + Co + Ci + L)
+    gz = torch.randn(B, Co, L, generator=g)
+    x = torch.randn(B, Ci, L, generator=g) + 0.2
+    want = torch.einsum("bol,bil->oi", gz.double(), x.double())
+    g_hi, g_lo = ct.split_planes(gz.cuda())
+    x_hi, x_lo = ct.split_planes(x.cuda())
+    dw = ct.wgrad(g_hi, g_lo, x_hi, x_lo, passes=3)
+    assert _rel(dw, want) < 1e-4
+    assert torch.equal(dw, ct.wgrad(g_hi, g_lo, x_hi, x_lo, passes=3)), "wgrad is not deterministic"
+    assert _rel(ct.wgrad(g_hi, g_lo, x_hi, x_lo, passes=1), want) < 2e-2
+
+
+def _mlp_pair(cin, widths, ndim, dropout=0.0, seed=0, relu=True):
+    from regnet_for_3d_grasping_b200.nn_layers import SharedMLP
+    torch.manual_seed(seed)
+    ours = SharedMLP(cin, widths, ndim=ndim, dropout_prob=dropout)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for blk in ours:
+            blk.bn.weight.copy_(torch.randn(blk.bn.weight.shape, generator=g))       # both signs
+            blk.bn.bias.copy_(torch.randn(blk.bn.bias.shape, generator=g) * 0.3)
+            if not relu:
+                blk.relu = None
+    import copy
+    ref = copy.deepcopy(ours).double()
+    return ours.cuda().train(), ref.train()
+
+
+CHAIN_CASES = [((2, 6, 40, 64), (128, 128, 256), True), ((3, 259, 16, 64), (256, 512), True),
+               ((2, 515, 1280), (256, 256, 256), False), ((2, 1536, 256), (1024, 1024), False)]
+
+
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("shape,widths,pooled", CHAIN_CASES)
+def test_mlp_chain_matches_float64_torch(lib_path, monkeypatch, shape, widths, pooled, relu):
+    """Values, input gradient and every weight / gamma / beta gradient of the chained MLP (conv -> BN(batch stats) -> ReLU
+    [-> max over 64 neighbours]) against the same modules in float64 torch.
+    relu=False: nothing but the pooled arg-max decides where a gradient goes (and the reference is given our arg-max), so
+    every gradient is held to 2e-4 of its peak, element by element.  relu=True: the ReLU mask of an activation within fp32
+    rounding of zero differs between fp32 and float64 (about one element per million), which moves O(1) gradient at those
+    positions; gradients are then held to 2e-4 after discarding the 1 % largest deviations, and to 1e-2 in relative L2."""
+    from helpers import rel_l2, robust_rel_err
+    from regnet_for_3d_grasping_b200 import conv_train as ct
+    ndim = len(shape) - 2
+    ours, ref = _mlp_pair(shape[1], widths, ndim, relu=relu)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(shape, generator=g)
+    xo = x.cuda().requires_grad_(True)
+    xr = x.double().requires_grad_(True)
+    assert ct.chain_supported(ours, xo)
+    arg = None
+    if pooled:
+        # the reference routes the pooled gradient to the position OUR forward picked (near-ties inside a row)
+        import copy
+        with torch.no_grad():
+            arg = copy.deepcopy(ours)(xo.detach()).argmax(dim=3, keepdim=True).cpu()
+    yo = ours.forward_max_over_neighbours(xo) if pooled else ours(xo)
+    monkeypatch.setenv("REGNET_TRAIN_TORCH", "1")
+    yr = ref(xr)
+    if pooled:
+        assert (yr.detach().gather(3, arg).squeeze(3) - yr.detach().max(dim=3)[0]).abs().max() < 1e-4 * yr.detach().abs().max()
+        yr = yr.gather(3, arg).squeeze(3)
+    monkeypatch.delenv("REGNET_TRAIN_TORCH")
+    dy = torch.randn(yr.shape, generator=g)
+    yo.backward(dy.cuda())
+    yr.backward(dy.double())
+    torch.cuda.synchronize()
+    assert _rel(yo, yr.detach()) < 1e-4
+
+    def grad_ok(got, want, what):
+        if relu:
+            assert robust_rel_err(got, want, 0.01) < 2e-4, what
+            assert rel_l2(got, want) < 1e-2, what
+        else:
+            assert _rel(got, want) < 2e-4, what
+    grad_ok(xo.grad, xr.grad, "dx")
+    for i, (bo, br) in enumerate(zip(ours, ref)):
+        grad_ok(bo.conv.weight.grad, br.conv.weight.grad, f"dW{i}")
+        grad_ok(bo.bn.weight.grad, br.bn.weight.grad, f"dgamma{i}")
+        grad_ok(bo.bn.bias.grad, br.bn.bias.grad, f"dbeta{i}")
+        assert _rel(bo.bn.running_mean, br.bn.running_mean) < 1e-4
+        assert _rel(bo.bn.running_var, br.bn.running_var) < 1e-4
+        assert int(bo.bn.num_batches_tracked) == 1
+
+
+def test_mlp_chain_dropout_is_a_consistent_mask(lib_path):
+    """Dropout inside the chain: the kept fraction is 1 - p, kept values are scaled by 1 / (1 - p), and the backward uses the
+    same mask (the gradient w.r.t. a dropped output element does not reach the input)."""
+    ours, _ = _mlp_pair(32, (64,), 1, dropout=0.5)
+    x = torch.randn(2, 32, 4096, device="cuda")
+    torch.manual_seed(3)
+    y = ours(x)
+    # reference values without dropout, from the same batch statistics
+    import copy
+    nod = copy.deepcopy(ours)
+    nod.dropout_prob = 0.0
+    y0 = nod(x)
+    pos = y0 > 1e-6
+    kept = (y != 0) & pos
+    frac = kept.sum().item() / pos.sum().item()
+    assert abs(frac - 0.5) < 0.01, frac
+    assert torch.allclose(y[kept], 2.0 * y0[kept], rtol=1e-5, atol=1e-6)
+    # same seed -> same mask
+    torch.manual_seed(3)
+    assert torch.equal(ours(x) != 0, y != 0)
+    # backward: gradient only flows through kept elements
+    xg = x.clone().requires_grad_(True)
+    torch.manual_seed(3)
+    yg = ours(xg)
+    gsel = torch.zeros_like(yg)
+    dropped = (~kept) & pos
+    gsel[dropped] = 1.0
+    yg.backward(gsel)
+    # BatchNorm couples positions through the batch statistics, but with an all-dropped upstream gradient everything is zero
+    assert float(xg.grad.abs().max()) == 0.0
+
+
+def test_scorenet_train_step_uses_no_library_gemm(lib_path):
+    """One ScoreNet training step (small cloud): no cuDNN / cuBLAS / cutlass kernel in the profile."""
+    from torch.profiler import ProfilerActivity, profile
+    from regnet_for_3d_grasping_b200 import synth, weights
+    from regnet_for_3d_grasping_b200.score_network import ScoreNetwork
+    net = ScoreNetwork(training=True).cuda()
+    net.load_state_dict(weights.random_scorenet_state(seed=0))
+    net.train()
+    pc = torch.from_numpy(synth.batch("table", [0, 1], 8192)).cuda()
+    tgt = torch.from_numpy(synth.scores_like_dataset(7, 2, 8192)).cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        _, _, loss = net(pc, tgt)
+        loss.sum().backward()
+        opt.step()
+    step()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    bad = [n for n in names if any(t in n.lower() for t in ("cudnn", "cutlass", "cublas", "gemm", "nchwtonhwc", "sgemm", "xmma"))
+           and "regnet" not in n]
+    assert not bad, bad
+    assert any("conv1x1_tc_kernel" in n for n in names) and any("wgrad_tc_kernel" in n for n in names)
