@@ -26,6 +26,7 @@ SEG_CHANNELS = (512, 256, 256, 128)
 class PointNet2Seg(nn.Module):
     _SA_MODULE = PointNetSAModule
     _FP_MODULE = PointnetFPModule
+    _MAX_PLANS = 4      # native plans kept per module (one per (batch, points, device)); least recently used is freed
 
     def __init__(self, input_chann=3, k_score=1, k_obj=2, add_channel_flag=False, dropout_prob=0.5):
         super().__init__()
@@ -79,19 +80,36 @@ class PointNet2Seg(nn.Module):
         return sparse_feature, self.sigmoid(x_score).view(B, N)
 
     # -- fused path (eval) ---------------------------------------------------------------------------------------
-    def _state_key(self):
-        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+    _STATE_FIELDS = ("weight", "bias", "running_mean", "running_var")
+
+    def _state_tensors(self):
+        """{state-dict name: tensor} of every conv / BN tensor, read through getattr on the sub-modules.  Unlike
+        state_dict() / parameters() this also works on the replicas nn.DataParallel creates (the reference's multi-GPU
+        mode, utils.py:129-133): a replica's `_parameters` is empty, its weights are plain tensor attributes."""
+        out = {}
+        for name, mod in self.named_modules():
+            if not isinstance(mod, (nn.modules.conv._ConvNd, nn.modules.batchnorm._BatchNorm)):
+                continue
+            for field in self._STATE_FIELDS:
+                t = getattr(mod, field, None)
+                if torch.is_tensor(t):
+                    out[f"{name}.{field}"] = t
+        return out
 
     def _plan_for(self, B, N, device):
         key = (B, N, str(device), self.engine)
         plan = self._plans.get(key)
         if plan is None:
+            while len(self._plans) >= self._MAX_PLANS:      # a plan owns GBs of workspace: keep only the most recent shapes
+                self._plans.pop(next(iter(self._plans))).close()
             plan = ScoreNetPlan(B, N, device, engine=self.engine)
             self._plans[key] = plan
-        state_key = self._state_key()
+        else:
+            self._plans[key] = self._plans.pop(key)         # most recently used last
+        tensors = self._state_tensors()
+        state_key = tuple((t.data_ptr(), t._version) for t in tensors.values())
         if plan._bound_key != state_key:       # parameters changed (or first use): fold BN again and upload
-            sd = {"x." + k: v for k, v in self.state_dict().items()}
-            plan.bind_state(sd, root="x.", key=state_key)
+            plan.bind_state({"x." + k: v for k, v in tensors.items()}, root="x.", key=state_key)
         return plan
 
     def _forward_fused(self, points):

@@ -16,8 +16,6 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from regnet_for_3d_grasping_b200 import sharding, synth, weights  # noqa: E402
-from regnet_for_3d_grasping_b200.score_network import ScoreNetwork  # noqa: E402
 
 
 def main():
@@ -34,38 +32,13 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(0)
-    net = ScoreNetwork(training=True).to(dev)
-    net.load_state_dict(weights.random_scorenet_state(seed=0))
-    net.train()
-    model = sharding.wrap_ddp(net, dev) if world > 1 else net
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
-    pc = torch.from_numpy(synth.batch("table", sharding.shard_seeds(rank, args.batch), args.points)).to(dev)
-    tgt = torch.from_numpy(synth.scores_like_dataset(7 + rank, args.batch, args.points)).to(dev)
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        _, _, loss = model(pc, tgt)
-        loss = loss.sum()
-        loss.backward()
-        opt.step()
-        return loss
-
-    for _ in range(args.warmup):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = sharding.max_over_ranks([e0.elapsed_time(e1)], dev)[0]
+    from regnet_for_3d_grasping_b200 import train_step as ts
+    stepper = ts.ScoreTrainStep(dev, rank, world, args.batch, args.points)
+    net = stepper.net
+    ms = ts.time_steps(stepper, args.steps, args.warmup, dev)
+    loss = stepper.last_loss
     nparam = sum(p.numel() for p in net.parameters())
+    ar_ms = ts.time_allreduce(stepper.grad_bytes, dev)      # collective: every rank
     if rank == 0:
         print(json.dumps({"metric": "clouds/s, ScoreNet training step (pretrain_score: fwd + MSE + bwd + all-reduce + Adam)",
                           "value": world * args.batch * args.steps / (ms * 1e-3), "unit": "clouds/s", "n_gpus": world,
@@ -73,7 +46,7 @@ def main():
                           "points": args.points, "loss": float(loss), "parameters": nparam,
                           "grad_allreduce_bytes_per_step": 4 * nparam if world > 1 else 0,
                           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
-                          "path": "modules.py op-by-op: this repo's point operators, BN+ReLU and max-pool training kernels + torch GEMMs / autograd"}))
+                          "allreduce_ms_isolated": ar_ms, "path": "modules.py: this repo's point operators + chained shared MLPs on the tcgen05 engine (conv_train.py), one flat gradient all-reduce"}))
     if world > 1:
         dist.destroy_process_group()
 

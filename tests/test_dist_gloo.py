@@ -51,6 +51,23 @@ def _worker(rank, world, port, out):
         res["local"] = local.flatten().tolist()          # plain lists: tensors would travel as shm handles
         res["ddp"] = net.extrat_featurePN2.conv_score.weight.grad.flatten().tolist()
         res["sa_grad_norm"] = net.extrat_featurePN2.sa_modules[0].mlp[0].conv.weight.grad.norm().item()
+        # the product's own exchange: gradients as views into one flat buffer, one all-reduce (sharding.FlatGrads)
+        net2 = ScoreNetwork(training=True)
+        net2.load_state_dict(weights.random_scorenet_state(seed=2))
+        net2.train()
+        fg = sharding.FlatGrads(net2.parameters())
+        fg.zero()
+        torch.manual_seed(123)
+        _, _, loss3 = net2(pc, tgt)
+        loss3.backward()
+        g = net2.extrat_featurePN2.conv_score.weight.grad
+        res["flat_is_view"] = fg.flat.data_ptr() <= g.data_ptr() < fg.flat.data_ptr() + fg.nbytes
+        fg.all_reduce()
+        res["flat"] = g.flatten().tolist()
+        res["flat_bytes"] = fg.nbytes
+        net2.zero_grad(set_to_none=True)            # a caller that drops the views: zero() re-attaches them
+        fg.zero()
+        res["flat_reattached"] = all(p.grad is not None and float(p.grad.abs().sum()) == 0.0 for p in net2.parameters())
         gathered = [None] * world
         dist.all_gather_object(gathered, res)
         if rank == 0:
@@ -78,4 +95,6 @@ def test_two_rank_gloo_sharding_and_ddp(oracle):
     avg = (torch.tensor(r0["local"]) + torch.tensor(r1["local"])) / 2
     assert torch.allclose(torch.tensor(r0["ddp"]), avg, rtol=1e-4, atol=1e-7)   # DDP = average of per-rank gradients
     assert r0["ddp"] == r1["ddp"]                                  # replicas stay in sync
+    assert r0["flat_is_view"] and r0["flat_reattached"] and r0["flat_bytes"] == 4 * 5542531
+    assert torch.allclose(torch.tensor(r0["flat"]), avg, rtol=1e-4, atol=1e-7) and r0["flat"] == r1["flat"]
     assert r0["sa_grad_norm"] > 0 and abs(r0["sa_grad_norm"] - r1["sa_grad_norm"]) < 1e-6 * max(1.0, r0["sa_grad_norm"])

@@ -55,6 +55,34 @@ def test_wgrad(lib_path, B, Co, Ci, L):
     assert _rel(ct.wgrad(g_hi, g_lo, x_hi, x_lo, passes=1), want) < 2e-2
 
 
+# every 1x1 convolution of ScoreNet (utils/pointnet2.py:43-46,82): (cin, cout), positions scaled down
+SCORENET_LAYERS = [(6, 128), (128, 128), (128, 256), (259, 256), (256, 256), (256, 512), (515, 512), (512, 512), (512, 1024),
+                   (1536, 1024), (1024, 1024), (1280, 512), (512, 512), (515, 256), (256, 256), (256, 512), (512, 256),
+                   (256, 128), (128, 1)]
+
+
+@pytest.mark.parametrize("cin,cout", SCORENET_LAYERS)
+def test_every_scorenet_layer_forward_dgrad_wgrad(lib_path, cin, cout):
+    """Output, input gradient and weight gradient of every SA / FP / seg / score convolution shape against float64,
+    with the feature tolerance of tests/helpers.py (1e-4 of the peak, and 1e-4 relative + 1e-4 rms element-wise)."""
+    from helpers import assert_features_close
+    from regnet_for_3d_grasping_b200 import conv_train as ct
+    B, L = 2, 1536
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(B, cin, L, generator=g).clamp_min(-0.5)          # post-ReLU-like: mostly positive, some zeros
+    w = torch.randn(cout, cin, generator=g) / cin ** 0.5
+    gz = torch.randn(B, cout, L, generator=g) * 1e-3
+    x_hi, x_lo = ct.split_planes(x.cuda())
+    g_hi, g_lo = ct.split_planes(gz.cuda())
+    w_hi, w_lo = ct.split_weight(w.cuda())
+    t_hi, t_lo = ct.split_weight(w.cuda(), transpose=True)
+    assert_features_close(ct.conv1x1(x_hi, x_lo, w_hi, w_lo, cout, cin), torch.einsum("oi,bil->bol", w.double(), x.double()),
+                          what="fprop")
+    assert_features_close(ct.conv1x1(g_hi, g_lo, t_hi, t_lo, cin, cout), torch.einsum("oi,bol->bil", w.double(), gz.double()),
+                          what="dgrad")
+    assert_features_close(ct.wgrad(g_hi, g_lo, x_hi, x_lo), torch.einsum("bol,bil->oi", gz.double(), x.double()), what="wgrad")
+
+
 def _mlp_pair(cin, widths, ndim, dropout=0.0, seed=0, relu=True):
     from regnet_for_3d_grasping_b200.nn_layers import SharedMLP
     torch.manual_seed(seed)
@@ -83,8 +111,9 @@ def test_mlp_chain_matches_float64_torch(lib_path, monkeypatch, shape, widths, p
     relu=False: nothing but the pooled arg-max decides where a gradient goes (and the reference is given our arg-max), so
     every gradient is held to 2e-4 of its peak, element by element.  relu=True: the ReLU mask of an activation within fp32
     rounding of zero differs between fp32 and float64 (about one element per million), which moves O(1) gradient at those
-    positions; gradients are then held to 2e-4 after discarding the 1 % largest deviations, and to 1e-2 in relative L2."""
-    from helpers import rel_l2, robust_rel_err
+    positions and, through the batch means of the BatchNorm backward, O(1/positions) gradient in the whole channel (these
+    test chains have only ~2 500 positions per channel); gradients are then held to 2e-3 after discarding the 1 % largest
+    deviations, and to 2e-2 in relative L2."""
     from regnet_for_3d_grasping_b200 import conv_train as ct
     ndim = len(shape) - 2
     ours, ref = _mlp_pair(shape[1], widths, ndim, relu=relu)
@@ -112,17 +141,28 @@ def test_mlp_chain_matches_float64_torch(lib_path, monkeypatch, shape, widths, p
     torch.cuda.synchronize()
     assert _rel(yo, yr.detach()) < 1e-4
 
-    def grad_ok(got, want, what):
+    # A gradient that is analytically zero (e.g. the BatchNorm shift of a block without ReLU in front of another
+    # BatchNorm) is compared against the largest gradient of its kind in the chain, not against itself.
+    floor = {"dW": max(float(b.conv.weight.grad.abs().max()) for b in ref),
+             "dgamma": max(float(b.bn.weight.grad.abs().max()) for b in ref),
+             "dbeta": max(float(b.bn.bias.grad.abs().max()) for b in ref), "dx": 0.0}
+
+    def grad_ok(got, want, kind, what):
+        got, want = got.double().cpu(), want.cpu()
+        scale = max(float(want.abs().max()), floor[kind], 1e-30)
+        err = (got - want).abs().flatten()
         if relu:
-            assert robust_rel_err(got, want, 0.01) < 2e-4, what
-            assert rel_l2(got, want) < 1e-2, what
+            k = int(0.01 * err.numel())
+            worst = float(err.kthvalue(err.numel() - k)[0]) if k > 0 else float(err.max())
+            assert worst < 2e-3 * scale, (what, worst, scale)
+            assert float((got - want).norm()) < 2e-2 * max(float(want.norm()), scale), what
         else:
-            assert _rel(got, want) < 2e-4, what
-    grad_ok(xo.grad, xr.grad, "dx")
+            assert float(err.max()) < 2e-4 * scale, (what, float(err.max()), scale)
+    grad_ok(xo.grad, xr.grad, "dx", "dx")
     for i, (bo, br) in enumerate(zip(ours, ref)):
-        grad_ok(bo.conv.weight.grad, br.conv.weight.grad, f"dW{i}")
-        grad_ok(bo.bn.weight.grad, br.bn.weight.grad, f"dgamma{i}")
-        grad_ok(bo.bn.bias.grad, br.bn.bias.grad, f"dbeta{i}")
+        grad_ok(bo.conv.weight.grad, br.conv.weight.grad, "dW", f"dW{i}")
+        grad_ok(bo.bn.weight.grad, br.bn.weight.grad, "dgamma", f"dgamma{i}")
+        grad_ok(bo.bn.bias.grad, br.bn.bias.grad, "dbeta", f"dbeta{i}")
         assert _rel(bo.bn.running_mean, br.bn.running_mean) < 1e-4
         assert _rel(bo.bn.running_var, br.bn.running_var) < 1e-4
         assert int(bo.bn.num_batches_tracked) == 1
