@@ -48,12 +48,15 @@ int regnet_check_index_errors(void);
 /* csrc/sampling.h:7-9 FarthestPointSample (kernel csrc/sampling_kernel.cu:47-117).
  * points: logical (B,3,N) fp32 with element strides (sb,sc,sn).  index: (B,M) int64, first pick = 0.
  * new_xyz (optional, may be NULL): (B,3,M) contiguous, the sampled coordinates (function.py:11-26 gather_points
- * fused).  Bit-exact with the reference including its tie rule.  EINVAL unless 0 < M <= N. */
+ * fused).  Bit-exact with the reference including its tie rule.  EINVAL unless 0 < M <= N.  Any N: clouds of up to
+ * 65 536 points stay register-resident in a thread-block cluster, larger ones take a generic one-CTA-per-cloud kernel
+ * with the min-distance array in global memory (scratch from cudaMallocAsync on `stream`). */
 int regnet_farthest_point_sample(const float* points, int64_t sb, int64_t sc, int64_t sn, int B, int N, int M,
                                  int64_t* index, float* new_xyz, void* stream);
 /* same, with explicit tuning (cluster_size in {0=auto,1,2,4,8}, threads in {0=auto,256,512,1024}; a negative
  * thread count selects the barrier.cluster exchange instead of st.async+mbarrier, for A/B measurements) and an
- * optional int32 copy of the indices for the fused path */
+ * optional int32 copy of the indices for the fused path.  Shapes without a compiled instance (the library carries the
+ * ones its policy selects) are served by the generic kernel: same indices. */
 int regnet_farthest_point_sample_ex(const float* points, int64_t sb, int64_t sc, int64_t sn, int B, int N, int M,
                                     int64_t* index64, int32_t* index32, float* new_xyz, int cluster_size,
                                     int threads, void* stream);
@@ -61,7 +64,7 @@ int regnet_farthest_point_sample_ex(const float* points, int64_t sb, int64_t sc,
 /* csrc/ball_query.h:7-11 BallQuery (kernel csrc/ball_query_kernel.cu:31-74).
  * points (B,3,N), centroids (B,3,M) strided as above; radius is a C float squared in fp32; strict d < r*r;
  * first K hits in ascending index order, first hit replicated into unused slots, no hit -> zeros.
- * index (B,M,K) int64, count (B,M) int64; index32 (optional) int32 copy.  K <= 128. */
+ * index (B,M,K) int64, count (B,M) int64; index32 (optional) int32 copy.  Any K (K > 128 takes a generic kernel). */
 int regnet_ball_query(const float* points, int64_t psb, int64_t psc, int64_t psn, const float* centroids,
                       int64_t csb, int64_t csc, int64_t csn, int B, int N, int M, float radius, int K,
                       int64_t* index, int64_t* count, int32_t* index32, void* stream);
@@ -78,6 +81,18 @@ int regnet_ball_query_ws(const float* points, int64_t psb, int64_t psc, int64_t 
 int regnet_point_search_ws(const float* query, int64_t qsb, int64_t qsc, int64_t qsn, const float* key, int64_t ksb,
                            int64_t ksc, int64_t ksn, int B, int Nq, int Nk, int k, int64_t* index, float* distance,
                            void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Double-precision instantiations of the three search operators (the reference dispatches over float and double:
+ * sampling_kernel.cu:149, ball_query_kernel.cu:112, interpolate_kernel.cu:113).  Same semantics, arithmetic in double in
+ * the reference's order; generic kernels (REGNet only passes float32, which the tuned kernels above serve). */
+int regnet_farthest_point_sample_f64(const double* points, int64_t sb, int64_t sc, int64_t sn, int B, int N, int M,
+                                     int64_t* index, void* stream);
+int regnet_ball_query_f64(const double* points, int64_t psb, int64_t psc, int64_t psn, const double* centroids, int64_t csb,
+                          int64_t csc, int64_t csn, int B, int N, int M, double radius, int K, int64_t* index,
+                          int64_t* count, void* stream);
+int regnet_point_search_f64(const double* query, int64_t qsb, int64_t qsc, int64_t qsn, const double* key, int64_t ksb,
+                            int64_t ksc, int64_t ksn, int B, int Nq, int Nk, int k, int64_t* index, double* distance,
+                            void* stream);
 
 /* csrc/grouping.h:7-14 GroupPointsForward / GroupPointsBackward (csrc/grouping_kernel.cu:29-51, 54-149).
  * input (B,C,N) strided; index (B,M,K) int64 contiguous; out (B,C,M,K) contiguous.

@@ -34,6 +34,9 @@ _SIGNATURES = {
     "regnet_farthest_point_sample": (c_int, _STRIDED + [c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "regnet_farthest_point_sample_ex": (c_int, _STRIDED + [c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_int, c_int, c_ptr]),
     "regnet_ball_query": (c_int, _STRIDED + _STRIDED + [c_int, c_int, c_int, c_f32, c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "regnet_farthest_point_sample_f64": (c_int, _STRIDED + [c_int, c_int, c_int, c_ptr, c_ptr]),
+    "regnet_ball_query_f64": (c_int, _STRIDED + _STRIDED + [c_int, c_int, c_int, ctypes.c_double, c_int, c_ptr, c_ptr, c_ptr]),
+    "regnet_point_search_f64": (c_int, _STRIDED + _STRIDED + [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "regnet_search_workspace_bytes": (c_i64, [c_int, c_int]),
     "regnet_ball_query_ws": (c_int, _STRIDED + _STRIDED + [c_int, c_int, c_int, c_f32, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "regnet_point_search_ws": (c_int, _STRIDED + _STRIDED + [c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),

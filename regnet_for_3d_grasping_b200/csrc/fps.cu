@@ -304,25 +304,95 @@ int launch_fps(const float* pts, Strides3 st, int B, int N, int M, int nbits, in
   return REGNET_OK;
 }
 
-template <int CS, int T>
-int dispatch_ppt(int ppt, const float* pts, Strides3 st, int B, int N, int M, int nbits, int64_t* idx64,
-                 int32_t* idx32, float* new_xyz, const int32_t* n_var, bool mbar, cudaStream_t stream) {
-  if (ppt <= 1) return launch_fps<CS, T, 1>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
-  if (ppt <= 2) return launch_fps<CS, T, 2>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
-  if (ppt <= 4) return launch_fps<CS, T, 4>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
-  if (ppt <= 8) return launch_fps<CS, T, 8>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
-  if constexpr (T <= 512) {
-    if (ppt <= 16) return launch_fps<CS, T, 16>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
+// Instantiated launch shapes: the ones the policy below and the ScoreNet plan's co-running FPS select, with the point counts
+// per thread they actually use, plus two barrier.cluster instances for A/B measurements.  Any other (cluster, threads)
+// request is served by fps_generic_kernel (same indices) -- the library used to carry 176 instances.
+struct FpsShape { int cs, t, ppt; bool mbar; };
+#define RN_FPS_SHAPES(X)                                                                                          \
+  X(1, 256, 1, true) X(1, 512, 1, true) X(1, 512, 2, true) X(1, 512, 4, true)                                        \
+  X(4, 256, 4, true) X(4, 256, 8, true) X(4, 256, 16, true)                                                          \
+  X(8, 128, 4, true) X(8, 128, 8, true) X(8, 128, 16, true) X(8, 128, 20, true) X(8, 128, 25, true) X(8, 128, 32, true) \
+  X(8, 512, 16, true) X(4, 128, 1, true) X(4, 128, 2, true) X(4, 128, 4, true)                                       \
+  X(8, 256, 16, true) X(8, 128, 32, false) X(8, 512, 16, false)
+
+int dispatch_shape(int cs, int t, int ppt, bool mbar, const float* pts, Strides3 st, int B, int N, int M, int nbits,
+                   int64_t* idx64, int32_t* idx32, float* new_xyz, const int32_t* n_var, cudaStream_t stream) {
+  if (cs == 1) mbar = true;   // a single CTA exchanges nothing: one variant
+  // smallest instantiated point count >= ppt for this (cluster, threads, exchange)
+  int best = 1 << 30;
+#define RN_FPS_PICK(CS, T, PPT, MB) if (cs == CS && t == T && mbar == MB && PPT >= ppt && PPT < best) best = PPT;
+  RN_FPS_SHAPES(RN_FPS_PICK)
+#undef RN_FPS_PICK
+#define RN_FPS_GO(CS, T, PPT, MB)                                                                                  \
+  if (cs == CS && t == T && mbar == MB && best == PPT)                                                               \
+    return launch_fps<CS, T, PPT>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, MB, stream);
+  RN_FPS_SHAPES(RN_FPS_GO)
+#undef RN_FPS_GO
+  return -1;   // no such instance
+}
+
+// ---- any size: the min-distance array in global memory ---------------------------------------------------------------------
+// Clouds beyond the register-resident limit (> 65 536 points), or launch shapes without an instance: one CTA of 1024
+// threads per cloud, the reference's scheme (sampling_kernel.cu:47-117) with the same squared distance and the same tie
+// order -- (max distance, min brev(j mod block) | j div block) -- so the indices are bit-identical here too.
+__global__ void __launch_bounds__(1024, 1)
+fps_generic_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, float* __restrict__ mind,
+                   int64_t* __restrict__ idx64, int32_t* __restrict__ idx32, float* __restrict__ new_xyz) {
+  const int cloud = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* __restrict__ p = pts + (int64_t)cloud * st.b;
+  float* __restrict__ md = mind + (int64_t)cloud * N;
+  const uint32_t mask = (1u << nbits) - 1u;
+  __shared__ uint32_t sd[2][32], stie[2][32];
+  for (int j = tid; j < N; j += 1024) md[j] = __int_as_float(0x7f800000);
+  int cur = 0;
+  if (tid == 0) {
+    if (idx64) idx64[(int64_t)cloud * M] = 0;
+    if (idx32) idx32[(int64_t)cloud * M] = 0;
+    if (new_xyz) {
+      float* o = new_xyz + (int64_t)cloud * 3 * M;
+      o[0] = p[0]; o[M] = p[st.c]; o[2 * (int64_t)M] = p[2 * st.c];
+    }
   }
-  if constexpr (T <= 128) {
-    // 25 = the BASELINE cloud (25 600 points over 8 CTAs x 128 threads): rounding it up to 32 slots per thread would
-    // add 7 dead points = 22 % more instructions to every one of the 5 119 dependent iterations
-    if (ppt <= 20) return launch_fps<CS, T, 20>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
-    if (ppt <= 25) return launch_fps<CS, T, 25>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
-    if (ppt <= 32) return launch_fps<CS, T, 32>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
+  __syncthreads();
+  for (int i = 1; i < M; ++i) {
+    const int par = i & 1;
+    const float cx = p[(int64_t)cur * st.n], cy = p[(int64_t)cur * st.n + st.c], cz = p[(int64_t)cur * st.n + 2 * st.c];
+    float best = 0.f;
+    int bj = -1;
+    for (int j = tid; j < N; j += 1024) {   // 1024 is a multiple of the reference block: one slot, ascending j
+      const float d = sqdist_ref(cx, cy, cz, p[(int64_t)j * st.n], p[(int64_t)j * st.n + st.c], p[(int64_t)j * st.n + 2 * st.c]);
+      const float m = fminf(md[j], d);
+      md[j] = m;
+      if (m > best) { best = m; bj = j; }
+    }
+    const uint32_t tie = (bj < 0) ? NO_TIE : (__brev((uint32_t)bj & mask) | ((uint32_t)bj >> nbits));
+    uint32_t dmax;
+    const int src1 = pick_lane(__float_as_uint(best), tie, dmax);
+    if (lane == src1) { sd[par][warp] = dmax; stie[par][warp] = tie; }
+    __syncthreads();
+    const int src2 = pick_lane(sd[par][lane], stie[par][lane], dmax);
+    const uint32_t wtie = stie[par][src2];
+    if (dmax != 0u) cur = (int)(((wtie & ((1u << (32 - nbits)) - 1u)) << nbits) | (__brev(wtie) & mask));
+    if (tid == 0) {
+      if (idx64) idx64[(int64_t)cloud * M + i] = cur;
+      if (idx32) idx32[(int64_t)cloud * M + i] = cur;
+      if (new_xyz) {
+        float* o = new_xyz + (int64_t)cloud * 3 * M + i;
+        o[0] = p[(int64_t)cur * st.n]; o[M] = p[(int64_t)cur * st.n + st.c]; o[2 * (int64_t)M] = p[(int64_t)cur * st.n + 2 * st.c];
+      }
+    }
   }
-  set_error("farthest_point_sample: %d points per thread exceeds the register-resident limit", ppt);
-  return REGNET_ELIMIT;
+}
+
+int fps_generic_launch(const float* pts, Strides3 st, int B, int N, int M, int nbits, int64_t* idx64, int32_t* idx32,
+                       float* new_xyz, cudaStream_t stream) {
+  float* mind = nullptr;
+  RN_CUDA(cudaMallocAsync(&mind, sizeof(float) * (size_t)B * N, stream));
+  fps_generic_kernel<<<B, 1024, 0, stream>>>(pts, st, N, M, nbits, mind, idx64, idx32, new_xyz);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(mind, stream);
+  if (e != cudaSuccess) return cuda_fail(e, "fps_generic_kernel");
+  return REGNET_OK;
 }
 
 }  // namespace
@@ -388,25 +458,25 @@ static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, i
   // CS=1,T=256 with more than 256 points violates it
   const int nbits = fps_block_log2(N);
   if ((cluster_size * threads) % (1 << nbits) != 0) threads = 512;
-  // grow the cluster until the cloud fits in registers
+  // grow the cluster until the cloud fits in registers; beyond that (and for per-cloud counts never) the generic kernel
   const int max_ppt = threads <= 128 ? 32 : threads <= 512 ? 16 : 8;
   while (cluster_size < 8 && ceil_div(N, cluster_size * threads) > max_ppt) cluster_size *= 2;
-  const int ppt = ceil_div(N, cluster_size * threads);
-  if (ppt > max_ppt) {
+  int ppt = ceil_div(N, cluster_size * threads);
+  if (ppt > max_ppt && !n_var) {
+    // try the two largest register-resident shapes before giving up on registers
+    if (ceil_div(N, 8 * 512) <= 16) { cluster_size = 8; threads = 512; ppt = ceil_div(N, 8 * 512); }
+    else return fps_generic_launch(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, stream);
+  }
+  if (ppt > max_ppt && n_var) {
     set_error("farthest_point_sample: N=%d exceeds the register-resident limit of %d points per cloud", N,
               8 * threads * max_ppt);
     return REGNET_ELIMIT;
   }
-#define RN_FPS_CASE(CS, T)                                                                              \
-  if (cluster_size == CS && threads == T)                                                               \
-    return dispatch_ppt<CS, T>(ppt, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, mbar, stream);
-  RN_FPS_CASE(1, 128) RN_FPS_CASE(2, 128) RN_FPS_CASE(4, 128) RN_FPS_CASE(8, 128)
-  RN_FPS_CASE(1, 256) RN_FPS_CASE(2, 256) RN_FPS_CASE(4, 256) RN_FPS_CASE(8, 256)
-  RN_FPS_CASE(1, 512) RN_FPS_CASE(2, 512) RN_FPS_CASE(4, 512) RN_FPS_CASE(8, 512)
-  RN_FPS_CASE(1, 1024) RN_FPS_CASE(2, 1024) RN_FPS_CASE(4, 1024) RN_FPS_CASE(8, 1024)
-#undef RN_FPS_CASE
-  set_error("farthest_point_sample: unreachable configuration");
-  return REGNET_EINVAL;
+  const int rc = dispatch_shape(cluster_size, threads, ppt, mbar, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, stream);
+  if (rc >= 0) return rc;
+  if (!n_var) return fps_generic_launch(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, stream);
+  set_error("farthest_point_sample: no instance for cluster %d x %d threads x %d points", cluster_size, threads, ppt);
+  return REGNET_ELIMIT;
 }
 
 }  // namespace regnet

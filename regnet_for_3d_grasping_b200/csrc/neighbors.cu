@@ -184,17 +184,64 @@ three_nn_kernel(const float* __restrict__ qry, Strides3 qst, const float* __rest
   }
 }
 
+// Any K (the reference has no limit, ball_query_kernel.cu:31-74): hits go straight to the global index array, one thread
+// per centroid, candidates staged through the same shared-memory tiles.  Used when K > 128 (the list of the kernel above
+// no longer fits in shared memory).
+__global__ void __launch_bounds__(BQ_THREADS)
+ball_query_anyk_kernel(const float* __restrict__ pts, Strides3 pst, const float* __restrict__ ctr, Strides3 cst, int N,
+                       int M, float radius, int K, int64_t* __restrict__ index, int64_t* __restrict__ count,
+                       int32_t* __restrict__ index32) {
+  __shared__ float4 tile[TILE_PTS];
+  const int b = blockIdx.y;
+  const int m = blockIdx.x * BQ_THREADS + threadIdx.x;
+  const bool live = m < M;
+  const float* __restrict__ p = pts + (int64_t)b * pst.b;
+  const float* __restrict__ c = ctr + (int64_t)b * cst.b;
+  const float r2 = __fmul_rn(radius, radius);
+  float x1 = 0.f, y1 = 0.f, z1 = 0.f;
+  if (live) {
+    x1 = c[(int64_t)m * cst.n];
+    y1 = c[(int64_t)m * cst.n + cst.c];
+    z1 = c[(int64_t)m * cst.n + 2 * cst.c];
+  }
+  const int64_t o = ((int64_t)b * M + m) * K;
+  int cnt = live ? 0 : K, first = 0;
+  for (int base = 0; base < N; base += TILE_PTS) {
+    const int n = min(TILE_PTS, N - base);
+    __syncthreads();
+    stage_points(tile, p, pst, base, n, N);
+    if (__syncthreads_and(cnt >= K)) break;
+    for (int t = 0; t < n && cnt < K; ++t) {
+      const float4 q = tile[t];
+      if (sqdist_ref(x1, y1, z1, q.x, q.y, q.z) < r2) {
+        if (cnt == 0) first = base + t;
+        if (index) index[o + cnt] = base + t;
+        if (index32) index32[o + cnt] = base + t;
+        ++cnt;
+      }
+    }
+  }
+  if (live) {
+    for (int k = cnt; k < K; ++k) {
+      if (index) index[o + k] = first;
+      if (index32) index32[o + k] = first;
+    }
+    if (count) count[(int64_t)b * M + m] = cnt;
+  }
+}
+
 }  // namespace
 
 int ball_query_launch(const float* pts, Strides3 pst, const float* ctr, Strides3 cst, int B, int N, int M,
                       float radius, int K, int64_t* index, int64_t* count, int32_t* index32, cudaStream_t stream) {
   RN_CHECK_ARG(B > 0 && N > 0 && M > 0, "ball_query: empty input (B=%d, N=%d, M=%d)", B, N, M);
   RN_CHECK_ARG(K > 0, "ball_query: num_neighbours must be > 0");
-  if (K > 128) {
-    set_error("ball_query: num_neighbours=%d exceeds the supported maximum of 128", K);
-    return REGNET_ELIMIT;
-  }
   dim3 grid(ceil_div(M, BQ_THREADS), B);
+  if (K > 128) {   // the shared-memory hit list holds 128 entries per centroid: beyond that, hits go straight to global
+    ball_query_anyk_kernel<<<grid, BQ_THREADS, 0, stream>>>(pts, pst, ctr, cst, N, M, radius, K, index, count, index32);
+    RN_LAUNCH_CHECK("ball_query_anyk_kernel");
+    return REGNET_OK;
+  }
   // per-device attribute; cheap enough to set on every launch (keeps multi-device processes correct)
   if (N <= 65536) {
     const size_t smem = sizeof(float4) * TILE_PTS + sizeof(uint16_t) * (size_t)K * (BQ_THREADS + 1);

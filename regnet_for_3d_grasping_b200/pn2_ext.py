@@ -21,7 +21,16 @@ def _need_cuda_f32(t, name):
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
     if t.dtype != torch.float32:
-        raise RuntimeError(f"{name} must be float32 (REGNet only uses fp32; the fp64 instantiation of the reference is not provided)")
+        raise RuntimeError(f"{name} must be float32")
+
+
+def _is_f64(*tensors):
+    """The reference dispatches over float and double (AT_DISPATCH_FLOATING_TYPES).  float64 inputs take the generic
+    double-precision kernels (csrc/generic_ops.cu) for the search operators and exact torch gathers / scatter-adds for
+    the value operators -- complete, not tuned: REGNet itself only passes float32."""
+    if all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 for t in tensors):
+        return True
+    return False
 
 
 def _need_index(t, name):
@@ -43,7 +52,9 @@ def _stream():
 
 def farthest_point_sample(points, num_centroids):
     """csrc/sampling_kernel.cu:126-170.  points (B,3,N) any stride -> index (B,M) int64."""
-    _need_cuda_f32(points, "points")
+    f64 = _is_f64(points)
+    if not f64:
+        _need_cuda_f32(points, "points")
     if points.dim() != 3 or points.size(1) != 3:
         raise RuntimeError("points.size(1) does not equal to 3")
     B, _, N = points.shape
@@ -56,14 +67,19 @@ def farthest_point_sample(points, num_centroids):
     if B == 0:
         return index
     with torch.cuda.device(points.device):
-        _lib.check(_lib.load().regnet_farthest_point_sample(*_strided3(points), B, N, M, _p(index), None, _stream()))
+        if f64:
+            _lib.check(_lib.load().regnet_farthest_point_sample_f64(*_strided3(points), B, N, M, _p(index), _stream()))
+        else:
+            _lib.check(_lib.load().regnet_farthest_point_sample(*_strided3(points), B, N, M, _p(index), None, _stream()))
     return index
 
 
 def ball_query(points, centroids, radius, num_neighbours):
     """csrc/ball_query_kernel.cu:87-131.  -> [index (B,M,K) int64, count (B,M) int64]."""
-    _need_cuda_f32(points, "points")
-    _need_cuda_f32(centroids, "centroids")
+    f64 = _is_f64(points, centroids)
+    if not f64:
+        _need_cuda_f32(points, "points")
+        _need_cuda_f32(centroids, "centroids")
     if points.dim() != 3 or points.size(1) != 3:
         raise RuntimeError("points.size(1) does not equal to 3")
     if centroids.dim() != 3 or centroids.size(1) != 3:
@@ -77,7 +93,10 @@ def ball_query(points, centroids, radius, num_neighbours):
         return [index, count]
     with torch.cuda.device(points.device):
         lib = _lib.load()
-        if K == 64 and 4096 <= N <= 65536:
+        if f64:
+            _lib.check(lib.regnet_ball_query_f64(*_strided3(points), *_strided3(centroids), B, N, M, float(radius), K,
+                                                 _p(index), _p(count), _stream()))
+        elif K == 64 and 4096 <= N <= 65536:
             # big clouds: the uniform-grid kernels (same results); scratch comes from torch's caching allocator
             nbytes = int(lib.regnet_search_workspace_bytes(B, N))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=points.device)
@@ -91,6 +110,10 @@ def ball_query(points, centroids, radius, num_neighbours):
 
 def group_points_forward(input, index):
     """csrc/grouping_kernel.cu:29-51.  input (B,C,N), index (B,M,K) -> (B,C,M,K)."""
+    if _is_f64(input):
+        B, C, _ = input.shape
+        _, M, K = index.shape
+        return input.gather(2, index.reshape(B, 1, M * K).expand(B, C, M * K)).view(B, C, M, K)
     _need_cuda_f32(input, "input")
     _need_index(index, "index")
     if input.dim() != 3 or index.dim() != 3 or index.size(0) != input.size(0):
@@ -108,6 +131,10 @@ def group_points_forward(input, index):
 
 def group_points_backward(grad_output, index, num_points):
     """csrc/grouping_kernel.cu:103-149.  grad (B,C,M,K) -> (B,C,N)."""
+    if _is_f64(grad_output):
+        B, C, M, K = grad_output.shape
+        out = torch.zeros(B, C, int(num_points), dtype=torch.float64, device=grad_output.device)
+        return out.scatter_add_(2, index.reshape(B, 1, M * K).expand(B, C, M * K), grad_output.reshape(B, C, M * K))
     _need_cuda_f32(grad_output, "grad_output")
     _need_index(index, "index")
     if grad_output.dim() != 4 or index.dim() != 3 or tuple(index.shape) != (grad_output.size(0), grad_output.size(2), grad_output.size(3)):
@@ -125,8 +152,10 @@ def group_points_backward(grad_output, index, num_points):
 
 def point_search(query_xyz, key_xyz, num_neighbours):
     """csrc/interpolate_kernel.cu:88-128.  -> [index (B,Nq,3) int64, squared distance (B,Nq,3)]."""
-    _need_cuda_f32(query_xyz, "query_xyz")
-    _need_cuda_f32(key_xyz, "key_xyz")
+    f64 = _is_f64(query_xyz, key_xyz)
+    if not f64:
+        _need_cuda_f32(query_xyz, "query_xyz")
+        _need_cuda_f32(key_xyz, "key_xyz")
     if key_xyz.size(0) != query_xyz.size(0) or query_xyz.size(1) != 3 or key_xyz.size(1) != 3:
         raise RuntimeError("point_search: expected (B,3,N1) and (B,3,N2)")
     if int(num_neighbours) != 3:
@@ -136,12 +165,15 @@ def point_search(query_xyz, key_xyz, num_neighbours):
     if Nk < 3:
         raise RuntimeError("num_key is not greater or equal than num_neighbours")
     index = torch.empty(B, Nq, 3, dtype=torch.int64, device=query_xyz.device)
-    dist = torch.empty(B, Nq, 3, dtype=torch.float32, device=query_xyz.device)
+    dist = torch.empty(B, Nq, 3, dtype=query_xyz.dtype, device=query_xyz.device)
     if B == 0 or Nq == 0:
         return [index, dist]
     with torch.cuda.device(query_xyz.device):
         lib = _lib.load()
-        if 4096 <= Nk <= 65536:
+        if f64:
+            _lib.check(lib.regnet_point_search_f64(*_strided3(query_xyz), *_strided3(key_xyz), B, Nq, Nk, 3, _p(index),
+                                                   _p(dist), _stream()))
+        elif 4096 <= Nk <= 65536:
             nbytes = int(lib.regnet_search_workspace_bytes(B, Nk))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=query_xyz.device)
             _lib.check(lib.regnet_point_search_ws(*_strided3(query_xyz), *_strided3(key_xyz), B, Nq, Nk, 3, _p(index),
@@ -154,6 +186,12 @@ def point_search(query_xyz, key_xyz, num_neighbours):
 
 def interpolate_forward(input, index, weight):
     """csrc/interpolate_kernel.cu:187-232.  input (B,C,Ns), index/weight (B,Nd,3) -> (B,C,Nd)."""
+    if _is_f64(input, weight):
+        B, C, _ = input.shape
+        Nd = index.size(1)
+        g = input.gather(2, index.reshape(B, 1, Nd * 3).expand(B, C, Nd * 3)).view(B, C, Nd, 3)
+        w = weight.unsqueeze(1)
+        return (g[..., 0] * w[..., 0] + g[..., 1] * w[..., 1]) + g[..., 2] * w[..., 2]
     _need_cuda_f32(input, "input")
     _need_index(index, "index")
     _need_cuda_f32(weight, "weight")
@@ -173,6 +211,11 @@ def interpolate_forward(input, index, weight):
 
 def interpolate_backward(grad_output, index, weight, num_inst):
     """csrc/interpolate_kernel.cu:292-337.  grad (B,C,Nd) -> (B,C,Ns)."""
+    if _is_f64(grad_output, weight):
+        B, C, Nd = grad_output.shape
+        out = torch.zeros(B, C, int(num_inst), dtype=torch.float64, device=grad_output.device)
+        contrib = (grad_output.unsqueeze(-1) * weight.unsqueeze(1)).reshape(B, C, Nd * 3)
+        return out.scatter_add_(2, index.reshape(B, 1, Nd * 3).expand(B, C, Nd * 3), contrib)
     _need_cuda_f32(grad_output, "grad_output")
     _need_index(index, "index")
     _need_cuda_f32(weight, "weight")

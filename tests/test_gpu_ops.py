@@ -154,7 +154,9 @@ def test_autograd_functions_on_gpu(ext, oracle):
     np.testing.assert_allclose(feat.grad.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
 
 
-def test_error_behaviour_matches_reference(ext):
+def test_bad_arguments_raise_like_the_reference(ext):
+    """The reference's TORCH_CHECK / CHECK_* failures (sampling_kernel.cu:130-137, interpolate_kernel.cu:97-105) surface as
+    RuntimeError here too; shapes that are legal there are legal here."""
     x = torch.rand(1, 3, 10, device="cuda")
     with pytest.raises(RuntimeError):
         ext.farthest_point_sample(x, 11)
@@ -167,10 +169,94 @@ def test_error_behaviour_matches_reference(ext):
     with pytest.raises(RuntimeError):
         ext.point_search(x, x[:, :, :2], 3)
     with pytest.raises(RuntimeError):
-        ext.farthest_point_sample(x.double(), 2)
+        ext.farthest_point_sample(x.cpu(), 2)              # CHECK_CUDA
+    with pytest.raises(RuntimeError):
+        ext.farthest_point_sample(x.half(), 2)             # only float / double are dispatched
     idx, cnt = ext.ball_query(x, x + 10.0, 0.1, 4)
     assert idx.abs().sum().item() == 0 and cnt.sum().item() == 0
     assert ext.farthest_point_sample(torch.rand(0, 3, 10, device="cuda"), 2).shape == (0, 2)
+
+
+def test_sizes_beyond_the_tuned_kernels_fall_back(ext, oracle):
+    """The reference has no size limits: more than 128 neighbours per ball and clouds of more than 65 536 points take
+    generic kernels here and still return the oracle's bits."""
+    from regnet_for_3d_grasping_b200 import synth
+    pts = synth.batch("table", [41], 6000)
+    xyz_c = torch.from_numpy(pts[:, :, :3]).permute(0, 2, 1)
+    xyz = torch.from_numpy(pts).cuda()[:, :, :3].permute(0, 2, 1)
+    ctr_c = xyz_c[:, :, ::40].contiguous()
+    bq, cnt = ext.ball_query(xyz, ctr_c.cuda(), 0.25, 200)                      # K = 200 > 128
+    wbq, wcnt = oracle.ball_query(xyz_c, ctr_c, 0.25, 200)
+    assert torch.equal(bq.cpu(), wbq) and torch.equal(cnt.cpu(), wcnt)
+    assert int(cnt.max()) > 128
+    big = synth.batch("table", [42], 70000)                                    # N = 70 000 > 65 536
+    big_c = torch.from_numpy(big[:, :, :3]).permute(0, 2, 1)
+    got = ext.farthest_point_sample(torch.from_numpy(big).cuda()[:, :, :3].permute(0, 2, 1), 96)
+    assert torch.equal(got.cpu(), oracle.farthest_point_sample(big_c, 96))
+
+
+def _ref_double_ext():
+    """The reference's own extension (oracle/_ref, built in the build container, travels with the snapshot): its double
+    kernels are the ground truth for the float64 path.  None when it is not on this box."""
+    try:
+        from oracle import build_ref
+        return build_ref.load()
+    except Exception:
+        return None
+
+
+def test_float64_operators(ext):
+    """float64 inputs (the reference instantiates float and double): search operators against the reference's own double
+    kernels when oracle/_ref is present, else against a float64 torch restatement; value operators against torch."""
+    from regnet_for_3d_grasping_b200 import synth
+    g = torch.Generator().manual_seed(77)
+    pts = torch.from_numpy(synth.batch("cube", [51, 52], 700)[:, :, :3]).double()
+    pts = pts + torch.rand(pts.shape, generator=g, dtype=torch.float64) * 1e-9       # not representable in float32
+    xyz = pts.cuda().permute(0, 2, 1)                                               # strided (B,3,N)
+    M, K, r = 200, 24, 0.22
+    idx = ext.farthest_point_sample(xyz, M)
+    new_xyz = xyz.gather(2, idx.unsqueeze(1).expand(2, 3, M))
+    bq, cnt = ext.ball_query(xyz, new_xyz, r, K)
+    nn, nnd = ext.point_search(xyz, new_xyz, 3)
+    assert nnd.dtype == torch.float64 and idx.dtype == torch.int64
+    ref = _ref_double_ext()
+    if ref is not None:
+        xc = xyz.contiguous()
+        assert torch.equal(idx, ref.farthest_point_sample(xc, M))
+        rbq, rcnt = ref.ball_query(xc, new_xyz.contiguous(), r, K)
+        assert torch.equal(bq, rbq) and torch.equal(cnt, rcnt)
+        rnn, rnnd = ref.point_search(xc, new_xyz.contiguous(), 3)
+        assert torch.equal(nn, rnn) and torch.equal(nnd, rnnd)
+    # float64 restatement in torch (greedy FPS, brute-force ball query / 3-NN)
+    P = pts.cuda()
+    d2 = ((P.unsqueeze(2) - P.unsqueeze(1)) ** 2)
+    D = d2[..., 1] + d2[..., 0] + d2[..., 2]
+    for b in range(2):
+        md = torch.full((700,), float("inf"), dtype=torch.float64, device="cuda")
+        cur, picks = 0, [0]
+        for _ in range(M - 1):
+            md = torch.minimum(md, D[b, cur])
+            cur = int(torch.argmax(md))
+            picks.append(cur)
+        same = (torch.tensor(picks, device="cuda") == idx[b]).float().mean().item()
+        assert same > 0.99, same          # identical up to exact ties (the reference's tie order is not argmax's)
+    Dq = ((new_xyz.permute(0, 2, 1).unsqueeze(2) - P.unsqueeze(1)) ** 2)
+    Dq = Dq[..., 1] + Dq[..., 0] + Dq[..., 2]
+    assert torch.equal(cnt, (Dq < r * r).sum(-1).clamp(max=K))
+    want_nn = Dq.topk(3, dim=-1, largest=False)
+    assert torch.allclose(nnd, want_nn.values, rtol=1e-12, atol=1e-18)
+    # value operators: exact gathers, double scatter-adds
+    feat = torch.randn(2, 5, 700, generator=g, dtype=torch.float64).cuda()
+    grouped = ext.group_points_forward(feat, bq)
+    assert grouped.dtype == torch.float64 and torch.equal(grouped[1, 3, 7, 2], feat[1, 3, bq[1, 7, 2]])
+    gin = ext.group_points_backward(torch.ones_like(grouped), bq, 700)
+    assert torch.allclose(gin.sum(), torch.tensor(float(grouped.numel()), dtype=torch.float64, device="cuda"))
+    w = torch.rand(2, M, 3, generator=g, dtype=torch.float64).cuda()
+    out = ext.interpolate_forward(feat, nn, w)
+    want = sum(feat.gather(2, nn[:, :, k].unsqueeze(1).expand(2, 5, M)) * w[:, :, k].unsqueeze(1) for k in range(3))
+    assert torch.allclose(out, want, rtol=1e-14)
+    back = ext.interpolate_backward(torch.ones(2, 5, M, dtype=torch.float64, device="cuda"), nn, w, 700)
+    assert torch.allclose(back.sum(dim=2), w.sum(dim=(1, 2)).unsqueeze(1).expand(2, 5), rtol=1e-12)
 
 
 def test_dgcnn_alias(ext):
