@@ -103,3 +103,18 @@ def seeded_state_like(state, seed=0):
             v = torch.randn(shape, generator=g) * 0.05
         out[name] = v.to(ref.dtype)
     return out
+
+
+def seeded_region_state(state, seed=0, residual_scale=0.1):
+    """seeded_state_like for a GripperRegionNetwork whose first-stage regression head is scaled down: an untrained head
+    emits O(1) residuals, i.e. grasp centres 6 cm (one gripper depth) away from their anchor, and the closing boxes of such
+    proposals are empty on a real cloud; with residuals of O(0.1) the proposals stay on the surface, like a trained
+    network's, and the refine stage has something to refine.  Used by the virtual-data fixture and its GPU test."""
+    out = seeded_state_like(state, seed)
+    # 40 regression channels = 4 anchors x (3 centre, 3 axis, 1 angle residuals + 3 scores): scale the 7 residuals only,
+    # the predicted scores keep their spread (they are thresholded in the first-stage selection)
+    scale = torch.ones(4, 10)
+    scale[:, :7] = residual_scale
+    for name in ("extrat_feature_region.bn_reg4.weight", "extrat_feature_region.bn_reg4.bias"):
+        out[name] = out[name] * scale.view(-1)
+    return out

@@ -147,6 +147,47 @@ def test_full_size_batch_properties(lib_path, oracle):
     assert torch.equal(f1[0], feat[3]) and torch.equal(s1[0], score[3])
 
 
+def test_full_size_batch_features_match_the_reference_gpu_path(lib_path):
+    """BASELINE configs[1] itself (B = 15 x 25 600): all_feature and the scores of the fused plan against the forward the
+    way the reference computes it on a GPU -- the reference's OWN CUDA kernels (oracle/_ref/pn2_ext_ref.so, built from the
+    reference's .cu files; travels with the repository snapshot) under the restated modules with torch's convolutions in
+    strict fp32.  Without the reference extension on the box, this repo's operators (bit-identical to it, see
+    test_gpu_ops.py) stand in under the same fp32 torch modules.  Indices exact, features within 1e-4 (helpers.py)."""
+    from helpers import assert_features_close
+    from oracle import ref_modules
+    from regnet_for_3d_grasping_b200 import pn2_ext, synth, weights
+    from regnet_for_3d_grasping_b200.scorenet import ScoreNetPlan
+    try:
+        from oracle import build_ref
+        ext = build_ref.load()
+        which = "reference CUDA kernels (oracle/_ref)"
+    except Exception:
+        ext, which = pn2_ext, "this repo's operators (oracle/_ref not on this box)"
+    B, N = 15, 25600
+    pc = torch.from_numpy(synth.batch("table", range(100, 100 + B), N)).cuda()
+    sd = {k: v.cuda() for k, v in weights.random_scorenet_state(seed=0).items()}
+    plan = ScoreNetPlan(B, N, "cuda")
+    plan.bind_state(sd)
+    feat, score = plan.forward(pc)
+    torch.cuda.synchronize()
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            rf, rs, dbg = ref_modules.scorenet_forward(sd, pc, ext, keep=True)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    for lvl, m in enumerate((5120, 1024, 256)):
+        assert torch.equal(plan.intermediate(f"fps{lvl}", torch.int32, (B, m)).long(), dbg[f"fps{lvl}"].long()), (which, lvl)
+        assert torch.equal(plan.intermediate(f"bq{lvl}", torch.int32, (B, m, 64)).long(), dbg[f"bq{lvl}"].long()), (which, lvl)
+    err = ((feat - rf).abs().max() / rf.abs().max()).item()
+    print(f"full-size all_feature vs {which}: max rel err {err:.3e}; score max abs err {(score - rs).abs().max().item():.3e}")
+    rows = torch.arange(0, N, 37, device="cuda")
+    for b in range(B):
+        assert_features_close(feat[b][rows], rf[b][rows], what=f"all_feature, cloud {b} ({which})")
+    assert err < 1e-4 and (score - rs).abs().max().item() < 1e-4
+
+
 def test_prefetch_pipeline_equals_plain_forward(lib_path):
     """Software-pipelined throughput mode (prefetch geometry of batch i+1 during the MLPs of batch i) returns
     exactly what independent forwards return, for alternating different inputs and both slot orders."""
