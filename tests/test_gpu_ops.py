@@ -243,19 +243,24 @@ def test_float64_operators(ext):
     Dq = ((new_xyz.permute(0, 2, 1).unsqueeze(2) - P.unsqueeze(1)) ** 2)
     Dq = Dq[..., 1] + Dq[..., 0] + Dq[..., 2]
     assert torch.equal(cnt, (Dq < r * r).sum(-1).clamp(max=K))
-    want_nn = Dq.topk(3, dim=-1, largest=False)
+    Dn = ((P.unsqueeze(2) - new_xyz.permute(0, 2, 1).unsqueeze(1)) ** 2)          # queries = the cloud, keys = the centroids
+    Dn = Dn[..., 1] + Dn[..., 0] + Dn[..., 2]
+    want_nn = Dn.topk(3, dim=-1, largest=False)
     assert torch.allclose(nnd, want_nn.values, rtol=1e-12, atol=1e-18)
+    assert (nn == want_nn.indices).float().mean().item() > 0.999
     # value operators: exact gathers, double scatter-adds
     feat = torch.randn(2, 5, 700, generator=g, dtype=torch.float64).cuda()
     grouped = ext.group_points_forward(feat, bq)
     assert grouped.dtype == torch.float64 and torch.equal(grouped[1, 3, 7, 2], feat[1, 3, bq[1, 7, 2]])
     gin = ext.group_points_backward(torch.ones_like(grouped), bq, 700)
     assert torch.allclose(gin.sum(), torch.tensor(float(grouped.numel()), dtype=torch.float64, device="cuda"))
-    w = torch.rand(2, M, 3, generator=g, dtype=torch.float64).cuda()
-    out = ext.interpolate_forward(feat, nn, w)
-    want = sum(feat.gather(2, nn[:, :, k].unsqueeze(1).expand(2, 5, M)) * w[:, :, k].unsqueeze(1) for k in range(3))
-    assert torch.allclose(out, want, rtol=1e-14)
-    back = ext.interpolate_backward(torch.ones(2, 5, M, dtype=torch.float64, device="cuda"), nn, w, 700)
+    sfeat = torch.randn(2, 5, M, generator=g, dtype=torch.float64).cuda()       # features at the M centroids (the keys)
+    w = torch.rand(2, 700, 3, generator=g, dtype=torch.float64).cuda()
+    out = ext.interpolate_forward(sfeat, nn, w)
+    want = sum(sfeat.gather(2, nn[:, :, k].unsqueeze(1).expand(2, 5, 700)) * w[:, :, k].unsqueeze(1) for k in range(3))
+    assert out.dtype == torch.float64 and torch.allclose(out, want, rtol=1e-14)
+    back = ext.interpolate_backward(torch.ones(2, 5, 700, dtype=torch.float64, device="cuda"), nn, w, M)
+    assert tuple(back.shape) == (2, 5, M)
     assert torch.allclose(back.sum(dim=2), w.sum(dim=(1, 2)).unsqueeze(1).expand(2, 5), rtol=1e-12)
 
 

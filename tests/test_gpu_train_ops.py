@@ -144,6 +144,9 @@ def test_training_gradients_fused_and_torch_paths_against_float64(lib_path, orac
         print(f"worst parameter-gradient error (relative L2) of this repo's path: {worst[0]:.3e} ({worst[1]})")
         assert checked >= 40
         for k in b0:      # running statistics / counters updated the same way (to the forward's accuracy)
+            if k.startswith(("extrat_featurePN2.mlp.1.", "extrat_featurePN2.mlp.2.", "extrat_featurePN2.mlp.3.",
+                             "extrat_featurePN2.bn_score.")) and "num_batches" not in k:
+                continue      # behind a dropout layer: the two paths draw different (equally distributed) masks
             diff = (b0[k].double() - b1[k].double()).abs().max().item()
             assert diff <= 2e-3 * max(b1[k].double().abs().max().item(), 1e-30), (k, diff)
     finally:
