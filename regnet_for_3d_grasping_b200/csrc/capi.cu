@@ -75,7 +75,7 @@ extern "C" {
 
 const char* regnet_last_error(void) { return g_err.c_str(); }
 
-int regnet_abi_version(void) { return 1; }
+int regnet_abi_version(void) { return 2; }
 
 int regnet_device_arch(int* sm_major, int* sm_minor, int* sm_count) {
   int dev = 0;

@@ -25,7 +25,7 @@ def test_library_is_sm100a_with_blackwell_instructions(lib_path):
 
 def test_abi_version_and_error_channel(lib_path):
     lib = _lib.load()
-    assert lib.regnet_abi_version() == 1
+    assert lib.regnet_abi_version() == 2
     # argument errors are detected before any CUDA call, so they work without a GPU
     rc = lib.regnet_farthest_point_sample(ctypes.c_void_p(16), 0, 0, 0, 1, 10, 11, ctypes.c_void_p(16), None, None)
     assert rc == 1 and b"num_points" in lib.regnet_last_error()
@@ -35,8 +35,14 @@ def test_abi_version_and_error_channel(lib_path):
     assert rc == 1 and b"3 neighbours" in lib.regnet_last_error()
     rc = lib.regnet_point_search(ctypes.c_void_p(16), 0, 0, 0, ctypes.c_void_p(16), 0, 0, 0, 1, 8, 2, 3, None, None, None)
     assert rc == 1 and b"at least 3" in lib.regnet_last_error()
-    rc = lib.regnet_ball_query(ctypes.c_void_p(16), 0, 0, 0, ctypes.c_void_p(16), 0, 0, 0, 1, 8, 8, 0.1, 500, None, None, None, None)
-    assert rc == 3 and b"128" in lib.regnet_last_error()
+    rc = lib.regnet_ball_query(ctypes.c_void_p(16), 0, 0, 0, ctypes.c_void_p(16), 0, 0, 0, 1, 8, 8, 0.1, 0, None, None, None, None)
+    assert rc == 1 and b"num_neighbours" in lib.regnet_last_error()
+    rc = lib.regnet_conv1x1_train(ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 8, 12, ctypes.c_void_p(16), ctypes.c_void_p(16),
+                                  8, 8, ctypes.c_void_p(16), None, 3, None)
+    assert rc == 1 and b"multiple of 8" in lib.regnet_last_error()
+    rc = lib.regnet_conv1x1_train(ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 8, 16, ctypes.c_void_p(16), ctypes.c_void_p(16),
+                                  8, 8, ctypes.c_void_p(16), None, 2, None)
+    assert rc == 1 and b"passes" in lib.regnet_last_error()
     cfg = _lib.ScoreNetConfig()
     cfg.batch, cfg.num_points = 1, 100
     for i, m in enumerate((200, 50, 10)):
