@@ -175,9 +175,16 @@ int regnet_scorenet_prefetch(regnet_scorenet* plan, const float* pc, void* strea
 /* Make `stream` wait for every outstanding prefetch (their side-stream work), e.g. before timing or reusing `pc`. */
 int regnet_scorenet_join_prefetch(regnet_scorenet* plan, void* stream);
 
+/* The geometry chain alone (FPS, ball query and 3-NN of every level), for callers that run the MLPs themselves -- the
+ * training path.  Consumes a matching regnet_scorenet_prefetch or computes the chain now; on return `stream` is ordered
+ * behind every result, readable through regnet_scorenet_intermediate ("fps*", "xyz*", "bq*", "nn*", "nnw*") until the next
+ * forward / geometry call that reuses the slot (two slots alternate). */
+int regnet_scorenet_geometry(regnet_scorenet* plan, const float* pc, void* stream);
+
 /* Read back intermediates of the last forward for parity tests (device pointers into the plan's workspace,
  * valid until the next forward).  what: "fps0".."fps2" int32 (B,M_i); "bq0".."bq2" int32 (B,M_i,64);
- * "nn0".."nn2" int32 (B,Nd_i,3); "sa0".."sa2" fp32 (B,M_i,C) point-major; "fp0".."fp2" fp32 point-major. */
+ * "nn0".."nn2" int32 (B,Nd_i,3); "nnw0".."nnw2" fp32 (B,Nd_i,3) interpolation weights; "xyz0".."xyz2" fp32 (B,3,M_i) sampled
+ * coordinates; "sa0".."sa2" fp32 (B,M_i,C) point-major; "fp0".."fp2" fp32 point-major. */
 int regnet_scorenet_intermediate(regnet_scorenet* plan, const char* what, void** ptr, int64_t* numel);
 
 /* Per-launch timing for bench.py's roofline block.  With profiling on, the forward runs every kernel on the
@@ -314,6 +321,19 @@ int regnet_bn_backward_ex(const float* dy, const float* z, int B, int C, int64_t
                           const float* save_invstd, const float* scale, const float* shift, int relu, float drop_p,
                           uint64_t drop_seed, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta,
                           void* workspace, int64_t workspace_bytes, void* stream);
+/* dgrad with the reduction pass of the previous block's BatchNorm backward fused into its epilogue: out = W^T g as
+ * regnet_conv1x1_train (rows = that block's channels), and sums (rows, 2) doubles = per-channel sum(h), sum(h * xhat) with
+ * h = out * dropout-mask * [bn(z_prev) > 0] and xhat = (z_prev - mean) * invstd -- what regnet_bn_backward_ex computes in
+ * a separate pass over out and z_prev.  regnet_bn_backward_from_sums then finishes that block's backward (dgamma, dbeta,
+ * the gradient w.r.t. z_prev as fp32 and / or planes) with the apply pass only; workspace >= 2 * C floats. */
+int regnet_conv1x1_train_dgrad_bnreduce(const void* g_hi, const void* g_lo, int B, int K, int64_t L, const void* a_hi,
+                                        const void* a_lo, int rows, int lda, float* out, const float* z_prev,
+                                        const float* mean, const float* invstd, const float* scale, const float* shift,
+                                        int relu, float drop_p, uint64_t drop_seed, double* sums, int passes, void* stream);
+int regnet_bn_backward_from_sums(const float* dy, const float* z, int B, int C, int64_t L, const float* save_mean,
+                                 const float* save_invstd, const float* scale, const float* shift, int relu, float drop_p,
+                                 uint64_t drop_seed, const double* sums, float* dz, void* dz_hi, void* dz_lo, float* dgamma,
+                                 float* dbeta, void* workspace, int64_t workspace_bytes, void* stream);
 /* the pooled block with given statistics: out[b,c,m] = max_k [relu](fma(z[b,c,m,k], scale, shift)), and its backward */
 int regnet_bn_apply_max64(const float* z, int B, int C, int64_t M, const float* scale, const float* shift, int relu,
                           float* out, uint8_t* argmax, void* stream);
@@ -321,6 +341,25 @@ int regnet_bn_max64_backward_ex(const float* dout, const uint8_t* argmax, const 
                                 const float* save_mean, const float* save_invstd, const float* scale, const float* shift,
                                 int relu, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta, void* workspace,
                                 int64_t workspace_bytes, void* stream);
+
+/* Operand producers of the training path (csrc/train_gather.cu): the input of a shared MLP written directly as planes.
+ * regnet_sa_group_planes: QueryGrouper.forward (modules.py:39-56) -- out[b, 0:3, m, k] = xyz[b, :, index[b,m,k]] -
+ * new_xyz[b, :, m], out[b, 3:, m, k] = feature[b, :, index[b,m,k]]; xyz (B,3,N) and feature (B,C,N) strided, new_xyz (B,3,M)
+ * contiguous, index (B,M,K) int64, K % 4 == 0; planes (B, 3 + C, M, K).
+ * regnet_fp_interp_planes: FeatureInterpolator.forward (modules.py:104-131) -- out[b, 0:C2, n] = sum_k sparse[b, :,
+ * index[b,n,k]] * weight[b,n,k], out[b, C2:, n] = dense[b, :, n]; planes (B, C2 + C1, Nd), Nd % 4 == 0.
+ * The two *_backward_strided calls are regnet_group_points_backward / regnet_interpolate_backward reading channels
+ * [c0, c0 + C) of a (B, Ctot, L) gradient in place (batch_stride = Ctot * L elements); source rows of at most 12 288 points. */
+int regnet_sa_group_planes(const float* xyz, int64_t xsb, int64_t xsc, int64_t xsn, const float* new_xyz, const float* feature,
+                           int64_t fsb, int64_t fsc, int64_t fsn, const int64_t* index, int B, int C, int N, int M, int K,
+                           void* out_hi, void* out_lo, void* stream);
+int regnet_fp_interp_planes(const float* sparse, int64_t ssb, int64_t ssc, int64_t ssn, const float* dense, int64_t dsb,
+                            int64_t dsc, int64_t dsn, const int64_t* index, const float* weight, int B, int C2, int C1, int Ns,
+                            int Nd, void* out_hi, void* out_lo, void* stream);
+int regnet_group_points_backward_strided(const float* grad_out, int64_t batch_stride, int c0, const int64_t* index, int B,
+                                         int C, int N, int M, int K, float* grad_in, void* stream);
+int regnet_interpolate_backward_strided(const float* grad_out, int64_t batch_stride, int c0, const int64_t* index,
+                                        const float* weight, int B, int C, int Ns, int Nd, float* grad_in, void* stream);
 
 /* ---- 4. building blocks exposed for tests / micro-benchmarks ------------------------------------------- */
 

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "regnet_scorenet_forward": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "regnet_scorenet_prefetch": (c_int, [c_ptr, c_ptr, c_ptr]),
     "regnet_scorenet_join_prefetch": (c_int, [c_ptr, c_ptr]),
+    "regnet_scorenet_geometry": (c_int, [c_ptr, c_ptr, c_ptr]),
     "regnet_scorenet_intermediate": (c_int, [c_ptr, ctypes.c_char_p, ctypes.POINTER(c_ptr), ctypes.POINTER(c_i64)]),
     "regnet_scorenet_launch_count": (c_int, [c_ptr]),
     "regnet_scorenet_set_profiling": (c_int, [c_ptr, c_int]),
@@ -80,6 +81,19 @@ _SIGNATURES = {
                                    c_ptr, c_ptr]),
     "regnet_bn_backward_ex": (c_int, [c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32,
                                       ctypes.c_uint64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "regnet_conv1x1_train_dgrad_bnreduce": (c_int, [c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_int, c_int, c_ptr,
+                                                    c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32, ctypes.c_uint64, c_ptr,
+                                                    c_int, c_ptr]),
+    "regnet_bn_backward_from_sums": (c_int, [c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32,
+                                             ctypes.c_uint64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "regnet_sa_group_planes": (c_int, _STRIDED + [c_ptr] + _STRIDED + [c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
+                                                            c_ptr]),
+    "regnet_fp_interp_planes": (c_int, _STRIDED + _STRIDED + [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr,
+                                                              c_ptr]),
+    "regnet_group_points_backward_strided": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr,
+                                                     c_ptr]),
+    "regnet_interpolate_backward_strided": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr,
+                                                    c_ptr]),
     "regnet_bn_apply_max64": (c_int, [c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "regnet_bn_max64_backward_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
                                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),

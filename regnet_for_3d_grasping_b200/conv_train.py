@@ -108,54 +108,114 @@ class _Spec:
         self.seeds = seeds          # one dropout seed per block (unused when dropout_p == 0)
 
 
+def _chain_forward(hi, lo, B, L, spec, weights, gammas, betas):
+    """Blocks of one shared MLP over input planes (B, C0, L): -> (out fp32, saved tensors [hi, lo, z, stats] per block, arg)."""
+    lib = _lib.load()
+    dev = hi.device
+    n = len(spec.bns)
+    saved, out, arg = [], None, None
+    for i in range(n):
+        w = weights[i]
+        cout, cin = w.shape[0], w.shape[1]
+        a_hi, a_lo = split_weight(w.reshape(cout, cin))
+        z, moments = conv1x1(hi, lo, a_hi, a_lo, cout, cin, want_moments=True, passes=spec.passes)
+        bn = spec.bns[i]
+        stats = torch.empty(4, cout, dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
+        _lib.check(lib.regnet_bn_finalize_moments(
+            _p(moments), cout, float(B) * float(L), _p(gammas[i]), _p(betas[i]), float(bn.eps), float(bn.momentum),
+            _p(bn.running_mean), _p(bn.running_var), _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]), _stream()))
+        saved += [hi, lo, z, stats]
+        last = i == n - 1
+        if last and spec.pooled:
+            M = L // 64
+            out = torch.empty(B, cout, M, dtype=torch.float32, device=dev)
+            arg = torch.empty(B, cout, M, dtype=torch.uint8, device=dev)
+            _lib.check(lib.regnet_bn_apply_max64(_p(z), B, cout, M, _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
+                                                 _p(out), _p(arg), _stream()))
+        elif last:
+            out = torch.empty(B, cout, L, dtype=torch.float32, device=dev)
+            _lib.check(lib.regnet_bn_apply_ex(_p(z), B, cout, L, _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
+                                              spec.dropout_p, spec.seeds[i], _p(out), None, None, _stream()))
+        else:
+            hi = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
+            lo = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.regnet_bn_apply_ex(_p(z), B, cout, L, _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
+                                              spec.dropout_p, spec.seeds[i], None, _p(hi), _p(lo), _stream()))
+    return out, saved, arg
+
+
+def _chain_backward(dout, B, L, spec, weights, saved, arg, need_w, need_dx):
+    """-> (dx fp32 (B, C0, L) or None, dW list, dgamma list, dbeta list)."""
+    lib = _lib.load()
+    dev = dout.device
+    n = len(spec.bns)
+    dws, dgs, dbs = [None] * n, [None] * n, [None] * n
+    dy = dout.contiguous()
+    # The reduction pass of a block's BatchNorm backward can ride in the dgrad epilogue of the block above
+    # (REGNET_TRAIN_FUSED_BNREDUCE=1).  Measured on B200 it is a loss: the per-thread 128-byte loads of z stretch the
+    # epilogue (dgrad 7.0 -> 9.5 ms per step) by more than the separate HBM-roofline pass costs (3.3 ms), so it is off.
+    fuse = os.environ.get("REGNET_TRAIN_FUSED_BNREDUCE", "0") == "1"
+    sums = None                     # (C, 2) fp64 from the dgrad epilogue of the block above, when fused
+    for i in range(n - 1, -1, -1):
+        hi, lo, z, stats = saved[4 * i:4 * i + 4]
+        w = weights[i]
+        cout, cin = w.shape[0], w.shape[1]
+        g_hi = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
+        g_lo = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
+        dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
+        ws, nbytes = _bn_ws(lib, B, cout, L, dev)
+        if i == n - 1 and spec.pooled:
+            _lib.check(lib.regnet_bn_max64_backward_ex(
+                _p(dy), _p(arg), _p(z), B, cout, L // 64, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
+                int(spec.relu[i]), None, _p(g_hi), _p(g_lo), _p(dgamma), _p(dbeta), _p(ws), nbytes, _stream()))
+        elif sums is not None:
+            _lib.check(lib.regnet_bn_backward_from_sums(
+                _p(dy), _p(z), B, cout, L, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
+                int(spec.relu[i]), spec.dropout_p, spec.seeds[i], _p(sums), None, _p(g_hi), _p(g_lo), _p(dgamma),
+                _p(dbeta), _p(ws), nbytes, _stream()))
+        else:
+            _lib.check(lib.regnet_bn_backward_ex(
+                _p(dy), _p(z), B, cout, L, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
+                int(spec.relu[i]), spec.dropout_p, spec.seeds[i], None, _p(g_hi), _p(g_lo), _p(dgamma), _p(dbeta),
+                _p(ws), nbytes, _stream()))
+        dgs[i], dbs[i] = dgamma, dbeta
+        sums = None
+        if need_w[i]:
+            dws[i] = wgrad(g_hi, g_lo, hi, lo, passes=spec.passes).view(w.shape)
+        if i > 0 or need_dx:
+            t_hi, t_lo = split_weight(w.reshape(cout, cin), transpose=True)
+            if i > 0 and fuse:
+                # dgrad + the reduction pass of block i-1's BatchNorm backward in one kernel
+                zp, sp = saved[4 * (i - 1) + 2], saved[4 * (i - 1) + 3]
+                dy = torch.empty(B, cin, L, dtype=torch.float32, device=dev)
+                sums = torch.empty(cin, 2, dtype=torch.float64, device=dev)
+                _lib.check(lib.regnet_conv1x1_train_dgrad_bnreduce(
+                    _p(g_hi), _p(g_lo), B, cout, L, _p(t_hi), _p(t_lo), cin, t_hi.shape[1], _p(dy), _p(zp), _p(sp[0]),
+                    _p(sp[1]), _p(sp[2]), _p(sp[3]), int(spec.relu[i - 1]), spec.dropout_p, spec.seeds[i - 1],
+                    _p(sums), spec.passes, _stream()))
+            else:
+                dy = conv1x1(g_hi, g_lo, t_hi, t_lo, cin, cout, passes=spec.passes)
+        else:
+            dy = None
+        del g_hi, g_lo
+    return dy, dws, dgs, dbs
+
+
 class _MLPChainTrain(torch.autograd.Function):
+    """Shared MLP on an fp32 input tensor (B, C0, ...)."""
+
     @staticmethod
     def forward(ctx, x, spec, *params):
         n = len(spec.bns)
         weights, gammas, betas = params[:n], params[n:2 * n], params[2 * n:3 * n]
-        lib = _lib.load()
-        dev = x.device
         shape = x.shape
         B, C0 = shape[0], shape[1]
         L = x.numel() // max(B * C0, 1)
-        x3 = x.contiguous().view(B, C0, L)
-        saved = []
-        with torch.cuda.device(dev):
-            hi, lo = split_planes(x3)
-            out = None
-            arg = None
-            for i in range(n):
-                w = weights[i]
-                cout, cin = w.shape[0], w.shape[1]
-                a_hi, a_lo = split_weight(w.reshape(cout, cin))
-                z, moments = conv1x1(hi, lo, a_hi, a_lo, cout, cin, want_moments=True, passes=spec.passes)
-                bn = spec.bns[i]
-                stats = torch.empty(4, cout, dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
-                _lib.check(lib.regnet_bn_finalize_moments(
-                    _p(moments), cout, float(B) * float(L), _p(gammas[i]), _p(betas[i]), float(bn.eps), float(bn.momentum),
-                    _p(bn.running_mean), _p(bn.running_var), _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
-                    _stream()))
-                saved += [hi, lo, z, stats]
-                last = i == n - 1
-                if last and spec.pooled:
-                    M = L // 64
-                    out = torch.empty(B, cout, M, dtype=torch.float32, device=dev)
-                    arg = torch.empty(B, cout, M, dtype=torch.uint8, device=dev)
-                    _lib.check(lib.regnet_bn_apply_max64(_p(z), B, cout, M, _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
-                                                         _p(out), _p(arg), _stream()))
-                elif last:
-                    out = torch.empty(B, cout, L, dtype=torch.float32, device=dev)
-                    _lib.check(lib.regnet_bn_apply_ex(_p(z), B, cout, L, _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
-                                                      spec.dropout_p, spec.seeds[i], _p(out), None, None, _stream()))
-                else:
-                    hi = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
-                    lo = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
-                    _lib.check(lib.regnet_bn_apply_ex(_p(z), B, cout, L, _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
-                                                      spec.dropout_p, spec.seeds[i], None, _p(hi), _p(lo), _stream()))
-        ctx.spec = spec
-        ctx.n = n
-        ctx.in_shape = shape
-        ctx.L = L
+        with torch.cuda.device(x.device):
+            hi, lo = split_planes(x.contiguous().view(B, C0, L))
+            out, saved, arg = _chain_forward(hi, lo, B, L, spec, weights, gammas, betas)
+        ctx.spec, ctx.n, ctx.in_shape, ctx.L = spec, n, shape, L
         ctx.save_for_backward(*(list(weights) + saved + ([arg] if arg is not None else [])))
         if spec.pooled:
             return out.view(B, out.shape[1], shape[2])
@@ -165,44 +225,106 @@ class _MLPChainTrain(torch.autograd.Function):
     def backward(ctx, dout):
         spec, n, L = ctx.spec, ctx.n, ctx.L
         tensors = ctx.saved_tensors
-        weights = tensors[:n]
-        saved = tensors[n:n + 4 * n]
+        weights, saved = tensors[:n], tensors[n:n + 4 * n]
         arg = tensors[n + 4 * n] if spec.pooled else None
-        lib = _lib.load()
-        dev = dout.device
         B = ctx.in_shape[0]
-        dws, dgs, dbs = [None] * n, [None] * n, [None] * n
-        dy = dout.contiguous()
-        with torch.cuda.device(dev):
-            for i in range(n - 1, -1, -1):
-                hi, lo, z, stats = saved[4 * i:4 * i + 4]
-                w = weights[i]
-                cout, cin = w.shape[0], w.shape[1]
-                g_hi = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
-                g_lo = torch.empty(B, cout, L, dtype=torch.bfloat16, device=dev)
-                dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
-                dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
-                ws, nbytes = _bn_ws(lib, B, cout, L, dev)
-                if i == n - 1 and spec.pooled:
-                    _lib.check(lib.regnet_bn_max64_backward_ex(
-                        _p(dy), _p(arg), _p(z), B, cout, L // 64, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
-                        int(spec.relu[i]), None, _p(g_hi), _p(g_lo), _p(dgamma), _p(dbeta), _p(ws), nbytes, _stream()))
-                else:
-                    _lib.check(lib.regnet_bn_backward_ex(
-                        _p(dy), _p(z), B, cout, L, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
-                        int(spec.relu[i]), spec.dropout_p, spec.seeds[i], None, _p(g_hi), _p(g_lo), _p(dgamma), _p(dbeta),
-                        _p(ws), nbytes, _stream()))
-                dgs[i], dbs[i] = dgamma, dbeta
-                if ctx.needs_input_grad[2 + i]:
-                    dws[i] = wgrad(g_hi, g_lo, hi, lo, passes=spec.passes).view(w.shape)
-                if i > 0 or ctx.needs_input_grad[0]:
-                    t_hi, t_lo = split_weight(w.reshape(cout, cin), transpose=True)
-                    dy = conv1x1(g_hi, g_lo, t_hi, t_lo, cin, cout, passes=spec.passes)
-                else:
-                    dy = None
-                del g_hi, g_lo
-        dx = dy.view(ctx.in_shape) if dy is not None else None
+        with torch.cuda.device(dout.device):
+            dx, dws, dgs, dbs = _chain_backward(dout, B, L, spec, weights, saved, arg,
+                                                [ctx.needs_input_grad[2 + i] for i in range(n)], ctx.needs_input_grad[0])
+        dx = dx.view(ctx.in_shape) if dx is not None else None
         return (dx, None) + tuple(dws) + tuple(dgs) + tuple(dbs)
+
+
+class _SAGroupedChainTrain(torch.autograd.Function):
+    """Set-abstraction body in train mode: QueryGrouper (pn2_utils/modules.py:39-56: group xyz and features by the ball-query
+    index, centre the coordinates, concat [xyz_rel | feature]) written directly as operand planes, then the pooled shared MLP.
+    `feature` (B, C, N) is the only differentiable input; xyz / new_xyz / index ride in the spec."""
+
+    @staticmethod
+    def forward(ctx, feature, spec, *params):
+        n = len(spec.bns)
+        weights, gammas, betas = params[:n], params[n:2 * n], params[2 * n:3 * n]
+        xyz, new_xyz, index = spec.xyz, spec.new_xyz, spec.index
+        B, _, N = xyz.shape
+        M, K = index.shape[1], index.shape[2]
+        C = feature.shape[1]
+        L = M * K
+        dev = xyz.device
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            hi = torch.empty(B, C + 3, L, dtype=torch.bfloat16, device=dev)
+            lo = torch.empty(B, C + 3, L, dtype=torch.bfloat16, device=dev)
+            nx = new_xyz.contiguous()
+            _lib.check(lib.regnet_sa_group_planes(_p(xyz), xyz.stride(0), xyz.stride(1), xyz.stride(2), _p(nx), _p(feature),
+                                                  feature.stride(0), feature.stride(1), feature.stride(2), _p(index), B, C, N,
+                                                  M, K, _p(hi), _p(lo), _stream()))
+            out, saved, arg = _chain_forward(hi, lo, B, L, spec, weights, gammas, betas)
+        ctx.spec, ctx.n, ctx.dims = spec, n, (B, C, N, M, K)
+        ctx.save_for_backward(*(list(weights) + saved + [arg]))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, n = ctx.spec, ctx.n
+        B, C, N, M, K = ctx.dims
+        tensors = ctx.saved_tensors
+        weights, saved, arg = tensors[:n], tensors[n:n + 4 * n], tensors[n + 4 * n]
+        dfeat = None
+        with torch.cuda.device(dout.device):
+            dx, dws, dgs, dbs = _chain_backward(dout, B, M * K, spec, weights, saved, arg,
+                                                [ctx.needs_input_grad[2 + i] for i in range(n)], ctx.needs_input_grad[0])
+            if dx is not None:
+                # scatter-add of the feature channels (3 ..) of the operand gradient, read in place
+                dfeat = torch.empty(B, C, N, dtype=torch.float32, device=dout.device)
+                _lib.check(_lib.load().regnet_group_points_backward_strided(
+                    _p(dx), (C + 3) * M * K, 3, _p(spec.index), B, C, N, M, K, _p(dfeat), _stream()))
+        return (dfeat, None) + tuple(dws) + tuple(dgs) + tuple(dbs)
+
+
+class _FPInterpChainTrain(torch.autograd.Function):
+    """Feature-propagation body in train mode: FeatureInterpolator (modules.py:104-131: 3-NN weighted interpolation of the
+    sparse features, concat [interpolated | dense]) written directly as operand planes, then the shared MLP."""
+
+    @staticmethod
+    def forward(ctx, sparse, dense, spec, *params):
+        n = len(spec.bns)
+        weights, gammas, betas = params[:n], params[n:2 * n], params[2 * n:3 * n]
+        index, weight = spec.index, spec.weight
+        B, C2, Ns = sparse.shape
+        Nd = index.shape[1]
+        C1 = 0 if dense is None else dense.shape[1]
+        dev = sparse.device
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            hi = torch.empty(B, C2 + C1, Nd, dtype=torch.bfloat16, device=dev)
+            lo = torch.empty(B, C2 + C1, Nd, dtype=torch.bfloat16, device=dev)
+            ds = (0, 0, 0) if dense is None else dense.stride()
+            _lib.check(lib.regnet_fp_interp_planes(_p(sparse), sparse.stride(0), sparse.stride(1), sparse.stride(2), _p(dense),
+                                                   ds[0], ds[1], ds[2], _p(index), _p(weight), B, C2, C1, Ns, Nd, _p(hi),
+                                                   _p(lo), _stream()))
+            out, saved, _ = _chain_forward(hi, lo, B, Nd, spec, weights, gammas, betas)
+        ctx.spec, ctx.n, ctx.dims = spec, n, (B, C2, C1, Ns, Nd)
+        ctx.save_for_backward(*(list(weights) + saved))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, n = ctx.spec, ctx.n
+        B, C2, C1, Ns, Nd = ctx.dims
+        tensors = ctx.saved_tensors
+        weights, saved = tensors[:n], tensors[n:n + 4 * n]
+        need_s, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and C1 > 0
+        dsparse = ddense = None
+        with torch.cuda.device(dout.device):
+            dx, dws, dgs, dbs = _chain_backward(dout, B, Nd, spec, weights, saved, None,
+                                                [ctx.needs_input_grad[3 + i] for i in range(n)], need_s or need_d)
+            if need_s:
+                dsparse = torch.empty(B, C2, Ns, dtype=torch.float32, device=dout.device)
+                _lib.check(_lib.load().regnet_interpolate_backward_strided(
+                    _p(dx), (C2 + C1) * Nd, 0, _p(spec.index), _p(spec.weight), B, C2, Ns, Nd, _p(dsparse), _stream()))
+            if need_d:
+                ddense = dx[:, C2:, :]
+        return (dsparse, ddense, None) + tuple(dws) + tuple(dgs) + tuple(dbs)
 
 
 def chain_supported(mlp, x):
@@ -225,17 +347,86 @@ def chain_supported(mlp, x):
     return True
 
 
-def mlp_chain_train(mlp, x, pooled):
-    """SharedMLP.forward (pooled=False) or torch.max(SharedMLP.forward(x), 3)[0] (pooled=True) in train mode."""
+def _spec_and_params(mlp, pooled):
     blocks = list(mlp)
     p = float(mlp.dropout_prob) if mlp.training else 0.0
     seeds = [int(s) for s in torch.randint(0, 2 ** 62, (len(blocks),))] if p > 0.0 else [0] * len(blocks)
     spec = _Spec(blocks, pooled, p, default_passes(), seeds)
     params = [b.conv.weight for b in blocks] + [b.bn.weight for b in blocks] + [b.bn.bias for b in blocks]
-    y = _MLPChainTrain.apply(x, spec, *params)
+    return blocks, spec, params
+
+
+def _count_batches(blocks):
     for b in blocks:
         if b.bn.num_batches_tracked is not None:
             b.bn.num_batches_tracked.add_(1)
+
+
+def mlp_chain_train(mlp, x, pooled):
+    """SharedMLP.forward (pooled=False) or torch.max(SharedMLP.forward(x), 3)[0] (pooled=True) in train mode."""
+    blocks, spec, params = _spec_and_params(mlp, pooled)
+    y = _MLPChainTrain.apply(x, spec, *params)
+    _count_batches(blocks)
+    return y
+
+
+def _blocks_ok(mlp, B, L):
+    if not enabled() or L % 8 != 0 or B * L <= 1 or B > 1023 or len(mlp) == 0:
+        return False
+    for blk in mlp:
+        bn, conv = blk.bn, blk.conv
+        if bn is None or conv.bias is not None or not (bn.training and bn.affine and bn.track_running_stats):
+            return False
+        if bn.momentum is None or any(k != 1 for k in conv.kernel_size) or B * conv.out_channels > 65535:
+            return False
+    return True
+
+
+def _f32_cuda(*tensors):
+    return all(t is not None and t.is_cuda and t.dtype == torch.float32 and t.dim() == 3 and t.numel() > 0 for t in tensors)
+
+
+def sa_grouped_supported(mlp, xyz, new_xyz, feature, index):
+    """The fused set-abstraction body: 64 neighbours, a feature tensor, no dropout, source clouds whose scatter-add row
+    fits in shared memory when the features need a gradient."""
+    if not (mlp.training and mlp.ndim == 2 and mlp.dropout_prob == 0.0 and _f32_cuda(xyz, new_xyz, feature)):
+        return False
+    if index.dtype != torch.int64 or index.dim() != 3 or index.size(2) != 64 or not index.is_contiguous():
+        return False
+    if feature.requires_grad and xyz.size(2) > 12288:
+        return False
+    if os.environ.get("REGNET_TRAIN_UNFUSED_OPERANDS", "0") == "1":
+        return False
+    return _blocks_ok(mlp, xyz.size(0), index.size(1) * 64)
+
+
+def sa_grouped_chain_train(mlp, xyz, new_xyz, feature, index):
+    """torch.max(mlp(cat([group(xyz) - new_xyz, group(feature)], 1)), 3)[0] -- modules.py:44-52 + :245 -- in train mode."""
+    blocks, spec, params = _spec_and_params(mlp, True)
+    spec.xyz, spec.new_xyz, spec.index = xyz.detach(), new_xyz.detach(), index
+    y = _SAGroupedChainTrain.apply(feature, spec, *params)
+    _count_batches(blocks)
+    return y
+
+
+def fp_interp_supported(mlp, sparse_feature, dense_feature, index, weight):
+    if not (mlp.training and mlp.ndim == 1 and _f32_cuda(sparse_feature) and (dense_feature is None or _f32_cuda(dense_feature))):
+        return False
+    if index.dtype != torch.int64 or index.dim() != 3 or index.size(2) != 3 or not (index.is_contiguous() and weight.is_contiguous()):
+        return False
+    if sparse_feature.size(2) > 12288 or index.size(1) % 8 != 0:
+        return False
+    if os.environ.get("REGNET_TRAIN_UNFUSED_OPERANDS", "0") == "1":
+        return False
+    return _blocks_ok(mlp, sparse_feature.size(0), index.size(1))
+
+
+def fp_interp_chain_train(mlp, sparse_feature, dense_feature, index, weight):
+    """mlp(cat([interpolate(sparse_feature, index, weight), dense_feature], 1)) -- modules.py:127-131, 508-509 -- in train mode."""
+    blocks, spec, params = _spec_and_params(mlp, False)
+    spec.index, spec.weight = index, weight.detach()
+    y = _FPInterpChainTrain.apply(sparse_feature, dense_feature, spec, *params)
+    _count_batches(blocks)
     return y
 
 

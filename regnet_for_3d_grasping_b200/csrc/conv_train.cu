@@ -22,6 +22,7 @@
 
 #include "internal.cuh"
 #include "tc_ptx.cuh"
+#include "train_common.cuh"
 
 namespace regnet {
 
@@ -51,11 +52,30 @@ struct ConvDims {
   uint32_t lbo, sbo;   // MN-major descriptor offsets of the activation operand (bytes)
 };
 
-template <bool STATS>
+// dgrad with the reduction pass of the PREVIOUS block's BatchNorm backward fused into the epilogue: the output tile is the
+// gradient dy w.r.t. that block's activation y = dropout(relu(bn(z))); with z (the block's convolution output) read next to
+// it, every epilogue thread -- one channel -- accumulates sum(g) and sum(g * xhat), g = dy * dropout * [bn(z) > 0], which
+// is all the batch-norm backward needs before its apply pass (train_ops.cu bn_bwd_reduce_ex_kernel does the same in a
+// separate pass over dy and z).
+struct BnReduce {
+  const float* z = nullptr;        // (B, rows, L) convolution output of the block whose gradient is being produced
+  const float* mean = nullptr;     // (rows) batch statistics / affine map of that block's BatchNorm
+  const float* invstd = nullptr;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int relu = 1;
+  DropCfg drop = {0, 0, 1.f};
+  double* sums = nullptr;          // (rows, 2): sum g, sum g * xhat (zeroed by the launcher)
+};
+
+constexpr int MODE_PLAIN = 0, MODE_MOMENTS = 1, MODE_BNREDUCE = 2;
+
+template <int MODE>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_constant__ CUtensorMap map_alo,
                   const __grid_constant__ CUtensorMap map_xhi, const __grid_constant__ CUtensorMap map_xlo,
-                  const __grid_constant__ CUtensorMap map_out, ConvDims d, double* __restrict__ moments) {
+                  const __grid_constant__ CUtensorMap map_out, ConvDims d, double* __restrict__ moments, BnReduce br) {
+  constexpr bool STATS = MODE == MODE_MOMENTS;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_base = smem_u32(smem);
@@ -177,11 +197,47 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       float pivot = 0.f, s1 = 0.f, s2 = 0.f;
+      // MODE_BNREDUCE: this thread's channel of the previous block
+      const int brow = row0 + lane;
+      const bool bok = MODE == MODE_BNREDUCE && brow < d.rows;
+      float bmu = 0.f, bis = 0.f, bsc = 0.f, bsh = 0.f;
+      const float* __restrict__ zrow = nullptr;
+      if (bok) {
+        bmu = br.mean[brow]; bis = br.invstd[brow]; bsc = br.scale[brow]; bsh = br.shift[brow];
+        zrow = br.z + ((int64_t)b * d.rows + brow) * d.L + l0;
+      }
 #pragma unroll 1
       for (int ch = 0; ch < CT_BN / 32; ++ch) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * CT_BN + ch * 32, v);
         const int ncols = min(32, d.L - (l0 + ch * 32));
+        float4 zv[8];
+        if (MODE == MODE_BNREDUCE) {   // z loads fly while the accumulator chunk is read from tensor memory
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            zv[j] = (bok && 4 * j + 4 <= ncols) ? __ldg(reinterpret_cast<const float4*>(zrow + ch * 32) + j)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * CT_BN + ch * 32, v);
+        if (MODE == MODE_BNREDUCE) {
+          const int64_t e0 = ((int64_t)b * d.rows + brow) * d.L + l0 + ch * 32;   // element index of this chunk (dropout mask)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g0 = __uint_as_float(v[4 * j]), g1 = __uint_as_float(v[4 * j + 1]), g2 = __uint_as_float(v[4 * j + 2]),
+                  g3 = __uint_as_float(v[4 * j + 3]);
+            if (!(bok && 4 * j + 4 <= ncols)) g0 = g1 = g2 = g3 = 0.f;    // L is a multiple of 8: whole vectors only
+            if (br.drop.thr) {
+              const float4 m = drop_mult((uint64_t)(e0 + 4 * j) >> 2, br.drop.seed, br.drop.thr, br.drop.inv_keep);
+              g0 *= m.x; g1 *= m.y; g2 *= m.z; g3 *= m.w;
+            }
+            const float4 z = zv[j];
+            if (br.relu) {
+              g0 = fmaf(z.x, bsc, bsh) > 0.f ? g0 : 0.f; g1 = fmaf(z.y, bsc, bsh) > 0.f ? g1 : 0.f;
+              g2 = fmaf(z.z, bsc, bsh) > 0.f ? g2 : 0.f; g3 = fmaf(z.w, bsc, bsh) > 0.f ? g3 : 0.f;
+            }
+            s1 += (g0 + g1) + (g2 + g3);
+            s2 = fmaf(g0, (z.x - bmu) * bis, fmaf(g1, (z.y - bmu) * bis, fmaf(g2, (z.z - bmu) * bis, fmaf(g3, (z.w - bmu) * bis, s2))));
+          }
+        }
         if (STATS) {
           // deviations from the first value of the tile row: the sum of squares stays small, no cancellation
           if (ch == 0) pivot = __uint_as_float(v[0]);
@@ -222,6 +278,10 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (MODE == MODE_BNREDUCE && bok) {
+        atomicAdd(br.sums + 2 * brow, (double)s1);
+        atomicAdd(br.sums + 2 * brow + 1, (double)s2);
+      }
       if (STATS) {
         const int row = row0 + lane;
         const int n = min(CT_BN, d.L - l0);
@@ -462,15 +522,16 @@ int regnet_split_weight(const float* W, int rows, int cols, int transpose, int l
   return REGNET_OK;
 }
 
-int regnet_conv1x1_train(const void* x_hi, const void* x_lo, int B, int K, int64_t L, const void* a_hi, const void* a_lo,
-                         int rows, int lda, float* out, double* moments, int passes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int conv1x1_launch(const void* x_hi, const void* x_lo, int B, int K, int64_t L, const void* a_hi, const void* a_lo,
+                          int rows, int lda, float* out, double* moments, const BnReduce* br, int passes,
+                          cudaStream_t stream) {
   RN_CHECK_ARG(x_hi && x_lo && a_hi && a_lo && out, "conv1x1_train: null argument");
   RN_CHECK_ARG(B > 0 && K > 0 && L > 0 && rows > 0, "conv1x1_train: empty problem");
   RN_CHECK_ARG(passes == 1 || passes == 3, "conv1x1_train: passes must be 1 or 3");
   RN_CHECK_ARG(L % 8 == 0, "conv1x1_train: the position extent (%lld) must be a multiple of 8", (long long)L);
   RN_CHECK_ARG(lda % 8 == 0 && lda >= K, "conv1x1_train: weight leading dimension %d must be a multiple of 8 and >= %d", lda, K);
   RN_CHECK_ARG(L < (1LL << 31), "conv1x1_train: too many positions");
+  RN_CHECK_ARG(!(moments && br), "conv1x1_train: moments and the fused batch-norm reduction are exclusive");
   if (!gemm_tc_supported()) {
     set_error("conv1x1_train: tensor-map driver entry point unavailable");
     return REGNET_ECUDA;
@@ -484,24 +545,44 @@ int regnet_conv1x1_train(const void* x_hi, const void* x_lo, int B, int K, int64
   ConvDims d;
   d.rows = rows; d.K = K; d.L = (int)L; d.B = B; d.passes = passes;
   d.lbo = CT_BK * 128; d.sbo = 1024;
-  if (const char* e = getenv("REGNET_CONV_DESC_SWAP")) {   // bring-up switch: exchange the two descriptor offsets
-    if (atoi(e)) { d.lbo = 1024; d.sbo = CT_BK * 128; }
-  }
   int dev = 0, sms = 0;
   RN_CUDA(cudaGetDevice(&dev));
   RN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t n_tiles = (int64_t)((rows + CT_BM - 1) / CT_BM) * ((L + CT_BN - 1) / CT_BN) * B;
   const int grid = (int)std::min<int64_t>(n_tiles, sms);
+  const BnReduce none;
   if (moments) {
     RN_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * rows, stream));
-    RN_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
-    conv1x1_tc_kernel<true><<<grid, CT_THREADS, CT_SMEM, stream>>>(m_ahi, m_alo, m_xhi, m_xlo, m_out, d, moments);
+    RN_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel<MODE_MOMENTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+    conv1x1_tc_kernel<MODE_MOMENTS><<<grid, CT_THREADS, CT_SMEM, stream>>>(m_ahi, m_alo, m_xhi, m_xlo, m_out, d, moments, none);
+  } else if (br) {
+    RN_CUDA(cudaMemsetAsync(br->sums, 0, sizeof(double) * 2 * rows, stream));
+    RN_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel<MODE_BNREDUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+    conv1x1_tc_kernel<MODE_BNREDUCE><<<grid, CT_THREADS, CT_SMEM, stream>>>(m_ahi, m_alo, m_xhi, m_xlo, m_out, d, nullptr, *br);
   } else {
-    RN_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
-    conv1x1_tc_kernel<false><<<grid, CT_THREADS, CT_SMEM, stream>>>(m_ahi, m_alo, m_xhi, m_xlo, m_out, d, nullptr);
+    RN_CUDA(cudaFuncSetAttribute(conv1x1_tc_kernel<MODE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+    conv1x1_tc_kernel<MODE_PLAIN><<<grid, CT_THREADS, CT_SMEM, stream>>>(m_ahi, m_alo, m_xhi, m_xlo, m_out, d, nullptr, none);
   }
   RN_LAUNCH_CHECK("conv1x1_tc_kernel");
   return REGNET_OK;
+}
+
+int regnet_conv1x1_train(const void* x_hi, const void* x_lo, int B, int K, int64_t L, const void* a_hi, const void* a_lo,
+                         int rows, int lda, float* out, double* moments, int passes, void* stream_) {
+  return conv1x1_launch(x_hi, x_lo, B, K, L, a_hi, a_lo, rows, lda, out, moments, nullptr, passes, (cudaStream_t)stream_);
+}
+
+int regnet_conv1x1_train_dgrad_bnreduce(const void* g_hi, const void* g_lo, int B, int K, int64_t L, const void* a_hi,
+                                        const void* a_lo, int rows, int lda, float* out, const float* z_prev,
+                                        const float* mean, const float* invstd, const float* scale, const float* shift,
+                                        int relu, float drop_p, uint64_t drop_seed, double* sums, int passes, void* stream_) {
+  RN_CHECK_ARG(z_prev && mean && invstd && scale && shift && sums, "conv1x1_train_dgrad_bnreduce: null argument");
+  RN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "conv1x1_train_dgrad_bnreduce: dropout probability %f", drop_p);
+  RN_CHECK_ARG((reinterpret_cast<uintptr_t>(z_prev) & 15) == 0, "conv1x1_train_dgrad_bnreduce: z_prev must be 16-byte aligned");
+  BnReduce br;
+  br.z = z_prev; br.mean = mean; br.invstd = invstd; br.scale = scale; br.shift = shift; br.relu = relu;
+  br.drop = make_drop(drop_p, drop_seed); br.sums = sums;
+  return conv1x1_launch(g_hi, g_lo, B, K, L, a_hi, a_lo, rows, lda, out, nullptr, &br, passes, (cudaStream_t)stream_);
 }
 
 static int wgrad_splits(int Co, int Ci, int64_t total_kb, int sms) {

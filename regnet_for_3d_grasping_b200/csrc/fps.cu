@@ -313,7 +313,7 @@ struct FpsShape { int cs, t, ppt; bool mbar; };
   X(4, 256, 4, true) X(4, 256, 8, true) X(4, 256, 16, true)                                                          \
   X(8, 128, 4, true) X(8, 128, 8, true) X(8, 128, 16, true) X(8, 128, 20, true) X(8, 128, 25, true) X(8, 128, 32, true) \
   X(8, 512, 16, true) X(4, 128, 1, true) X(4, 128, 2, true) X(4, 128, 4, true)                                       \
-  X(8, 256, 16, true) X(8, 128, 32, false) X(8, 512, 16, false)
+  X(8, 256, 16, true) X(4, 256, 25, true) X(4, 512, 16, true) X(8, 128, 32, false) X(8, 512, 16, false)
 
 int dispatch_shape(int cs, int t, int ppt, bool mbar, const float* pts, Strides3 st, int B, int N, int M, int nbits,
                    int64_t* idx64, int32_t* idx32, float* new_xyz, const int32_t* n_var, cudaStream_t stream) {
@@ -459,7 +459,7 @@ static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, i
   const int nbits = fps_block_log2(N);
   if ((cluster_size * threads) % (1 << nbits) != 0) threads = 512;
   // grow the cluster until the cloud fits in registers; beyond that (and for per-cloud counts never) the generic kernel
-  const int max_ppt = threads <= 128 ? 32 : threads <= 512 ? 16 : 8;
+  const int max_ppt = threads <= 256 ? 32 : threads <= 512 ? 16 : 8;
   while (cluster_size < 8 && ceil_div(N, cluster_size * threads) > max_ppt) cluster_size *= 2;
   int ppt = ceil_div(N, cluster_size * threads);
   if (ppt > max_ppt && !n_var) {

@@ -827,6 +827,43 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   return REGNET_OK;
 }
 
+// Geometry only (FPS, ball query, 3-NN of all levels) for callers that run the MLPs themselves -- the training path
+// (pointnet2.py _forward_modules): consumes a matching prefetch or computes the chain now, leaves `stream` ordered behind
+// every result, and exposes them through regnet_scorenet_intermediate ("fps*", "xyz*", "bq*", "nn*", "nnw*").
+int regnet_scorenet_geometry(regnet_scorenet* p, const float* pc, void* stream_) {
+  cudaStream_t ms = (cudaStream_t)stream_;
+  RN_CHECK_ARG(p && pc, "scorenet_geometry: null argument");
+  const bool fork = p->side != nullptr && p->profiling != 1;
+  p->launches = 0;
+  int slot = p->next_slot;
+  const int oldest = p->geom[p->next_slot].pending ? p->next_slot : (p->next_slot ^ 1);
+  if (p->geom[oldest].pending && p->geom[oldest].pc == pc && p->profiling != 1) {
+    slot = oldest;
+    p->launches = p->prefetch_launches;
+  } else {
+    if (p->geom[slot].pending) slot ^= 1;
+    if (p->geom[slot].pending) {
+      set_error("scorenet_geometry: input does not match the pending prefetches");
+      return REGNET_EINVAL;
+    }
+    RN_TRY(geometry_enqueue(p, pc, slot, ms, false));
+    if (slot == p->next_slot) p->next_slot ^= 1;
+  }
+  regnet_scorenet::Geom& G = p->geom[slot];
+  G.pending = false;
+  p->last_slot = slot;
+  const bool mode3 = fork && p->cfg.use_side_stream == 3 && p->side2 != nullptr;
+  const bool fps_only = fork && (p->cfg.use_side_stream == 2 || (p->cfg.use_side_stream == 3 && !mode3));
+  const Levels L = make_levels(p, G, pc);
+  for (int i = 0; i < 3; ++i) {
+    if (fork) RN_CUDA(cudaStreamWaitEvent(ms, G.ev_bq[i], 0));
+    if (fps_only || (mode3 && i == 0)) RN_TRY(ball_query_level(p, G, L, i, ms));
+  }
+  if (fork) RN_CUDA(cudaStreamWaitEvent(ms, G.ev_nn, 0));
+  if (fps_only) RN_TRY(three_nn_all(p, G, L, ms));
+  return REGNET_OK;
+}
+
 int regnet_scorenet_set_profiling(regnet_scorenet* p, int on) {
   RN_CHECK_ARG(p != nullptr, "scorenet_set_profiling: null plan");
   p->profiling = on;

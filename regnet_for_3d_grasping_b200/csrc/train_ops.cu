@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "internal.cuh"
+#include "train_common.cuh"
 
 namespace regnet {
 
@@ -379,43 +380,8 @@ bn_max64_bwd_apply_kernel(const float* __restrict__ dout, const uint8_t* __restr
 }
 
 
-// ---- fused-chain variants (conv_train.cu produces Z and its moments; the MLP chain keeps activations as bf16 planes) ------
-// Dropout (nn/modules/mlp.py:101-105: F.dropout after every block of the seg MLP) is a counter-based mask: element 4i..4i+3
-// of the tensor take 16 bits each of splitmix64(i, seed), so forward and backward regenerate the same mask from the seed
-// and no mask tensor exists.
-__device__ __forceinline__ uint64_t drop_bits(uint64_t i, uint64_t seed) {
-  uint64_t z = i + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-// keep-or-zero multipliers of the four elements of vector i: keep when the 16-bit draw is >= thr = round(p * 65536)
-__device__ __forceinline__ float4 drop_mult(uint64_t i, uint64_t seed, uint32_t thr, float inv_keep) {
-  const uint64_t r = drop_bits(i, seed);
-  float4 m;
-  m.x = (uint32_t)(r & 0xffff) >= thr ? inv_keep : 0.f;
-  m.y = (uint32_t)((r >> 16) & 0xffff) >= thr ? inv_keep : 0.f;
-  m.z = (uint32_t)((r >> 32) & 0xffff) >= thr ? inv_keep : 0.f;
-  m.w = (uint32_t)(r >> 48) >= thr ? inv_keep : 0.f;
-  return m;
-}
-
-struct DropCfg {
-  uint64_t seed;
-  uint32_t thr;     // 0 = no dropout
-  float inv_keep;
-};
-
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t i, float4 v) {
-  __nv_bfloat16 h[4], l[4];
-  split_bf16(v.x, h[0], l[0]);
-  split_bf16(v.y, h[1], l[1]);
-  split_bf16(v.z, h[2], l[2]);
-  split_bf16(v.w, h[3], l[3]);
-  *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<uint2*>(h);
-  *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<uint2*>(l);
-}
-
+// ---- fused-chain variants (conv_train.cu produces Z and its moments; the MLP chain keeps activations as bf16 planes);
+// the dropout mask and plane helpers live in train_common.cuh -----------------------------------------------------------
 // per-channel (sum, sum of squares) in fp64 -> mean / invstd / scale / shift + running statistics (as bn_finalize_kernel)
 __global__ void __launch_bounds__(128)
 bn_finalize_moments_kernel(const double* __restrict__ moments, int C, double count, const float* __restrict__ gamma,
@@ -436,6 +402,20 @@ bn_finalize_moments_kernel(const double* __restrict__ moments, int C, double cou
   shift[c] = fmaf(-mu, sc, bt);
   if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mu;
   if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * count / fmax(count - 1.0, 1.0));
+}
+
+// sums (C, 2) in fp64 = (sum g, sum g * xhat) accumulated by the dgrad epilogue (conv_train.cu BnReduce) -> dgamma, dbeta and
+// the two batch means the apply pass subtracts
+__global__ void __launch_bounds__(128)
+bn_bwd_finalize_sums_kernel(const double* __restrict__ sums, int C, double count, float* __restrict__ dgamma,
+                            float* __restrict__ dbeta, float* __restrict__ k1, float* __restrict__ k2) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  const double a = sums[2 * c], b = sums[2 * c + 1];
+  dbeta[c] = (float)a;
+  dgamma[c] = (float)b;
+  k1[c] = (float)(a / count);
+  k2[c] = (float)(b / count);
 }
 
 // y = dropout([relu](fma(z, scale, shift))) written as fp32 and / or as bf16 hi/lo planes
@@ -564,13 +544,6 @@ bn_max64_bwd_apply_ex_kernel(const float* __restrict__ dout, const uint8_t* __re
   }
 }
 
-DropCfg make_drop(float p, uint64_t seed) {
-  DropCfg dc;
-  dc.seed = seed;
-  dc.thr = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
-  dc.inv_keep = p > 0.f ? 65536.f / (float)(65536u - dc.thr) : 1.f;   // exact keep probability of the 16-bit draw
-  return dc;
-}
 
 inline unsigned apply_grid_x(int64_t L, int rows_bc) {
   int64_t gx = (L / 4 + TB - 1) / TB;
@@ -761,6 +734,33 @@ int regnet_bn_backward_ex(const float* dy, const float* z, int B, int C, int64_t
   RN_LAUNCH_CHECK("bn_bwd_reduce_ex_kernel");
   bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, s>>>(partial, P, C, (double)B * (double)L, dgamma, dbeta, k1, k2);
   RN_LAUNCH_CHECK("bn_bwd_finalize_kernel");
+  const dim3 grid(apply_grid_x(L, B * C), B * C);
+  __nv_bfloat16* hi = (__nv_bfloat16*)dz_hi;
+  __nv_bfloat16* lo = (__nv_bfloat16*)dz_lo;
+#define RN_BWD_APPLY(R, D) \
+  bn_bwd_apply_ex_kernel<R, D><<<grid, TB, 0, s>>>(dy, z, save_mean, save_invstd, scale, shift, k1, k2, C, L, dc, dz, hi, lo)
+  if (dc.thr) { if (relu) RN_BWD_APPLY(true, true); else RN_BWD_APPLY(false, true); }
+  else { if (relu) RN_BWD_APPLY(true, false); else RN_BWD_APPLY(false, false); }
+#undef RN_BWD_APPLY
+  RN_LAUNCH_CHECK("bn_bwd_apply_ex_kernel");
+  return REGNET_OK;
+}
+
+int regnet_bn_backward_from_sums(const float* dy, const float* z, int B, int C, int64_t L, const float* save_mean,
+                                 const float* save_invstd, const float* scale, const float* shift, int relu, float drop_p,
+                                 uint64_t drop_seed, const double* sums, float* dz, void* dz_hi, void* dz_lo, float* dgamma,
+                                 float* dbeta, void* workspace, int64_t workspace_bytes, void* stream_) {
+  RN_CHECK_ARG(dy && z && save_mean && save_invstd && scale && shift && sums && (dz || (dz_hi && dz_lo)) && dgamma && dbeta &&
+                   workspace, "bn_backward_from_sums: null argument");
+  RN_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "bn_backward_from_sums: dropout probability %f", drop_p);
+  RN_TRY(check_shape(B, C, L));
+  RN_CHECK_ARG(workspace_bytes >= (int64_t)(2 * C * sizeof(float)), "bn_backward_from_sums: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const DropCfg dc = make_drop(drop_p, drop_seed);
+  float* k1 = reinterpret_cast<float*>(workspace);
+  float* k2 = k1 + C;
+  bn_bwd_finalize_sums_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, (double)B * (double)L, dgamma, dbeta, k1, k2);
+  RN_LAUNCH_CHECK("bn_bwd_finalize_sums_kernel");
   const dim3 grid(apply_grid_x(L, B * C), B * C);
   __nv_bfloat16* hi = (__nv_bfloat16*)dz_hi;
   __nv_bfloat16* lo = (__nv_bfloat16*)dz_lo;

@@ -8,6 +8,7 @@ The eval-mode fast path does not go through these forwards: see scorenet.py."""
 import torch
 from torch import nn
 
+from . import conv_train
 from . import function as _F
 from .nn_layers import SharedMLP
 
@@ -32,9 +33,10 @@ class QueryGrouper(nn.Module):
         self.radius = radius
         self.num_neighbours = num_neighbours
 
-    def forward(self, new_xyz, xyz, feature, use_xyz):
-        with torch.no_grad():
-            index, _ = _F.ball_query(xyz, new_xyz, self.radius, self.num_neighbours)
+    def forward(self, new_xyz, xyz, feature, use_xyz, index=None):
+        if index is None:
+            with torch.no_grad():
+                index, _ = _F.ball_query(xyz, new_xyz, self.radius, self.num_neighbours)
         group_xyz = _F.group_points(xyz, index) - new_xyz.unsqueeze(-1)   # centre on the centroid
         if feature is None:
             return group_xyz, group_xyz
@@ -53,11 +55,16 @@ class FeatureInterpolator(nn.Module):
         self.num_neighbors = num_neighbors
         self._eps = eps
 
-    def forward(self, dense_xyz, sparse_xyz, dense_feature, sparse_feature):
+    def search(self, dense_xyz, sparse_xyz):
+        """3-NN indices and normalised inverse-distance weights (modules.py:117-122)."""
         with torch.no_grad():
             index, distance = _F.search_nn_distance(dense_xyz, sparse_xyz, self.num_neighbors)
             inv = 1.0 / torch.clamp(distance, min=self._eps)
             weight = inv / torch.sum(inv, dim=2, keepdim=True)
+        return index, weight
+
+    def forward(self, dense_xyz, sparse_xyz, dense_feature, sparse_feature, search=None):
+        index, weight = search if search is not None else self.search(dense_xyz, sparse_xyz)
         out = _F.feature_interpolate(sparse_feature, index, weight)
         if dense_feature is not None:
             out = torch.cat([out, dense_feature], dim=1)                  # interpolated channels first
@@ -85,7 +92,9 @@ class PointNetSAModule(nn.Module):
             assert num_neighbours > 0 and radius > 0.0
             self.grouper = QueryGrouper(radius, num_neighbours)
 
-    def forward(self, xyz, feature=None):
+    def forward(self, xyz, feature=None, geometry=None):
+        """geometry (optional, not in the reference): (new_xyz (B,3,M), ball-query index (B,M,K) int64) computed elsewhere
+        for exactly this `xyz` (PointNet2Seg passes the native plan's results in train mode)."""
         if self.num_centroids == 0:       # one group holding every point, centred on the origin
             assert self.grouper is None
             new_xyz = xyz.new_zeros(xyz.size(0), 3, 1)
@@ -93,8 +102,20 @@ class PointNetSAModule(nn.Module):
             if self.use_xyz:
                 group_feature = torch.cat([xyz.unsqueeze(2), group_feature], dim=1)
         else:
-            new_xyz = xyz if self.num_centroids == -1 else _F.gather_points(xyz, self.sampler(xyz))
-            group_feature, _ = self.grouper(new_xyz, xyz, feature, use_xyz=self.use_xyz)
+            if geometry is not None:
+                new_xyz, index = geometry
+            else:
+                new_xyz = xyz if self.num_centroids == -1 else _F.gather_points(xyz, self.sampler(xyz))
+                index = None
+            if self.training and self.use_xyz and feature is not None and xyz.is_cuda:
+                # train mode on CUDA: grouping + centring + concat written straight as the MLP's operand planes, the MLP
+                # and the max over the neighbours as one autograd function (conv_train.py)
+                if index is None:
+                    with torch.no_grad():
+                        index, _ = _F.ball_query(xyz, new_xyz, self.grouper.radius, self.grouper.num_neighbours)
+                if conv_train.sa_grouped_supported(self.mlp, xyz, new_xyz, feature, index):
+                    return new_xyz, conv_train.sa_grouped_chain_train(self.mlp, xyz, new_xyz, feature, index)
+            group_feature, _ = self.grouper(new_xyz, xyz, feature, use_xyz=self.use_xyz, index=index)
         new_feature = self.mlp.forward_max_over_neighbours(group_feature)   # torch.max(self.mlp(x), 3)[0], modules.py:245
         return new_xyz, new_feature
 
@@ -120,12 +141,18 @@ class PointnetFPModule(nn.Module):
         else:
             raise ValueError('Expected value 1 or 3, but {} given.'.format(num_neighbors))
 
-    def forward(self, dense_xyz, sparse_xyz, dense_feature, sparse_feature):
+    def forward(self, dense_xyz, sparse_xyz, dense_feature, sparse_feature, search=None):
+        """search (optional, not in the reference): (index, weight) of the 3-NN interpolation computed elsewhere."""
         if self.interpolator is None:
             assert sparse_xyz.size(2) == 1 and sparse_feature.size(2) == 1
             x = torch.cat([sparse_feature.expand(-1, -1, dense_xyz.size(2)), dense_feature], dim=1)
         else:
-            x = self.interpolator(dense_xyz, sparse_xyz, dense_feature, sparse_feature)
+            if self.training and sparse_feature.is_cuda:
+                index, weight = search if search is not None else self.interpolator.search(dense_xyz, sparse_xyz)
+                if conv_train.fp_interp_supported(self.mlp, sparse_feature, dense_feature, index, weight):
+                    return conv_train.fp_interp_chain_train(self.mlp, sparse_feature, dense_feature, index, weight)
+                search = (index, weight)
+            x = self.interpolator(dense_xyz, sparse_xyz, dense_feature, sparse_feature, search=search)
         return self.mlp(x)
 
     def init_weights(self, init_fn=None):

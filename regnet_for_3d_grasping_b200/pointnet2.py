@@ -10,6 +10,8 @@ Both return what the reference returns: (sparse_feature (B,256,N), x_score (B,N)
 a transposed view of the plan's point-major (B,N,256) buffer, so ScoreNetwork's `.transpose(2,1)` hands the
 caller a contiguous (B,N,256) tensor.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -49,21 +51,30 @@ class PointNet2Seg(nn.Module):
         self.sigmoid = nn.Sigmoid()
         self._fusable = (input_chann == 6 and k_score == 1 and not add_channel_flag)
         self._plans = {}
+        self._geom_plans = {}
         self.engine = None  # None = library default (tcgen05); tests may force _lib.ENGINE_SIMT
 
     # -- op-by-op path (training) ---------------------------------------------------------------------------
     def _forward_modules(self, points, add_channel1=None, add_channel2=None):
         B, _, N = points.size()
         xyz, feature = points[:, :3, :], points[:, 3:6, :]
+        geom = self._train_geometry(points)
         level_xyz, level_feature = [xyz], [feature]
-        for sa in self.sa_modules:
-            xyz, feature = sa(xyz, feature)
+        for i, sa in enumerate(self.sa_modules):
+            if geom is None:
+                xyz, feature = sa(xyz, feature)
+            else:
+                xyz, feature = sa(xyz, feature, geometry=(geom["new_xyz"][i], geom["nbr"][i]))
             level_xyz.append(xyz)
             level_feature.append(feature)
         sparse_xyz, sparse_feature = xyz, feature
         for i, fp in enumerate(self.fp_modules):
             dense_xyz, dense_feature = level_xyz[-2 - i], level_feature[-2 - i]
-            sparse_feature = fp(dense_xyz, sparse_xyz, dense_feature, sparse_feature)
+            if geom is None:
+                sparse_feature = fp(dense_xyz, sparse_xyz, dense_feature, sparse_feature)
+            else:
+                sparse_feature = fp(dense_xyz, sparse_xyz, dense_feature, sparse_feature,
+                                    search=(geom["nn_idx"][i], geom["nn_w"][i]))
             sparse_xyz = dense_xyz
         if add_channel1 is not None and add_channel2 is not None:
             c = sparse_feature.shape[1]
@@ -78,6 +89,30 @@ class PointNet2Seg(nn.Module):
         else:
             x_score = self.bn_score(self.conv_score(x)).transpose(2, 1).contiguous()
         return sparse_feature, self.sigmoid(x_score).view(B, N)
+
+    def _geometry_plan(self, B, N, device):
+        key = (B, N, str(device))
+        plan = self._geom_plans.get(key)
+        if plan is None:
+            while len(self._geom_plans) >= self._MAX_PLANS:
+                self._geom_plans.pop(next(iter(self._geom_plans))).close()
+            plan = ScoreNetPlan(B, N, device)       # no weights bound: only its geometry chain is used
+            self._geom_plans[key] = plan
+        return plan
+
+    def _train_geometry(self, points):
+        """Train mode on CUDA: FPS / ball query / 3-NN of every level from the native plan's geometry chain -- the same
+        kernels as the operator path (bit-identical indices), but the three levels and the 3-NN searches run on the plan's
+        side streams while the first MLPs are already computing, and a prefetch() issued during the previous step's
+        backward takes the whole chain (FPS included) off the critical path.  None -> the modules search for themselves."""
+        if not (self.training and self._fusable and points.is_cuda and points.dtype == torch.float32
+                and points.size(2) >= NUM_CENTROIDS[0] and os.environ.get("REGNET_TRAIN_PLAN_GEOMETRY", "1") != "0"):
+            return None
+        pc = points.permute(0, 2, 1)
+        if not pc.is_contiguous():
+            pc = pc.contiguous()
+        with torch.no_grad():
+            return self._geometry_plan(pc.size(0), pc.size(1), pc.device).geometry(pc)
 
     # -- fused path (eval) ---------------------------------------------------------------------------------------
     _STATE_FIELDS = ("weight", "bias", "running_mean", "running_var")
@@ -120,16 +155,20 @@ class PointNet2Seg(nn.Module):
         return all_feature.transpose(1, 2), score
 
     def prefetch(self, pc):
-        """Throughput mode (eval only): start the geometry chain for a future batch `pc` (B,N,6) now, overlapped with
+        """Throughput mode: start the geometry chain for a future batch `pc` (B,N,6) now, overlapped with
         the forward issued next.  Later call forward on the same tensor."""
-        if self.training or not self._fusable:
+        if not self._fusable:
+            return
+        if self.training:
+            if os.environ.get("REGNET_TRAIN_PLAN_GEOMETRY", "1") != "0" and pc.is_cuda and pc.size(1) >= NUM_CENTROIDS[0]:
+                self._geometry_plan(pc.size(0), pc.size(1), pc.device).prefetch(pc)
             return
         plan = self._plan_for(pc.size(0), pc.size(1), pc.device)
         plan.prefetch(pc)
 
     def join_prefetch(self):
         """Make the current stream wait for the side-stream work of every outstanding prefetch()."""
-        for plan in self._plans.values():
+        for plan in list(self._plans.values()) + list(self._geom_plans.values()):
             plan.join_prefetch()
 
     def forward(self, points, add_channel1=None, add_channel2=None):
@@ -142,4 +181,5 @@ class PointNet2Seg(nn.Module):
     def __getstate__(self):  # plans hold native handles: never pickle them (torch.save(model), train.py:175-178)
         state = self.__dict__.copy()
         state["_plans"] = {}
+        state["_geom_plans"] = {}
         return state

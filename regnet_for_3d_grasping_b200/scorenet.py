@@ -138,6 +138,24 @@ class ScoreNetPlan:
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().regnet_scorenet_prefetch(self._h, _p(pc), _lib.current_stream_ptr()))
 
+    def geometry(self, pc):
+        """FPS / ball query / 3-NN of every level for `pc` (B,N,6) -- the search results the training path needs, computed
+        by the plan's kernels on its side streams (or taken from a matching prefetch()).  Returns a dict of fresh tensors:
+        new_xyz[i] (B,3,M_i), nbr[i] (B,M_i,64) int64, nn_idx[f] / nn_w[f] (B,Nd_f,3) for the three FP modules."""
+        if pc.device != self.device or pc.dtype != torch.float32 or not pc.is_contiguous() or tuple(pc.shape) != (self.batch, self.num_points, 6):
+            raise RuntimeError("geometry needs a contiguous (B, N, 6) float32 tensor on the plan's device")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().regnet_scorenet_geometry(self._h, _p(pc), _lib.current_stream_ptr()))
+        B, N, M = self.batch, self.num_points, self.num_centroids
+        nd = (M[1], M[0], N)
+        out = {"new_xyz": [], "nbr": [], "nn_idx": [], "nn_w": []}
+        for i in range(3):
+            out["new_xyz"].append(self.intermediate(f"xyz{i}", torch.float32, (B, 3, M[i])))
+            out["nbr"].append(self.intermediate(f"bq{i}", torch.int32, (B, M[i], 64)).long())
+            out["nn_idx"].append(self.intermediate(f"nn{i}", torch.int32, (B, nd[i], 3)).long())
+            out["nn_w"].append(self.intermediate(f"nnw{i}", torch.float32, (B, nd[i], 3)))
+        return out
+
     def join_prefetch(self):
         """Make the current stream wait for every outstanding prefetch()."""
         with torch.cuda.device(self.device):

@@ -43,9 +43,14 @@ class ScoreTrainStep:
     def grad_bytes(self):
         return self.grads.nbytes
 
+    def next_batch(self):
+        """The batch the NEXT step will train on (a data loader's look-ahead; here the synthetic batch itself)."""
+        return self.pc
+
     def step(self, i=0):
         self.grads.zero()
         _, _, loss = self.net(self.pc, self.tgt)
+        self.net.prefetch(self.next_batch())      # geometry chain of the next step, overlapped with this step's backward
         loss = loss.sum()
         loss.backward()
         self.grads.all_reduce()
@@ -74,6 +79,7 @@ class FullTrainStep(ScoreTrainStep):
         self.grads.zero()
         self.region_grads.zero()
         all_feature, output_score, loss = self.net(self.pc, self.tgt)
+        self.net.prefetch(self.next_batch())
         (center_pc, center_idx, gi, gp, gmi, gmp, labels) = region.get_grasp_allobj(
             self.pc, output_score.detach(), REGION_PARAMS, self.paths, seed=100 + i)
         out = self.region_net(gp, gmp, gi, gmi, center_pc, center_idx, self.pc, all_feature, GRIPPER_PARAMS, labels,

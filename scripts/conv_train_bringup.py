@@ -1,5 +1,5 @@
 """Bring-up of the training convolutions (csrc/conv_train.cu) on a GPU box: fprop with the MN-major activation operand
-under both readings of the descriptor offsets (REGNET_CONV_DESC_SWAP), wgrad, moments; errors against float64.
+wgrad, moments; errors against float64.
     python scripts/conv_train_bringup.py"""
 import os
 import sys
@@ -44,8 +44,7 @@ def wgrad_case(B, Co, Ci, L, passes):
 
 def main():
     torch.cuda.set_device(0)
-    for swap in ("0", "1"):
-        os.environ["REGNET_CONV_DESC_SWAP"] = swap
+    for swap in ("0",):
         for (B, K, L, rows) in [(1, 64, 256, 128), (2, 128, 512, 128), (2, 6, 320, 128), (3, 259, 1280, 256), (1, 128, 1024, 1),
                                 (2, 1536, 256, 1024)]:
             try:
@@ -55,7 +54,6 @@ def main():
             except Exception as ex:  # noqa: BLE001
                 print(f"swap={swap} fprop B={B} K={K} L={L} rows={rows}: FAILED {ex}", flush=True)
                 return
-    os.environ["REGNET_CONV_DESC_SWAP"] = "0"
     for (B, Co, Ci, L) in [(1, 128, 128, 256), (2, 128, 6, 320), (3, 256, 259, 1280), (2, 1024, 1536, 256), (2, 1, 128, 1024),
                            (15, 128, 128, 20480)]:
         try:

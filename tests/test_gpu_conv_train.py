@@ -226,3 +226,73 @@ def test_scorenet_train_step_uses_no_library_gemm(lib_path):
            and "regnet" not in n]
     assert not bad, bad
     assert any("conv1x1_tc_kernel" in n for n in names) and any("wgrad_tc_kernel" in n for n in names)
+
+
+def _clone_module(mod):
+    import copy
+    return copy.deepcopy(mod)
+
+
+def _grads(mod):
+    return {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
+
+
+def _assert_same_grads(a, b, tol=2e-5):
+    """Same gradients up to fp32 summation order.  A gradient that is analytically zero (the BatchNorm shift of a block in
+    front of another BatchNorm) is pure rounding noise: it is measured against the largest gradient of the set."""
+    assert a.keys() == b.keys()
+    top = max(float(v.abs().max()) for v in b.values())
+    for k in a:
+        scale = max(float(b[k].abs().max()), 1e-2 * top, 1e-30)
+        assert float((a[k] - b[k]).abs().max()) <= tol * scale, k
+
+
+def test_fused_operand_producers_match_the_unfused_modules(lib_path, monkeypatch):
+    """PointNetSAModule / PointnetFPModule in train mode: grouping (or interpolation) + concat written directly as operand
+    planes and the strided scatter-add backward, against the op-by-op module path (group_points / feature_interpolate /
+    torch.cat / split) on the same engine: same planes, hence the same values; gradients up to the scatter-add order."""
+    from regnet_for_3d_grasping_b200 import synth
+    from regnet_for_3d_grasping_b200.modules import PointNetSAModule, PointnetFPModule
+    torch.manual_seed(0)
+    pts = torch.from_numpy(synth.batch("table", [3, 4], 2048)).cuda()
+    xyz = pts[:, :, :3].permute(0, 2, 1)                      # strided views, as PointNet2Seg passes them
+    feat0 = torch.randn(2, 2048, 19, device="cuda").permute(0, 2, 1)
+    sa = PointNetSAModule(19, (32, 64), 256, 0.1, 64, use_xyz=True).cuda().train()
+    fp = PointnetFPModule(64 + 19, (48, 40), 3).cuda().train()
+    res = []
+    for unfused in ("0", "1"):
+        monkeypatch.setenv("REGNET_TRAIN_UNFUSED_OPERANDS", unfused)
+        sa_i, fp_i = _clone_module(sa), _clone_module(fp)
+        f = feat0.clone().requires_grad_(True)
+        new_xyz, new_feat = sa_i(xyz, f)
+        out = fp_i(xyz, new_xyz, f, new_feat)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        (out * torch.randn(out.shape, device="cuda", generator=g)).sum().backward()
+        res.append((new_feat.detach(), out.detach(), f.grad.clone(), _grads(sa_i), _grads(fp_i)))
+    (nf0, o0, df0, gs0, gf0), (nf1, o1, df1, gs1, gf1) = res
+    # (the batch moments are accumulated with fp64 atomics in arbitrary order: statistics may differ in the last bit)
+    assert float((nf0 - nf1).abs().max()) <= 2e-6 * float(nf1.abs().max())
+    assert float((o0 - o1).abs().max()) <= 2e-6 * float(o1.abs().max())
+    assert float((df0 - df1).abs().max()) <= 2e-5 * float(df1.abs().max())
+    _assert_same_grads(gs0, gs1)
+    _assert_same_grads(gf0, gf1)
+
+
+def test_bn_backward_reduction_fused_into_dgrad(lib_path, monkeypatch):
+    """The reduction pass of a block's BatchNorm backward fused into the dgrad epilogue of the block above (with and
+    without dropout) against the separate reduction kernel: same sums up to fp32 summation order."""
+    res = []
+    for drop in (0.0, 0.5):
+        pair = []
+        for fused in ("1", "0"):
+            monkeypatch.setenv("REGNET_TRAIN_FUSED_BNREDUCE", fused)
+            ours, _ = _mlp_pair(40, (64, 96, 32), 1, dropout=drop, seed=3)
+            x = torch.randn(3, 40, 2056, generator=torch.Generator().manual_seed(2)).cuda().requires_grad_(True)
+            torch.manual_seed(9)
+            y = ours(x)
+            y.backward(torch.randn(y.shape, generator=torch.Generator().manual_seed(4)).cuda())
+            pair.append((y.detach(), x.grad.clone(), _grads(ours)))
+        (y0, dx0, g0), (y1, dx1, g1) = pair
+        assert float((y0 - y1).abs().max()) <= 2e-6 * float(y1.abs().max())
+        assert float((dx0 - dx1).abs().max()) <= 2e-5 * float(dx1.abs().max())
+        _assert_same_grads(g0, g1)
