@@ -370,6 +370,14 @@ int regnet_interpolate_backward_strided(const float* grad_out, int64_t batch_str
 int regnet_mlp_layer(const float* X, const float* W, const float* scale, const float* shift, int64_t P, int cin,
                      int cout, int pool, int act, int engine, float* Y, void* stream);
 
+/* The same contraction on caller-owned bf16 hi/lo planes, without allocation or synchronisation (tcgen05 engine):
+ * X planes (P, ldx) with K valid columns, W planes (cout, ldw); Y = act(scale * (X W^T) + shift) as fp32 (P, ld_f32) and / or
+ * planes (P, ld_split); ldx, ldw, ld_split multiples of 8, ld_f32 a multiple of 4.  Used by the region / refine heads
+ * (multi_model/utils/pointnet2.py:165-197, 227-254 with BatchNorm folded in eval mode). */
+int regnet_linear_planes(const void* x_hi, const void* x_lo, int ldx, int64_t P, int K, const void* w_hi, const void* w_lo,
+                         int ldw, int cout, const float* scale, const float* shift, int act, float* out_f32, int ld_f32,
+                         void* out_hi, void* out_lo, int ld_split, void* stream);
+
 /* Set-abstraction level 0 as ONE kernel (csrc/sa0_chain.cu): group rgb / xyz by `nbr`, subtract the centroid, the three
  * 1x1 conv + BN + ReLU blocks 6 -> 128 -> 128 -> 256 and the max over each centroid's 64 neighbours
  * (pn2_utils/modules.py:44-52,241-245 with the channel plan of pointnet2.py:43).  pc (B,N,6) fp32 [xyz|rgb];

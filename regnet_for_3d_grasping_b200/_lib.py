@@ -112,6 +112,8 @@ _SIGNATURES = {
     "regnet_mask_sample": (c_int, [c_ptr, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_ptr, c_ptr, c_ptr]),
     "regnet_gather_max": (c_int, [c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "regnet_mlp_layer": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
+    "regnet_linear_planes": (c_int, [c_ptr, c_ptr, c_int, c_i64, c_int, c_ptr, c_ptr, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr,
+                                     c_int, c_ptr, c_ptr, c_int, c_ptr]),
     "regnet_sa0_chain": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int] + [c_ptr] * 9 + [c_ptr, c_ptr, c_int, c_ptr]),
 }
 

@@ -262,6 +262,22 @@ int regnet_mlp_layer(const float* X, const float* W, const float* scale, const f
   return rc;
 }
 
+// One 1x1-conv / linear layer with folded BatchNorm on the tcgen05 engine, operands and results as caller-owned planes:
+// the non-allocating, non-synchronising form of regnet_mlp_layer (used by the region / refine heads, region_heads.py).
+int regnet_linear_planes(const void* x_hi, const void* x_lo, int ldx, int64_t P, int K, const void* w_hi, const void* w_lo,
+                         int ldw, int cout, const float* scale, const float* shift, int act, float* out_f32, int ld_f32,
+                         void* out_hi, void* out_lo, int ld_split, void* stream) {
+  RN_CHECK_ARG(x_hi && x_lo && w_hi && w_lo, "linear_planes: null operand");
+  RN_CHECK_ARG(out_f32 || (out_hi && out_lo), "linear_planes: no output");
+  RN_CHECK_ARG(P >= 0 && K > 0 && cout > 0, "linear_planes: empty problem");
+  Epilogue ep;
+  ep.scale = scale; ep.shift = shift; ep.act = act; ep.pool = 0;
+  ep.out_f32 = out_f32; ep.ld_f32 = ld_f32;
+  ep.out_hi = (__nv_bfloat16*)out_hi; ep.out_lo = (__nv_bfloat16*)out_lo; ep.ld_split = ld_split;
+  return gemm_tc_launch((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, ldx, (const __nv_bfloat16*)w_hi,
+                        (const __nv_bfloat16*)w_lo, ldw, P, K, cout, ep, (cudaStream_t)stream);
+}
+
 int regnet_sa0_chain(const float* pc, const float* new_xyz, const int32_t* nbr, int B, int N, int M, const float* W0,
                      const float* scale0, const float* shift0, const float* W1, const float* scale1,
                      const float* shift1, const float* W2, const float* scale2, const float* shift2, float* out,
