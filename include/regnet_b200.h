@@ -175,6 +175,10 @@ int regnet_scorenet_prefetch(regnet_scorenet* plan, const float* pc, void* strea
 /* Make `stream` wait for every outstanding prefetch (their side-stream work), e.g. before timing or reusing `pc`. */
 int regnet_scorenet_join_prefetch(regnet_scorenet* plan, void* stream);
 
+/* Plan options.  "defer_prefetch" (default 0): 1 parks a prefetch until the next forward has launched its level-0 kernel
+ * (or until its results are needed) instead of enqueueing it at once -- an experiment switch, see csrc/scorenet.cu.  "dynamic_tiles": tile scheduling of the GEMM launches. */
+int regnet_scorenet_set_option(regnet_scorenet* plan, const char* name, int value);
+
 /* The geometry chain alone (FPS, ball query and 3-NN of every level), for callers that run the MLPs themselves -- the
  * training path.  Consumes a matching regnet_scorenet_prefetch or computes the chain now; on return `stream` is ordered
  * behind every result, readable through regnet_scorenet_intermediate ("fps*", "xyz*", "bq*", "nn*", "nnw*") until the next

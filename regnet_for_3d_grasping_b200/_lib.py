@@ -55,6 +55,7 @@ _SIGNATURES = {
     "regnet_scorenet_prefetch": (c_int, [c_ptr, c_ptr, c_ptr]),
     "regnet_scorenet_join_prefetch": (c_int, [c_ptr, c_ptr]),
     "regnet_scorenet_geometry": (c_int, [c_ptr, c_ptr, c_ptr]),
+    "regnet_scorenet_set_option": (c_int, [c_ptr, ctypes.c_char_p, c_int]),
     "regnet_scorenet_intermediate": (c_int, [c_ptr, ctypes.c_char_p, ctypes.POINTER(c_ptr), ctypes.POINTER(c_i64)]),
     "regnet_scorenet_launch_count": (c_int, [c_ptr]),
     "regnet_scorenet_set_profiling": (c_int, [c_ptr, c_int]),

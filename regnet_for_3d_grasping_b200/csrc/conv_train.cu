@@ -39,7 +39,10 @@ constexpr int CT_B_BYTES = CT_BN * CT_BK * 2;                      // one plane 
 constexpr int CT_STAGE_BYTES = 2 * CT_A_BYTES + 2 * CT_B_BYTES;    // 96 KB
 constexpr int CT_OFF_BAR = CT_STAGES * CT_STAGE_BYTES;             // 192 KB of tiles, then barriers
 constexpr int CT_OFF_OUT = CT_OFF_BAR + 1024;                      // store staging, 1024-byte aligned
-constexpr int CT_OUT_BYTES = 4 * 2 * 4096;                         // 4 warps x 2 buffers x [32 rows x 128 B]
+// 4 warps x [32 rows x 128 B].  One buffer per warp, not two: the kernel then leaves 17 KB of the SM's shared memory, enough
+// for a co-resident FPS CTA of the next step's prefetched geometry chain (with 226 KB taken, an FPS launch holding 120 SMs
+// made every convolution of the backward pass run on the remaining 28)
+constexpr int CT_OUT_BYTES = 4 * 4096;
 constexpr int CT_SMEM = CT_OFF_OUT + CT_OUT_BYTES + 1024;          // + slack for the manual alignment
 constexpr int CT_THREADS = 192;
 
@@ -186,7 +189,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
   } else {
     // ---- epilogue: warp q owns TMEM lanes [32q, 32q + 32) = 32 output channels; thread = one channel ----
     const int q = warp & 3;
-    const uint32_t stg = smem_base + CT_OFF_OUT + (warp - 2) * 8192;
+    const uint32_t stg = smem_base + CT_OFF_OUT + (warp - 2) * 4096;
     uint32_t it = 0, nstore = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       int mt, lt, b;
@@ -258,8 +261,8 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_cons
           }
         }
         if (ncols > 0 && row0 < d.rows) {   // warp-uniform
-          const uint32_t buf = stg + (nstore & 1) * 4096;
-          if (lane == 0) bulk_wait_read1();   // the store that used this buffer two chunks ago has read it
+          const uint32_t buf = stg;
+          if (lane == 0) bulk_wait_read();    // the previous chunk's store has read the buffer (it overlapped the TMEM load)
           __syncwarp();
           const uint32_t rowaddr = buf + (uint32_t)lane * 128u;
           const uint32_t sw = (uint32_t)lane & 7u;

@@ -274,6 +274,224 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
   if (CS > 1) cluster_sync_all();  // no CTA leaves while a peer may still address its shared memory
 }
 
+// ---- multi-pick rounds -----------------------------------------------------------------------------------------------------
+// The kernel above pays one cluster-wide exchange (~1 300 cycles: two warp arg-maxes, st.async to 8 CTAs, an mbarrier
+// wake-up) for EVERY pick.  Here one exchange serves several picks, and the result is still the reference's exact sequence:
+//
+//   round:  every warp publishes its K best points (distance, tie key, coordinates), best first, to every CTA;
+//           every warp then replays the selection on the NW * K candidates it now holds (4 per lane):
+//             - the best candidate is the next pick (always true for the first pick of a round: it is the old algorithm);
+//             - it is applied to the other candidates (their min-distance shrinks exactly as their owners will compute it)
+//               and to the warp's own register-resident points;
+//             - the next best candidate is again the global arg-max PROVIDED no point that was not published can beat
+//               it: an unpublished point of warp w was ranked after w's K-th record when the round began and min-distances
+//               only shrink, so a candidate whose distance is strictly greater than F = max_w (distance of w's K-th record)
+//               is safe.  The round ends at the first candidate that is not.
+//
+// Min-distances are the same fp32 values in the same order (min is order-independent, the squared distance is computed by
+// the same sqdist_ref from the same operands), the arg-max uses the same (distance, tie key) order, so picks are
+// bit-identical to the one-pick-per-exchange kernel; with heavy ties (lattices) rounds simply shrink to one pick.
+// Used for the shapes whose cluster has at most 32 warps (each lane then holds K = 4 of the <= 128 candidates).
+template <int CS, int T, int PPT>
+__global__ void __launch_bounds__(T, 1)
+fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, int64_t* __restrict__ idx64,
+                 int32_t* __restrict__ idx32, float* __restrict__ new_xyz, const int32_t* __restrict__ n_var) {
+  constexpr int W = T / 32, NW = CS * W, K = 4, NC = NW * K, CPL = (NC + 31) / 32;
+  static_assert(NW <= 32 && PPT <= 32, "multi-pick FPS: at most 32 warps per cluster and 32 points per thread");
+  if (n_var) {
+    N = n_var[blockIdx.x / CS];
+    if (N <= M) return;
+    nbits = N <= 1 ? 0 : 32 - __clz(N - 1);
+    nbits = min(9, max(4, nbits));
+  }
+  __shared__ uint32_t cand_d[2][NC];
+  __shared__ __align__(16) uint4 cand_r[2][NC];   // {tie, x, y, z}
+  __shared__ __align__(8) uint64_t bars[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = (CS > 1) ? cluster_ctarank() : 0u;
+  const int cloud = blockIdx.x / CS;
+  const float* __restrict__ p = pts + (int64_t)cloud * st.b;
+  const uint32_t mask = (1u << nbits) - 1u;
+
+  float px[PPT], py[PPT], pz[PPT], md[PPT];
+  const int jbase = (int)rank * T + tid;
+  float cx = p[0], cy = p[st.c], cz = p[2 * st.c];
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int j = jbase + k * CS * T;
+    if (j < N) {
+      px[k] = p[(int64_t)j * st.n];
+      py[k] = p[(int64_t)j * st.n + st.c];
+      pz[k] = p[(int64_t)j * st.n + 2 * st.c];
+      md[k] = sqdist_ref(cx, cy, cz, px[k], py[k], pz[k]);   // first pick (index 0) applied
+    } else {
+      px[k] = py[k] = pz[k] = 0.f;
+      md[k] = 0.f;
+    }
+  }
+  int cur = 0;
+  if (rank == 0 && tid == 0) {
+    if (idx64) idx64[(int64_t)cloud * M] = 0;
+    if (idx32) idx32[(int64_t)cloud * M] = 0;
+    if (new_xyz) {
+      float* o = new_xyz + (int64_t)cloud * 3 * M;
+      o[0] = cx; o[M] = cy; o[2 * (int64_t)M] = cz;
+    }
+  }
+  constexpr uint32_t TX_BYTES = NC * 20;
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arm(smem_u32(&bars[0]), TX_BYTES);   // round 0
+    mbar_arm(smem_u32(&bars[1]), TX_BYTES);   // round 1
+  }
+  if (CS > 1) cluster_sync_all(); else __syncthreads();
+
+  int done = 1;   // picks made so far (identical in every thread of the cluster)
+  for (uint32_t r = 0; done < M; ++r) {
+    const uint32_t par = r & 1;
+    // ---- this thread's two best points: (b1, k1) then (b2, k2), in (distance desc, k asc) order --------------------------
+    float b1 = 0.f, b2 = 0.f;
+    int k1 = -1, k2 = -1;
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const float m = md[k];
+      if (m > b1) { b2 = b1; k2 = k1; b1 = m; k1 = k; }
+      else if (m > b2) { b2 = m; k2 = k; }
+    }
+    // ---- the warp's K best records, best first, pushed to every CTA of the cluster ---------------------------------------
+    uint32_t taken = 0;
+    int pops = 0;
+#pragma unroll 1
+    for (int j = 0; j < K; ++j) {
+      const int bj = k1 < 0 ? -1 : jbase + k1 * CS * T;
+      const uint32_t tie = (bj < 0) ? NO_TIE : (__brev((uint32_t)bj & mask) | ((uint32_t)bj >> nbits));
+      uint32_t dmax;
+      const int src = pick_lane(__float_as_uint(b1), tie, dmax);
+      float bx = 0.f, by = 0.f, bz = 0.f;
+      if (lane == src) pick_coords<PPT>(k1, px, py, pz, bx, by, bz);
+      uint4 rec;
+      rec.x = __shfl_sync(FULL, tie, src);
+      rec.y = __shfl_sync(FULL, __float_as_uint(bx), src);
+      rec.z = __shfl_sync(FULL, __float_as_uint(by), src);
+      rec.w = __shfl_sync(FULL, __float_as_uint(bz), src);
+      if (dmax == 0u) rec.x = NO_TIE;   // nothing left in this warp: an empty record
+      if (lane < CS) {
+        const uint32_t slot = (rank * W + warp) * K + j;
+        const uint32_t dst_bar = mapa_u32(smem_u32(&bars[par]), (uint32_t)lane);
+        st_async_v4(mapa_u32(smem_u32(&cand_r[par][slot]), (uint32_t)lane), rec, dst_bar);
+        st_async_u32(mapa_u32(smem_u32(&cand_d[par][slot]), (uint32_t)lane), dmax, dst_bar);
+      }
+      // pop the winner's point: its second best moves up; a lane popped twice rescans its points
+      bool need = false;
+      if (lane == src && k1 >= 0) {
+        taken |= 1u << k1;
+        if (pops == 0) { b1 = b2; k1 = k2; pops = 1; }
+        else need = true;
+      }
+      if (__any_sync(FULL, need)) {
+        float nb = 0.f;
+        int nk = -1;
+#pragma unroll
+        for (int k = 0; k < PPT; ++k)
+          if (!((taken >> k) & 1u) && md[k] > nb) { nb = md[k]; nk = k; }
+        if (need) { b1 = nb; k1 = nk; }
+      }
+    }
+    mbar_wait_cluster(smem_u32(&bars[par]), (r >> 1) & 1u);
+    if (tid == 0) mbar_arm(smem_u32(&bars[par]), TX_BYTES);   // for round r + 2 (see the one-pick kernel for why this is safe)
+    // ---- replay: lane l holds candidates l, l + 32, ... --------------------------------------------------------------------
+    uint32_t cd[CPL];
+    uint4 cr[CPL];
+    uint32_t floor_bits = 0;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int slot = lane + 32 * c;
+      if (slot < NC) {
+        cd[c] = cand_d[par][slot];
+        cr[c] = cand_r[par][slot];
+        if (cr[c].x == NO_TIE) cd[c] = 0u;
+        if ((slot % K) == K - 1) floor_bits = max(floor_bits, cd[c]);
+      } else {
+        cd[c] = 0u;
+        cr[c] = make_uint4(NO_TIE, 0u, 0u, 0u);
+      }
+    }
+    const uint32_t F = __reduce_max_sync(FULL, floor_bits);
+    bool first = true;
+#pragma unroll 1
+    while (done < M) {
+      uint32_t ld = cd[0], lt = cr[0].x;
+      int lc = 0;
+#pragma unroll
+      for (int c = 1; c < CPL; ++c)
+        if (cd[c] > ld || (cd[c] == ld && cr[c].x < lt)) { ld = cd[c]; lt = cr[c].x; lc = c; }
+      uint32_t dmax;
+      const int src = pick_lane(ld, ld ? lt : NO_TIE, dmax);
+      if (!first && !(dmax > F)) break;      // an unpublished point could rank before this candidate: next round
+      if (dmax != 0u) {                      // (all distances 0: the reference repeats the previous pick)
+        uint4 win = cr[0];
+#pragma unroll
+        for (int c = 1; c < CPL; ++c)
+          if (lc == c) win = cr[c];
+        win.x = __shfl_sync(FULL, win.x, src);
+        win.y = __shfl_sync(FULL, win.y, src);
+        win.z = __shfl_sync(FULL, win.z, src);
+        win.w = __shfl_sync(FULL, win.w, src);
+        const uint32_t t = __brev(win.x) & mask;
+        cur = (int)(((win.x & ((1u << (32 - nbits)) - 1u)) << nbits) | t);
+        cx = __uint_as_float(win.y); cy = __uint_as_float(win.z); cz = __uint_as_float(win.w);
+        // the pick leaves the candidate set; the others see their min-distance shrink like their owners will compute it
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          if (lane == src && lc == c) { cd[c] = 0u; cr[c].x = NO_TIE; }
+          if (cr[c].x != NO_TIE) {
+            const float d = sqdist_ref(cx, cy, cz, __uint_as_float(cr[c].y), __uint_as_float(cr[c].z), __uint_as_float(cr[c].w));
+            cd[c] = __float_as_uint(fminf(__uint_as_float(cd[c]), d));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < PPT; ++k) md[k] = fminf(md[k], sqdist_ref(cx, cy, cz, px[k], py[k], pz[k]));
+      }
+      if (rank == 0 && tid == 0) {
+        if (idx64) idx64[(int64_t)cloud * M + done] = cur;
+        if (idx32) idx32[(int64_t)cloud * M + done] = cur;
+        if (new_xyz) {
+          float* o = new_xyz + (int64_t)cloud * 3 * M + done;
+          o[0] = cx; o[M] = cy; o[2 * (int64_t)M] = cz;
+        }
+      }
+      ++done;
+      first = false;
+      if (dmax == 0u) break;                 // nothing can change any more: one repeated pick per round
+    }
+  }
+  if (CS > 1) cluster_sync_all();
+}
+
+template <int CS, int T, int PPT>
+int launch_fps_multi(const float* pts, Strides3 st, int B, int N, int M, int nbits, int64_t* idx64, int32_t* idx32,
+                     float* new_xyz, const int32_t* n_var, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * CS));
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RN_CUDA(cudaFuncSetAttribute(fps_multi_kernel<CS, T, PPT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               (int)cudaSharedmemCarveoutMaxShared));
+  RN_CUDA(cudaLaunchKernelEx(&cfg, fps_multi_kernel<CS, T, PPT>, pts, st, N, M, nbits, idx64, idx32, new_xyz, n_var));
+  return REGNET_OK;
+}
+
 template <int CS, int T, int PPT>
 int launch_fps(const float* pts, Strides3 st, int B, int N, int M, int nbits, int64_t* idx64, int32_t* idx32,
                float* new_xyz, const int32_t* n_var, bool mbar, cudaStream_t stream) {
@@ -315,9 +533,28 @@ struct FpsShape { int cs, t, ppt; bool mbar; };
   X(8, 512, 16, true) X(4, 128, 1, true) X(4, 128, 2, true) X(4, 128, 4, true)                                       \
   X(8, 256, 16, true) X(4, 256, 25, true) X(4, 512, 16, true) X(8, 128, 32, false) X(8, 512, 16, false)
 
+// shapes with a multi-pick instance (clusters of at most 32 warps); REGNET_FPS_SINGLE=1 keeps one pick per exchange
+#define RN_FPS_MULTI_SHAPES(X)                                                                                      \
+  X(8, 128, 4) X(8, 128, 8) X(8, 128, 16) X(8, 128, 20) X(8, 128, 25) X(8, 128, 32)                                    \
+  X(4, 256, 4) X(4, 256, 8) X(4, 256, 16) X(4, 256, 25) X(4, 128, 1) X(4, 128, 2) X(4, 128, 4)
+
 int dispatch_shape(int cs, int t, int ppt, bool mbar, const float* pts, Strides3 st, int B, int N, int M, int nbits,
-                   int64_t* idx64, int32_t* idx32, float* new_xyz, const int32_t* n_var, cudaStream_t stream) {
+                   int64_t* idx64, int32_t* idx32, float* new_xyz, const int32_t* n_var, cudaStream_t stream,
+                   bool single_pick) {
   if (cs == 1) mbar = true;   // a single CTA exchanges nothing: one variant
+  static const int forced = getenv("REGNET_FPS_SINGLE") ? atoi(getenv("REGNET_FPS_SINGLE")) : -1;   // 1 / 0 force one way
+  const bool single = forced >= 0 ? forced != 0 : single_pick;
+  if (mbar && !single) {
+    int bestm = 1 << 30;
+#define RN_FPS_MPICK(CS, T, PPT) if (cs == CS && t == T && PPT >= ppt && PPT < bestm) bestm = PPT;
+    RN_FPS_MULTI_SHAPES(RN_FPS_MPICK)
+#undef RN_FPS_MPICK
+#define RN_FPS_MGO(CS, T, PPT)                                                                                      \
+    if (cs == CS && t == T && bestm == PPT)                                                                            \
+      return launch_fps_multi<CS, T, PPT>(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, stream);
+    RN_FPS_MULTI_SHAPES(RN_FPS_MGO)
+#undef RN_FPS_MGO
+  }
   // smallest instantiated point count >= ppt for this (cluster, threads, exchange)
   int best = 1 << 30;
 #define RN_FPS_PICK(CS, T, PPT, MB) if (cs == CS && t == T && mbar == MB && PPT >= ppt && PPT < best) best = PPT;
@@ -409,12 +646,13 @@ int fps_block_log2(int N) {  // sampling_kernel.cu:32-40 get_block + the switch'
 // `threads` selects the CTA size (0 = auto); a NEGATIVE value selects the barrier.cluster exchange variant with
 // |threads| threads (kept for A/B measurements against the st.async + mbarrier exchange).
 static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx64, int32_t* idx32,
-                           float* new_xyz, const int32_t* n_var, int cluster_size, int threads, cudaStream_t stream);
+                           float* new_xyz, const int32_t* n_var, int cluster_size, int threads, cudaStream_t stream,
+                           bool single_pick = false);
 
 int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx64, int32_t* idx32, float* new_xyz,
-               int cluster_size, int threads, cudaStream_t stream) {
+               int cluster_size, int threads, cudaStream_t stream, bool single_pick) {
   RN_CHECK_ARG(N >= M, "farthest_point_sample: num_points (%d) must be >= num_centroids (%d)", N, M);
-  return fps_launch_impl(pts, st, B, N, M, idx64, idx32, new_xyz, nullptr, cluster_size, threads, stream);
+  return fps_launch_impl(pts, st, B, N, M, idx64, idx32, new_xyz, nullptr, cluster_size, threads, stream, single_pick);
 }
 
 // per-cloud point counts n_per_cloud[b] <= Nmax (device array); clouds with n <= M are skipped (output untouched)
@@ -425,7 +663,8 @@ int fps_launch_var(const float* pts, Strides3 st, int B, int Nmax, int M, const 
 }
 
 static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx64, int32_t* idx32,
-                           float* new_xyz, const int32_t* n_var, int cluster_size, int threads, cudaStream_t stream) {
+                           float* new_xyz, const int32_t* n_var, int cluster_size, int threads, cudaStream_t stream,
+                           bool single_pick) {
   RN_CHECK_ARG(B > 0 && N > 0, "farthest_point_sample: empty input (B=%d, N=%d)", B, N);
   RN_CHECK_ARG(M > 0, "farthest_point_sample: num_centroids must be > 0 (got %d)", M);
   RN_CHECK_ARG(idx64 || idx32, "farthest_point_sample: no index output");
@@ -472,7 +711,8 @@ static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, i
               8 * threads * max_ppt);
     return REGNET_ELIMIT;
   }
-  const int rc = dispatch_shape(cluster_size, threads, ppt, mbar, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, stream);
+  const int rc = dispatch_shape(cluster_size, threads, ppt, mbar, pts, st, B, N, M, nbits, idx64, idx32, new_xyz, n_var, stream,
+                                single_pick);
   if (rc >= 0) return rc;
   if (!n_var) return fps_generic_launch(pts, st, B, N, M, nbits, idx64, idx32, new_xyz, stream);
   set_error("farthest_point_sample: no instance for cluster %d x %d threads x %d points", cluster_size, threads, ppt);

@@ -6,8 +6,10 @@
 namespace regnet {
 
 int fps_block_log2(int N);
+// single_pick: one pick per cluster exchange (the lighter instruction stream, for a launch that co-runs with tensor
+// kernels) instead of the multi-pick rounds (faster alone) -- identical indices either way
 int fps_launch(const float* pts, Strides3 st, int B, int N, int M, int64_t* idx64, int32_t* idx32, float* new_xyz,
-               int cluster_size, int threads, cudaStream_t stream);
+               int cluster_size, int threads, cudaStream_t stream, bool single_pick = false);
 int ball_query_launch(const float* pts, Strides3 pst, const float* ctr, Strides3 cst, int B, int N, int M,
                       float radius, int K, int64_t* index, int64_t* count, int32_t* index32, cudaStream_t stream);
 int three_nn_launch(const float* qry, Strides3 qst, const float* key, Strides3 kst, int B, int Nq, int Nk,

@@ -59,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int sa_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; int corun_small = 1; int corun1_cs = 8; int corun1_threads = 128; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int sa_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; int corun_small = 1; int corun1_cs = 8; int corun1_threads = 128; int corun_single = 1; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
@@ -82,6 +82,13 @@ struct regnet_scorenet {
     const float* pc = nullptr;   // input this slot was computed for (prefetched and not yet consumed)
     bool pending = false;
   } geom[2];
+  // Optional (defer_prefetch = 1, off by default): a prefetch is not enqueued at once but parked until the next forward has
+  // launched its level-0 kernel (sa0_chain needs all but 2.8 KB of an SM's shared memory, the multi-pick FPS needs 5 KB --
+  // they cannot share an SM), or until something needs its results (flush_deferred).  Measured: no gain over the
+  // one-pick FPS co-running from the start of the step (7.24 vs 7.26 ms per step), so it stays an experiment switch.
+  const float* deferred_pc = nullptr;
+  int deferred_slot = -1;
+  int defer_prefetch = 0;
   int next_slot = 0;   // slot the next geometry pass writes
   int last_slot = 0;   // slot the last forward consumed (regnet_scorenet_intermediate)
   // features (fp32, point-major)
@@ -238,6 +245,8 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   if (const char* e = getenv("REGNET_FPS_CORUN")) sscanf(e, "%d,%d", &p->cfg.corun_cs, &p->cfg.corun_threads);
   if (const char* e = getenv("REGNET_FPS_CORUN_SMALL")) p->cfg.corun_small = atoi(e);
   if (const char* e = getenv("REGNET_FPS_CORUN1")) sscanf(e, "%d,%d", &p->cfg.corun1_cs, &p->cfg.corun1_threads);
+  if (const char* e = getenv("REGNET_DEFER_PREFETCH")) p->defer_prefetch = atoi(e);
+  if (const char* e = getenv("REGNET_FPS_CORUN_SINGLE")) p->cfg.corun_single = atoi(e);
   if (const char* e = getenv("REGNET_SIDE_MODE")) { if (p->cfg.use_side_stream >= 2) p->cfg.use_side_stream = atoi(e); }
   p->B = cfg->batch;
   p->N = cfg->num_points;
@@ -490,7 +499,11 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
       cs = L.n[i] > 12288 ? p->cfg.corun_cs : L.n[i] > 2048 ? p->cfg.corun1_cs : 4;
       th = L.n[i] > 12288 ? p->cfg.corun_threads : L.n[i] > 2048 ? p->cfg.corun1_threads : 128;
     }
-    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], cs, th, gs_i));
+    // a co-running FPS takes the one-pick-per-exchange kernel: fewer instructions per pick (it shares its schedulers with
+    // the tensor kernels' epilogue warps) and 1.3 KB of shared memory (fits next to sa0_chain); alone, the multi-pick rounds
+    // are 20 % faster (profiles/README.md)
+    RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], cs, th, gs_i,
+                      corun && p->cfg.corun_single));
     prof_end(p, gs_i);
     ++p->launches;
     if (!fps_only && !(mode3 && i == 0)) RN_TRY(ball_query_level(p, G, L, i, gs_i));
@@ -502,6 +515,21 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
   return REGNET_OK;
 }
 
+// enqueue a parked prefetch now, ordered behind everything already queued on `ms`
+static int flush_deferred(regnet_scorenet* p, cudaStream_t ms, bool overlapped) {
+  if (p->deferred_slot < 0) return REGNET_OK;
+  const int slot = p->deferred_slot;
+  const float* pc = p->deferred_pc;
+  p->deferred_slot = -1;
+  p->deferred_pc = nullptr;
+  const int saved = p->launches;
+  p->launches = 0;
+  RN_TRY(geometry_enqueue(p, pc, slot, ms, overlapped));
+  p->prefetch_launches = p->launches;
+  p->launches = saved;
+  return REGNET_OK;
+}
+
 int regnet_scorenet_prefetch(regnet_scorenet* p, const float* pc, void* stream_) {
   RN_CHECK_ARG(p && pc, "scorenet_prefetch: null argument");
   const int slot = p->next_slot;
@@ -509,19 +537,27 @@ int regnet_scorenet_prefetch(regnet_scorenet* p, const float* pc, void* stream_)
     set_error("scorenet_prefetch: both geometry slots hold unconsumed prefetches; call regnet_scorenet_forward first");
     return REGNET_EINVAL;
   }
+  RN_TRY(flush_deferred(p, (cudaStream_t)stream_, true));      // at most one prefetch is parked
+  p->geom[slot].pc = pc;
+  p->geom[slot].pending = true;
+  p->next_slot ^= 1;
+  if (p->defer_prefetch && p->side != nullptr && p->profiling != 1) {
+    p->deferred_pc = pc;
+    p->deferred_slot = slot;
+    p->prefetch_launches = 0;
+    return REGNET_OK;
+  }
   const int saved = p->launches;
   p->launches = 0;
   RN_TRY(geometry_enqueue(p, pc, slot, (cudaStream_t)stream_, true));
   p->prefetch_launches = p->launches;
   p->launches = saved;
-  p->geom[slot].pc = pc;
-  p->geom[slot].pending = true;
-  p->next_slot ^= 1;
   return REGNET_OK;
 }
 
 int regnet_scorenet_join_prefetch(regnet_scorenet* p, void* stream_) {
   RN_CHECK_ARG(p, "scorenet_join_prefetch: null plan");
+  RN_TRY(flush_deferred(p, (cudaStream_t)stream_, true));
   if (!p->side) return REGNET_OK;   // single-stream plans: prefetches are already in `stream` order
   for (int g = 0; g < 2; ++g) {
     if (!p->geom[g].pending) continue;
@@ -541,6 +577,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   p->launches = 0;
   p->last_allfeat = all_feature;
   // geometry: consume the oldest prefetch if it was made for this input, otherwise compute it now
+  if (p->deferred_slot >= 0 && (p->deferred_pc == pc || p->profiling == 1)) RN_TRY(flush_deferred(p, ms, false));
   int slot = p->next_slot;
   const int oldest = p->geom[p->next_slot].pending ? p->next_slot : (p->next_slot ^ 1);
   if (p->geom[oldest].pending && p->geom[oldest].pc == pc && p->profiling != 1) {
@@ -597,6 +634,11 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
                               counter, p->cfg.sa0_variant, ms));
       prof_end(p, ms);
       ++p->launches;
+      {   // the next step's geometry chain starts here, behind the level-0 kernel (see deferred_pc)
+        const int keep = p->launches;
+        RN_TRY(flush_deferred(p, ms, true));
+        p->launches = keep;
+      }
       feat = p->sa_out[i];
       feat_c = feat_ld = SA_CH[i][2];
       feat_bs = (int64_t)M[i] * feat_c;
@@ -691,6 +733,11 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     p->pool_planes_level = p->cfg.engine == REGNET_ENGINE_TC ? i : -1;   // picked up by run_layer_impl
     RN_TRY(run_layer(p, GEMM_LABEL[i][2], p->layers[i][2], a2, P, 1, 64, nullptr, p->sa_out[i], SA_CH[i][2], ms));
     p->pool_planes_level = -1;
+    if (i == 0) {
+      const int keep = p->launches;
+      RN_TRY(flush_deferred(p, ms, true));
+      p->launches = keep;
+    }
     feat = p->sa_out[i];
     feat_c = feat_ld = SA_CH[i][2];
     feat_bs = (int64_t)M[i] * feat_c;
@@ -835,6 +882,7 @@ int regnet_scorenet_geometry(regnet_scorenet* p, const float* pc, void* stream_)
   RN_CHECK_ARG(p && pc, "scorenet_geometry: null argument");
   const bool fork = p->side != nullptr && p->profiling != 1;
   p->launches = 0;
+  RN_TRY(flush_deferred(p, ms, p->deferred_pc != pc));
   int slot = p->next_slot;
   const int oldest = p->geom[p->next_slot].pending ? p->next_slot : (p->next_slot ^ 1);
   if (p->geom[oldest].pending && p->geom[oldest].pc == pc && p->profiling != 1) {
@@ -861,6 +909,18 @@ int regnet_scorenet_geometry(regnet_scorenet* p, const float* pc, void* stream_)
   }
   if (fork) RN_CUDA(cudaStreamWaitEvent(ms, G.ev_nn, 0));
   if (fps_only) RN_TRY(three_nn_all(p, G, L, ms));
+  return REGNET_OK;
+}
+
+int regnet_scorenet_set_option(regnet_scorenet* p, const char* name, int value) {
+  RN_CHECK_ARG(p && name, "scorenet_set_option: null argument");
+  const std::string k(name);
+  if (k == "defer_prefetch") p->defer_prefetch = value;
+  else if (k == "dynamic_tiles") p->cfg.dynamic_tiles = value;
+  else {
+    set_error("scorenet_set_option: unknown option '%s'", name);
+    return REGNET_EINVAL;
+  }
   return REGNET_OK;
 }
 

@@ -97,6 +97,7 @@ class PointNet2Seg(nn.Module):
             while len(self._geom_plans) >= self._MAX_PLANS:
                 self._geom_plans.pop(next(iter(self._geom_plans))).close()
             plan = ScoreNetPlan(B, N, device)       # no weights bound: only its geometry chain is used
+            plan.set_option("defer_prefetch", 0)    # nothing to hide behind in train mode: a prefetch starts at once
             self._geom_plans[key] = plan
         return plan
 

@@ -138,6 +138,9 @@ class ScoreNetPlan:
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().regnet_scorenet_prefetch(self._h, _p(pc), _lib.current_stream_ptr()))
 
+    def set_option(self, name, value):
+        _lib.check(_lib.load().regnet_scorenet_set_option(self._h, name.encode(), int(value)))
+
     def geometry(self, pc):
         """FPS / ball query / 3-NN of every level for `pc` (B,N,6) -- the search results the training path needs, computed
         by the plan's kernels on its side streams (or taken from a matching prefetch()).  Returns a dict of fresh tensors:
