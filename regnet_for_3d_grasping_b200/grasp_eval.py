@@ -89,6 +89,22 @@ def _region_tests(cloud, to_local, shift, depth, width):
     return y, close.sum(1), back.sum(1), finger.sum(1), region
 
 
+NORMAL_RADIUS, NORMAL_MAX_NN = 0.01, 30      # dataset_utils/eval_score/eval_utils/config.py
+
+
+def _estimate_scene_normals(points):
+    """pointcloud.py:27-43 of the reference's evaluation utilities."""
+    import numpy as np
+    import open3d
+    cloud = open3d.geometry.PointCloud()
+    cloud.points = open3d.utility.Vector3dVector(np.asarray(points, dtype=np.float64))
+    cloud.estimate_normals(search_param=open3d.geometry.KDTreeSearchParamHybrid(radius=NORMAL_RADIUS, max_nn=NORMAL_MAX_NN),
+                           fast_normal_computation=False)
+    cloud.normalize_normals()
+    cloud.orient_normals_towards_camera_location(np.zeros(3))
+    return np.asarray(cloud.normals)
+
+
 def eval_validate(formal_dict, predicted_grasp, view_num, table_height, depth, width, gpu, batch=128):
     """Drop-in for dataset_utils.eval_score.eval.eval_validate (EvalDataValidate.run_collision,
     evaluation_data_generator.py:231-538): grasps (B,8) -> (number of grasps without a SCENE collision, sum of their
@@ -108,9 +124,20 @@ def eval_validate(formal_dict, predicted_grasp, view_num, table_height, depth, w
     grasp = grasp.to(dev).view(-1, 8)
     view = as_t(formal_dict["view_cloud"]).float().to(dev)[:, :3].t().contiguous()
     scene = as_t(formal_dict["scene_cloud"]).float().to(dev)[:, :3].t().contiguous()
-    if "scene_normal" not in formal_dict:
-        raise RuntimeError("eval_validate: the scene file carries no 'scene_normal' (estimate them once with open3d and store them)")
-    normal = as_t(formal_dict["scene_normal"]).float().to(dev)[:, :3].t().contiguous()
+    if "scene_normal" in formal_dict:
+        normals_np = formal_dict["scene_normal"]
+    else:
+        # the reference estimates them on the fly in this case (eval_utils/torch_scene_point_cloud.py:17-19 ->
+        # pointcloud.py:27-43: hybrid kNN/radius search, normalised, oriented towards the origin): same recipe through
+        # `open3d` -- the real package or this repository's stand-in -- cached on the scene dictionary for the next call
+        normals_np = formal_dict.get("_estimated_scene_normal")
+        if normals_np is None:
+            normals_np = _estimate_scene_normals(np.asarray(as_t(formal_dict["scene_cloud"]).cpu())[:, :3])
+            try:
+                formal_dict["_estimated_scene_normal"] = normals_np
+            except TypeError:      # an NpzFile is read-only: estimate again next time
+                pass
+    normal = as_t(normals_np).float().to(dev)[:, :3].t().contiguous()
     frame, center, _ = grasp_frames(grasp)
     B = frame.shape[0]
     per_grasp_depth = isinstance(depth, torch.Tensor) and depth.numel() > 1

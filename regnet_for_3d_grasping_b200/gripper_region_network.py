@@ -204,6 +204,14 @@ class GripperRegionNetwork(nn.Module):
         D = ground.shape[2]
         flat = ground.reshape(-1, D)
         gmask = torch.nonzero(flat[:, -1] != -1).view(-1)
+        if gmask.numel() == 0:
+            # a batch without a single labelled centre: the reference's means over empty selections are NaN and its refine
+            # stage then sees no grasp (returns None); same here, without tripping over empty concatenations
+            nan = first_grasp.new_tensor(float("nan"))
+            loss = first_grasp.sum() * 0.0 + nan
+            zero = first_grasp.new_tensor(0.0)
+            return (first_grasp.new_zeros((0, D)), (loss,) + (nan,) * 9, (zero, zero), first_grasp.new_zeros((0, D)),
+                    first_grasp.new_zeros((0, 7)), gmask)
         anchors, first_grasp, first_cls = anchors[gmask], first_grasp[gmask], first_cls[gmask]
         next_grasp, predict, _ = self.decode_first_stage(first_grasp, anchors, first_cls)
         m, A = first_cls.shape

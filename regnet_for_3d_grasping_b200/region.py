@@ -86,6 +86,8 @@ def get_group_pc(pc, center_pc, center_pc_index, group_num, width, height, depth
 
 _SCENE_CACHE = {}          # (path, mtime, size, device) -> annotation tensors; insertion-ordered, oldest evicted
 _SCENE_CACHE_MAX = 2048
+_SCENE_CACHE_MAX_BYTES = int(float(__import__("os").environ.get("REGNET_SCENE_CACHE_MB", "512")) * 2 ** 20)
+_scene_cache_bytes = 0
 
 
 def _load_scene_grasps(path, device):
@@ -101,9 +103,16 @@ def _load_scene_grasps(path, device):
         return _SCENE_CACHE[key]
     out = _read_scene_grasps(path, device)
     if use_cache:
-        if len(_SCENE_CACHE) >= _SCENE_CACHE_MAX:
-            _SCENE_CACHE.pop(next(iter(_SCENE_CACHE)))
-        _SCENE_CACHE[key] = out
+        # bounded by entries AND by bytes (512 MB of device memory by default, REGNET_SCENE_CACHE_MB): scenes with long
+        # grasp lists must not pin gigabytes next to a training run
+        global _scene_cache_bytes
+        nbytes = sum(t.numel() * t.element_size() for t in set(out))
+        while _SCENE_CACHE and (len(_SCENE_CACHE) >= _SCENE_CACHE_MAX or _scene_cache_bytes + nbytes > _SCENE_CACHE_MAX_BYTES):
+            old = _SCENE_CACHE.pop(next(iter(_SCENE_CACHE)))
+            _scene_cache_bytes -= sum(t.numel() * t.element_size() for t in set(old))
+        if nbytes <= _SCENE_CACHE_MAX_BYTES:
+            _SCENE_CACHE[key] = out
+            _scene_cache_bytes += nbytes
     return out
 
 
@@ -224,6 +233,8 @@ def sample_mask_rows(mask, num, min_count=5, seed=None, return_count=False):
     rows, G = m.shape
     index = torch.empty(rows, num, dtype=torch.int64, device=m.device)
     count = torch.empty(rows, dtype=torch.int32, device=m.device)
+    if rows == 0:                      # an empty tensor has a null data pointer: nothing to ask the library
+        return (index, count) if return_count else index
     with torch.cuda.device(m.device):
         _lib.check(_lib.load().regnet_mask_sample(_p(m), rows, G, int(num), int(min_count), _seed(seed), _p(index), _p(count),
                                                   _lib.current_stream_ptr()))
@@ -245,6 +256,8 @@ def closing_box_mask(group_points, centre, rot, x_limit, y_limit, z_limit):
     if (xr is not None and xr.numel() != M) or (yr is not None and yr.numel() != M):
         raise RuntimeError("closing_box_mask: per-grasp limits must have one value per grasp")
     mask = torch.empty(M, G, dtype=torch.uint8, device=pts.device)
+    if M == 0 or G == 0:
+        return mask
     with torch.cuda.device(pts.device):
         for lo in range(0, M, 65535):
             hi = min(M, lo + 65535)

@@ -430,3 +430,42 @@ def test_reference_train_py_runs_unchanged_on_the_dropin():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "dry run ok: pretrain_score" in r.stdout and "regnet_for_3d_grasping_b200.score_network.ScoreNetwork" in r.stdout
     assert r.stdout.count("train Epoch: 0") == 2 and "validate Epoch: 0" in r.stdout
+
+
+def test_region_loss_without_any_labelled_centre():
+    """a training batch whose centres have no ground-truth grasp must not crash: NaN losses (what the
+    reference's empty means give), no grasp handed to the refine stage."""
+    import torch
+    from regnet_for_3d_grasping_b200.gripper_region_network import GripperRegionNetwork
+    net = GripperRegionNetwork(training=True, group_num=16, gripper_num=8, grasp_score_threshold=0.4, radius=0.06, reg_channel=10)
+    M, A = 6, 4
+    first_grasp = torch.randn(M, A, 10, requires_grad=True)
+    anchors = torch.randn(M, A, 7)
+    first_cls = torch.randn(M, A)
+    ground = -torch.ones(2, 3, 10)
+    next_grasp, loss_tuple, correct, next_gt, tt_gt, gmask = net.compute_loss(first_grasp, anchors, first_cls, ground)
+    assert next_grasp.shape == (0, 10) and next_gt.shape == (0, 10) and tt_gt.shape == (0, 7) and gmask.numel() == 0
+    assert len(loss_tuple) == 10 and bool(torch.isnan(loss_tuple[0])) and loss_tuple[0].requires_grad
+    assert float(correct[0]) == 0.0 and float(correct[1]) == 0.0
+
+
+def test_eval_validate_estimates_missing_scene_normals():
+    """a scene file without 'scene_normal' gets its normals estimated (as the reference does through open3d)
+    instead of raising; the estimate is cached on the dictionary."""
+    import numpy as np
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dropin = os.path.join(root, "regnet_for_3d_grasping_b200", "dropin")
+    if dropin not in sys.path:
+        sys.path.insert(0, dropin)
+    from regnet_for_3d_grasping_b200 import grasp_eval
+    rng = np.random.default_rng(0)
+    xy = rng.uniform(-0.1, 0.1, size=(4000, 2))
+    scene = np.c_[xy, 0.75 + 0.001 * rng.standard_normal(4000)].astype(np.float32)       # a table top
+    normals = grasp_eval._estimate_scene_normals(scene)
+    assert normals.shape == (4000, 3) and np.abs(np.abs(normals[:, 2]) - 1.0).mean() < 0.05
+    d = {"view_cloud": scene[::4].copy(), "scene_cloud": scene}
+    grasp = torch.tensor([[0.0, 0.0, 0.80, 0.0, 1.0, 0.0, 0.0, 0.5]])
+    out = grasp_eval.eval_validate(d, grasp, None, 0.75, 0.06, 0.08, -1)
+    assert "_estimated_scene_normal" in d and out is not None
