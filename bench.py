@@ -179,7 +179,7 @@ def cpu_reference_run(steps, warmup, clouds_per_step=1):
             f"{warmup} warm-up; oracle port: C/OpenMP FPS+ball-query+3-NN, torch-CPU fp32 conv/BN"}
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, rank, emit):
     if rank != 0:
         return
     steps = min(args.steps, 2)      # one step = the full 15-cloud batch, ~10 s of host time
@@ -194,7 +194,7 @@ def run_reference_arm(args, rank):
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -213,9 +213,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the JSON record: anything a library writes to file descriptor 1 meanwhile (NCCL
+    # prints its version banner there) is diverted to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, emit)
         return
 
     import torch
@@ -544,7 +553,7 @@ def main():
                               "ms_per_step": ms_long / k_long, "warmup_steps": warm_steps,
                               "note": "same loop over >= 1 s, after >= 1 s of warm-up (clocks under sustained load)"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train": train}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
