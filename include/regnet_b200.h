@@ -365,6 +365,23 @@ int regnet_group_points_backward_strided(const float* grad_out, int64_t batch_st
 int regnet_interpolate_backward_strided(const float* grad_out, int64_t batch_stride, int c0, const int64_t* index,
                                         const float* weight, int B, int C, int Ns, int Nd, float* grad_in, void* stream);
 
+/* First convolution of a set-abstraction / feature-propagation MLP applied per SOURCE point (linear operations commute
+ * with grouping and interpolation; the eval plan does the same): the grouped pre-activation
+ *   Z[b,c,m,k] = Y[b,c,index[b,m,k]] + sum_d Wx[c,d] * xyz_rel[b,d,m,k]            (Y = W_f f, a GEMM over the N source points)
+ *   Z[b,c,n]   = sum_k weight[b,n,k] * Ys[b,c,index[b,n,k]] + sum_d Wd[c,d] * dense[b,d,n]   (Ys = W_s s; nd <= 4 dense channels)
+ * in fp32 with its batch moments (C0, 2) fp64 -- what regnet_conv1x1_train would have produced on the grouped operand -- and
+ * the matching backward pieces: dY = scatter-add of dZ by index with dWx_part[b,c,d] = sum dZ * xyz_rel, and
+ * dWd_part[b,c,d] = sum_n dZ * dense.  Y, Z, dZ, dY contiguous (B, C0, .); xyz_rel (B, 3, M*K); rows of <= 12 288 points. */
+int regnet_sa_gather_linear(const float* Y, const int64_t* index, const float* xyz_rel, const float* Wx, int ldwx, int B, int C0,
+                            int N, int M, int K, float* Z, double* moments, void* stream);
+int regnet_sa_scatter_linear(const float* dZ, const int64_t* index, const float* xyz_rel, int B, int C0, int N, int M, int K,
+                             float* dY, float* dwx_part, void* stream);
+int regnet_fp_gather_linear(const float* Ys, const int64_t* index, const float* weight, const float* dense, int64_t dsb,
+                            int64_t dsc, int64_t dsn, int nd, const float* Wd, int ldwd, int B, int C0, int Ns, int Nd, float* Z,
+                            double* moments, void* stream);
+int regnet_fp_dense_wgrad(const float* dZ, const float* dense, int64_t dsb, int64_t dsc, int64_t dsn, int nd, int B, int C0, int Nd,
+                          float* part, void* stream);
+
 /* ---- 4. building blocks exposed for tests / micro-benchmarks ------------------------------------------- */
 
 /* Y = act(scale * (X W^T) + shift), X (P,cin) fp32 row-major, W (cout,cin) fp32 row-major.

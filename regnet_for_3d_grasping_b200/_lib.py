@@ -95,6 +95,11 @@ _SIGNATURES = {
                                                      c_ptr]),
     "regnet_interpolate_backward_strided": (c_int, [c_ptr, c_i64, c_int, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_ptr,
                                                     c_ptr]),
+    "regnet_sa_gather_linear": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "regnet_sa_scatter_linear": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "regnet_fp_gather_linear": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_int, c_int, c_int, c_int,
+                                        c_int, c_ptr, c_ptr, c_ptr]),
+    "regnet_fp_dense_wgrad": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
     "regnet_bn_apply_max64": (c_int, [c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "regnet_bn_max64_backward_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
                                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),

@@ -108,17 +108,23 @@ class _Spec:
         self.seeds = seeds          # one dropout seed per block (unused when dropout_p == 0)
 
 
-def _chain_forward(hi, lo, B, L, spec, weights, gammas, betas):
-    """Blocks of one shared MLP over input planes (B, C0, L): -> (out fp32, saved tensors [hi, lo, z, stats] per block, arg)."""
+def _chain_forward(hi, lo, B, L, spec, weights, gammas, betas, first=None):
+    """Blocks of one shared MLP over input planes (B, C0, L): -> (out fp32, saved tensors [hi, lo, z, stats] per block, arg).
+    first = (z0, moments0): the first block's convolution output and batch moments were produced elsewhere (the
+    linear-first bodies below); hi / lo are then unused placeholders."""
     lib = _lib.load()
-    dev = hi.device
+    dev = weights[0].device
     n = len(spec.bns)
     saved, out, arg = [], None, None
     for i in range(n):
         w = weights[i]
         cout, cin = w.shape[0], w.shape[1]
-        a_hi, a_lo = split_weight(w.reshape(cout, cin))
-        z, moments = conv1x1(hi, lo, a_hi, a_lo, cout, cin, want_moments=True, passes=spec.passes)
+        if i == 0 and first is not None:
+            z, moments = first
+            hi = lo = torch.empty(0, dtype=torch.bfloat16, device=dev)
+        else:
+            a_hi, a_lo = split_weight(w.reshape(cout, cin))
+            z, moments = conv1x1(hi, lo, a_hi, a_lo, cout, cin, want_moments=True, passes=spec.passes)
         bn = spec.bns[i]
         stats = torch.empty(4, cout, dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
         _lib.check(lib.regnet_bn_finalize_moments(
@@ -144,8 +150,10 @@ def _chain_forward(hi, lo, B, L, spec, weights, gammas, betas):
     return out, saved, arg
 
 
-def _chain_backward(dout, B, L, spec, weights, saved, arg, need_w, need_dx):
-    """-> (dx fp32 (B, C0, L) or None, dW list, dgamma list, dbeta list)."""
+def _chain_backward(dout, B, L, spec, weights, saved, arg, need_w, need_dx, first_linear=False):
+    """-> (dx fp32 (B, C0, L) or None, dW list, dgamma list, dbeta list).
+    first_linear: block 0's convolution lives outside the chain; its BatchNorm backward then writes the gradient w.r.t.
+    the convolution OUTPUT as fp32 and that tensor is returned in place of dx (dW[0] stays None)."""
     lib = _lib.load()
     dev = dout.device
     n = len(spec.bns)
@@ -165,6 +173,24 @@ def _chain_backward(dout, B, L, spec, weights, saved, arg, need_w, need_dx):
         dgamma = torch.empty(cout, dtype=torch.float32, device=dev)
         dbeta = torch.empty(cout, dtype=torch.float32, device=dev)
         ws, nbytes = _bn_ws(lib, B, cout, L, dev)
+        if i == 0 and first_linear:
+            del g_hi, g_lo
+            dz0 = torch.empty(B, cout, L, dtype=torch.float32, device=dev)
+            if n == 1 and spec.pooled:
+                _lib.check(lib.regnet_bn_max64_backward_ex(
+                    _p(dy), _p(arg), _p(z), B, cout, L // 64, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
+                    int(spec.relu[i]), _p(dz0), None, None, _p(dgamma), _p(dbeta), _p(ws), nbytes, _stream()))
+            elif sums is not None:
+                _lib.check(lib.regnet_bn_backward_from_sums(
+                    _p(dy), _p(z), B, cout, L, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
+                    spec.dropout_p, spec.seeds[i], _p(sums), _p(dz0), None, None, _p(dgamma), _p(dbeta), _p(ws), nbytes,
+                    _stream()))
+            else:
+                _lib.check(lib.regnet_bn_backward_ex(
+                    _p(dy), _p(z), B, cout, L, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]), int(spec.relu[i]),
+                    spec.dropout_p, spec.seeds[i], _p(dz0), None, None, _p(dgamma), _p(dbeta), _p(ws), nbytes, _stream()))
+            dgs[i], dbs[i] = dgamma, dbeta
+            return dz0, dws, dgs, dbs
         if i == n - 1 and spec.pooled:
             _lib.check(lib.regnet_bn_max64_backward_ex(
                 _p(dy), _p(arg), _p(z), B, cout, L // 64, _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
@@ -327,6 +353,136 @@ class _FPInterpChainTrain(torch.autograd.Function):
         return (dsparse, ddense, None) + tuple(dws) + tuple(dgs) + tuple(dbs)
 
 
+class _SALinearChainTrain(torch.autograd.Function):
+    """Set-abstraction body with the first convolution applied per SOURCE point: Y = W_f feature (a GEMM over the N points
+    of the previous level instead of M * 64 grouped positions), Z0 = gather(Y) + W_x (xyz - centre) with its batch moments
+    (regnet_sa_gather_linear), then the rest of the pooled MLP; backward = scatter-add of dZ0 (+ the tiny W_x reduction),
+    wgrad / dgrad over N points.  Same function as _SAGroupedChainTrain (linear operations commute with the grouping)."""
+
+    @staticmethod
+    def forward(ctx, feature, spec, *params):
+        n = len(spec.bns)
+        weights, gammas, betas = params[:n], params[n:2 * n], params[2 * n:3 * n]
+        xyz, new_xyz, index = spec.xyz, spec.new_xyz, spec.index
+        B, _, N = xyz.shape
+        M, K = index.shape[1], index.shape[2]
+        C = feature.shape[1]
+        L = M * K
+        dev = xyz.device
+        lib = _lib.load()
+        w0 = weights[0].reshape(weights[0].shape[0], C + 3)
+        C0 = w0.shape[0]
+        with torch.cuda.device(dev):
+            f_hi, f_lo = split_planes(feature.contiguous())
+            wf_hi, wf_lo = split_weight(w0[:, 3:])
+            y = conv1x1(f_hi, f_lo, wf_hi, wf_lo, C0, C, passes=spec.passes)                       # (B, C0, N)
+            from . import pn2_ext
+            xr = (pn2_ext.group_points_forward(xyz, index) - new_xyz.unsqueeze(-1)).view(B, 3, L)      # (B, 3, M*K), tiny
+            wx = w0[:, :3].contiguous()
+            z0 = torch.empty(B, C0, L, dtype=torch.float32, device=dev)
+            moments = torch.empty(C0, 2, dtype=torch.float64, device=dev)
+            _lib.check(lib.regnet_sa_gather_linear(_p(y), _p(index), _p(xr), _p(wx), 3, B, C0, N, M, K, _p(z0), _p(moments),
+                                                   _stream()))
+            del y
+            out, saved, arg = _chain_forward(None, None, B, L, spec, weights, gammas, betas, first=(z0, moments))
+        ctx.spec, ctx.n, ctx.dims = spec, n, (B, C, N, M, K, C0)
+        ctx.save_for_backward(*(list(weights) + saved + [arg, f_hi, f_lo, xr]))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, n = ctx.spec, ctx.n
+        B, C, N, M, K, C0 = ctx.dims
+        tensors = ctx.saved_tensors
+        weights, saved = tensors[:n], tensors[n:n + 4 * n]
+        arg, f_hi, f_lo, xr = tensors[n + 4 * n:n + 4 * n + 4]
+        dev = dout.device
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            dz0, dws, dgs, dbs = _chain_backward(dout, B, M * K, spec, weights, saved, arg,
+                                                 [ctx.needs_input_grad[2 + i] for i in range(n)], True, first_linear=True)
+            dy = torch.empty(B, C0, N, dtype=torch.float32, device=dev)
+            dwx_part = torch.empty(B, C0, 3, dtype=torch.float32, device=dev)
+            _lib.check(lib.regnet_sa_scatter_linear(_p(dz0), _p(spec.index), _p(xr), B, C0, N, M, K, _p(dy), _p(dwx_part),
+                                                    _stream()))
+            del dz0
+            g_hi, g_lo = split_planes(dy)
+            dfeat = None
+            w0 = weights[0].reshape(C0, C + 3)
+            if ctx.needs_input_grad[2]:
+                dwf = wgrad(g_hi, g_lo, f_hi, f_lo, passes=spec.passes)
+                dws[0] = torch.cat([dwx_part.sum(dim=0), dwf], dim=1).view(weights[0].shape)
+            if ctx.needs_input_grad[0]:
+                t_hi, t_lo = split_weight(w0[:, 3:], transpose=True)
+                dfeat = conv1x1(g_hi, g_lo, t_hi, t_lo, C, C0, passes=spec.passes)
+        return (dfeat, None) + tuple(dws) + tuple(dgs) + tuple(dbs)
+
+
+class _FPLinearChainTrain(torch.autograd.Function):
+    """Feature-propagation body with the first convolution applied before the interpolation: Ys = W_s sparse (a GEMM over the
+    Ns sparse points instead of Nd dense ones), Z0 = interp(Ys) + W_d dense for a dense input of at most 4 channels that
+    needs no gradient (the rgb skip of the last FP module), then the rest of the MLP."""
+
+    @staticmethod
+    def forward(ctx, sparse, spec, *params):
+        n = len(spec.bns)
+        weights, gammas, betas = params[:n], params[n:2 * n], params[2 * n:3 * n]
+        index, weight, dense = spec.index, spec.weight, spec.dense
+        B, C2, Ns = sparse.shape
+        Nd = index.shape[1]
+        nd = 0 if dense is None else dense.shape[1]
+        dev = sparse.device
+        lib = _lib.load()
+        w0 = weights[0].reshape(weights[0].shape[0], C2 + nd)
+        C0 = w0.shape[0]
+        with torch.cuda.device(dev):
+            s_hi, s_lo = split_planes(sparse.contiguous())
+            ws_hi, ws_lo = split_weight(w0[:, :C2])
+            ys = conv1x1(s_hi, s_lo, ws_hi, ws_lo, C0, C2, passes=spec.passes)                    # (B, C0, Ns)
+            wd = w0[:, C2:].contiguous() if nd else None
+            ds = (0, 0, 0) if dense is None else dense.stride()
+            z0 = torch.empty(B, C0, Nd, dtype=torch.float32, device=dev)
+            moments = torch.empty(C0, 2, dtype=torch.float64, device=dev)
+            _lib.check(lib.regnet_fp_gather_linear(_p(ys), _p(index), _p(weight), _p(dense), ds[0], ds[1], ds[2], nd, _p(wd),
+                                                   max(nd, 1), B, C0, Ns, Nd, _p(z0), _p(moments), _stream()))
+            del ys
+            out, saved, _ = _chain_forward(None, None, B, Nd, spec, weights, gammas, betas, first=(z0, moments))
+        ctx.spec, ctx.n, ctx.dims = spec, n, (B, C2, nd, Ns, Nd, C0)
+        ctx.save_for_backward(*(list(weights) + saved + [s_hi, s_lo]))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, n = ctx.spec, ctx.n
+        B, C2, nd, Ns, Nd, C0 = ctx.dims
+        tensors = ctx.saved_tensors
+        weights, saved = tensors[:n], tensors[n:n + 4 * n]
+        s_hi, s_lo = tensors[n + 4 * n:n + 4 * n + 2]
+        dev = dout.device
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            dz0, dws, dgs, dbs = _chain_backward(dout, B, Nd, spec, weights, saved, None,
+                                                 [ctx.needs_input_grad[2 + i] for i in range(n)], True, first_linear=True)
+            from . import pn2_ext
+            dys = pn2_ext.interpolate_backward(dz0, spec.index, spec.weight, Ns)                     # (B, C0, Ns)
+            g_hi, g_lo = split_planes(dys)
+            w0 = weights[0].reshape(C0, C2 + nd)
+            dsparse = None
+            if ctx.needs_input_grad[2]:
+                dw_s = wgrad(g_hi, g_lo, s_hi, s_lo, passes=spec.passes)
+                if nd:
+                    dense = spec.dense
+                    part = torch.empty(B, C0, nd, dtype=torch.float32, device=dev)
+                    _lib.check(lib.regnet_fp_dense_wgrad(_p(dz0), _p(dense), dense.stride(0), dense.stride(1), dense.stride(2),
+                                                         nd, B, C0, Nd, _p(part), _stream()))
+                    dw_s = torch.cat([dw_s, part.sum(dim=0)], dim=1)
+                dws[0] = dw_s.view(weights[0].shape)
+            if ctx.needs_input_grad[0]:
+                t_hi, t_lo = split_weight(w0[:, :C2], transpose=True)
+                dsparse = conv1x1(g_hi, g_lo, t_hi, t_lo, C2, C0, passes=spec.passes)
+        return (dsparse, None) + tuple(dws) + tuple(dgs) + tuple(dbs)
+
+
 def chain_supported(mlp, x):
     """The chained path takes fp32 CUDA tensors whose per-entry position count is a multiple of 8, blocks of
     1x1 conv (no bias) + affine BatchNorm with running statistics."""
@@ -404,7 +560,12 @@ def sa_grouped_chain_train(mlp, xyz, new_xyz, feature, index):
     """torch.max(mlp(cat([group(xyz) - new_xyz, group(feature)], 1)), 3)[0] -- modules.py:44-52 + :245 -- in train mode."""
     blocks, spec, params = _spec_and_params(mlp, True)
     spec.xyz, spec.new_xyz, spec.index = xyz.detach(), new_xyz.detach(), index
-    y = _SAGroupedChainTrain.apply(feature, spec, *params)
+    # levels whose input features come from a previous level (C >= 64 channels over <= 12 288 points): the first
+    # convolution runs per source point (REGNET_TRAIN_LINEAR_FIRST=0 keeps it on the grouped positions)
+    linear = (os.environ.get("REGNET_TRAIN_LINEAR_FIRST", "1") != "0" and feature.size(1) >= 64 and xyz.size(2) <= 12288
+              and feature.size(2) % 8 == 0 and len(blocks) >= 1)
+    fn = _SALinearChainTrain if linear else _SAGroupedChainTrain
+    y = fn.apply(feature, spec, *params)
     _count_batches(blocks)
     return y
 
@@ -425,7 +586,14 @@ def fp_interp_chain_train(mlp, sparse_feature, dense_feature, index, weight):
     """mlp(cat([interpolate(sparse_feature, index, weight), dense_feature], 1)) -- modules.py:127-131, 508-509 -- in train mode."""
     blocks, spec, params = _spec_and_params(mlp, False)
     spec.index, spec.weight = index, weight.detach()
-    y = _FPInterpChainTrain.apply(sparse_feature, dense_feature, spec, *params)
+    small_dense = dense_feature is None or (dense_feature.size(1) <= 4 and not dense_feature.requires_grad)
+    if (os.environ.get("REGNET_TRAIN_LINEAR_FIRST", "1") != "0" and small_dense and sparse_feature.size(2) % 8 == 0
+            and sparse_feature.size(2) <= 12288):
+        # the last FP module (512 interpolated channels + rgb): first convolution per SPARSE point, then interpolate
+        spec.dense = None if dense_feature is None else dense_feature.detach()
+        y = _FPLinearChainTrain.apply(sparse_feature, spec, *params)
+    else:
+        y = _FPInterpChainTrain.apply(sparse_feature, dense_feature, spec, *params)
     _count_batches(blocks)
     return y
 

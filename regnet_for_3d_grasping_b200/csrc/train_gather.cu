@@ -135,6 +135,170 @@ interp_backward_strided_kernel(const float* __restrict__ gout, int64_t gbs, int 
   for (int j = threadIdx.x; j < Ns; j += TG) o[j] = acc[j];
 }
 
+// ---- first convolution applied per SOURCE point (linear operations commute with grouping / interpolation) ------------------
+// W [x_rel ; f_j] = W_x x_rel + (W_f f)_j: the feature part of a set-abstraction module's first 1x1 convolution is evaluated
+// once per point of the previous level (Y = W_f f, a GEMM over N points instead of M*64 grouped positions) and the grouped
+// pre-activation is a gather of Y plus the three-term coordinate part; likewise W [interp(s) ; d] = interp(W_s s) + W_d d
+// for a feature-propagation module.  The eval plan does the same (gather.cu sa_gather_affine / fp_interp_affine); here the
+// result is the convolution OUTPUT Z0 in fp32 together with its batch moments, i.e. exactly what conv1x1_tc_kernel<MOMENTS>
+// would have produced, and the backward is a scatter-add of dZ0 (plus tiny reductions for W_x / W_d).
+// One CTA per (b, c) row: the row of Y (<= 12 288 floats) is staged in shared memory.
+__device__ __forceinline__ void block_moments(float s1, float s2, float pivot, int64_t n, double* __restrict__ mom) {
+  __shared__ float red[2][TG / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < TG / 32; ++i) { a += red[0][i]; b += red[1][i]; }
+    // sums of deviations from the pivot -> raw moments in fp64
+    const double nd = (double)n, mean = (double)pivot + a / nd;
+    const double m2 = fmax(b - a * a / nd, 0.0);
+    atomicAdd(mom, nd * mean);
+    atomicAdd(mom + 1, m2 + nd * mean * mean);
+  }
+}
+
+__global__ void __launch_bounds__(TG)
+sa_gather_linear_kernel(const float* __restrict__ Y, const int64_t* __restrict__ index, const float* __restrict__ xr,
+                        const float* __restrict__ Wx, int ldwx, int C0, int N, int64_t MK, float* __restrict__ Z,
+                        double* __restrict__ moments, int* __restrict__ oob) {
+  extern __shared__ float row[];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* __restrict__ y = Y + ((int64_t)b * C0 + c) * N;
+  for (int j = threadIdx.x; j < N; j += TG) row[j] = y[j];
+  __syncthreads();
+  const float w0 = Wx[(int64_t)c * ldwx], w1 = Wx[(int64_t)c * ldwx + 1], w2 = Wx[(int64_t)c * ldwx + 2];
+  const int64_t* __restrict__ idx = index + (int64_t)b * MK;
+  const float* __restrict__ x0 = xr + (int64_t)b * 3 * MK;
+  float* __restrict__ z = Z + ((int64_t)b * C0 + c) * MK;
+  float s1 = 0.f, s2 = 0.f;
+  const float pivot = row[min((int64_t)N - 1, max((int64_t)0, idx[0]))];
+  for (int64_t e = (int64_t)threadIdx.x * 4; e < MK; e += TG * 4) {
+    const longlong2 j01 = *reinterpret_cast<const longlong2*>(idx + e), j23 = *reinterpret_cast<const longlong2*>(idx + e + 2);
+    const float4 a0 = *reinterpret_cast<const float4*>(x0 + e), a1 = *reinterpret_cast<const float4*>(x0 + MK + e),
+                 a2 = *reinterpret_cast<const float4*>(x0 + 2 * MK + e);
+    const int64_t j[4] = {j01.x, j01.y, j23.x, j23.y};
+    const float ax[4] = {a0.x, a0.y, a0.z, a0.w}, ay[4] = {a1.x, a1.y, a1.z, a1.w}, az[4] = {a2.x, a2.y, a2.z, a2.w};
+    float v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float g = 0.f;
+      if (j[t] < 0 || j[t] >= N) *oob = 1; else g = row[j[t]];
+      v[t] = fmaf(w2, az[t], fmaf(w1, ay[t], fmaf(w0, ax[t], g)));
+      const float d = v[t] - pivot;
+      s1 += d;
+      s2 = fmaf(d, d, s2);
+    }
+    *reinterpret_cast<float4*>(z + e) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  block_moments(s1, s2, pivot, MK, moments + 2 * c);
+}
+
+// dY[b, c, :] = scatter-add of dZ[b, c, :] by index;  dWx_part[b, c, d] = sum_e dZ[b, c, e] * xr[b, d, e]
+__global__ void __launch_bounds__(TG)
+sa_scatter_linear_kernel(const float* __restrict__ dZ, const int64_t* __restrict__ index, const float* __restrict__ xr, int C0,
+                         int N, int64_t MK, float* __restrict__ dY, float* __restrict__ dwx_part, int* __restrict__ oob) {
+  extern __shared__ float acc[];
+  __shared__ float red[3][TG / 32];
+  const int c = blockIdx.x, b = blockIdx.y;
+  for (int j = threadIdx.x; j < N; j += TG) acc[j] = 0.f;
+  __syncthreads();
+  const float* __restrict__ g = dZ + ((int64_t)b * C0 + c) * MK;
+  const int64_t* __restrict__ idx = index + (int64_t)b * MK;
+  const float* __restrict__ x0 = xr + (int64_t)b * 3 * MK;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+  for (int64_t e = threadIdx.x; e < MK; e += TG) {
+    const float gv = g[e];
+    const int64_t j = idx[e];
+    if (j < 0 || j >= N) *oob = 1; else atomicAdd(acc + j, gv);
+    t0 = fmaf(gv, x0[e], t0);
+    t1 = fmaf(gv, x0[MK + e], t1);
+    t2 = fmaf(gv, x0[2 * MK + e], t2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+    t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+    t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = t0; red[1][threadIdx.x >> 5] = t1; red[2][threadIdx.x >> 5] = t2; }
+  __syncthreads();
+  float* __restrict__ o = dY + ((int64_t)b * C0 + c) * N;
+  for (int j = threadIdx.x; j < N; j += TG) o[j] = acc[j];
+  if (threadIdx.x < 3) {
+    float a = 0.f;
+    for (int i = 0; i < TG / 32; ++i) a += red[threadIdx.x][i];
+    dwx_part[((int64_t)b * C0 + c) * 3 + threadIdx.x] = a;
+  }
+}
+
+// Z[b, c, n] = sum_k w[b,n,k] * Ys[b, c, idx[b,n,k]] + sum_d Wd[c, d] * dense[b, d, n]   (nd dense channels, <= 4)
+__global__ void __launch_bounds__(TG)
+fp_gather_linear_kernel(const float* __restrict__ Ys, const int64_t* __restrict__ index, const float* __restrict__ weight,
+                        const float* __restrict__ dense, Strides3 dst, int nd, const float* __restrict__ Wd, int ldwd, int C0,
+                        int Ns, int Nd, float* __restrict__ Z, double* __restrict__ moments, int* __restrict__ oob) {
+  extern __shared__ float row[];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* __restrict__ y = Ys + ((int64_t)b * C0 + c) * Ns;
+  for (int j = threadIdx.x; j < Ns; j += TG) row[j] = y[j];
+  __syncthreads();
+  float wd[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int d = 0; d < nd; ++d) wd[d] = Wd[(int64_t)c * ldwd + d];
+  const int64_t* __restrict__ idx = index + (int64_t)b * Nd * 3;
+  const float* __restrict__ w = weight + (int64_t)b * Nd * 3;
+  const float* __restrict__ dn = dense + (int64_t)b * dst.b;
+  float* __restrict__ z = Z + ((int64_t)b * C0 + c) * Nd;
+  float s1 = 0.f, s2 = 0.f;
+  const float pivot = row[min((int64_t)Ns - 1, max((int64_t)0, idx[0]))];
+  for (int n = threadIdx.x; n < Nd; n += TG) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int64_t j = idx[(int64_t)n * 3 + k];
+      if (j < 0 || j >= Ns) { *oob = 1; continue; }
+      acc = fmaf(row[j], w[(int64_t)n * 3 + k], acc);
+    }
+    for (int d = 0; d < nd; ++d) acc = fmaf(wd[d], dn[(int64_t)d * dst.c + (int64_t)n * dst.n], acc);
+    z[n] = acc;
+    const float dv = acc - pivot;
+    s1 += dv;
+    s2 = fmaf(dv, dv, s2);
+  }
+  block_moments(s1, s2, pivot, Nd, moments + 2 * c);
+}
+
+// dWd_part[b, c, d] = sum_n dZ[b, c, n] * dense[b, d, n]
+__global__ void __launch_bounds__(TG)
+fp_dense_wgrad_kernel(const float* __restrict__ dZ, const float* __restrict__ dense, Strides3 dst, int nd, int C0, int Nd,
+                      float* __restrict__ part) {
+  __shared__ float red[4][TG / 32];
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* __restrict__ g = dZ + ((int64_t)b * C0 + c) * Nd;
+  const float* __restrict__ dn = dense + (int64_t)b * dst.b;
+  float t[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n = threadIdx.x; n < Nd; n += TG) {
+    const float gv = g[n];
+    for (int d = 0; d < nd; ++d) t[d] = fmaf(gv, dn[(int64_t)d * dst.c + (int64_t)n * dst.n], t[d]);
+  }
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t[d] += __shfl_xor_sync(0xffffffffu, t[d], o);
+    if ((threadIdx.x & 31) == 0) red[d][threadIdx.x >> 5] = t[d];
+  }
+  __syncthreads();
+  if (threadIdx.x < nd) {
+    float a = 0.f;
+    for (int i = 0; i < TG / 32; ++i) a += red[threadIdx.x][i];
+    part[((int64_t)b * C0 + c) * nd + threadIdx.x] = a;
+  }
+}
+
 unsigned grid_x(int64_t elems4) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>((elems4 + TG - 1) / TG, 64));
 }
@@ -195,6 +359,54 @@ int regnet_interpolate_backward_strided(const float* grad_out, int64_t batch_str
   interp_backward_strided_kernel<<<dim3(C, B), TG, sizeof(float) * (size_t)Ns, (cudaStream_t)stream>>>(
       grad_out, batch_stride, c0, index, weight, C, Ns, Nd, grad_in, oob_flag());
   RN_LAUNCH_CHECK("interp_backward_strided_kernel");
+  return REGNET_OK;
+}
+
+
+int regnet_sa_gather_linear(const float* Y, const int64_t* index, const float* xyz_rel, const float* Wx, int ldwx, int B, int C0,
+                            int N, int M, int K, float* Z, double* moments, void* stream) {
+  RN_CHECK_ARG(Y && index && xyz_rel && Wx && Z && moments, "sa_gather_linear: null argument");
+  RN_CHECK_ARG(B > 0 && C0 > 0 && N > 0 && M > 0 && K > 0 && K % 4 == 0, "sa_gather_linear: bad shape");
+  RN_CHECK_ARG(N <= ROWS_MAX && B <= 65535, "sa_gather_linear: at most %d source points per cloud", ROWS_MAX);
+  cudaStream_t s = (cudaStream_t)stream;
+  RN_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * C0, s));
+  sa_gather_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)N, s>>>(Y, index, xyz_rel, Wx, ldwx, C0, N, (int64_t)M * K, Z,
+                                                                            moments, oob_flag());
+  RN_LAUNCH_CHECK("sa_gather_linear_kernel");
+  return REGNET_OK;
+}
+
+int regnet_sa_scatter_linear(const float* dZ, const int64_t* index, const float* xyz_rel, int B, int C0, int N, int M, int K,
+                             float* dY, float* dwx_part, void* stream) {
+  RN_CHECK_ARG(dZ && index && xyz_rel && dY && dwx_part, "sa_scatter_linear: null argument");
+  RN_CHECK_ARG(B > 0 && C0 > 0 && N > 0 && M > 0 && K > 0, "sa_scatter_linear: bad shape");
+  RN_CHECK_ARG(N <= ROWS_MAX && B <= 65535, "sa_scatter_linear: at most %d source points per cloud", ROWS_MAX);
+  sa_scatter_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)N, (cudaStream_t)stream>>>(
+      dZ, index, xyz_rel, C0, N, (int64_t)M * K, dY, dwx_part, oob_flag());
+  RN_LAUNCH_CHECK("sa_scatter_linear_kernel");
+  return REGNET_OK;
+}
+
+int regnet_fp_gather_linear(const float* Ys, const int64_t* index, const float* weight, const float* dense, int64_t dsb,
+                            int64_t dsc, int64_t dsn, int nd, const float* Wd, int ldwd, int B, int C0, int Ns, int Nd, float* Z,
+                            double* moments, void* stream) {
+  RN_CHECK_ARG(Ys && index && weight && Z && moments && (nd == 0 || (dense && Wd)), "fp_gather_linear: null argument");
+  RN_CHECK_ARG(B > 0 && C0 > 0 && Ns > 0 && Nd > 0 && nd >= 0 && nd <= 4, "fp_gather_linear: bad shape (at most 4 dense channels)");
+  RN_CHECK_ARG(Ns <= ROWS_MAX && B <= 65535, "fp_gather_linear: at most %d sparse points per cloud", ROWS_MAX);
+  cudaStream_t s = (cudaStream_t)stream;
+  RN_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * C0, s));
+  fp_gather_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)Ns, s>>>(Ys, index, weight, dense, Strides3{dsb, dsc, dsn}, nd,
+                                                                             Wd, ldwd, C0, Ns, Nd, Z, moments, oob_flag());
+  RN_LAUNCH_CHECK("fp_gather_linear_kernel");
+  return REGNET_OK;
+}
+
+int regnet_fp_dense_wgrad(const float* dZ, const float* dense, int64_t dsb, int64_t dsc, int64_t dsn, int nd, int B, int C0, int Nd,
+                          float* part, void* stream) {
+  RN_CHECK_ARG(dZ && dense && part, "fp_dense_wgrad: null argument");
+  RN_CHECK_ARG(B > 0 && C0 > 0 && Nd > 0 && nd > 0 && nd <= 4 && B <= 65535, "fp_dense_wgrad: bad shape");
+  fp_dense_wgrad_kernel<<<dim3(C0, B), TG, 0, (cudaStream_t)stream>>>(dZ, dense, Strides3{dsb, dsc, dsn}, nd, C0, Nd, part);
+  RN_LAUNCH_CHECK("fp_dense_wgrad_kernel");
   return REGNET_OK;
 }
 

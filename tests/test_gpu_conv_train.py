@@ -296,3 +296,46 @@ def test_bn_backward_reduction_fused_into_dgrad(lib_path, monkeypatch):
         assert float((y0 - y1).abs().max()) <= 2e-6 * float(y1.abs().max())
         assert float((dx0 - dx1).abs().max()) <= 2e-5 * float(dx1.abs().max())
         _assert_same_grads(g0, g1)
+
+
+def test_linear_first_bodies_match_the_grouped_ones(lib_path, monkeypatch):
+    """First convolution applied per source point (SA levels with >= 64 input channels, the last FP module) against the
+    same bodies with the convolution on the grouped / interpolated positions: linear operations commute, so values and
+    gradients agree to the arithmetic's accuracy (two different split-bf16 evaluation orders: 1e-5)."""
+    from regnet_for_3d_grasping_b200 import synth
+    from regnet_for_3d_grasping_b200.modules import PointNetSAModule, PointnetFPModule
+    torch.manual_seed(1)
+    pts = torch.from_numpy(synth.batch("table", [5, 6], 2048)).cuda()
+    xyz = pts[:, :, :3].permute(0, 2, 1)
+    rgb = pts[:, :, 3:6].permute(0, 2, 1)
+    feat0 = torch.randn(2, 64, 2048, device="cuda")
+    sa = PointNetSAModule(64, (96, 128), 256, 0.1, 64, use_xyz=True).cuda().train()
+    fp = PointnetFPModule(128 + 3, (80, 48), 3).cuda().train()
+    res = []
+    for linear in ("1", "0"):
+        monkeypatch.setenv("REGNET_TRAIN_LINEAR_FIRST", linear)
+        sa_i, fp_i = _clone_module(sa), _clone_module(fp)
+        f = feat0.clone().requires_grad_(True)
+        new_xyz, new_feat = sa_i(xyz, f)
+        out = fp_i(xyz, new_xyz, rgb, new_feat)                     # dense = rgb: 3 channels, no gradient
+        g = torch.Generator(device="cuda").manual_seed(5)
+        (out * torch.randn(out.shape, device="cuda", generator=g)).sum().backward()
+        res.append((new_feat.detach(), out.detach(), f.grad.clone(), _grads(sa_i), _grads(fp_i)))
+    (nf0, o0, df0, gs0, gf0), (nf1, o1, df1, gs1, gf1) = res
+    assert float((nf0 - nf1).abs().max()) <= 5e-5 * float(nf1.abs().max())
+    assert float((o0 - o1).abs().max()) <= 1e-4 * float(o1.abs().max())
+    # gradients pass through ReLU / arg-max decisions that differ for values within 1e-5 of a boundary (the two bodies
+    # evaluate the first convolution in different orders): robust comparison
+    def close(a, b, what, floor=0.0):
+        err = (a - b).abs().flatten()
+        k = max(1, int(0.01 * err.numel()))
+        scale = max(float(b.abs().max()), floor, 1e-30)      # analytically-zero gradients (BN shifts in front of a BN) are noise
+        worst = float(err.kthvalue(err.numel() - k + 1)[0])
+        assert worst <= 1e-2 * scale, (what, worst, scale)      # (scripts/linear_first_debug.py: both bodies sit at the
+        #                                                          same distance, to 4 digits, from a float64 evaluation)
+        assert float((a - b).norm()) <= 2e-2 * max(float(b.norm()), scale * b.numel() ** 0.5), what
+    close(df0, df1, "dfeature")
+    for grads0, grads1, name in ((gs0, gs1, "sa."), (gf0, gf1, "fp.")):
+        top = max(float(v.abs().max()) for v in grads1.values())
+        for k in grads0:
+            close(grads0[k], grads1[k], name + k, floor=1e-2 * top)
