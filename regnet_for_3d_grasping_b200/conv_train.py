@@ -542,6 +542,11 @@ def _f32_cuda(*tensors):
     return all(t is not None and t.is_cuda and t.dtype == torch.float32 and t.dim() == 3 and t.numel() > 0 for t in tensors)
 
 
+def _sa_linear_first(xyz, feature):
+    return (os.environ.get("REGNET_TRAIN_LINEAR_FIRST", "1") != "0" and feature.size(1) >= 64 and xyz.size(2) <= 12288
+            and feature.size(2) % 8 == 0)
+
+
 def sa_grouped_supported(mlp, xyz, new_xyz, feature, index):
     """The fused set-abstraction body: 64 neighbours, a feature tensor, no dropout, source clouds whose scatter-add row
     fits in shared memory when the features need a gradient."""
@@ -549,8 +554,8 @@ def sa_grouped_supported(mlp, xyz, new_xyz, feature, index):
         return False
     if index.dtype != torch.int64 or index.dim() != 3 or index.size(2) != 64 or not index.is_contiguous():
         return False
-    if feature.requires_grad and xyz.size(2) > 12288:
-        return False
+    if not _sa_linear_first(xyz, feature) and feature.requires_grad and xyz.size(2) > 12288:
+        return False                                 # the grouped body's strided scatter-add keeps one row in shared memory
     if os.environ.get("REGNET_TRAIN_UNFUSED_OPERANDS", "0") == "1":
         return False
     return _blocks_ok(mlp, xyz.size(0), index.size(1) * 64)
@@ -560,10 +565,11 @@ def sa_grouped_chain_train(mlp, xyz, new_xyz, feature, index):
     """torch.max(mlp(cat([group(xyz) - new_xyz, group(feature)], 1)), 3)[0] -- modules.py:44-52 + :245 -- in train mode."""
     blocks, spec, params = _spec_and_params(mlp, True)
     spec.xyz, spec.new_xyz, spec.index = xyz.detach(), new_xyz.detach(), index
-    # levels whose input features come from a previous level (C >= 64 channels over <= 12 288 points): the first
-    # convolution runs per source point (REGNET_TRAIN_LINEAR_FIRST=0 keeps it on the grouped positions)
-    linear = (os.environ.get("REGNET_TRAIN_LINEAR_FIRST", "1") != "0" and feature.size(1) >= 64 and xyz.size(2) <= 12288
-              and feature.size(2) % 8 == 0 and len(blocks) >= 1)
+    # levels fed by a previous level (>= 64 feature channels over <= 12 288 source points): the first convolution runs per
+    # source point, then a gather builds the grouped pre-activation (REGNET_TRAIN_LINEAR_FIRST=0 keeps it on the grouped
+    # positions).  Level 0 (3 rgb channels over 25 600 points) keeps the grouped body: a 100 KB row per CTA leaves two CTAs
+    # per SM and the shared-memory scatter-add of its 327 680 positions per row took 15 ms (measured).
+    linear = _sa_linear_first(xyz, feature) and len(blocks) >= 1
     fn = _SALinearChainTrain if linear else _SAGroupedChainTrain
     y = fn.apply(feature, spec, *params)
     _count_batches(blocks)

@@ -87,7 +87,15 @@ fp_interp_planes_kernel(const float* __restrict__ sparse, Strides3 sst, const fl
   }
 }
 
-constexpr int ROWS_MAX = 12288;   // floats of one source row kept in shared memory (48 KB)
+constexpr int ROWS_MAX = 12288;   // floats of one source row kept in shared memory (48 KB) by the strided scatter-adds
+constexpr int ROWS_BIG = 53248;   // linear-first gather / scatter: up to 208 KB of dynamic shared memory (opt-in)
+
+template <typename Kern>
+int allow_big_rows(Kern kernel, int n_floats) {
+  if (n_floats * 4 > 48 * 1024)
+    RN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n_floats * 4));
+  return REGNET_OK;
+}
 
 // gin[b, c, :] = scatter-add of gout[b, c0 + c, :] (row stride MK, batch stride gbs) by index -- one CTA per (b, c) row,
 // the row accumulated in shared memory and written once
@@ -367,8 +375,9 @@ int regnet_sa_gather_linear(const float* Y, const int64_t* index, const float* x
                             int N, int M, int K, float* Z, double* moments, void* stream) {
   RN_CHECK_ARG(Y && index && xyz_rel && Wx && Z && moments, "sa_gather_linear: null argument");
   RN_CHECK_ARG(B > 0 && C0 > 0 && N > 0 && M > 0 && K > 0 && K % 4 == 0, "sa_gather_linear: bad shape");
-  RN_CHECK_ARG(N <= ROWS_MAX && B <= 65535, "sa_gather_linear: at most %d source points per cloud", ROWS_MAX);
+  RN_CHECK_ARG(N <= ROWS_BIG && B <= 65535, "sa_gather_linear: at most %d source points per cloud", ROWS_BIG);
   cudaStream_t s = (cudaStream_t)stream;
+  RN_TRY(allow_big_rows(sa_gather_linear_kernel, N));
   RN_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * C0, s));
   sa_gather_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)N, s>>>(Y, index, xyz_rel, Wx, ldwx, C0, N, (int64_t)M * K, Z,
                                                                             moments, oob_flag());
@@ -380,7 +389,8 @@ int regnet_sa_scatter_linear(const float* dZ, const int64_t* index, const float*
                              float* dY, float* dwx_part, void* stream) {
   RN_CHECK_ARG(dZ && index && xyz_rel && dY && dwx_part, "sa_scatter_linear: null argument");
   RN_CHECK_ARG(B > 0 && C0 > 0 && N > 0 && M > 0 && K > 0, "sa_scatter_linear: bad shape");
-  RN_CHECK_ARG(N <= ROWS_MAX && B <= 65535, "sa_scatter_linear: at most %d source points per cloud", ROWS_MAX);
+  RN_CHECK_ARG(N <= ROWS_BIG && B <= 65535, "sa_scatter_linear: at most %d source points per cloud", ROWS_BIG);
+  RN_TRY(allow_big_rows(sa_scatter_linear_kernel, N));
   sa_scatter_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)N, (cudaStream_t)stream>>>(
       dZ, index, xyz_rel, C0, N, (int64_t)M * K, dY, dwx_part, oob_flag());
   RN_LAUNCH_CHECK("sa_scatter_linear_kernel");
@@ -392,8 +402,9 @@ int regnet_fp_gather_linear(const float* Ys, const int64_t* index, const float* 
                             double* moments, void* stream) {
   RN_CHECK_ARG(Ys && index && weight && Z && moments && (nd == 0 || (dense && Wd)), "fp_gather_linear: null argument");
   RN_CHECK_ARG(B > 0 && C0 > 0 && Ns > 0 && Nd > 0 && nd >= 0 && nd <= 4, "fp_gather_linear: bad shape (at most 4 dense channels)");
-  RN_CHECK_ARG(Ns <= ROWS_MAX && B <= 65535, "fp_gather_linear: at most %d sparse points per cloud", ROWS_MAX);
+  RN_CHECK_ARG(Ns <= ROWS_BIG && B <= 65535, "fp_gather_linear: at most %d sparse points per cloud", ROWS_BIG);
   cudaStream_t s = (cudaStream_t)stream;
+  RN_TRY(allow_big_rows(fp_gather_linear_kernel, Ns));
   RN_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * C0, s));
   fp_gather_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)Ns, s>>>(Ys, index, weight, dense, Strides3{dsb, dsc, dsn}, nd,
                                                                              Wd, ldwd, C0, Ns, Nd, Z, moments, oob_flag());

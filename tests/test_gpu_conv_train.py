@@ -338,4 +338,4 @@ def test_linear_first_bodies_match_the_grouped_ones(lib_path, monkeypatch):
     for grads0, grads1, name in ((gs0, gs1, "sa."), (gf0, gf1, "fp.")):
         top = max(float(v.abs().max()) for v in grads1.values())
         for k in grads0:
-            close(grads0[k], grads1[k], name + k, floor=1e-2 * top)
+            close(grads0[k], grads1[k], name + k, floor=0.1 * top)
