@@ -100,6 +100,11 @@ _SIGNATURES = {
     "regnet_fp_gather_linear": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_int, c_int, c_int, c_int,
                                         c_int, c_ptr, c_ptr, c_ptr]),
     "regnet_fp_dense_wgrad": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
+    "regnet_sa0_input_moments": (c_int, _STRIDED + [c_ptr] + _STRIDED + [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
+    "regnet_sa0_apply_planes": (c_int, _STRIDED + [c_ptr] + _STRIDED + [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
+                                                             c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "regnet_sa0_backward_sums": (c_int, _STRIDED + [c_ptr] + _STRIDED + [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
+                                                              c_ptr, c_int, c_int, c_ptr, c_ptr]),
     "regnet_bn_apply_max64": (c_int, [c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr]),
     "regnet_bn_max64_backward_ex": (c_int, [c_ptr, c_ptr, c_ptr, c_int, c_int, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
                                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),

@@ -418,6 +418,97 @@ class _SALinearChainTrain(torch.autograd.Function):
         return (dfeat, None) + tuple(dws) + tuple(dgs) + tuple(dbs)
 
 
+class _SubSpec:
+    """Blocks [start:] of a chain spec (the same static fields, sliced)."""
+
+    def __init__(self, spec, start):
+        self.bns, self.relu, self.seeds = spec.bns[start:], spec.relu[start:], spec.seeds[start:]
+        self.pooled, self.dropout_p, self.passes = spec.pooled, spec.dropout_p, spec.passes
+
+
+def _sym6(tri):
+    """21 upper-triangle sums (row-major, d1 <= d2) -> the symmetric (6, 6) matrix."""
+    iu = torch.triu_indices(6, 6, device=tri.device)
+    m = torch.zeros(6, 6, dtype=tri.dtype, device=tri.device)
+    m[iu[0], iu[1]] = tri
+    m[iu[1], iu[0]] = tri
+    return m
+
+
+class _SA0RecomputeChainTrain(torch.autograd.Function):
+    """Set-abstraction level 0 (3 feature channels that need no gradient): the first block's pre-activation Z0 = W0 [xyz_rel |
+    rgb] over the M * 64 grouped positions is never written.  Its batch moments follow from the 27 first and second sums of
+    the 6 inputs, its activation is recomputed from the inputs as the next block's operand planes, and its whole backward
+    (dW0, dgamma, dbeta) follows from 7 sums per channel taken in one pass over the incoming gradient (csrc/train_gather.cu,
+    "set-abstraction level 0, first block")."""
+
+    @staticmethod
+    def forward(ctx, spec, *params):
+        n = len(spec.bns)
+        weights, gammas, betas = params[:n], params[n:2 * n], params[2 * n:3 * n]
+        xyz, new_xyz, index, feature = spec.xyz, spec.new_xyz, spec.index, spec.feature
+        B, _, N = xyz.shape
+        M, K = index.shape[1], index.shape[2]
+        L = M * K
+        dev = xyz.device
+        lib = _lib.load()
+        C0 = weights[0].shape[0]
+        w0 = weights[0].detach().reshape(C0, 6).contiguous()
+        bn = spec.bns[0]
+        with torch.cuda.device(dev):
+            geo = (_p(xyz), xyz.stride(0), xyz.stride(1), xyz.stride(2), _p(new_xyz), _p(feature), feature.stride(0),
+                   feature.stride(1), feature.stride(2), _p(index), B, N, M, K)
+            sums = torch.empty(27, dtype=torch.float64, device=dev)
+            _lib.check(lib.regnet_sa0_input_moments(*geo, _p(sums), _stream()))
+            w64 = w0.double()
+            sx, sxx = sums[:6], _sym6(sums[6:])
+            moments = torch.stack([w64 @ sx, ((w64 @ sxx) * w64).sum(dim=1)], dim=1).contiguous()
+            stats = torch.empty(4, C0, dtype=torch.float32, device=dev)
+            _lib.check(lib.regnet_bn_finalize_moments(
+                _p(moments), C0, float(B) * float(L), _p(gammas[0]), _p(betas[0]), float(bn.eps), float(bn.momentum),
+                _p(bn.running_mean), _p(bn.running_var), _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]), _stream()))
+            hi = torch.empty(B, C0, L, dtype=torch.bfloat16, device=dev)
+            lo = torch.empty(B, C0, L, dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.regnet_sa0_apply_planes(*geo, _p(w0), _p(stats[2]), _p(stats[3]), C0, int(spec.relu[0]), _p(hi),
+                                                   _p(lo), _stream()))
+            out, saved, arg = _chain_forward(hi, lo, B, L, _SubSpec(spec, 1), weights[1:], gammas[1:], betas[1:])
+        ctx.spec, ctx.n, ctx.dims = spec, n, (B, N, M, K, C0)
+        ctx.save_for_backward(*(list(weights[1:]) + saved + [arg, w0, stats, sums]))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, n = ctx.spec, ctx.n
+        B, N, M, K, C0 = ctx.dims
+        L = M * K
+        tensors = ctx.saved_tensors
+        weights, saved = tensors[:n - 1], tensors[n - 1:n - 1 + 4 * (n - 1)]
+        arg, w0, stats, sums = tensors[n - 1 + 4 * (n - 1):]
+        xyz, new_xyz, index, feature = spec.xyz, spec.new_xyz, spec.index, spec.feature
+        dev = dout.device
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            dy0, dws, dgs, dbs = _chain_backward(dout, B, L, _SubSpec(spec, 1), weights, saved, arg,
+                                                 [ctx.needs_input_grad[2 + i] for i in range(n - 1)], True)
+            G = torch.empty(C0, 7, dtype=torch.float64, device=dev)
+            _lib.check(lib.regnet_sa0_backward_sums(
+                _p(xyz), xyz.stride(0), xyz.stride(1), xyz.stride(2), _p(new_xyz), _p(feature), feature.stride(0),
+                feature.stride(1), feature.stride(2), _p(index), B, N, M, K, _p(dy0), _p(w0), _p(stats[2]), _p(stats[3]), C0,
+                int(spec.relu[0]), _p(G), _stream()))
+            del dy0
+            cnt = float(B) * float(L)
+            w64 = w0.double()
+            sx, sxx = sums[:6], _sym6(sums[6:])
+            mu, istd, sc = (w64 @ sx) / cnt, stats[1].double(), stats[2].double()
+            g0, gx = G[:, 0], G[:, 1:]
+            dbeta = g0
+            dgamma = istd * ((w64 * gx).sum(dim=1) - mu * g0)                    # sum g * xhat
+            zx = w64 @ sxx - mu[:, None] * sx[None, :]                           # sum (z - mu) x_d
+            dw0 = sc[:, None] * (gx - (g0 / cnt)[:, None] * sx[None, :] - (dgamma * istd / cnt)[:, None] * zx)
+            dw0 = dw0.float().view(C0, 6, 1, 1) if ctx.needs_input_grad[1] else None
+        return (None, dw0) + tuple(dws) + (dgamma.float(),) + tuple(dgs) + (dbeta.float(),) + tuple(dbs)
+
+
 class _FPLinearChainTrain(torch.autograd.Function):
     """Feature-propagation body with the first convolution applied before the interpolation: Ys = W_s sparse (a GEMM over the
     Ns sparse points instead of Nd dense ones), Z0 = interp(Ys) + W_d dense for a dense input of at most 4 channels that
@@ -570,8 +661,14 @@ def sa_grouped_chain_train(mlp, xyz, new_xyz, feature, index):
     # positions).  Level 0 (3 rgb channels over 25 600 points) keeps the grouped body: a 100 KB row per CTA leaves two CTAs
     # per SM and the shared-memory scatter-add of its 327 680 positions per row took 15 ms (measured).
     linear = _sa_linear_first(xyz, feature) and len(blocks) >= 1
-    fn = _SALinearChainTrain if linear else _SAGroupedChainTrain
-    y = fn.apply(feature, spec, *params)
+    if (os.environ.get("REGNET_TRAIN_SA0_RECOMPUTE", "1") != "0" and feature.size(1) == 3 and not feature.requires_grad
+            and len(blocks) >= 2 and spec.dropout_p == 0.0 and blocks[0].conv.weight.dim() == 4):
+        # level 0: the first block's 2.5 GB pre-activation is never written (moments, activation and backward from its 6 inputs)
+        spec.feature, spec.new_xyz = feature.detach(), new_xyz.detach().contiguous()
+        y = _SA0RecomputeChainTrain.apply(spec, *params)
+    else:
+        fn = _SALinearChainTrain if linear else _SAGroupedChainTrain
+        y = fn.apply(feature, spec, *params)
     _count_batches(blocks)
     return y
 

@@ -307,6 +307,186 @@ fp_dense_wgrad_kernel(const float* __restrict__ dZ, const float* __restrict__ de
   }
 }
 
+// ---- set-abstraction level 0, first block, without its 2.5 GB pre-activation --------------------------------------------------
+// The first block of level 0 maps 6 inputs per grouped position ([xyz - centre | rgb]) to 128 channels over 4.9 M positions:
+// as a convolution it writes Z0 (2.5 GB), BatchNorm reads it twice, and the backward reads and writes it again.  Z0 is a
+// LINEAR function of 6 numbers, so
+//   * its batch moments follow from the 6 sums and 21 products of the inputs:  E[z_c] = w_c . E[x],  E[z_c^2] = w_c' E[x x'] w_c
+//     (sa0_input_moments_kernel: one pass over the inputs, 27 numbers);
+//   * the activation y = relu(bn(z)) is recomputed from the inputs wherever it is needed (sa0_apply_planes_kernel writes it
+//     once, as the next block's operand planes);
+//   * the whole backward of the block needs 7 sums per channel over g = dy * [bn(z) > 0]:  G0_c = sum g,  G_cd = sum g x_d
+//     (sa0_backward_sums_kernel: one pass over dy, z recomputed for the mask); with them
+//       dbeta = G0,  dgamma = is (w_c . G_c - mu G0),  dW_cd = sc (G_cd - m1 Sx_d - m2 is (w_c' Sxx_d - mu Sx_d)),
+//     m1 = G0 / n, m2 = dgamma / n  (conv_train.py) -- the inputs need no gradient, so dZ0 is never formed.
+// Every thread owns 8 consecutive positions (one centroid: K is a multiple of 8) and loops over the channels.
+constexpr int SA0_PPT = 8;
+
+struct Sa0In {
+  const float* xyz; Strides3 xst; const float* new_xyz; const float* feat; Strides3 fst; const int64_t* index;
+  int N, M, K;
+};
+
+__device__ __forceinline__ void sa0_load_inputs(const Sa0In& a, int b, int64_t e, float (&x)[SA0_PPT][6], int* oob) {
+  const int64_t MK = (int64_t)a.M * a.K;
+  const int64_t* __restrict__ idx = a.index + (int64_t)b * MK + e;
+  const int m = (int)(e / a.K);
+  const float c0 = a.new_xyz[((int64_t)b * 3 + 0) * a.M + m], c1 = a.new_xyz[((int64_t)b * 3 + 1) * a.M + m],
+              c2 = a.new_xyz[((int64_t)b * 3 + 2) * a.M + m];
+  const float* __restrict__ px = a.xyz + (int64_t)b * a.xst.b;
+  const float* __restrict__ pf = a.feat + (int64_t)b * a.fst.b;
+#pragma unroll
+  for (int t = 0; t < SA0_PPT; ++t) {
+    int64_t j = idx[t];
+    if (j < 0 || j >= a.N) { *oob = 1; j = 0; }
+    x[t][0] = __fsub_rn(px[j * a.xst.n], c0);
+    x[t][1] = __fsub_rn(px[j * a.xst.n + a.xst.c], c1);
+    x[t][2] = __fsub_rn(px[j * a.xst.n + 2 * a.xst.c], c2);
+    x[t][3] = pf[j * a.fst.n];
+    x[t][4] = pf[j * a.fst.n + a.fst.c];
+    x[t][5] = pf[j * a.fst.n + 2 * a.fst.c];
+  }
+}
+
+__device__ __forceinline__ float sa0_z(const float (&w)[6], const float (&x)[6]) {
+  float z = __fmul_rn(w[0], x[0]);
+#pragma unroll
+  for (int d = 1; d < 6; ++d) z = __fmaf_rn(w[d], x[d], z);
+  return z;
+}
+
+// sums[0..5] = sum x_d, sums[6 + pair(d1 <= d2)] = sum x_d1 x_d2   (fp64, accumulated over the whole batch)
+__global__ void __launch_bounds__(TG)
+sa0_input_moments_kernel(Sa0In a, int B, double* __restrict__ sums, int* __restrict__ oob) {
+  const int64_t MK = (int64_t)a.M * a.K, per_b = MK / SA0_PPT, total = per_b * B;
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  for (int64_t g = (int64_t)blockIdx.x * TG + threadIdx.x; g < total; g += (int64_t)gridDim.x * TG) {
+    const int b = (int)(g / per_b);
+    const int64_t e = (g % per_b) * SA0_PPT;
+    float x[SA0_PPT][6];
+    sa0_load_inputs(a, b, e, x, oob);
+#pragma unroll
+    for (int t = 0; t < SA0_PPT; ++t) {
+      int p = 6;
+#pragma unroll
+      for (int d1 = 0; d1 < 6; ++d1) {
+        acc[d1] += x[t][d1];
+#pragma unroll
+        for (int d2 = d1; d2 < 6; ++d2, ++p) acc[p] = fmaf(x[t][d1], x[t][d2], acc[p]);
+      }
+    }
+  }
+  __shared__ float red[27][TG / 32];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double v = 0.0;
+    for (int i = 0; i < TG / 32; ++i) v += red[threadIdx.x][i];
+    atomicAdd(sums + threadIdx.x, v);
+  }
+}
+
+// y[b, c, e] = relu(fma(W0[c,:] . x[b,e,:], scale[c], shift[c])) as bf16 hi/lo planes (B, C0, M*K)
+__global__ void __launch_bounds__(TG)
+sa0_apply_planes_kernel(Sa0In a, int B, const float* __restrict__ W0, const float* __restrict__ scale,
+                        const float* __restrict__ shift, int C0, int relu, __nv_bfloat16* __restrict__ hi,
+                        __nv_bfloat16* __restrict__ lo, int* __restrict__ oob) {
+  extern __shared__ float sw[];        // [C0][8]: w0..w5, scale, shift
+  for (int i = threadIdx.x; i < C0 * 8; i += TG) {
+    const int c = i >> 3, d = i & 7;
+    sw[i] = d < 6 ? W0[c * 6 + d] : d == 6 ? scale[c] : shift[c];
+  }
+  __syncthreads();
+  const int64_t MK = (int64_t)a.M * a.K, per_b = MK / SA0_PPT, total = per_b * B;
+  for (int64_t g = (int64_t)blockIdx.x * TG + threadIdx.x; g < total; g += (int64_t)gridDim.x * TG) {
+    const int b = (int)(g / per_b);
+    const int64_t e = (g % per_b) * SA0_PPT;
+    float x[SA0_PPT][6];
+    sa0_load_inputs(a, b, e, x, oob);
+    const int64_t out0 = (int64_t)b * C0 * MK + e;
+#pragma unroll 2
+    for (int c = 0; c < C0; ++c) {
+      const float4 wa = *reinterpret_cast<const float4*>(sw + c * 8), wb = *reinterpret_cast<const float4*>(sw + c * 8 + 4);
+      const float w[6] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y};
+      float y[SA0_PPT];
+#pragma unroll
+      for (int t = 0; t < SA0_PPT; ++t) {
+        const float v = __fmaf_rn(sa0_z(w, x[t]), wb.z, wb.w);
+        y[t] = relu ? fmaxf(v, 0.f) : v;
+      }
+      store_planes4(hi, lo, out0 + (int64_t)c * MK, make_float4(y[0], y[1], y[2], y[3]));
+      store_planes4(hi, lo, out0 + (int64_t)c * MK + 4, make_float4(y[4], y[5], y[6], y[7]));
+    }
+  }
+}
+
+// G[c][0] = sum g, G[c][1 + d] = sum g x_d with g = dy * [fma(z, scale, shift) > 0]   (fp64 accumulators (C0, 7))
+__global__ void __launch_bounds__(TG)
+sa0_backward_sums_kernel(Sa0In a, int B, const float* __restrict__ dy, const float* __restrict__ W0,
+                         const float* __restrict__ scale, const float* __restrict__ shift, int C0, int relu,
+                         double* __restrict__ G, int* __restrict__ oob) {
+  extern __shared__ float sm[];        // [C0][8] weights, then [C0][7] per-CTA accumulators
+  float* sw = sm;
+  float* sg = sm + C0 * 8;
+  for (int i = threadIdx.x; i < C0 * 8; i += TG) {
+    const int c = i >> 3, d = i & 7;
+    sw[i] = d < 6 ? W0[c * 6 + d] : d == 6 ? scale[c] : shift[c];
+  }
+  for (int i = threadIdx.x; i < C0 * 7; i += TG) sg[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t MK = (int64_t)a.M * a.K, per_b = MK / SA0_PPT, total = per_b * B;
+  // warp-uniform trip count: the tail of the last warp works on a clamped position with zero weight
+  const int64_t g0 = (int64_t)blockIdx.x * TG + (threadIdx.x & ~31);
+  for (int64_t gw = g0; gw < total; gw += (int64_t)gridDim.x * TG) {
+    const int64_t g = gw + lane;
+    const bool live = g < total;
+    const int64_t gc = live ? g : total - 1;
+    const int b = (int)(gc / per_b);
+    const int64_t e = (gc % per_b) * SA0_PPT;
+    float x[SA0_PPT][6];
+    sa0_load_inputs(a, b, e, x, oob);
+    const float* __restrict__ dyb = dy + (int64_t)b * C0 * MK + e;
+#pragma unroll 1
+    for (int c = 0; c < C0; ++c) {
+      const float4 wa = *reinterpret_cast<const float4*>(sw + c * 8), wb = *reinterpret_cast<const float4*>(sw + c * 8 + 4);
+      const float w[6] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y};
+      const float4 d0 = *reinterpret_cast<const float4*>(dyb + (int64_t)c * MK), d1 = *reinterpret_cast<const float4*>(dyb + (int64_t)c * MK + 4);
+      const float dv[SA0_PPT] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < SA0_PPT; ++t) {
+        const float v = __fmaf_rn(sa0_z(w, x[t]), wb.z, wb.w);
+        const float gq = (live && (!relu || v > 0.f)) ? dv[t] : 0.f;
+        acc[0] += gq;
+#pragma unroll
+        for (int d = 0; d < 6; ++d) acc[1 + d] = fmaf(gq, x[t][d], acc[1 + d]);
+      }
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+      }
+      if (lane < 7) {
+        float v = acc[0];
+#pragma unroll
+        for (int i = 1; i < 7; ++i) v = lane == i ? acc[i] : v;
+        atomicAdd(sg + c * 7 + lane, v);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C0 * 7; i += TG) atomicAdd(G + i, (double)sg[i]);
+}
+
 unsigned grid_x(int64_t elems4) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>((elems4 + TG - 1) / TG, 64));
 }
@@ -418,6 +598,63 @@ int regnet_fp_dense_wgrad(const float* dZ, const float* dense, int64_t dsb, int6
   RN_CHECK_ARG(B > 0 && C0 > 0 && Nd > 0 && nd > 0 && nd <= 4 && B <= 65535, "fp_dense_wgrad: bad shape");
   fp_dense_wgrad_kernel<<<dim3(C0, B), TG, 0, (cudaStream_t)stream>>>(dZ, dense, Strides3{dsb, dsc, dsn}, nd, C0, Nd, part);
   RN_LAUNCH_CHECK("fp_dense_wgrad_kernel");
+  return REGNET_OK;
+}
+
+
+static int sa0_args(const char* who, const float* xyz, const float* new_xyz, const float* feature, const int64_t* index, int B,
+                    int N, int M, int K) {
+  if (!(xyz && new_xyz && feature && index)) { set_error("%s: null argument", who); return REGNET_EINVAL; }
+  if (!(B > 0 && N > 0 && M > 0 && K > 0 && K % SA0_PPT == 0)) {
+    set_error("%s: bad shape (the neighbour count must be a multiple of %d)", who, SA0_PPT);
+    return REGNET_EINVAL;
+  }
+  return REGNET_OK;
+}
+
+static unsigned sa0_grid(int64_t threads_needed) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>((threads_needed + TG - 1) / TG, 148LL * 8));
+}
+
+int regnet_sa0_input_moments(const float* xyz, int64_t xsb, int64_t xsc, int64_t xsn, const float* new_xyz, const float* feature,
+                             int64_t fsb, int64_t fsc, int64_t fsn, const int64_t* index, int B, int N, int M, int K,
+                             double* sums27, void* stream) {
+  RN_TRY(sa0_args("sa0_input_moments", xyz, new_xyz, feature, index, B, N, M, K));
+  RN_CHECK_ARG(sums27 != nullptr, "sa0_input_moments: null output");
+  cudaStream_t s = (cudaStream_t)stream;
+  RN_CUDA(cudaMemsetAsync(sums27, 0, sizeof(double) * 27, s));
+  const Sa0In a{xyz, Strides3{xsb, xsc, xsn}, new_xyz, feature, Strides3{fsb, fsc, fsn}, index, N, M, K};
+  sa0_input_moments_kernel<<<sa0_grid((int64_t)B * M * K / SA0_PPT), TG, 0, s>>>(a, B, sums27, oob_flag());
+  RN_LAUNCH_CHECK("sa0_input_moments_kernel");
+  return REGNET_OK;
+}
+
+int regnet_sa0_apply_planes(const float* xyz, int64_t xsb, int64_t xsc, int64_t xsn, const float* new_xyz, const float* feature,
+                            int64_t fsb, int64_t fsc, int64_t fsn, const int64_t* index, int B, int N, int M, int K,
+                            const float* W0, const float* scale, const float* shift, int C0, int relu, void* y_hi, void* y_lo,
+                            void* stream) {
+  RN_TRY(sa0_args("sa0_apply_planes", xyz, new_xyz, feature, index, B, N, M, K));
+  RN_CHECK_ARG(W0 && scale && shift && y_hi && y_lo && C0 > 0 && C0 <= 1024, "sa0_apply_planes: null argument or bad width");
+  const Sa0In a{xyz, Strides3{xsb, xsc, xsn}, new_xyz, feature, Strides3{fsb, fsc, fsn}, index, N, M, K};
+  sa0_apply_planes_kernel<<<sa0_grid((int64_t)B * M * K / SA0_PPT), TG, sizeof(float) * 8 * C0, (cudaStream_t)stream>>>(
+      a, B, W0, scale, shift, C0, relu, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, oob_flag());
+  RN_LAUNCH_CHECK("sa0_apply_planes_kernel");
+  return REGNET_OK;
+}
+
+int regnet_sa0_backward_sums(const float* xyz, int64_t xsb, int64_t xsc, int64_t xsn, const float* new_xyz, const float* feature,
+                             int64_t fsb, int64_t fsc, int64_t fsn, const int64_t* index, int B, int N, int M, int K,
+                             const float* dy, const float* W0, const float* scale, const float* shift, int C0, int relu,
+                             double* G, void* stream) {
+  RN_TRY(sa0_args("sa0_backward_sums", xyz, new_xyz, feature, index, B, N, M, K));
+  RN_CHECK_ARG(dy && W0 && scale && shift && G && C0 > 0 && C0 <= 1024, "sa0_backward_sums: null argument or bad width");
+  RN_CHECK_ARG((reinterpret_cast<uintptr_t>(dy) & 15) == 0, "sa0_backward_sums: dy must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  RN_CUDA(cudaMemsetAsync(G, 0, sizeof(double) * 7 * C0, s));
+  const Sa0In a{xyz, Strides3{xsb, xsc, xsn}, new_xyz, feature, Strides3{fsb, fsc, fsn}, index, N, M, K};
+  sa0_backward_sums_kernel<<<sa0_grid((int64_t)B * M * K / SA0_PPT), TG, sizeof(float) * 15 * C0, s>>>(
+      a, B, dy, W0, scale, shift, C0, relu, G, oob_flag());
+  RN_LAUNCH_CHECK("sa0_backward_sums_kernel");
   return REGNET_OK;
 }
 

