@@ -386,12 +386,7 @@ __device__ __forceinline__ void store_oct(const OperandOut& o, int64_t off, floa
     uint32_t ph[4], pl[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[2 * u], h0, l0);
-      split_bf16(v[2 * u + 1], h1, l1);
-      __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
-      ph[u] = *reinterpret_cast<uint32_t*>(&hh);
-      pl[u] = *reinterpret_cast<uint32_t*>(&ll);
+      split_bf16_pair(v[2 * u], v[2 * u + 1], ph[u], pl[u]);
     }
     *reinterpret_cast<uint4*>(o.hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
     *reinterpret_cast<uint4*>(o.lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);

@@ -52,6 +52,19 @@ int sa_gather_affine_launch(const float* Z, int ldz, int n_prev, const float* xy
                             const float* Wx, int ldw, const int32_t* nbr, const float* scale, const float* shift, int B,
                             int M, int cout, float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo,
                             cudaStream_t stream);
+// SA levels 1, 2, second layer with its operand produced in the kernel (gemm_fused_a.cu): sa_fold_launch turns the per-point
+// GEMM output Z into Z' = scale * (Z + W_x xyz) in place and writes T = shift - scale * W_x centre per centroid; the GEMM then
+// builds a[p] = relu(Z'[g(p)] + T[p / 64]) in shared memory.
+int sa_fold_launch(float* Z, int ldz, int n_prev, const float* xyz, Strides3 xst, const float* new_xyz, int M, const float* Wx,
+                   int ldw, const float* scale, const float* shift, int B, int C, float* T, cudaStream_t stream);
+// the same operand materialised as bf16 hi/lo planes (rows, C), bit-identical to what gemm_fused_a builds in shared memory
+int sa_gather_add_launch(const float* Z, int ldz, int n_prev, const float* T, const int32_t* nbr, int rows_per_cloud, int C,
+                         int64_t rows, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t stream);
+int gemm_fused_a_supported(int64_t P, int K, int rows_per_cloud);
+int gemm_fused_a_launch(const float* Z, int ldz, const float* T, const int32_t* nbr, int rows_per_cloud, int n_prev,
+                        const __nv_bfloat16* Whi, const __nv_bfloat16* Wlo, int ldw, int64_t P, int K, int cout,
+                        const float* scale, const float* shift, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ld_out,
+                        unsigned int* tile_counter, cudaStream_t stream);
 int fp_interp_affine_launch(const float* Y, int64_t y_bstride, int ldy, const float* D, int ldd, const float* dense3,
                             int64_t dense3_bstride, int dense3_ld, const float* Wd3, int ldw3, const int32_t* idx,
                             const float* w, const float* scale, const float* shift, int B, int Nd, int cout,

@@ -59,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int sa_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; int corun_small = 1; int corun1_cs = 8; int corun1_threads = 128; int corun_single = 1; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int sa_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; int corun_small = 1; int corun1_cs = 8; int corun1_threads = 128; int corun_single = 1; int sa_fused_a = 2; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
@@ -103,6 +103,7 @@ struct regnet_scorenet {
   __nv_bfloat16* fp_lo[2] = {nullptr, nullptr};
   float* fp_y = nullptr;
   float* fp_d = nullptr;
+  float* sa_t = nullptr;   // SA levels 1, 2: T = shift0 - scale0 * W_x centre per centroid (gemm_fused_a.cu)
   float* sa_z = nullptr;   // SA levels 1, 2: Z = previous level's features x W_f^T, per point (gather.cu sa_gather_affine_kernel)
   __nv_bfloat16* xyzrel_hi = nullptr;
   __nv_bfloat16* xyzrel_lo = nullptr;
@@ -241,6 +242,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
   if (const char* e = getenv("REGNET_FP_LINEAR_FIRST")) p->cfg.fp_linear_first = atoi(e);
   if (const char* e = getenv("REGNET_SA_LINEAR_FIRST")) p->cfg.sa_linear_first = atoi(e);
   if (const char* e = getenv("REGNET_DYNAMIC_TILES")) p->cfg.dynamic_tiles = atoi(e);
+  if (const char* e = getenv("REGNET_SA_FUSED_A")) p->cfg.sa_fused_a = atoi(e);
   if (const char* e = getenv("REGNET_USE_GRID")) p->cfg.use_grid = atoi(e);
   if (const char* e = getenv("REGNET_FPS_CORUN")) sscanf(e, "%d,%d", &p->cfg.corun_cs, &p->cfg.corun_threads);
   if (const char* e = getenv("REGNET_FPS_CORUN_SMALL")) p->cfg.corun_small = atoi(e);
@@ -282,6 +284,7 @@ int regnet_scorenet_create(const regnet_scorenet_config* cfg, regnet_scorenet** 
     A((void**)&p->fp_y, sizeof(float) * ymax);
     A((void**)&p->fp_d, sizeof(float) * dmax);
     A((void**)&p->sa_z, sizeof(float) * std::max((size_t)B * M[0] * SA_CH[1][0], (size_t)B * M[1] * SA_CH[2][0]));
+    A((void**)&p->sa_t, sizeof(float) * std::max((size_t)B * M[1] * SA_CH[1][0], (size_t)B * M[2] * SA_CH[2][0]));
     const size_t pmax = (size_t)B * std::max(M[1], M[2]) * 64;
     A((void**)&p->xyzrel_hi, sizeof(__nv_bfloat16) * pmax * 16);
     A((void**)&p->xyzrel_lo, sizeof(__nv_bfloat16) * pmax * 16);
@@ -596,6 +599,8 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
   G.pending = false;
   p->last_slot = slot;
   p->gemm_idx = 0;
+  // a prefetch for the next batch is outstanding: its FPS CTAs will share the SMs with this forward's kernels
+  const bool corunning = p->geom[slot ^ 1].pending || p->deferred_slot >= 0;
   if (p->cfg.engine == REGNET_ENGINE_TC && p->cfg.dynamic_tiles)
     RN_CUDA(cudaMemsetAsync(p->tile_counters, 0, sizeof(unsigned int) * 64, ms));
   const bool mode3 = fork && p->cfg.use_side_stream == 3 && p->side2 != nullptr;
@@ -688,11 +693,42 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
                             L0.cout, ez, ms));
       prof_end(p, ms);
       ++p->launches;
-      prof_begin(p, SAOP_LABEL[i], ms);
-      RN_TRY(sa_gather_affine_launch(p->sa_z, L0.cout, lvl_n[i], lvl_xyz[i], lvl_st[i], G.new_xyz[i], L0.w_f32 + feat_c,
-                                     L0.kpad, G.nbr[i], L0.scale, L0.shift, B, M[i], L0.cout, nullptr, a1.hi, a1.lo, ms));
-      prof_end(p, ms);
-      ++p->launches;
+      const Layer& L1 = p->layers[i][1];
+      if (p->cfg.sa_fused_a && p->cfg.dynamic_tiles && p->gemm_idx < 64 && L1.set && L1.cin == L0.cout &&
+          gemm_fused_a_supported(P, L0.cout, M[i] * 64)) {
+        // Fold the xyz term into the per-point table and a per-centroid vector (gemm_fused_a.cu): the grouped activation
+        // is then relu(Z'[g] + T).  sa_fused_a = 1: the second layer's GEMM builds that operand tile in shared memory and
+        // it is never materialised; 3: it is materialised by a gather-add pass and fed to the plain GEMM -- identical bits;
+        // 2 (default): the fused GEMM unless a prefetched FPS is co-running.  Measured (B = 15, 25 600 points): the fused
+        // kernel's eight producer warps take a single forward from 10.0 to 8.9 ms, but next to a co-resident FPS they
+        // cost it more issue slots than the saved pass returns (pipelined step 7.1 -> 7.8 ms).
+        const bool fused = p->cfg.sa_fused_a == 1 || (p->cfg.sa_fused_a == 2 && !corunning);
+        prof_begin(p, i == 1 ? "sa_fold.1" : "sa_fold.2", ms);
+        RN_TRY(sa_fold_launch(p->sa_z, L0.cout, lvl_n[i], lvl_xyz[i], lvl_st[i], G.new_xyz[i], M[i], L0.w_f32 + feat_c, L0.kpad,
+                              L0.scale, L0.shift, B, L0.cout, p->sa_t, ms));
+        prof_end(p, ms);
+        ++p->launches;
+        if (fused) {
+          prof_begin(p, GEMM_LABEL[i][1], ms);
+          RN_TRY(gemm_fused_a_launch(p->sa_z, L0.cout, p->sa_t, G.nbr[i], M[i] * 64, lvl_n[i], L1.w_hi, L1.w_lo, L1.kpad, P,
+                                     L1.cin, L1.cout, L1.scale, L1.shift, a2.hi, a2.lo, a2.ld,
+                                     p->tile_counters + (p->gemm_idx++), ms));
+          prof_end(p, ms);
+          ++p->launches;
+          need_l1 = false;
+        } else {
+          prof_begin(p, SAOP_LABEL[i], ms);
+          RN_TRY(sa_gather_add_launch(p->sa_z, L0.cout, lvl_n[i], p->sa_t, G.nbr[i], M[i] * 64, L0.cout, P, a1.hi, a1.lo, ms));
+          prof_end(p, ms);
+          ++p->launches;
+        }
+      } else {
+        prof_begin(p, SAOP_LABEL[i], ms);
+        RN_TRY(sa_gather_affine_launch(p->sa_z, L0.cout, lvl_n[i], lvl_xyz[i], lvl_st[i], G.new_xyz[i], L0.w_f32 + feat_c,
+                                       L0.kpad, G.nbr[i], L0.scale, L0.shift, B, M[i], L0.cout, nullptr, a1.hi, a1.lo, ms));
+        prof_end(p, ms);
+        ++p->launches;
+      }
     } else if (i > 0 && (p->cfg.gather_a >> (i - 1) & 1) && p->cfg.engine == REGNET_ENGINE_TC && feat_c % 64 == 0 &&
                p->sa_hi[i - 1]) {
       // the grouping is fused into the first layer's TMA producer (tile::gather4 from the previous level's pooled
@@ -917,6 +953,7 @@ int regnet_scorenet_set_option(regnet_scorenet* p, const char* name, int value) 
   const std::string k(name);
   if (k == "defer_prefetch") p->defer_prefetch = value;
   else if (k == "dynamic_tiles") p->cfg.dynamic_tiles = value;
+  else if (k == "sa_fused_a") p->cfg.sa_fused_a = value;
   else {
     set_error("scorenet_set_option: unknown option '%s'", name);
     return REGNET_EINVAL;

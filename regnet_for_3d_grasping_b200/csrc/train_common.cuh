@@ -40,13 +40,11 @@ inline DropCfg make_drop(float p, uint64_t seed) {
 }
 
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t i, float4 v) {
-  __nv_bfloat16 h[4], l[4];
-  split_bf16(v.x, h[0], l[0]);
-  split_bf16(v.y, h[1], l[1]);
-  split_bf16(v.z, h[2], l[2]);
-  split_bf16(v.w, h[3], l[3]);
-  *reinterpret_cast<uint2*>(hi + i) = *reinterpret_cast<uint2*>(h);
-  *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<uint2*>(l);
+  uint32_t h[2], l[2];
+  split_bf16_pair(v.x, v.y, h[0], l[0]);
+  split_bf16_pair(v.z, v.w, h[1], l[1]);
+  *reinterpret_cast<uint2*>(hi + i) = make_uint2(h[0], h[1]);
+  *reinterpret_cast<uint2*>(lo + i) = make_uint2(l[0], l[1]);
 }
 
 }  // namespace regnet

@@ -241,6 +241,7 @@ def test_warp_producers_and_stream_modes_give_identical_bits(lib_path, monkeypat
     from regnet_for_3d_grasping_b200.scorenet import ScoreNetPlan
     sd = weights.random_scorenet_state(seed=6)
     pc = torch.from_numpy(synth.batch("table", range(300, 300 + B), N)).cuda()
+    monkeypatch.setenv("REGNET_SA_FUSED_A", "0")     # keep the set-abstraction producers in the comparison
 
     def run(side_stream):
         plan = ScoreNetPlan(B, N, "cuda", side_stream=side_stream)
@@ -256,3 +257,42 @@ def test_warp_producers_and_stream_modes_give_identical_bits(lib_path, monkeypat
     monkeypatch.setenv("REGNET_AFFINE_V1", "1")
     f1, s1 = run(3)
     assert torch.equal(f3, f1) and torch.equal(s3, s1), "warp-cooperative producers differ from the per-thread producers"
+
+
+@pytest.mark.parametrize("B,N", [(15, 25600), (3, 6144)])
+def test_fused_operand_layers_match_the_materialised_ones(lib_path, B, N):
+    """Set-abstraction levels 1 and 2, second layer: the operand relu(Z'[g] + T) built inside the GEMM (gemm_fused_a.cu,
+    option sa_fused_a = 1) against the same operand materialised by a gather-add pass and fed to the plain GEMM (= 3): the
+    two feed identical bits to identical MMA sequences, so every output must be EQUAL.  Against the older form that keeps
+    the xyz term as W_x (xyz - centre) in the producer (= 0) the folded form W_x xyz - W_x centre differs by a few ulps of
+    the operand: 2e-5 on the features."""
+    from regnet_for_3d_grasping_b200 import synth, weights
+    from regnet_for_3d_grasping_b200.scorenet import ScoreNetPlan
+    sd = weights.random_scorenet_state(seed=8)
+    pc = torch.from_numpy(synth.batch("table", range(400, 400 + B), N)).cuda()
+    out = {}
+    for mode in (1, 3, 0):
+        plan = ScoreNetPlan(B, N, "cuda")
+        plan.set_option("sa_fused_a", mode)
+        plan.bind_state(sd)
+        f, s = plan.forward(pc)
+        torch.cuda.synchronize()
+        names = [label for label, _ in plan.profile_forward(pc)]
+        assert ("sa_fold.1" in names) == (mode != 0) and ("sa_operand.1" in names) == (mode != 1), (mode, names)
+        out[mode] = (f.clone(), s.clone())
+        plan.close()
+    assert torch.equal(out[1][0], out[3][0]) and torch.equal(out[1][1], out[3][1]), "fused and materialised operands differ"
+    scale = float(out[0][0].abs().max())
+    assert float((out[1][0] - out[0][0]).abs().max()) <= 2e-5 * scale
+    assert float((out[1][1] - out[0][1]).abs().max()) <= 1e-5
+    # default policy: fused for a lone forward, materialised next to a prefetch -- the same bits either way
+    plan = ScoreNetPlan(B, N, "cuda")
+    plan.bind_state(sd)
+    f_alone, _ = plan.forward(pc)
+    pc2 = pc.clone()
+    plan.prefetch(pc2)
+    f_co, _ = plan.forward(pc)
+    f_next, _ = plan.forward(pc2)
+    torch.cuda.synchronize()
+    assert torch.equal(f_alone, out[1][0]) and torch.equal(f_co, f_alone) and torch.equal(f_next, f_alone)
+    plan.close()
