@@ -384,8 +384,8 @@ int regnet_fp_dense_wgrad(const float* dZ, const float* dense, int64_t dsb, int6
 
 /* First block of a set-abstraction MLP whose grouped input has 6 channels ([xyz - centre | 3 feature channels], level 0 of
  * ScoreNet) WITHOUT materialising its pre-activation: Z0 is linear in 6 numbers per position, so (csrc/train_gather.cu)
- *   regnet_sa0_input_moments   sums27 = [sum x_d (6) | sum x_d1 x_d2, d1 <= d2 (21)] over all grouped positions, fp64; the
- *                              batch moments of Z0 follow from them and the weights;
+ *   regnet_sa0_input_moments   sums27 = [sum x_d (6) | sum x_d1 x_d2, d1 <= d2 (21)] over all grouped positions, fp64, and
+ *                              (moments != NULL) the batch moments (C0, 2) = (sum z, sum z^2) of Z0 that follow from them;
  *   regnet_sa0_apply_planes    y = [relu](scale * (W0 x) + shift) recomputed from the inputs, written as planes (B, C0, M*K);
  *   regnet_sa0_backward_sums   G (C0, 7) fp64 = [sum g | sum g x_d] with g = dy * [scale * (W0 x) + shift > 0]: everything the
  *                              block's backward needs (dgamma, dbeta, dW0) in closed form; its inputs need no gradient.
@@ -393,7 +393,11 @@ int regnet_fp_dense_wgrad(const float* dZ, const float* dense, int64_t dsb, int6
  * [xyz | feature] order; dy (B, C0, M*K) fp32. */
 int regnet_sa0_input_moments(const float* xyz, int64_t xsb, int64_t xsc, int64_t xsn, const float* new_xyz, const float* feature,
                              int64_t fsb, int64_t fsc, int64_t fsn, const int64_t* index, int B, int N, int M, int K,
-                             double* sums27, void* stream);
+                             const float* W0, int C0, double* sums27, double* moments, void* stream);
+/* dbeta, dgamma and dW0 (C0, 6; may be null) of that block in closed form from G (regnet_sa0_backward_sums), the 27 input sums,
+ * the weights and the batch statistics (invstd, scale = gamma * invstd); count = B * M * K. */
+int regnet_sa0_backward_finalize(const double* G, const double* sums27, const float* W0, const float* invstd, const float* scale,
+                                 int C0, double count, float* dW0, float* dgamma, float* dbeta, void* stream);
 int regnet_sa0_apply_planes(const float* xyz, int64_t xsb, int64_t xsc, int64_t xsn, const float* new_xyz, const float* feature,
                             int64_t fsb, int64_t fsc, int64_t fsn, const int64_t* index, int B, int N, int M, int K,
                             const float* W0, const float* scale, const float* shift, int C0, int relu, void* y_hi, void* y_lo,

@@ -100,7 +100,9 @@ _SIGNATURES = {
     "regnet_fp_gather_linear": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_int, c_int, c_int, c_int,
                                         c_int, c_ptr, c_ptr, c_ptr]),
     "regnet_fp_dense_wgrad": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
-    "regnet_sa0_input_moments": (c_int, _STRIDED + [c_ptr] + _STRIDED + [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr]),
+    "regnet_sa0_input_moments": (c_int, _STRIDED + [c_ptr] + _STRIDED + [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_int, c_ptr,
+                                                              c_ptr, c_ptr]),
+    "regnet_sa0_backward_finalize": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, ctypes.c_double, c_ptr, c_ptr, c_ptr, c_ptr]),
     "regnet_sa0_apply_planes": (c_int, _STRIDED + [c_ptr] + _STRIDED + [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,
                                                              c_int, c_int, c_ptr, c_ptr, c_ptr]),
     "regnet_sa0_backward_sums": (c_int, _STRIDED + [c_ptr] + _STRIDED + [c_ptr, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr,

@@ -426,15 +426,6 @@ class _SubSpec:
         self.pooled, self.dropout_p, self.passes = spec.pooled, spec.dropout_p, spec.passes
 
 
-def _sym6(tri):
-    """21 upper-triangle sums (row-major, d1 <= d2) -> the symmetric (6, 6) matrix."""
-    iu = torch.triu_indices(6, 6, device=tri.device)
-    m = torch.zeros(6, 6, dtype=tri.dtype, device=tri.device)
-    m[iu[0], iu[1]] = tri
-    m[iu[1], iu[0]] = tri
-    return m
-
-
 class _SA0RecomputeChainTrain(torch.autograd.Function):
     """Set-abstraction level 0 (3 feature channels that need no gradient): the first block's pre-activation Z0 = W0 [xyz_rel |
     rgb] over the M * 64 grouped positions is never written.  Its batch moments follow from the 27 first and second sums of
@@ -459,10 +450,8 @@ class _SA0RecomputeChainTrain(torch.autograd.Function):
             geo = (_p(xyz), xyz.stride(0), xyz.stride(1), xyz.stride(2), _p(new_xyz), _p(feature), feature.stride(0),
                    feature.stride(1), feature.stride(2), _p(index), B, N, M, K)
             sums = torch.empty(27, dtype=torch.float64, device=dev)
-            _lib.check(lib.regnet_sa0_input_moments(*geo, _p(sums), _stream()))
-            w64 = w0.double()
-            sx, sxx = sums[:6], _sym6(sums[6:])
-            moments = torch.stack([w64 @ sx, ((w64 @ sxx) * w64).sum(dim=1)], dim=1).contiguous()
+            moments = torch.empty(C0, 2, dtype=torch.float64, device=dev)
+            _lib.check(lib.regnet_sa0_input_moments(*geo, _p(w0), C0, _p(sums), _p(moments), _stream()))
             stats = torch.empty(4, C0, dtype=torch.float32, device=dev)
             _lib.check(lib.regnet_bn_finalize_moments(
                 _p(moments), C0, float(B) * float(L), _p(gammas[0]), _p(betas[0]), float(bn.eps), float(bn.momentum),
@@ -496,17 +485,14 @@ class _SA0RecomputeChainTrain(torch.autograd.Function):
                 feature.stride(1), feature.stride(2), _p(index), B, N, M, K, _p(dy0), _p(w0), _p(stats[2]), _p(stats[3]), C0,
                 int(spec.relu[0]), _p(G), _stream()))
             del dy0
-            cnt = float(B) * float(L)
-            w64 = w0.double()
-            sx, sxx = sums[:6], _sym6(sums[6:])
-            mu, istd, sc = (w64 @ sx) / cnt, stats[1].double(), stats[2].double()
-            g0, gx = G[:, 0], G[:, 1:]
-            dbeta = g0
-            dgamma = istd * ((w64 * gx).sum(dim=1) - mu * g0)                    # sum g * xhat
-            zx = w64 @ sxx - mu[:, None] * sx[None, :]                           # sum (z - mu) x_d
-            dw0 = sc[:, None] * (gx - (g0 / cnt)[:, None] * sx[None, :] - (dgamma * istd / cnt)[:, None] * zx)
-            dw0 = dw0.float().view(C0, 6, 1, 1) if ctx.needs_input_grad[1] else None
-        return (None, dw0) + tuple(dws) + (dgamma.float(),) + tuple(dgs) + (dbeta.float(),) + tuple(dbs)
+            dw0 = torch.empty(C0, 6, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+            dgamma = torch.empty(C0, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(C0, dtype=torch.float32, device=dev)
+            _lib.check(lib.regnet_sa0_backward_finalize(_p(G), _p(sums), _p(w0), _p(stats[1]), _p(stats[2]), C0,
+                                                        float(B) * float(L), _p(dw0), _p(dgamma), _p(dbeta), _stream()))
+            if dw0 is not None:
+                dw0 = dw0.view(C0, 6, 1, 1)
+        return (None, dw0) + tuple(dws) + (dgamma,) + tuple(dgs) + (dbeta,) + tuple(dbs)
 
 
 class _FPLinearChainTrain(torch.autograd.Function):

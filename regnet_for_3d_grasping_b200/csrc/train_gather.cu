@@ -487,6 +487,63 @@ sa0_backward_sums_kernel(Sa0In a, int B, const float* __restrict__ dy, const flo
   for (int i = threadIdx.x; i < C0 * 7; i += TG) atomicAdd(G + i, (double)sg[i]);
 }
 
+// closed forms of the level-0 first block (see above): tri(d1, d2) indexes the 21 upper-triangle sums behind the 6 first sums
+__device__ __forceinline__ double sa0_sxx(const double* __restrict__ sums, int d1, int d2) {
+  if (d1 > d2) { const int t = d1; d1 = d2; d2 = t; }
+  return sums[6 + d1 * 6 - d1 * (d1 - 1) / 2 + (d2 - d1)];
+}
+
+// moments[c] = (sum z_c, sum z_c^2) = (w_c . Sx, w_c' Sxx w_c)
+__global__ void __launch_bounds__(128)
+sa0_moments_from_sums_kernel(const double* __restrict__ sums, const float* __restrict__ W0, int C0, double* __restrict__ moments) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C0) return;
+  double w[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) w[d] = (double)W0[c * 6 + d];
+  double m1 = 0.0, m2 = 0.0;
+#pragma unroll
+  for (int d1 = 0; d1 < 6; ++d1) {
+    m1 += w[d1] * sums[d1];
+#pragma unroll
+    for (int d2 = 0; d2 < 6; ++d2) m2 += w[d1] * w[d2] * sa0_sxx(sums, d1, d2);
+  }
+  moments[2 * c] = m1;
+  moments[2 * c + 1] = m2;
+}
+
+// dbeta = G0, dgamma = is (w . G - mu G0), dW_d = sc (G_d - (G0 / n) Sx_d - (dgamma is / n) (w' Sxx_d - mu Sx_d))
+__global__ void __launch_bounds__(128)
+sa0_backward_finalize_kernel(const double* __restrict__ G, const double* __restrict__ sums, const float* __restrict__ W0,
+                             const float* __restrict__ invstd, const float* __restrict__ scale, int C0, double count,
+                             float* __restrict__ dW0, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C0) return;
+  double w[6];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) w[d] = (double)W0[c * 6 + d];
+  double mu = 0.0, wg = 0.0;
+#pragma unroll
+  for (int d = 0; d < 6; ++d) {
+    mu += w[d] * sums[d];
+    wg += w[d] * G[c * 7 + 1 + d];
+  }
+  mu /= count;
+  const double g0 = G[c * 7], is = (double)invstd[c], sc = (double)scale[c];
+  const double dg = is * (wg - mu * g0);
+  dbeta[c] = (float)g0;
+  dgamma[c] = (float)dg;
+  if (dW0) {
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      double zx = -mu * sums[d];
+#pragma unroll
+      for (int e = 0; e < 6; ++e) zx += w[e] * sa0_sxx(sums, e, d);
+      dW0[c * 6 + d] = (float)(sc * (G[c * 7 + 1 + d] - g0 / count * sums[d] - dg * is / count * zx));
+    }
+  }
+}
+
 unsigned grid_x(int64_t elems4) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>((elems4 + TG - 1) / TG, 64));
 }
@@ -618,14 +675,28 @@ static unsigned sa0_grid(int64_t threads_needed) {
 
 int regnet_sa0_input_moments(const float* xyz, int64_t xsb, int64_t xsc, int64_t xsn, const float* new_xyz, const float* feature,
                              int64_t fsb, int64_t fsc, int64_t fsn, const int64_t* index, int B, int N, int M, int K,
-                             double* sums27, void* stream) {
+                             const float* W0, int C0, double* sums27, double* moments, void* stream) {
   RN_TRY(sa0_args("sa0_input_moments", xyz, new_xyz, feature, index, B, N, M, K));
-  RN_CHECK_ARG(sums27 != nullptr, "sa0_input_moments: null output");
+  RN_CHECK_ARG(sums27 != nullptr && (moments == nullptr || (W0 != nullptr && C0 > 0)), "sa0_input_moments: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   RN_CUDA(cudaMemsetAsync(sums27, 0, sizeof(double) * 27, s));
   const Sa0In a{xyz, Strides3{xsb, xsc, xsn}, new_xyz, feature, Strides3{fsb, fsc, fsn}, index, N, M, K};
   sa0_input_moments_kernel<<<sa0_grid((int64_t)B * M * K / SA0_PPT), TG, 0, s>>>(a, B, sums27, oob_flag());
   RN_LAUNCH_CHECK("sa0_input_moments_kernel");
+  if (moments) {
+    sa0_moments_from_sums_kernel<<<(C0 + 127) / 128, 128, 0, s>>>(sums27, W0, C0, moments);
+    RN_LAUNCH_CHECK("sa0_moments_from_sums_kernel");
+  }
+  return REGNET_OK;
+}
+
+int regnet_sa0_backward_finalize(const double* G, const double* sums27, const float* W0, const float* invstd, const float* scale,
+                                 int C0, double count, float* dW0, float* dgamma, float* dbeta, void* stream) {
+  RN_CHECK_ARG(G && sums27 && W0 && invstd && scale && dgamma && dbeta && C0 > 0 && count > 0.0,
+               "sa0_backward_finalize: null argument or bad shape");
+  sa0_backward_finalize_kernel<<<(C0 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(G, sums27, W0, invstd, scale, C0, count, dW0,
+                                                                                    dgamma, dbeta);
+  RN_LAUNCH_CHECK("sa0_backward_finalize_kernel");
   return REGNET_OK;
 }
 
