@@ -15,7 +15,7 @@ OBJ_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libregnet_b200.so")
 SOURCES = ["capi.cu", "fps.cu", "neighbors.cu", "gather.cu", "gemm_simt.cu", "gemm_tc.cu", "scorenet.cu", "region.cu", "grid.cu", "sa0_front.cu", "sa0_chain.cu", "train_ops.cu", "conv_train.cu", "generic_ops.cu", "train_gather.cu", "gemm_fused_a.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+              "-Xptxas", "-v", "--expt-relaxed-constexpr", "-Xfatbin", "-compress-all"]
 
 
 def _deps():
