@@ -176,7 +176,10 @@ int regnet_scorenet_prefetch(regnet_scorenet* plan, const float* pc, void* strea
 int regnet_scorenet_join_prefetch(regnet_scorenet* plan, void* stream);
 
 /* Plan options.  "defer_prefetch" (default 0): 1 parks a prefetch until the next forward has launched its level-0 kernel
- * (or until its results are needed) instead of enqueueing it at once -- an experiment switch, see csrc/scorenet.cu.  "dynamic_tiles": tile scheduling of the GEMM launches. */
+ * (or until its results are needed) instead of enqueueing it at once -- an experiment switch, see csrc/scorenet.cu.  "dynamic_tiles": tile scheduling of the GEMM launches.
+ * "sa_fused_a" (default 2): how the second layer of set-abstraction levels 1-2 gets its operand relu(Z'[g] + T) --
+ * 1 = built inside the GEMM by producer warps (csrc/gemm_fused_a.cu), 3 = materialised by a gather-add pass (identical
+ * bits), 2 = the former unless a prefetched FPS is co-running, 0 = the round-1 gather-affine producer (no folded tables). */
 int regnet_scorenet_set_option(regnet_scorenet* plan, const char* name, int value);
 
 /* The geometry chain alone (FPS, ball query and 3-NN of every level), for callers that run the MLPs themselves -- the
