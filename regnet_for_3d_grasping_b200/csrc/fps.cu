@@ -292,6 +292,8 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
 // the same sqdist_ref from the same operands), the arg-max uses the same (distance, tie key) order, so picks are
 // bit-identical to the one-pick-per-exchange kernel; with heavy ties (lattices) rounds simply shrink to one pick.
 // Used for the shapes whose cluster has at most 32 warps (each lane then holds K = 4 of the <= 128 candidates).
+__device__ unsigned int g_fps_dbg[4];   // TEMPORARY instrumentation: [0] rounds of cloud 0
+
 template <int CS, int T, int PPT>
 __global__ void __launch_bounds__(T, 1)
 fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, int64_t* __restrict__ idx64,
@@ -351,6 +353,7 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
 
   int done = 1;   // picks made so far (identical in every thread of the cluster)
   for (uint32_t r = 0; done < M; ++r) {
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&g_fps_dbg[0], 1u);
     const uint32_t par = r & 1;
     // ---- this thread's two best points: (b1, k1) then (b2, k2), in (distance desc, k asc) order --------------------------
     float b1 = 0.f, b2 = 0.f;
@@ -421,13 +424,27 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
     }
     const uint32_t F = __reduce_max_sync(FULL, floor_bits);
     bool first = true;
+    // The update of this thread's own points with pick i (25 independent distance / min pairs, ~175 instructions) does not
+    // feed the selection of pick i + 1 (that runs on the candidates), so it is applied ONE PICK LATE, at the top of the next
+    // trip: it then shares a basic block with the arg-max / redux / ballot chain of the next selection and fills that
+    // chain's stalls instead of sitting serially behind it.  (cx, cy, cz) always holds the last pick; re-applying it is
+    // idempotent, which keeps the update unconditional (first trip of a round: the previous round's last pick again).
 #pragma unroll 1
     while (done < M) {
-      uint32_t ld = cd[0], lt = cr[0].x;
+#pragma unroll
+      for (int k = 0; k < PPT; ++k) md[k] = fminf(md[k], sqdist_ref(cx, cy, cz, px[k], py[k], pz[k]));
+      // this lane's best candidate by (distance desc, tie asc) as ONE 64-bit key: the two-condition form compiled into a
+      // tree of divergent branches (9 BRA + 3 BSSY / BSYNC per pick), the key compare into selects
+      unsigned long long lk = ((unsigned long long)cd[0] << 32) | (uint32_t)~cr[0].x;
       int lc = 0;
 #pragma unroll
-      for (int c = 1; c < CPL; ++c)
-        if (cd[c] > ld || (cd[c] == ld && cr[c].x < lt)) { ld = cd[c]; lt = cr[c].x; lc = c; }
+      for (int c = 1; c < CPL; ++c) {
+        const unsigned long long kc = ((unsigned long long)cd[c] << 32) | (uint32_t)~cr[c].x;
+        const bool better = kc > lk;
+        lk = better ? kc : lk;
+        lc = better ? c : lc;
+      }
+      const uint32_t ld = (uint32_t)(lk >> 32), lt = ~(uint32_t)lk;
       uint32_t dmax;
       const int src = pick_lane(ld, ld ? lt : NO_TIE, dmax);
       if (!first && !(dmax > F)) break;      // an unpublished point could rank before this candidate: next round
@@ -452,8 +469,6 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
             cd[c] = __float_as_uint(fminf(__uint_as_float(cd[c]), d));
           }
         }
-#pragma unroll
-        for (int k = 0; k < PPT; ++k) md[k] = fminf(md[k], sqdist_ref(cx, cy, cz, px[k], py[k], pz[k]));
       }
       if (rank == 0 && tid == 0) {
         if (idx64) idx64[(int64_t)cloud * M + done] = cur;
@@ -467,6 +482,9 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
       first = false;
       if (dmax == 0u) break;                 // nothing can change any more: one repeated pick per round
     }
+    // the round's last pick reaches the own points before the next round's scan
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) md[k] = fminf(md[k], sqdist_ref(cx, cy, cz, px[k], py[k], pz[k]));
   }
   if (CS > 1) cluster_sync_all();
 }
@@ -632,7 +650,18 @@ int fps_generic_launch(const float* pts, Strides3 st, int B, int N, int M, int n
   return REGNET_OK;
 }
 
+unsigned int* fps_dbg_symbol_read(unsigned int* out, int reset) {
+  cudaMemcpyFromSymbol(out, g_fps_dbg, sizeof(unsigned int) * 4);
+  if (reset) { unsigned int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_fps_dbg, z, sizeof(z)); }
+  return out;
+}
+
 }  // namespace
+
+extern "C" int regnet_debug_fps_counters(unsigned int* out, int reset) {
+  fps_dbg_symbol_read(out, reset);
+  return 0;
+}
 
 int fps_block_log2(int N) {  // sampling_kernel.cu:32-40 get_block + the switch's floor of 16
   int cnt = 0;
