@@ -352,6 +352,26 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
   if (CS > 1) cluster_sync_all(); else __syncthreads();
 
   int done = 1;   // picks made so far (identical in every thread of the cluster)
+  // Results leave through a per-lane buffer: pick number q of the current window is kept by lane q (four selects per pick),
+  // and warp 0 of rank 0 writes a window of up to 32 picks with coalesced stores.  The per-pick form -- one thread of one
+  // warp computing five 64-bit addresses and storing inside a divergent region -- made that warp the slowest of the
+  // cluster on EVERY pick, and every round waits for its slowest warp.
+  const bool writer = rank == 0 && warp == 0;
+  int wq = 0;                                  // picks buffered in this window (warp-uniform)
+  int w_cur = 0;
+  float w_x = 0.f, w_y = 0.f, w_z = 0.f;
+  auto flush = [&]() {
+    if (writer && lane < wq) {
+      const int64_t at = (int64_t)cloud * M + (done - wq + lane);
+      if (idx64) idx64[at] = w_cur;
+      if (idx32) idx32[at] = w_cur;
+      if (new_xyz) {
+        float* o = new_xyz + (int64_t)cloud * 3 * M + (done - wq + lane);
+        o[0] = w_x; o[M] = w_y; o[2 * (int64_t)M] = w_z;
+      }
+    }
+    wq = 0;
+  };
   for (uint32_t r = 0; done < M; ++r) {
     if (blockIdx.x == 0 && tid == 0) atomicAdd(&g_fps_dbg[0], 1u);
     const uint32_t par = r & 1;
@@ -470,18 +490,20 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
           }
         }
       }
-      if (rank == 0 && tid == 0) {
-        if (idx64) idx64[(int64_t)cloud * M + done] = cur;
-        if (idx32) idx32[(int64_t)cloud * M + done] = cur;
-        if (new_xyz) {
-          float* o = new_xyz + (int64_t)cloud * 3 * M + done;
-          o[0] = cx; o[M] = cy; o[2 * (int64_t)M] = cz;
-        }
+      {
+        const bool mine = lane == wq;
+        w_cur = mine ? cur : w_cur;
+        w_x = mine ? cx : w_x;
+        w_y = mine ? cy : w_y;
+        w_z = mine ? cz : w_z;
       }
+      ++wq;
       ++done;
       first = false;
+      if (wq == 32) flush();
       if (dmax == 0u) break;                 // nothing can change any more: one repeated pick per round
     }
+    flush();
     // the round's last pick reaches the own points before the next round's scan
 #pragma unroll
     for (int k = 0; k < PPT; ++k) md[k] = fminf(md[k], sqdist_ref(cx, cy, cz, px[k], py[k], pz[k]));

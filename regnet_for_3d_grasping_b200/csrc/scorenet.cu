@@ -639,7 +639,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
                               counter, p->cfg.sa0_variant, ms));
       prof_end(p, ms);
       ++p->launches;
-      {   // the next step's geometry chain starts here, behind the level-0 kernel (see deferred_pc)
+      if (p->defer_prefetch <= 1) {   // the next step's geometry chain starts here, behind the level-0 kernel (see deferred_pc)
         const int keep = p->launches;
         RN_TRY(flush_deferred(p, ms, true));
         p->launches = keep;
@@ -769,7 +769,7 @@ int regnet_scorenet_forward(regnet_scorenet* p, const float* pc, float* all_feat
     p->pool_planes_level = p->cfg.engine == REGNET_ENGINE_TC ? i : -1;   // picked up by run_layer_impl
     RN_TRY(run_layer(p, GEMM_LABEL[i][2], p->layers[i][2], a2, P, 1, 64, nullptr, p->sa_out[i], SA_CH[i][2], ms));
     p->pool_planes_level = -1;
-    if (i == 0) {
+    if (i == (p->defer_prefetch <= 1 ? 0 : p->defer_prefetch - 1) || i == 2) {   // defer_prefetch = 2, 3: behind SA level 1, 2
       const int keep = p->launches;
       RN_TRY(flush_deferred(p, ms, true));
       p->launches = keep;
