@@ -455,20 +455,35 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
       for (int k = 0; k < PPT; ++k) md[k] = fminf(md[k], sqdist_ref(cx, cy, cz, px[k], py[k], pz[k]));
       // this lane's best candidate by (distance desc, tie asc) as ONE 64-bit key: the two-condition form compiled into a
       // tree of divergent branches (9 BRA + 3 BSSY / BSYNC per pick), the key compare into selects
-      unsigned long long lk = ((unsigned long long)cd[0] << 32) | (uint32_t)~cr[0].x;
-      int lc = 0;
+      unsigned long long key[CPL];
 #pragma unroll
-      for (int c = 1; c < CPL; ++c) {
-        const unsigned long long kc = ((unsigned long long)cd[c] << 32) | (uint32_t)~cr[c].x;
-        const bool better = kc > lk;
-        lk = better ? kc : lk;
-        lc = better ? c : lc;
+      for (int c = 0; c < CPL; ++c) key[c] = ((unsigned long long)cd[c] << 32) | (uint32_t)~cr[c].x;
+      unsigned long long lk;
+      int lc;
+      if (CPL == 4) {                          // two levels instead of three dependent compares
+        const bool b01 = key[1] > key[0], b23 = key[3 % CPL] > key[2 % CPL];
+        const unsigned long long k01 = b01 ? key[1] : key[0], k23 = b23 ? key[3 % CPL] : key[2 % CPL];
+        const bool hi = k23 > k01;
+        lk = hi ? k23 : k01;
+        lc = hi ? (b23 ? 3 : 2) : (b01 ? 1 : 0);
+      } else {
+        lk = key[0];
+        lc = 0;
+#pragma unroll
+        for (int c = 1; c < CPL; ++c) {
+          const bool better = key[c] > lk;
+          lk = better ? key[c] : lk;
+          lc = better ? c : lc;
+        }
       }
       const uint32_t ld = (uint32_t)(lk >> 32), lt = ~(uint32_t)lk;
       uint32_t dmax;
       const int src = pick_lane(ld, ld ? lt : NO_TIE, dmax);
       if (!first && !(dmax > F)) break;      // an unpublished point could rank before this candidate: next round
-      if (dmax != 0u) {                      // (all distances 0: the reference repeats the previous pick)
+      {
+        // (all distances 0 -- dmax == 0 -- : the reference repeats the previous pick; the record below is then some dead
+        // candidate's, nothing is taken from it, and the updates are no-ops on distances that are already 0)
+        const bool live_pick = dmax != 0u;
         uint4 win = cr[0];
 #pragma unroll
         for (int c = 1; c < CPL; ++c)
@@ -478,8 +493,11 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
         win.z = __shfl_sync(FULL, win.z, src);
         win.w = __shfl_sync(FULL, win.w, src);
         const uint32_t t = __brev(win.x) & mask;
-        cur = (int)(((win.x & ((1u << (32 - nbits)) - 1u)) << nbits) | t);
-        cx = __uint_as_float(win.y); cy = __uint_as_float(win.z); cz = __uint_as_float(win.w);
+        const int ncur = (int)(((win.x & ((1u << (32 - nbits)) - 1u)) << nbits) | t);
+        cur = live_pick ? ncur : cur;
+        cx = live_pick ? __uint_as_float(win.y) : cx;
+        cy = live_pick ? __uint_as_float(win.z) : cy;
+        cz = live_pick ? __uint_as_float(win.w) : cz;
         // the pick leaves the candidate set; the others see their min-distance shrink like their owners will compute it
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
