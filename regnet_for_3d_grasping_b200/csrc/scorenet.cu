@@ -59,7 +59,7 @@ struct Act {  // an activation matrix (rows, ld) in the layout of the selected e
 }  // namespace
 
 struct regnet_scorenet {
-  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int sa_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; int corun_small = 1; int corun1_cs = 8; int corun1_threads = 128; int corun_single = 1; int sa_fused_a = 2; } cfg;
+  struct Cfg : regnet_scorenet_config { int fuse_sa0 = 3; int sa0_variant = 0; int gather_a = 1; int fp_linear_first = 1; int sa_linear_first = 1; int dynamic_tiles = 1; int use_grid = 1; int corun_cs = 8; int corun_threads = 128; int corun_small = 1; int corun1_cs = 8; int corun1_threads = 128; int corun_single = 0; int sa_fused_a = 2; } cfg;
   void* grid_ws[2] = {nullptr, nullptr};   // [0]: level-0 points, [1]: level-1 points (rebuilt per use)
   unsigned int* tile_counters = nullptr;   // one zeroed counter per GEMM launch of a forward (dynamic tile scheduling)
   int gemm_idx = 0;
@@ -82,13 +82,14 @@ struct regnet_scorenet {
     const float* pc = nullptr;   // input this slot was computed for (prefetched and not yet consumed)
     bool pending = false;
   } geom[2];
-  // Optional (defer_prefetch = 1, off by default): a prefetch is not enqueued at once but parked until the next forward has
-  // launched its level-0 kernel (sa0_chain needs all but 2.8 KB of an SM's shared memory, the multi-pick FPS needs 5 KB --
-  // they cannot share an SM), or until something needs its results (flush_deferred).  Measured: no gain over the
-  // one-pick FPS co-running from the start of the step (7.24 vs 7.26 ms per step), so it stays an experiment switch.
+  // defer_prefetch = 1 (default): a prefetch is not enqueued at once but parked until the next forward has launched its
+  // level-0 kernel (sa0_chain needs all but 2.8 KB of an SM's shared memory, the multi-pick FPS needs 5 KB -- they cannot
+  // share an SM), or until something needs its results (flush_deferred); 2 / 3 park it until SA level 1 / 2 is enqueued,
+  // 0 enqueues at once.  With the round-2 multi-pick FPS (1.5 ms alone) the parked multi-pick prefetch beats the one-pick
+  // FPS co-running from the start of the step: 6.77 vs 7.01 ms per step (before the replay loop was tightened, 7.24 vs 7.26).
   const float* deferred_pc = nullptr;
   int deferred_slot = -1;
-  int defer_prefetch = 0;
+  int defer_prefetch = 1;
   int next_slot = 0;   // slot the next geometry pass writes
   int last_slot = 0;   // slot the last forward consumed (regnet_scorenet_intermediate)
   // features (fp32, point-major)
@@ -502,9 +503,10 @@ static int geometry_enqueue(regnet_scorenet* p, const float* pc, int slot, cudaS
       cs = L.n[i] > 12288 ? p->cfg.corun_cs : L.n[i] > 2048 ? p->cfg.corun1_cs : 4;
       th = L.n[i] > 12288 ? p->cfg.corun_threads : L.n[i] > 2048 ? p->cfg.corun1_threads : 128;
     }
-    // a co-running FPS takes the one-pick-per-exchange kernel: fewer instructions per pick (it shares its schedulers with
-    // the tensor kernels' epilogue warps) and 1.3 KB of shared memory (fits next to sa0_chain); alone, the multi-pick rounds
-    // are 20 % faster (profiles/README.md)
+    // corun_single = 1: a co-running FPS takes the one-pick-per-exchange kernel (1.3 KB of shared memory: fits next to
+    // sa0_chain, so it may start with the step).  Default 0: multi-pick rounds everywhere -- since the replay loop was
+    // tightened they are 2.3x faster alone (1.53 vs 3.56 ms) and, parked behind sa0_chain (defer_prefetch), also give the
+    // shorter pipelined step (profiles/README.md)
     RN_TRY(fps_launch(L.xyz[i], L.st[i], p->B, L.n[i], p->M[i], nullptr, G.fps_idx[i], G.new_xyz[i], cs, th, gs_i,
                       corun && p->cfg.corun_single));
     prof_end(p, gs_i);
