@@ -426,7 +426,9 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
     mbar_wait_cluster(smem_u32(&bars[par]), (r >> 1) & 1u);
     if (tid == 0) mbar_arm(smem_u32(&bars[par]), TX_BYTES);   // for round r + 2 (see the one-pick kernel for why this is safe)
     // ---- replay: lane l holds candidates l, l + 32, ... --------------------------------------------------------------------
-    uint32_t cd[CPL];
+    // cd = current min-distance bits (0 = empty or already picked: a zero distance can never be a live pick), ct = ~tie (the
+    // low half of the selection key, so that a smaller tie wins), cr = the record as published
+    uint32_t cd[CPL], ct[CPL];
     uint4 cr[CPL];
     uint32_t floor_bits = 0;
 #pragma unroll
@@ -441,6 +443,7 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
         cd[c] = 0u;
         cr[c] = make_uint4(NO_TIE, 0u, 0u, 0u);
       }
+      ct[c] = ~cr[c].x;
     }
     const uint32_t F = __reduce_max_sync(FULL, floor_bits);
     bool first = true;
@@ -457,7 +460,7 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
       // tree of divergent branches (9 BRA + 3 BSSY / BSYNC per pick), the key compare into selects
       unsigned long long key[CPL];
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) key[c] = ((unsigned long long)cd[c] << 32) | (uint32_t)~cr[c].x;
+      for (int c = 0; c < CPL; ++c) key[c] = ((unsigned long long)cd[c] << 32) | ct[c];
       unsigned long long lk;
       int lc;
       if (CPL == 4) {                          // two levels instead of three dependent compares
@@ -500,12 +503,11 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
         cz = live_pick ? __uint_as_float(win.w) : cz;
         // the pick leaves the candidate set; the others see their min-distance shrink like their owners will compute it
 #pragma unroll
+        // (a picked or empty candidate keeps distance 0 under the update: min(0, d) = 0, no marker needed)
         for (int c = 0; c < CPL; ++c) {
-          if (lane == src && lc == c) { cd[c] = 0u; cr[c].x = NO_TIE; }
-          if (cr[c].x != NO_TIE) {
-            const float d = sqdist_ref(cx, cy, cz, __uint_as_float(cr[c].y), __uint_as_float(cr[c].z), __uint_as_float(cr[c].w));
-            cd[c] = __float_as_uint(fminf(__uint_as_float(cd[c]), d));
-          }
+          if (lane == src && lc == c) cd[c] = 0u;
+          const float d = sqdist_ref(cx, cy, cz, __uint_as_float(cr[c].y), __uint_as_float(cr[c].z), __uint_as_float(cr[c].w));
+          cd[c] = __float_as_uint(fminf(__uint_as_float(cd[c]), d));
         }
       }
       {
