@@ -292,8 +292,6 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
 // the same sqdist_ref from the same operands), the arg-max uses the same (distance, tie key) order, so picks are
 // bit-identical to the one-pick-per-exchange kernel; with heavy ties (lattices) rounds simply shrink to one pick.
 // Used for the shapes whose cluster has at most 32 warps (each lane then holds K = 4 of the <= 128 candidates).
-__device__ unsigned int g_fps_dbg[4];   // TEMPORARY instrumentation: [0] rounds of cloud 0
-
 template <int CS, int T, int PPT>
 __global__ void __launch_bounds__(T, 1)
 fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, int64_t* __restrict__ idx64,
@@ -373,7 +371,6 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
     wq = 0;
   };
   for (uint32_t r = 0; done < M; ++r) {
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&g_fps_dbg[0], 1u);
     const uint32_t par = r & 1;
     // ---- this thread's two best points: (b1, k1) then (b2, k2), in (distance desc, k asc) order --------------------------
     float b1 = 0.f, b2 = 0.f;
@@ -446,14 +443,18 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
       ct[c] = ~cr[c].x;
     }
     const uint32_t F = __reduce_max_sync(FULL, floor_bits);
-    bool first = true;
+    // A pick is taken while the best candidate's distance is strictly above `lim`: 0 for the first pick of a round (always
+    // valid -- unless every distance is 0, the reference's "repeat the previous pick" case, handled at the loop's exit),
+    // F afterwards.  A round takes at most 32 picks: one window of the output buffer, flushed once per round.
+    uint32_t lim = 0u;
+    const int cap = min(M - done, 32);
     // The update of this thread's own points with pick i (25 independent distance / min pairs, ~175 instructions) does not
     // feed the selection of pick i + 1 (that runs on the candidates), so it is applied ONE PICK LATE, at the top of the next
     // trip: it then shares a basic block with the arg-max / redux / ballot chain of the next selection and fills that
     // chain's stalls instead of sitting serially behind it.  (cx, cy, cz) always holds the last pick; re-applying it is
     // idempotent, which keeps the update unconditional (first trip of a round: the previous round's last pick again).
 #pragma unroll 1
-    while (done < M) {
+    for (wq = 0; wq < cap;) {
 #pragma unroll
       for (int k = 0; k < PPT; ++k) md[k] = fminf(md[k], sqdist_ref(cx, cy, cz, px[k], py[k], pz[k]));
       // this lane's best candidate by (distance desc, tie asc) as ONE 64-bit key: the two-condition form compiled into a
@@ -482,11 +483,18 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
       const uint32_t ld = (uint32_t)(lk >> 32), lt = ~(uint32_t)lk;
       uint32_t dmax;
       const int src = pick_lane(ld, ld ? lt : NO_TIE, dmax);
-      if (!first && !(dmax > F)) break;      // an unpublished point could rank before this candidate: next round
+      if (!(dmax > lim)) {                   // an unpublished point could rank before this candidate: next round
+        if (wq == 0) {                         // first pick and every distance is 0: the previous pick is repeated
+          w_cur = lane == 0 ? cur : w_cur;
+          w_x = lane == 0 ? cx : w_x;
+          w_y = lane == 0 ? cy : w_y;
+          w_z = lane == 0 ? cz : w_z;
+          wq = 1;
+        }
+        break;
+      }
+      lim = F;
       {
-        // (all distances 0 -- dmax == 0 -- : the reference repeats the previous pick; the record below is then some dead
-        // candidate's, nothing is taken from it, and the updates are no-ops on distances that are already 0)
-        const bool live_pick = dmax != 0u;
         uint4 win = cr[0];
 #pragma unroll
         for (int c = 1; c < CPL; ++c)
@@ -496,11 +504,8 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
         win.z = __shfl_sync(FULL, win.z, src);
         win.w = __shfl_sync(FULL, win.w, src);
         const uint32_t t = __brev(win.x) & mask;
-        const int ncur = (int)(((win.x & ((1u << (32 - nbits)) - 1u)) << nbits) | t);
-        cur = live_pick ? ncur : cur;
-        cx = live_pick ? __uint_as_float(win.y) : cx;
-        cy = live_pick ? __uint_as_float(win.z) : cy;
-        cz = live_pick ? __uint_as_float(win.w) : cz;
+        cur = (int)(((win.x & ((1u << (32 - nbits)) - 1u)) << nbits) | t);
+        cx = __uint_as_float(win.y); cy = __uint_as_float(win.z); cz = __uint_as_float(win.w);
         // the pick leaves the candidate set; the others see their min-distance shrink like their owners will compute it
 #pragma unroll
         // (a picked or empty candidate keeps distance 0 under the update: min(0, d) = 0, no marker needed)
@@ -518,11 +523,8 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
         w_z = mine ? cz : w_z;
       }
       ++wq;
-      ++done;
-      first = false;
-      if (wq == 32) flush();
-      if (dmax == 0u) break;                 // nothing can change any more: one repeated pick per round
     }
+    done += wq;
     flush();
     // the round's last pick reaches the own points before the next round's scan
 #pragma unroll
@@ -692,18 +694,8 @@ int fps_generic_launch(const float* pts, Strides3 st, int B, int N, int M, int n
   return REGNET_OK;
 }
 
-unsigned int* fps_dbg_symbol_read(unsigned int* out, int reset) {
-  cudaMemcpyFromSymbol(out, g_fps_dbg, sizeof(unsigned int) * 4);
-  if (reset) { unsigned int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_fps_dbg, z, sizeof(z)); }
-  return out;
-}
-
 }  // namespace
 
-extern "C" int regnet_debug_fps_counters(unsigned int* out, int reset) {
-  fps_dbg_symbol_read(out, reset);
-  return 0;
-}
 
 int fps_block_log2(int N) {  // sampling_kernel.cu:32-40 get_block + the switch's floor of 16
   int cnt = 0;
