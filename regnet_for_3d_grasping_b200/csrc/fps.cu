@@ -745,7 +745,8 @@ static int fps_launch_impl(const float* pts, Strides3 st, int B, int N, int M, i
   if (cluster_size == 0 && threads == 0) {
     // (re-measured with the warp-push exchange, profiles/r01_fps_sweep_push.txt: 25 600 points 8x128 4.19 ms vs 8x512
     // 4.52 ms; 5 120 points 4x256 0.58 ms vs 8x256 0.70 ms -- both clusters of 32 warps, the push exchange's limit)
-    if (N <= 2048) { cluster_size = 1; threads = 256; }
+    if (N <= 512) { cluster_size = 1; threads = 256; }
+    else if (N <= 2048) { cluster_size = 4; threads = 128; }   // multi-pick rounds: 1 024 -> 256 in 0.07 ms (one CTA: 0.12)
     else if (N <= 12288) { cluster_size = 4; threads = 256; }
     else if (N <= 32768) { cluster_size = 8; threads = 128; }   // 32 register-resident points per thread at most
     else { cluster_size = 8; threads = 512; }
