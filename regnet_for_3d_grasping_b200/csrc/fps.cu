@@ -284,9 +284,9 @@ fps_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int nbits, 
 //             - it is applied to the other candidates (their min-distance shrinks exactly as their owners will compute it)
 //               and to the warp's own register-resident points;
 //             - the next best candidate is again the global arg-max PROVIDED no point that was not published can beat
-//               it: an unpublished point of warp w was ranked after w's K-th record when the round began and min-distances
-//               only shrink, so a candidate whose distance is strictly greater than F = max_w (distance of w's K-th record)
-//               is safe.  The round ends at the first candidate that is not.
+//               it: every warp also publishes the distance of its best UNPUBLISHED point (its (K+1)-th best when the round
+//               began), min-distances only shrink, so a candidate whose distance is strictly greater than
+//               F = max_w (that distance) is safe.  The round ends at the first candidate that is not (or after 32 picks).
 //
 // Min-distances are the same fp32 values in the same order (min is order-independent, the squared distance is computed by
 // the same sqdist_ref from the same operands), the arg-max uses the same (distance, tie key) order, so picks are
@@ -306,6 +306,7 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
   }
   __shared__ uint32_t cand_d[2][NC];
   __shared__ __align__(16) uint4 cand_r[2][NC];   // {tie, x, y, z}
+  __shared__ uint32_t cand_f[2][NW];              // every warp's best UNPUBLISHED distance (its (K+1)-th best)
   __shared__ __align__(8) uint64_t bars[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -339,7 +340,7 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
       o[0] = cx; o[M] = cy; o[2 * (int64_t)M] = cz;
     }
   }
-  constexpr uint32_t TX_BYTES = NC * 20;
+  constexpr uint32_t TX_BYTES = NC * 20 + NW * 4;
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1);
     mbar_init(smem_u32(&bars[1]), 1);
@@ -420,6 +421,15 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
         if (need) { b1 = nb; k1 = nk; }
       }
     }
+    {
+      // the floor of the round: no unpublished point of this warp is farther than its best remaining one (min-distances
+      // only shrink).  Publishing it -- instead of taking the K-th record as the bound -- keeps the K-th record pickable and
+      // lowers the floor: on evenly spread inputs (the output of a previous FPS) 3.1 -> 4.4 picks per round.
+      const uint32_t fl = __reduce_max_sync(FULL, __float_as_uint(b1));
+      if (lane < CS)
+        st_async_u32(mapa_u32(smem_u32(&cand_f[par][rank * W + warp]), (uint32_t)lane), fl,
+                     mapa_u32(smem_u32(&bars[par]), (uint32_t)lane));
+    }
     mbar_wait_cluster(smem_u32(&bars[par]), (r >> 1) & 1u);
     if (tid == 0) mbar_arm(smem_u32(&bars[par]), TX_BYTES);   // for round r + 2 (see the one-pick kernel for why this is safe)
     // ---- replay: lane l holds candidates l, l + 32, ... --------------------------------------------------------------------
@@ -427,7 +437,7 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
     // low half of the selection key, so that a smaller tie wins), cr = the record as published
     uint32_t cd[CPL], ct[CPL];
     uint4 cr[CPL];
-    uint32_t floor_bits = 0;
+    const uint32_t floor_bits = lane < NW ? cand_f[par][lane] : 0u;
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
       const int slot = lane + 32 * c;
@@ -435,7 +445,6 @@ fps_multi_kernel(const float* __restrict__ pts, Strides3 st, int N, int M, int n
         cd[c] = cand_d[par][slot];
         cr[c] = cand_r[par][slot];
         if (cr[c].x == NO_TIE) cd[c] = 0u;
-        if ((slot % K) == K - 1) floor_bits = max(floor_bits, cd[c]);
       } else {
         cd[c] = 0u;
         cr[c] = make_uint4(NO_TIE, 0u, 0u, 0u);
