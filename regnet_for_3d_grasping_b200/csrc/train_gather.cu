@@ -9,6 +9,7 @@
 //   *_backward_strided the scatter-adds of grouping_kernel.cu:54-149 / interpolate_kernel.cu:239-337 reading a channel
 //                      slice of the (B, Ctot, L) input gradient in place (no .contiguous() copy of the slice).
 #include <algorithm>
+#include <cstdlib>
 
 #include "internal.cuh"
 #include "train_common.cuh"
@@ -89,6 +90,9 @@ fp_interp_planes_kernel(const float* __restrict__ sparse, Strides3 sst, const fl
 
 constexpr int ROWS_MAX = 12288;   // floats of one source row kept in shared memory (48 KB) by the strided scatter-adds
 constexpr int ROWS_BIG = 53248;   // linear-first gather / scatter: up to 208 KB of dynamic shared memory (opt-in)
+
+// four channels per CTA (the *4 kernels): REGNET_TRAIN_GATHER_CH4=0 keeps one row per CTA
+bool use_ch4(int C0, int n_rows);
 
 template <typename Kern>
 int allow_big_rows(Kern kernel, int n_floats) {
@@ -243,6 +247,144 @@ sa_scatter_linear_kernel(const float* __restrict__ dZ, const int64_t* __restrict
     for (int i = 0; i < TG / 32; ++i) a += red[threadIdx.x][i];
     dwx_part[((int64_t)b * C0 + c) * 3 + threadIdx.x] = a;
   }
+}
+
+// ---- four channels per CTA ------------------------------------------------------------------------------------------------
+// The one-row kernels above re-read the index (8 B) and the coordinate / weight rows (12 B) of every position once per
+// CHANNEL: 20 B x 983 040 positions x 256 channels = 5 GB of L2 traffic per level-1 launch, more than the 1 GB they write
+// (ncu: DRAM 18 %, profiles/r02_ncu_full_train_gather.txt).  With four channels per CTA the rows sit interleaved in shared
+// memory (one float4 per source point: one LDS.128 gathers all four) and that traffic drops 4x.  Used by the two gathers
+// when C0 % 4 == 0 and the four rows fit 100 KB (two CTAs per SM); same arithmetic per element, so the values are
+// bit-identical.  Level-1 gather 0.70 -> 0.26 ms, level 2 0.30 -> 0.26 ms total 1.00 -> 0.51 ms, FP gather 0.78 -> 0.64 ms.
+constexpr int CH4_MAX_ROWS = 6400;
+
+__device__ __forceinline__ void block_moments4(const float (&s1)[4], const float (&s2)[4], const float (&pivot)[4], int64_t n,
+                                               double* __restrict__ mom) {
+  __shared__ float red4[8][TG / 32];
+  __shared__ float piv4[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    if (threadIdx.x == 0) piv4[ch] = pivot[ch];
+    float a = s1[ch], b = s2[ch];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red4[2 * ch][threadIdx.x >> 5] = a; red4[2 * ch + 1][threadIdx.x >> 5] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int ch = threadIdx.x;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < TG / 32; ++i) { a += red4[2 * ch][i]; b += red4[2 * ch + 1][i]; }
+    const double nd = (double)n, mean = (double)piv4[ch] + a / nd;
+    const double m2 = fmax(b - a * a / nd, 0.0);
+    atomicAdd(mom + 2 * ch, nd * mean);
+    atomicAdd(mom + 2 * ch + 1, m2 + nd * mean * mean);
+  }
+}
+
+// stage rows c0 .. c0 + 3 of a (C, n) matrix as float4 per column
+__device__ __forceinline__ void stage_rows4(const float* __restrict__ y, int64_t ld, int n, float4* __restrict__ row4) {
+  for (int j = threadIdx.x; j < n; j += TG) row4[j] = make_float4(y[j], y[ld + j], y[2 * ld + j], y[3 * ld + j]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(TG)
+sa_gather_linear4_kernel(const float* __restrict__ Y, const int64_t* __restrict__ index, const float* __restrict__ xr,
+                         const float* __restrict__ Wx, int ldwx, int C0, int N, int64_t MK, float* __restrict__ Z,
+                         double* __restrict__ moments, int* __restrict__ oob) {
+  extern __shared__ float4 row4[];
+  const int c0 = blockIdx.x * 4, b = blockIdx.y;
+  stage_rows4(Y + ((int64_t)b * C0 + c0) * N, N, N, row4);
+  float w[4][3];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) w[ch][d] = Wx[(int64_t)(c0 + ch) * ldwx + d];
+  const int64_t* __restrict__ idx = index + (int64_t)b * MK;
+  const float* __restrict__ x0 = xr + (int64_t)b * 3 * MK;
+  float* __restrict__ z = Z + ((int64_t)b * C0 + c0) * MK;
+  const float4 pv = row4[min((int64_t)N - 1, max((int64_t)0, idx[0]))];
+  const float pivot[4] = {pv.x, pv.y, pv.z, pv.w};
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t e = (int64_t)threadIdx.x * 4; e < MK; e += TG * 4) {
+    const longlong2 j01 = *reinterpret_cast<const longlong2*>(idx + e), j23 = *reinterpret_cast<const longlong2*>(idx + e + 2);
+    const float4 a0 = *reinterpret_cast<const float4*>(x0 + e), a1 = *reinterpret_cast<const float4*>(x0 + MK + e),
+                 a2 = *reinterpret_cast<const float4*>(x0 + 2 * MK + e);
+    const int64_t j[4] = {j01.x, j01.y, j23.x, j23.y};
+    const float ax[4] = {a0.x, a0.y, a0.z, a0.w}, ay[4] = {a1.x, a1.y, a1.z, a1.w}, az[4] = {a2.x, a2.y, a2.z, a2.w};
+    float v[4][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j[t] < 0 || j[t] >= N) *oob = 1; else g = row4[j[t]];
+      const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        v[ch][t] = fmaf(w[ch][2], az[t], fmaf(w[ch][1], ay[t], fmaf(w[ch][0], ax[t], gg[ch])));
+        const float d = v[ch][t] - pivot[ch];
+        s1[ch] += d;
+        s2[ch] = fmaf(d, d, s2[ch]);
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      *reinterpret_cast<float4*>(z + ch * MK + e) = make_float4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]);
+  }
+  block_moments4(s1, s2, pivot, MK, moments + 2 * c0);
+}
+
+__global__ void __launch_bounds__(TG)
+fp_gather_linear4_kernel(const float* __restrict__ Ys, const int64_t* __restrict__ index, const float* __restrict__ weight,
+                         const float* __restrict__ dense, Strides3 dst, int nd, const float* __restrict__ Wd, int ldwd, int C0,
+                         int Ns, int Nd, float* __restrict__ Z, double* __restrict__ moments, int* __restrict__ oob) {
+  extern __shared__ float4 row4[];
+  const int c0 = blockIdx.x * 4, b = blockIdx.y;
+  stage_rows4(Ys + ((int64_t)b * C0 + c0) * Ns, Ns, Ns, row4);
+  float wd[4][4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) wd[ch][d] = d < nd ? Wd[(int64_t)(c0 + ch) * ldwd + d] : 0.f;
+  const int64_t* __restrict__ idx = index + (int64_t)b * Nd * 3;
+  const float* __restrict__ w = weight + (int64_t)b * Nd * 3;
+  const float* __restrict__ dn = dense + (int64_t)b * dst.b;
+  float* __restrict__ z = Z + ((int64_t)b * C0 + c0) * Nd;
+  const float4 pv = row4[min((int64_t)Ns - 1, max((int64_t)0, idx[0]))];
+  const float pivot[4] = {pv.x, pv.y, pv.z, pv.w};
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int n = threadIdx.x; n < Nd; n += TG) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int64_t j = idx[(int64_t)n * 3 + k];
+      if (j < 0 || j >= Ns) { *oob = 1; continue; }
+      const float4 g = row4[j];
+      const float wk = w[(int64_t)n * 3 + k];
+      acc[0] = fmaf(g.x, wk, acc[0]);
+      acc[1] = fmaf(g.y, wk, acc[1]);
+      acc[2] = fmaf(g.z, wk, acc[2]);
+      acc[3] = fmaf(g.w, wk, acc[3]);
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      if (d < nd) {
+        const float dv = dn[(int64_t)d * dst.c + (int64_t)n * dst.n];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) acc[ch] = fmaf(wd[ch][d], dv, acc[ch]);
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      z[(int64_t)ch * Nd + n] = acc[ch];
+      const float dv = acc[ch] - pivot[ch];
+      s1[ch] += dv;
+      s2[ch] = fmaf(dv, dv, s2[ch]);
+    }
+  }
+  block_moments4(s1, s2, pivot, Nd, moments + 2 * c0);
 }
 
 // Z[b, c, n] = sum_k w[b,n,k] * Ys[b, c, idx[b,n,k]] + sum_d Wd[c, d] * dense[b, d, n]   (nd dense channels, <= 4)
@@ -548,6 +690,11 @@ unsigned grid_x(int64_t elems4) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>((elems4 + TG - 1) / TG, 64));
 }
 
+bool use_ch4(int C0, int n_rows) {
+  static const int on = getenv("REGNET_TRAIN_GATHER_CH4") ? atoi(getenv("REGNET_TRAIN_GATHER_CH4")) : 1;
+  return on && C0 % 4 == 0 && n_rows <= CH4_MAX_ROWS;
+}
+
 }  // namespace
 
 }  // namespace regnet
@@ -614,8 +761,15 @@ int regnet_sa_gather_linear(const float* Y, const int64_t* index, const float* x
   RN_CHECK_ARG(B > 0 && C0 > 0 && N > 0 && M > 0 && K > 0 && K % 4 == 0, "sa_gather_linear: bad shape");
   RN_CHECK_ARG(N <= ROWS_BIG && B <= 65535, "sa_gather_linear: at most %d source points per cloud", ROWS_BIG);
   cudaStream_t s = (cudaStream_t)stream;
-  RN_TRY(allow_big_rows(sa_gather_linear_kernel, N));
   RN_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * C0, s));
+  if (use_ch4(C0, N)) {
+    RN_TRY(allow_big_rows(sa_gather_linear4_kernel, 4 * N));
+    sa_gather_linear4_kernel<<<dim3(C0 / 4, B), TG, sizeof(float4) * (size_t)N, s>>>(Y, index, xyz_rel, Wx, ldwx, C0, N,
+                                                                                     (int64_t)M * K, Z, moments, oob_flag());
+    RN_LAUNCH_CHECK("sa_gather_linear4_kernel");
+    return REGNET_OK;
+  }
+  RN_TRY(allow_big_rows(sa_gather_linear_kernel, N));
   sa_gather_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)N, s>>>(Y, index, xyz_rel, Wx, ldwx, C0, N, (int64_t)M * K, Z,
                                                                             moments, oob_flag());
   RN_LAUNCH_CHECK("sa_gather_linear_kernel");
@@ -627,6 +781,7 @@ int regnet_sa_scatter_linear(const float* dZ, const int64_t* index, const float*
   RN_CHECK_ARG(dZ && index && xyz_rel && dY && dwx_part, "sa_scatter_linear: null argument");
   RN_CHECK_ARG(B > 0 && C0 > 0 && N > 0 && M > 0 && K > 0, "sa_scatter_linear: bad shape");
   RN_CHECK_ARG(N <= ROWS_BIG && B <= 65535, "sa_scatter_linear: at most %d source points per cloud", ROWS_BIG);
+  // (a four-channel form of the scatter was measured slower: 80 KB of rows halve the resident CTAs, 1.10 -> 1.23 ms)
   RN_TRY(allow_big_rows(sa_scatter_linear_kernel, N));
   sa_scatter_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)N, (cudaStream_t)stream>>>(
       dZ, index, xyz_rel, C0, N, (int64_t)M * K, dY, dwx_part, oob_flag());
@@ -641,8 +796,15 @@ int regnet_fp_gather_linear(const float* Ys, const int64_t* index, const float* 
   RN_CHECK_ARG(B > 0 && C0 > 0 && Ns > 0 && Nd > 0 && nd >= 0 && nd <= 4, "fp_gather_linear: bad shape (at most 4 dense channels)");
   RN_CHECK_ARG(Ns <= ROWS_BIG && B <= 65535, "fp_gather_linear: at most %d sparse points per cloud", ROWS_BIG);
   cudaStream_t s = (cudaStream_t)stream;
-  RN_TRY(allow_big_rows(fp_gather_linear_kernel, Ns));
   RN_CUDA(cudaMemsetAsync(moments, 0, sizeof(double) * 2 * C0, s));
+  if (use_ch4(C0, Ns)) {
+    RN_TRY(allow_big_rows(fp_gather_linear4_kernel, 4 * Ns));
+    fp_gather_linear4_kernel<<<dim3(C0 / 4, B), TG, sizeof(float4) * (size_t)Ns, s>>>(
+        Ys, index, weight, dense, Strides3{dsb, dsc, dsn}, nd, Wd, ldwd, C0, Ns, Nd, Z, moments, oob_flag());
+    RN_LAUNCH_CHECK("fp_gather_linear4_kernel");
+    return REGNET_OK;
+  }
+  RN_TRY(allow_big_rows(fp_gather_linear_kernel, Ns));
   fp_gather_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)Ns, s>>>(Ys, index, weight, dense, Strides3{dsb, dsc, dsn}, nd,
                                                                              Wd, ldwd, C0, Ns, Nd, Z, moments, oob_flag());
   RN_LAUNCH_CHECK("fp_gather_linear_kernel");
