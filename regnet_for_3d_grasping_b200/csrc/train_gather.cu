@@ -612,16 +612,28 @@ sa0_backward_sums_kernel(Sa0In a, int B, const float* __restrict__ dy, const flo
 #pragma unroll
         for (int d = 0; d < 6; ++d) acc[1 + d] = fmaf(gq, x[t][d], acc[1 + d]);
       }
+      // transpose-reduce of the 7 (+1 pad) partial sums: every exchange halves the values a lane carries -- 4 + 2 + 1
+      // shuffles, then two more on the single value left -- 9 shuffles instead of 35 butterflies; lanes 4k hold sum k
+      {
+        const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+        float w4[4], w2[2];
 #pragma unroll
-      for (int i = 0; i < 7; ++i) {
+        for (int i = 0; i < 4; ++i) {
+          const float hi_v = i + 4 < 7 ? acc[i + 4] : 0.f;
+          const float send = h16 ? acc[i] : hi_v, keep = h16 ? hi_v : acc[i];
+          w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-      }
-      if (lane < 7) {
-        float v = acc[0];
-#pragma unroll
-        for (int i = 1; i < 7; ++i) v = lane == i ? acc[i] : v;
-        atomicAdd(sg + c * 7 + lane, v);
+        for (int i = 0; i < 2; ++i) {
+          const float send = h8 ? w4[i] : w4[i + 2], keep = h8 ? w4[i + 2] : w4[i];
+          w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        const float send = h4 ? w2[0] : w2[1], keep = h4 ? w2[1] : w2[0];
+        float tot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        const int k = (h16 ? 4 : 0) + (h8 ? 2 : 0) + (h4 ? 1 : 0);
+        if ((lane & 3) == 0 && k < 7) atomicAdd(sg + c * 7 + k, tot);
       }
     }
   }
