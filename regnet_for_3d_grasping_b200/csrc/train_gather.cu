@@ -564,8 +564,13 @@ sa0_apply_planes_kernel(Sa0In a, int B, const float* __restrict__ W0, const floa
         const float v = __fmaf_rn(sa0_z(w, x[t]), wb.z, wb.w);
         y[t] = relu ? fmaxf(v, 0.f) : v;
       }
-      store_planes4(hi, lo, out0 + (int64_t)c * MK, make_float4(y[0], y[1], y[2], y[3]));
-      store_planes4(hi, lo, out0 + (int64_t)c * MK + 4, make_float4(y[4], y[5], y[6], y[7]));
+      // one 16-byte store per plane: the warp writes 512 contiguous bytes (two 8-byte stores left every sector half written
+      // per instruction)
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) split_bf16_pair(y[2 * u], y[2 * u + 1], ph[u], pl[u]);
+      *reinterpret_cast<uint4*>(hi + out0 + (int64_t)c * MK) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      *reinterpret_cast<uint4*>(lo + out0 + (int64_t)c * MK) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
     }
   }
 }
