@@ -469,3 +469,54 @@ def test_eval_validate_estimates_missing_scene_normals():
     grasp = torch.tensor([[0.0, 0.0, 0.80, 0.0, 1.0, 0.0, 0.0, 0.5]])
     out = grasp_eval.eval_validate(d, grasp, None, 0.75, 0.06, 0.08, -1)
     assert "_estimated_scene_normal" in d and out is not None
+
+
+def test_level0_recompute_closed_forms_match_autograd():
+    """The algebra behind csrc/train_gather.cu "set-abstraction level 0, first block" (no stored pre-activation), in float64
+    on the CPU: batch moments of z = W x from the 6 sums and 21 products of x, and dW / dgamma / dbeta of
+    y = relu(bn(z)) from 7 sums per channel over g = dy * [bn(z) > 0] -- against autograd through the plain formulation."""
+    torch.manual_seed(3)
+    P, C, eps = 4096, 16, 1e-5
+    x = torch.randn(P, 6, dtype=torch.float64) * torch.tensor([0.02, 0.02, 0.02, 0.5, 0.5, 0.5], dtype=torch.float64) + 0.1
+    W = torch.randn(C, 6, dtype=torch.float64, requires_grad=True)
+    gamma = (torch.rand(C, dtype=torch.float64) + 0.5).requires_grad_(True)
+    beta = (torch.rand(C, dtype=torch.float64) - 0.5).requires_grad_(True)
+    z = x @ W.t()
+    mu, var = z.mean(0), z.var(0, unbiased=False)
+    y = torch.relu((z - mu) / torch.sqrt(var + eps) * gamma + beta)
+    dy = torch.randn(P, C, dtype=torch.float64)
+    (y * dy).sum().backward()
+    with torch.no_grad():
+        sx, sxx = x.sum(0), x.t() @ x                              # what sa0_input_moments_kernel accumulates (27 numbers)
+        m1, m2 = W @ sx, ((W @ sxx) * W).sum(1)                    # sa0_moments_from_sums_kernel
+        assert torch.allclose(m1 / P, mu, rtol=1e-12, atol=1e-14)
+        assert torch.allclose(m2 / P - (m1 / P) ** 2, var, rtol=1e-9, atol=1e-14)
+        istd = 1.0 / torch.sqrt(var + eps)
+        sc = gamma * istd
+        g = dy * (((z - mu) * sc + beta) > 0)                      # sa0_backward_sums_kernel: mask recomputed from the inputs
+        g0, gx = g.sum(0), g.t() @ x                               # the 7 sums per channel
+        dbeta = g0                                                 # sa0_backward_finalize_kernel
+        dgamma = istd * ((W * gx).sum(1) - mu * g0)
+        zx = W @ sxx - mu[:, None] * sx[None, :]
+        dW = sc[:, None] * (gx - (g0 / P)[:, None] * sx[None, :] - (dgamma * istd / P)[:, None] * zx)
+    assert torch.allclose(dbeta, beta.grad, rtol=1e-10, atol=1e-12)
+    assert torch.allclose(dgamma, gamma.grad, rtol=1e-9, atol=1e-10)
+    assert torch.allclose(dW, W.grad, rtol=1e-8, atol=1e-9)
+
+
+def test_folded_set_abstraction_operand_is_the_grouped_first_block():
+    """The fold behind csrc/gemm_fused_a.cu, in float64 on the CPU: relu(scale (W_f f_j + W_x (xyz_j - c_m)) + shift) ==
+    relu(Z'[j] + T[m]) with Z' = scale (W_f f + W_x xyz) per source point and T = shift - scale W_x c per centroid."""
+    torch.manual_seed(4)
+    N, M, K, Cf, C0 = 200, 20, 8, 12, 10
+    f = torch.randn(N, Cf, dtype=torch.float64)
+    xyz = torch.rand(N, 3, dtype=torch.float64)
+    ctr = xyz[torch.randperm(N)[:M]]
+    nbr = torch.randint(0, N, (M, K))
+    Wf, Wx = torch.randn(C0, Cf, dtype=torch.float64), torch.randn(C0, 3, dtype=torch.float64)
+    scale, shift = torch.rand(C0, dtype=torch.float64) + 0.5, torch.randn(C0, dtype=torch.float64)
+    grouped = torch.relu((f[nbr] @ Wf.t() + (xyz[nbr] - ctr[:, None, :]) @ Wx.t()) * scale + shift)      # (M, K, C0)
+    zp = (f @ Wf.t() + xyz @ Wx.t()) * scale
+    t = shift - (ctr @ Wx.t()) * scale
+    folded = torch.relu(zp[nbr] + t[:, None, :])
+    assert torch.allclose(folded, grouped, rtol=1e-12, atol=1e-12)
