@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(TG)
 fp_interp_planes_kernel(const float* __restrict__ sparse, Strides3 sst, const float* __restrict__ dense, Strides3 dst,
                         const int64_t* __restrict__ index, const float* __restrict__ weight, int C2, int C1, int Ns, int Nd,
                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int* __restrict__ oob) {
-  const int c = blockIdx.y, b = blockIdx.z;
+  // grid.y = C2 + C1 (one channel per row) or C2 / 4 + C1 (four interpolated channels per row, then the dense channels)
+  const bool four = (int)gridDim.y != C2 + C1;
+  const int c = four ? ((int)blockIdx.y < C2 / 4 ? (int)blockIdx.y * 4 : (int)blockIdx.y - C2 / 4 + C2) : (int)blockIdx.y;
+  const int b = blockIdx.z;
   const int64_t out0 = ((int64_t)b * (C2 + C1) + c) * Nd;
   if (c >= C2) {   // dense (skip) channels: a strided copy
     const float* __restrict__ src = dense + (int64_t)b * dst.b + (int64_t)(c - C2) * dst.c;
@@ -70,6 +73,36 @@ fp_interp_planes_kernel(const float* __restrict__ sparse, Strides3 sst, const fl
   const float* __restrict__ src = sparse + (int64_t)b * sst.b + (int64_t)c * sst.c;
   const int64_t* __restrict__ idx = index + (int64_t)b * Nd * 3;
   const float* __restrict__ w = weight + (int64_t)b * Nd * 3;
+  // CPB interpolated channels per CTA row (host: 4 when C2 % 4 == 0, else 1): the 36 bytes of index and weight per dense
+  // point are read once for all of them instead of once per channel
+  const int cpb = (int)gridDim.y == C2 + C1 ? 1 : 4;
+  if (cpb == 4) {
+    const int c4 = blockIdx.y * 4;           // the host lays the 4-channel rows first: blockIdx.y < C2 / 4
+    const float* __restrict__ s4 = sparse + (int64_t)b * sst.b + (int64_t)c4 * sst.c;
+    const int64_t o4 = ((int64_t)b * (C2 + C1) + c4) * Nd;
+    for (int64_t n = ((int64_t)blockIdx.x * TG + threadIdx.x) * 4; n < Nd; n += (int64_t)gridDim.x * TG * 4) {
+      float v[4][4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int64_t o = (n + t) * 3;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int64_t j = idx[o + k];
+          if (j < 0 || j >= Ns) { *oob = 1; continue; }
+          const float wk = w[o + k];
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) acc[ch] = fmaf(s4[(int64_t)ch * sst.c + j * sst.n], wk, acc[ch]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) v[ch][t] = acc[ch];
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        store_planes4(hi, lo, o4 + (int64_t)ch * Nd + n, make_float4(v[ch][0], v[ch][1], v[ch][2], v[ch][3]));
+    }
+    return;
+  }
   for (int64_t n = ((int64_t)blockIdx.x * TG + threadIdx.x) * 4; n < Nd; n += (int64_t)gridDim.x * TG * 4) {
     float v[4];
 #pragma unroll
@@ -742,7 +775,8 @@ int regnet_fp_interp_planes(const float* sparse, int64_t ssb, int64_t ssc, int64
   RN_CHECK_ARG(B > 0 && C2 > 0 && C1 >= 0 && Ns > 0 && Nd > 0, "fp_interp_planes: empty input");
   RN_CHECK_ARG(Nd % 4 == 0, "fp_interp_planes: the dense point count (%d) must be a multiple of 4", Nd);
   RN_CHECK_ARG(B <= 65535 && C2 + C1 <= 65535, "fp_interp_planes: grid limit");
-  fp_interp_planes_kernel<<<dim3(grid_x(Nd / 4), C2 + C1, B), TG, 0, (cudaStream_t)stream>>>(
+  const int rows_y = (C2 % 4 == 0 && use_ch4(4, 0)) ? C2 / 4 + C1 : C2 + C1;
+  fp_interp_planes_kernel<<<dim3(grid_x(Nd / 4), rows_y, B), TG, 0, (cudaStream_t)stream>>>(
       sparse, Strides3{ssb, ssc, ssn}, dense, Strides3{dsb, dsc, dsn}, index, weight, C2, C1, Ns, Nd, (__nv_bfloat16*)out_hi,
       (__nv_bfloat16*)out_lo, oob_flag());
   RN_LAUNCH_CHECK("fp_interp_planes_kernel");
