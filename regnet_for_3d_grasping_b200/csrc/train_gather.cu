@@ -160,12 +160,36 @@ interp_backward_strided_kernel(const float* __restrict__ gout, int64_t gbs, int 
                                const float* __restrict__ weight, int C, int Ns, int Nd, float* __restrict__ gin,
                                int* __restrict__ oob) {
   extern __shared__ float acc[];
-  const int c = blockIdx.x, b = blockIdx.y;
+  const int b = blockIdx.y;
+  const int64_t* __restrict__ idx = index + (int64_t)b * Nd * 3;
+  const float* __restrict__ w = weight + (int64_t)b * Nd * 3;
+  if ((int)gridDim.x != C) {
+    // four channels per CTA (host: C % 4 == 0 and four planar rows of at most 48 KB): the 36 bytes of index and weight per
+    // dense point are read once for all four; the rows stay planar so that the four atomics of a point hit different banks
+    const int c4 = blockIdx.x * 4;
+    for (int j = threadIdx.x; j < 4 * Ns; j += TG) acc[j] = 0.f;
+    __syncthreads();
+    const float* __restrict__ g4 = gout + (int64_t)b * gbs + (int64_t)(c0 + c4) * Nd;
+    for (int n = threadIdx.x; n < Nd; n += TG) {
+      const float gv[4] = {g4[n], g4[Nd + n], g4[2 * (int64_t)Nd + n], g4[3 * (int64_t)Nd + n]};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int64_t j = idx[(int64_t)n * 3 + k];
+        if (j < 0 || j >= Ns) { *oob = 1; continue; }
+        const float wk = w[(int64_t)n * 3 + k];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) atomicAdd(acc + ch * Ns + j, __fmul_rn(gv[ch], wk));
+      }
+    }
+    __syncthreads();
+    float* __restrict__ o4 = gin + ((int64_t)b * C + c4) * Ns;
+    for (int j = threadIdx.x; j < 4 * Ns; j += TG) o4[j] = acc[j];
+    return;
+  }
+  const int c = blockIdx.x;
   for (int j = threadIdx.x; j < Ns; j += TG) acc[j] = 0.f;
   __syncthreads();
   const float* __restrict__ g = gout + (int64_t)b * gbs + (int64_t)(c0 + c) * Nd;
-  const int64_t* __restrict__ idx = index + (int64_t)b * Nd * 3;
-  const float* __restrict__ w = weight + (int64_t)b * Nd * 3;
   for (int n = threadIdx.x; n < Nd; n += TG) {
     const float gv = g[n];
 #pragma unroll
@@ -799,6 +823,12 @@ int regnet_interpolate_backward_strided(const float* grad_out, int64_t batch_str
   RN_CHECK_ARG(grad_out && index && weight && grad_in, "interpolate_backward_strided: null argument");
   RN_CHECK_ARG(B > 0 && C > 0 && Ns > 0 && Nd > 0 && c0 >= 0, "interpolate_backward_strided: empty input");
   RN_CHECK_ARG(Ns <= ROWS_MAX && B <= 65535, "interpolate_backward_strided: at most %d sparse points per cloud", ROWS_MAX);
+  if (C % 4 == 0 && 4 * Ns <= ROWS_MAX && use_ch4(4, 0)) {
+    interp_backward_strided_kernel<<<dim3(C / 4, B), TG, sizeof(float) * 4 * (size_t)Ns, (cudaStream_t)stream>>>(
+        grad_out, batch_stride, c0, index, weight, C, Ns, Nd, grad_in, oob_flag());
+    RN_LAUNCH_CHECK("interp_backward_strided_kernel");
+    return REGNET_OK;
+  }
   interp_backward_strided_kernel<<<dim3(C, B), TG, sizeof(float) * (size_t)Ns, (cudaStream_t)stream>>>(
       grad_out, batch_stride, c0, index, weight, C, Ns, Nd, grad_in, oob_flag());
   RN_LAUNCH_CHECK("interp_backward_strided_kernel");
