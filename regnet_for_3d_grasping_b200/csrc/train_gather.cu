@@ -444,6 +444,48 @@ fp_gather_linear4_kernel(const float* __restrict__ Ys, const int64_t* __restrict
   block_moments4(s1, s2, pivot, Nd, moments + 2 * c0);
 }
 
+// Scatter with TWO planar rows per CTA: index and coordinates read once per two channels, and 40 KB of rows still leave five
+// CTAs per SM (four rows -- 80 KB, two CTAs -- were measured slower than one: 1.10 -> 1.23 ms).
+__global__ void __launch_bounds__(TG)
+sa_scatter_linear2_kernel(const float* __restrict__ dZ, const int64_t* __restrict__ index, const float* __restrict__ xr, int C0,
+                          int N, int64_t MK, float* __restrict__ dY, float* __restrict__ dwx_part, int* __restrict__ oob) {
+  extern __shared__ float acc[];
+  __shared__ float red[6][TG / 32];
+  const int c0 = blockIdx.x * 2, b = blockIdx.y;
+  for (int j = threadIdx.x; j < 2 * N; j += TG) acc[j] = 0.f;
+  __syncthreads();
+  const float* __restrict__ g = dZ + ((int64_t)b * C0 + c0) * MK;
+  const int64_t* __restrict__ idx = index + (int64_t)b * MK;
+  const float* __restrict__ x0 = xr + (int64_t)b * 3 * MK;
+  float t[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  for (int64_t e = threadIdx.x; e < MK; e += TG) {
+    const int64_t j = idx[e];
+    const float xa = x0[e], xb = x0[MK + e], xc = x0[2 * MK + e];
+    const float g0 = g[e], g1 = g[MK + e];
+    if (j < 0 || j >= N) *oob = 1;
+    else { atomicAdd(acc + j, g0); atomicAdd(acc + N + j, g1); }
+    t[0][0] = fmaf(g0, xa, t[0][0]); t[0][1] = fmaf(g0, xb, t[0][1]); t[0][2] = fmaf(g0, xc, t[0][2]);
+    t[1][0] = fmaf(g1, xa, t[1][0]); t[1][1] = fmaf(g1, xb, t[1][1]); t[1][2] = fmaf(g1, xc, t[1][2]);
+  }
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      float a = t[ch][d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if ((threadIdx.x & 31) == 0) red[3 * ch + d][threadIdx.x >> 5] = a;
+    }
+  __syncthreads();
+  float* __restrict__ o = dY + ((int64_t)b * C0 + c0) * N;
+  for (int j = threadIdx.x; j < 2 * N; j += TG) o[j] = acc[j];
+  if (threadIdx.x < 6) {
+    float a = 0.f;
+    for (int i = 0; i < TG / 32; ++i) a += red[threadIdx.x][i];
+    dwx_part[((int64_t)b * C0 + c0) * 3 + threadIdx.x] = a;
+  }
+}
+
 // Z[b, c, n] = sum_k w[b,n,k] * Ys[b, c, idx[b,n,k]] + sum_d Wd[c, d] * dense[b, d, n]   (nd dense channels, <= 4)
 __global__ void __launch_bounds__(TG)
 fp_gather_linear_kernel(const float* __restrict__ Ys, const int64_t* __restrict__ index, const float* __restrict__ weight,
@@ -862,7 +904,12 @@ int regnet_sa_scatter_linear(const float* dZ, const int64_t* index, const float*
   RN_CHECK_ARG(dZ && index && xyz_rel && dY && dwx_part, "sa_scatter_linear: null argument");
   RN_CHECK_ARG(B > 0 && C0 > 0 && N > 0 && M > 0 && K > 0, "sa_scatter_linear: bad shape");
   RN_CHECK_ARG(N <= ROWS_BIG && B <= 65535, "sa_scatter_linear: at most %d source points per cloud", ROWS_BIG);
-  // (a four-channel form of the scatter was measured slower: 80 KB of rows halve the resident CTAs, 1.10 -> 1.23 ms)
+  if (C0 % 2 == 0 && N <= CH4_MAX_ROWS && use_ch4(4, 0)) {
+    sa_scatter_linear2_kernel<<<dim3(C0 / 2, B), TG, sizeof(float) * 2 * (size_t)N, (cudaStream_t)stream>>>(
+        dZ, index, xyz_rel, C0, N, (int64_t)M * K, dY, dwx_part, oob_flag());
+    RN_LAUNCH_CHECK("sa_scatter_linear2_kernel");
+    return REGNET_OK;
+  }
   RN_TRY(allow_big_rows(sa_scatter_linear_kernel, N));
   sa_scatter_linear_kernel<<<dim3(C0, B), TG, sizeof(float) * (size_t)N, (cudaStream_t)stream>>>(
       dZ, index, xyz_rel, C0, N, (int64_t)M * K, dY, dwx_part, oob_flag());
