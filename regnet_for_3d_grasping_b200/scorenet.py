@@ -137,6 +137,10 @@ class ScoreNetPlan:
             raise RuntimeError("prefetch needs the contiguous (B, N, 6) float32 tensor that forward() will receive")
         with torch.cuda.device(self.device):
             _lib.check(_lib.load().regnet_scorenet_prefetch(self._h, _p(pc), _lib.current_stream_ptr()))
+        # The library keeps only the pointer, and a parked (deferred) prefetch reads it later: hold the tensors of the (at
+        # most two) outstanding prefetches so that a caller who drops its reference cannot leave that pointer dangling.
+        held = getattr(self, "_prefetched", [])
+        self._prefetched = (held + [pc])[-2:]
 
     def set_option(self, name, value):
         _lib.check(_lib.load().regnet_scorenet_set_option(self._h, name.encode(), int(value)))
